@@ -1,0 +1,83 @@
+// Internal structures shared by the host planner and the kernels of libsigb200.so.
+#pragma once
+#include <stdint.h>
+
+#define SIGB_MAX_SEC 16       // sections per fused chain launch (longer cascades are split)
+#define SIGB_SCAN_L 16        // rows per sub-chunk in the time-parallel scan kernel
+
+enum { SRC_OSC = 0, SRC_BUF = 1, SRC_CONST = 2 };
+
+// section kind bits (uniform over the channels of a chain)
+enum { SEC_HP = 1, SEC_FIRST_ORDER = 2 };
+
+enum { EW_COPY = 0, EW_GAIN = 1, EW_MIX = 2, EW_RINGMOD = 3, EW_AMP = 4 };
+
+// One fused per-channel chain:  source -> nsec state-variable sections -> gain -> store.
+// All per-channel tables are dense arrays of C entries (the host replicates broadcasts).
+struct ChainDev {
+    int32_t C;
+    int32_t src_kind;
+    int32_t wave;
+    int32_t nsec;
+    int32_t rate;
+    int32_t frames;                 // rows this launch covers
+    int64_t position;               // absolute index of row 0
+    uint8_t sec_kind[SIGB_MAX_SEC];
+    // SRC_OSC
+    const double* hertz;            // [C]
+    const double* phase;            // [C]
+    const unsigned long long* theta0;   // [C] frac(phase)    in Q0.64 (sine fast path)
+    const unsigned long long* dtheta;   // [C] frac(hertz/rate) in Q0.64
+    // SRC_BUF: src[row*src_ld + c*src_cs]; rows >= src_rows read as zero
+    const float* src;
+    int64_t src_ld;
+    int32_t src_cs;
+    int64_t src_rows;
+    // SRC_CONST
+    const float* constv;            // [C]
+    // sections: coef[(s*3+k)*C + c], k: 0=g 1=c(=r2+g) 2=d(=1/(1+r2 g+g^2));
+    //           first-order: 0=G(=g/(1+g))
+    const float* coef;
+    const float* gain;              // [C] or nullptr
+    double* state;                  // [(s*2+k)*C + c] integrator states (carried across launches)
+    // scan helpers (time-parallel kernel): transition A^L per section, and the zero-input
+    // output response of each state over one sub-chunk
+    const double* apow;             // [(s*4+k)*C + c], row-major 2x2
+    const float* ztab;              // [((s*L + k)*2 + j)*C + c]
+    float* out;
+    int64_t ld_out;
+};
+
+struct EwiseDev {
+    int32_t op;
+    int32_t C;
+    int32_t frames;
+    float* out; int64_t ld_out;
+    const float* a; int64_t lda; int32_t acs; int64_t a_rows;   // a_rows<0: unlimited
+    const float* b; int64_t ldb; int32_t bcs; int64_t b_rows;
+    const float* p;                 // per-channel parameter [C] (gain / mix / exp) or nullptr
+};
+
+struct ReduceDev {
+    int32_t C;          // input channels
+    int32_t groups;     // GROUPSUM: output channels; PANSUM: 2
+    int32_t frames;
+    int32_t pan;        // 0 = group sum, 1 = pan sum
+    const float* in; int64_t ld_in; int32_t ics; int64_t in_rows;
+    const float* w;     // PANSUM: pan[C]
+    float* out; int64_t ld_out;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+// launch wrappers implemented in sigb_kernels.cu; return cudaError_t as int
+int sigb_launch_chain_seq(const ChainDev* a, void* stream);
+int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stream, int* rows_done);
+int sigb_launch_ewise(const EwiseDev* a, void* stream);
+int sigb_launch_reduce(const ReduceDev* a, void* stream);
+int sigb_scan_rows_per_step(int nsec, int variant);
+int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,583 @@
+// Hand-written sm_100a kernels for the `signals` block-render hot path.
+//
+//   k_chain_seq   one thread per channel walking time sequentially (state in registers);
+//                 stateless chains (no filter sections) are tiled over time as well.
+//   k_chain_scan  the time-parallel kernel: a CTA owns a tile of 32 channels and walks time in
+//                 steps; each worker warp renders one sub-chunk of a step from zero filter state,
+//                 a scanner warp chains the sub-chunk end states with the fp64 2x2 transition
+//                 A^L of each state-variable section, and the workers add the zero-input
+//                 response of the true initial state before storing.
+//   k_ewise       binary / pointwise nodes on materialised blocks (Mix, RingMod, Amp, Gain, copy).
+//   k_reduce      channel reductions (GroupSum, PanSum) of a materialised block.
+//
+// Reference semantics being reproduced (file:line under /root/reference/src/signals/chain):
+//   osc.py:26-62   cycles = frame_range / rate * hertz + phase (float64, that op order), waveforms
+//   fx.py:35-60    Mix / RingMod / Gain / Amp
+//   fx.py:85-121   per-channel Butterworth low/high-pass == cascade of bilinear 2nd-order sections;
+//                  run here as zero-delay-feedback state-variable sections (same transfer function,
+//                  far better float32 behaviour at low cutoffs than the direct form scipy uses)
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "sigb200.h"
+#include "sigb_internal.h"
+
+namespace {
+
+constexpr int L = SIGB_SCAN_L;
+
+// ------------------------------------------------------------------------------------------
+// oscillators
+// ------------------------------------------------------------------------------------------
+
+// sin(2*pi*r) for r in [-0.5, 0.5], float32.  Folds to [-1/4, 1/4] (exact in float32) so the
+// MUFU.SIN absolute error and the 2*pi scaling error stay below ~2e-7.
+template <int VARIANT>
+__device__ __forceinline__ float sin2pi(float r) {
+    if (VARIANT == 0) {
+        return __sinf(r * 6.2831853071795864f);
+    } else {
+        float f = copysignf(0.5f, r) - r;          // exact (Sterbenz) when |r| >= 1/4
+        r = fabsf(r) > 0.25f ? f : r;
+        if (VARIANT == 1) {
+            return __sinf(r * 6.2831853071795864f);
+        } else {
+            float u = r * r;                        // x * P4(x^2), max error 1.7e-7
+            float p = 39.53670883178711f;
+            p = fmaf(p, u, -76.5497817993164f);
+            p = fmaf(p, u, 81.60100555419922f);
+            p = fmaf(p, u, -41.34165573120117f);
+            p = fmaf(p, u, 6.283185005187988f);
+            return p * r;
+        }
+    }
+}
+
+#ifndef SIGB_SIN_VARIANT
+#define SIGB_SIN_VARIANT 1
+#endif
+
+// numpy float remainder np.mod(a, b) for b in {1, 0.5}: fmod, then shift negatives up by b,
+// and +0.0 for an exact zero (npy_divmod semantics; osc.py:49,55,61-62 rely on them).
+template <int HALF>
+__device__ __forceinline__ double np_mod(double a) {
+    double m = HALF ? a - trunc(a * 2.0) * 0.5 : a - trunc(a);   // == fmod(a, b), exact
+    if (m != 0.0) {
+        if (m < 0.0) m = __dadd_rn(m, HALF ? 0.5 : 1.0);
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
+
+__device__ __forceinline__ double np_sign(double v) {
+    return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : v));   // NaN stays NaN
+}
+
+// osc.py:32 with the reference's exact float64 op order and no FMA contraction.
+__device__ __forceinline__ double osc_cycles(double tn, double hertz, double phase) {
+    return __dadd_rn(__dmul_rn(tn, hertz), phase);
+}
+
+__device__ __forceinline__ float osc_wave(int wave, double cyc) {
+    switch (wave) {
+        case SIGB_WAVE_SINE: {
+            double r = cyc - rint(cyc);                                   // exact
+            return sin2pi<SIGB_SIN_VARIANT>((float)r);
+        }
+        case SIGB_WAVE_SQUARE:                                           // osc.py:49
+            return (float)np_sign(__dadd_rn(0.5, -np_mod<0>(cyc)));
+        case SIGB_WAVE_SAWTOOTH:                                              // osc.py:55
+            return (float)__dadd_rn(__dmul_rn(2.0, np_mod<0>(__dadd_rn(cyc, -0.5))), -1.0);
+        default: {                                                        // osc.py:61-62
+            double t = __dadd_rn(cyc, -0.25);
+            double a = __dadd_rn(__dmul_rn(4.0, np_mod<1>(t)), -1.0);
+            double s = np_sign(__dadd_rn(np_mod<0>(t), -0.5));
+            return (float)__dmul_rn(a, s);
+        }
+    }
+}
+
+// sine from a Q0.64 phase accumulator: the top 32 bits as a signed fraction of a cycle
+__device__ __forceinline__ float sine_q64(unsigned long long th) {
+    int hi = (int)(th >> 32);
+    return sin2pi<SIGB_SIN_VARIANT>((float)hi * 2.3283064365386963e-10f);
+}
+
+// ------------------------------------------------------------------------------------------
+// zero-delay-feedback state-variable section (one 2nd-order Butterworth factor)
+//   hp = d (x - c s1 - s2);  bp = g hp + s1;  s1' = g hp + bp;  lp = g bp + s2;  s2' = g bp + lp
+// first-order section: v = G (x - s1); lp = v + s1; s1' = lp + v; hp = x - lp
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float svf_lp2(float x, float g, float c, float d, float& s1, float& s2) {
+    float t = fmaf(-c, s1, x);
+    float hp = (t - s2) * d;
+    float bp = fmaf(g, hp, s1);
+    s1 = fmaf(g, hp, bp);
+    float lp = fmaf(g, bp, s2);
+    s2 = fmaf(g, bp, lp);
+    return lp;
+}
+
+__device__ __forceinline__ float svf_any(int kind, float x, float g, float c, float d, float& s1, float& s2) {
+    if (kind & SEC_FIRST_ORDER) {
+        float v = (x - s1) * g;
+        float lp = v + s1;
+        s1 = lp + v;
+        return (kind & SEC_HP) ? x - lp : lp;
+    }
+    float t = fmaf(-c, s1, x);
+    float hp = (t - s2) * d;
+    float bp = fmaf(g, hp, s1);
+    s1 = fmaf(g, hp, bp);
+    float lp = fmaf(g, bp, s2);
+    s2 = fmaf(g, bp, lp);
+    return (kind & SEC_HP) ? hp : lp;
+}
+
+__device__ __forceinline__ float load_src(const ChainDev& a, int64_t row, int c) {
+    if (row >= a.src_rows) return 0.0f;
+    return __ldg(a.src + row * a.src_ld + (int64_t)c * a.src_cs);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_chain_seq
+// ------------------------------------------------------------------------------------------
+template <int SRC, int NSEC>
+__global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_per_seg) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.C) return;
+    int r0 = 0, r1 = a.frames;
+    if (NSEC == 0) {                      // stateless: time is tiled over blockIdx.y
+        r0 = blockIdx.y * rows_per_seg;
+        r1 = min(a.frames, r0 + rows_per_seg);
+    }
+    float g[NSEC > 0 ? NSEC : 1], cc[NSEC > 0 ? NSEC : 1], d[NSEC > 0 ? NSEC : 1];
+    float s1[NSEC > 0 ? NSEC : 1], s2[NSEC > 0 ? NSEC : 1];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        g[s] = a.coef[(size_t)(s * 3 + 0) * a.C + c];
+        cc[s] = a.coef[(size_t)(s * 3 + 1) * a.C + c];
+        d[s] = a.coef[(size_t)(s * 3 + 2) * a.C + c];
+        s1[s] = (float)a.state[(size_t)(s * 2 + 0) * a.C + c];
+        s2[s] = (float)a.state[(size_t)(s * 2 + 1) * a.C + c];
+    }
+    const float gain = a.gain ? a.gain[c] : 1.0f;
+    double hz = 0.0, ph = 0.0;
+    float cv = 0.0f;
+    if (SRC == SRC_OSC) { hz = a.hertz[c]; ph = a.phase[c]; }
+    if (SRC == SRC_CONST) cv = a.constv[c];
+    const double rate = (double)a.rate;
+    float* outp = a.out + (int64_t)r0 * a.ld_out + c;
+    for (int r = r0; r < r1; ++r) {
+        float x;
+        if (SRC == SRC_OSC) {
+            double tn = __ddiv_rn((double)(a.position + r), rate);
+            x = osc_wave(a.wave, osc_cycles(tn, hz, ph));
+        } else if (SRC == SRC_BUF) {
+            x = load_src(a, r, c);
+        } else {
+            x = cv;
+        }
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) x = svf_any(a.sec_kind[s], x, g[s], cc[s], d[s], s1[s], s2[s]);
+        __stcs(outp, x * gain);
+        outp += a.ld_out;
+    }
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        a.state[(size_t)(s * 2 + 0) * a.C + c] = (double)s1[s];
+        a.state[(size_t)(s * 2 + 1) * a.C + c] = (double)s2[s];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_chain_scan
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// NG groups of WG worker warps + 1 scanner warp.  Group g renders steps g, g+NG, g+2NG, ...;
+// a step is WG sub-chunks of L rows.  Named barrier 1+2g: "end states of group g published",
+// 2+2g: "initial states for group g published".
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
+__global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const ChainDev a, int nsteps) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * L;                    // rows per step
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* zs = reinterpret_cast<float2*>(smem_raw);             // [NW][32] sub-chunk end states
+    float2* si = zs + NW * 32;                                     // [NW][32] true initial states
+    float2* tab = si + NW * 32;                                    // [NSEC][L][32] zero-input responses
+    double* tnb = reinterpret_cast<double*>(tab + NSEC * L * 32);  // [NW][L] n/rate (generic osc)
+
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const bool live = c < a.C;
+    const int cc = live ? c : a.C - 1;
+    const size_t C = (size_t)a.C;
+
+    for (int i = threadIdx.x; i < NSEC * L * 32; i += blockDim.x) {
+        int l = i & 31, k = (i >> 5) % L, s = (i >> 5) / L;
+        int ch = min(blockIdx.x * 32 + l, a.C - 1);
+        tab[i] = make_float2(a.ztab[((size_t)(s * L + k) * 2 + 0) * C + ch],
+                             a.ztab[((size_t)(s * L + k) * 2 + 1) * C + ch]);
+    }
+    __syncthreads();
+
+    if (w == NW) {
+        // ---------------- scanner warp: lane = channel, fp64 carries ----------------
+        double m[NSEC][4], c1[NSEC], c2[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m[s][k] = a.apow[(size_t)(s * 4 + k) * C + cc];
+            c1[s] = a.state[(size_t)(s * 2 + 0) * C + cc];
+            c2[s] = a.state[(size_t)(s * 2 + 1) * C + cc];
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            const int grp = step % NG;
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                constexpr int ZB = 8;                       // end states fetched ZB at a time
+                for (int q0 = 0; q0 < WG; q0 += ZB) {
+                    float2 z[ZB];
+#pragma unroll
+                    for (int j = 0; j < ZB; ++j)
+                        if (q0 + j < WG) z[j] = zs[(grp * WG + q0 + j) * 32 + lane];
+#pragma unroll
+                    for (int j = 0; j < ZB; ++j) {
+                        if (q0 + j < WG) {
+                            si[(grp * WG + q0 + j) * 32 + lane] = make_float2((float)c1[s], (float)c2[s]);
+                            double n1 = fma(m[s][0], c1[s], fma(m[s][1], c2[s], (double)z[j].x));
+                            double n2 = fma(m[s][2], c1[s], fma(m[s][3], c2[s], (double)z[j].y));
+                            c1[s] = n1;
+                            c2[s] = n2;
+                        }
+                    }
+                }
+                bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                a.state[(size_t)(s * 2 + 0) * C + c] = c1[s];
+                a.state[(size_t)(s * 2 + 1) * C + c] = c2[s];
+            }
+        }
+        return;
+    }
+
+    // ---------------- worker warps: lane = channel, warp = sub-chunk ----------------
+    const int grp = w / WG, q = w % WG;
+    float g[NSEC], cf[NSEC], d[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        g[s] = a.coef[(size_t)(s * 3 + 0) * C + cc];
+        cf[s] = a.coef[(size_t)(s * 3 + 1) * C + cc];
+        d[s] = a.coef[(size_t)(s * 3 + 2) * C + cc];
+    }
+    const float gain = a.gain ? a.gain[cc] : 1.0f;
+    // first row of this warp's first sub-chunk; advances by NG*STEP rows per iteration
+    int64_t row = (int64_t)grp * STEP + (int64_t)q * L;
+    const int64_t row_stride = (int64_t)NG * STEP;
+    float* outp = a.out + row * a.ld_out + c;
+    const int64_t out_stride = row_stride * a.ld_out;
+    unsigned long long th = 0, dth = 0, th_skip = 0;
+    double hz = 0.0, ph = 0.0;
+    float cv = 0.0f;
+    if (SRC == SRC_OSC) {
+        if (FASTSINE) {
+            dth = a.dtheta[cc];
+            th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
+            th_skip = dth * (unsigned long long)(row_stride - L);
+        } else {
+            hz = a.hertz[cc];
+            ph = a.phase[cc];
+        }
+    }
+    if (SRC == SRC_CONST) cv = a.constv[cc];
+    const double rate = (double)a.rate;
+
+    for (int step = grp; step < nsteps; step += NG) {
+        float v[L];
+        if (SRC == SRC_OSC) {
+            if (FASTSINE) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    v[k] = sine_q64(th);
+                    th += dth;
+                }
+                th += th_skip;
+            } else {
+                if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < L; ++k) v[k] = osc_wave(a.wave, osc_cycles(tnb[w * L + k], hz, ph));
+                __syncwarp();
+            }
+        } else if (SRC == SRC_BUF) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) v[k] = live ? load_src(a, row + k, c) : 0.0f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) v[k] = cv;
+        }
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            float s1 = 0.0f, s2 = 0.0f;
+            if (ALLLP) {
+#pragma unroll
+                for (int k = 0; k < L; ++k) v[k] = svf_lp2(v[k], g[s], cf[s], d[s], s1, s2);
+            } else {
+                const int kind = a.sec_kind[s];
+#pragma unroll
+                for (int k = 0; k < L; ++k) v[k] = svf_any(kind, v[k], g[s], cf[s], d[s], s1, s2);
+            }
+            zs[w * 32 + lane] = make_float2(s1, s2);
+            bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+            bar_sync(2 + 2 * grp, (WG + 1) * 32);
+            const float2 i0 = si[w * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                const float2 t = tab[(s * L + k) * 32 + lane];
+                v[k] = fmaf(t.x, i0.x, fmaf(t.y, i0.y, v[k]));
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < L; ++k) __stcs(outp + (int64_t)k * a.ld_out, v[k] * gain);
+        }
+        outp += out_stride;
+        row += row_stride;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ewise / k_reduce
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ew_load(const float* p, int64_t ld, int cs, int64_t rows, int64_t r, int c) {
+    if (rows >= 0 && r >= rows) return 0.0f;
+    return __ldg(p + r * ld + (int64_t)c * cs);
+}
+
+__global__ void __launch_bounds__(256) k_ewise(const EwiseDev a) {
+    const int64_t total = (int64_t)a.frames * a.C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / a.C;
+        const int c = (int)(i - r * a.C);
+        const float x = ew_load(a.a, a.lda, a.acs, a.a_rows, r, c);
+        float y;
+        switch (a.op) {
+            case EW_COPY: y = x; break;
+            case EW_GAIN: y = x * a.p[c]; break;                                   // fx.py:52
+            case EW_MIX: {                                                          // fx.py:40
+                const float m = a.p[c];
+                y = m * x + (1.0f - m) * ew_load(a.b, a.ldb, a.bcs, a.b_rows, r, c);
+                break;
+            }
+            case EW_RINGMOD: y = x * ew_load(a.b, a.ldb, a.bcs, a.b_rows, r, c); break;   // fx.py:46
+            default: y = copysignf(powf(x, a.p[c]), x); break;                      // fx.py:60
+        }
+        a.out[r * a.ld_out + c] = y;
+    }
+}
+
+// one warp per (row, group): float32 lane partials, float64 cross-lane tree (fixed order)
+__global__ void __launch_bounds__(256) k_reduce(const ReduceDev a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int ngroups = a.pan ? 1 : a.groups;
+    const int per = a.C / ngroups;
+    for (int64_t item = warp; item < (int64_t)a.frames * ngroups; item += nwarps) {
+        const int64_t r = item / ngroups;
+        const int gidx = (int)(item - r * ngroups);
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int j0 = 0; j0 < per; j0 += 32 * 32) {
+            float p0 = 0.0f, p1 = 0.0f;                 // <=32 terms in float32, then float64
+            for (int j = j0 + lane; j < min(per, j0 + 32 * 32); j += 32) {
+                const int c = gidx * per + j;
+                const float x = ew_load(a.in, a.ld_in, a.ics, a.in_rows, r, c);
+                if (a.pan) {
+                    const float pn = a.w[c];
+                    p0 = fmaf(x, 1.0f - pn, p0);
+                    p1 = fmaf(x, pn, p1);
+                } else {
+                    p0 += x;
+                }
+            }
+            acc0 += (double)p0;
+            acc1 += (double)p1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        if (lane == 0) {
+            if (a.pan) {
+                a.out[r * a.ld_out + 0] = (float)acc0;
+                a.out[r * a.ld_out + 1] = (float)acc1;
+            } else {
+                a.out[r * a.ld_out + gidx] = (float)acc0;
+            }
+        }
+    }
+}
+
+__global__ void k_probe_sin(const double* r, int n, float* out, int variant) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = (float)r[i];
+    out[i] = variant == 0 ? sin2pi<0>(x) : (variant == 1 ? sin2pi<1>(x) : sin2pi<2>(x));
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+template <int SRC>
+cudaError_t launch_seq_src(const ChainDev& a, cudaStream_t st) {
+    dim3 block(128);
+    dim3 grid((a.C + 127) / 128, 1);
+    int rows_per_seg = a.frames;
+    int nsec = a.nsec;
+    if (nsec == 0) {
+        // stateless: tile time so the grid fills the machine
+        int want = (148 * 16 + (int)grid.x - 1) / (int)grid.x;
+        int segs = max(1, min(want, (a.frames + 63) / 64));
+        segs = min(segs, 65535);
+        rows_per_seg = (a.frames + segs - 1) / segs;
+        grid.y = (a.frames + rows_per_seg - 1) / rows_per_seg;
+    }
+#define SEQ_CASE(N) k_chain_seq<SRC, N><<<grid, block, 0, st>>>(a, rows_per_seg)
+    if (nsec == 0) SEQ_CASE(0);
+    else if (nsec == 1) SEQ_CASE(1);
+    else if (nsec == 2) SEQ_CASE(2);
+    else if (nsec <= 4) SEQ_CASE(4);
+    else if (nsec <= 8) SEQ_CASE(8);
+    else SEQ_CASE(16);
+#undef SEQ_CASE
+    return cudaGetLastError();
+}
+
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
+cudaError_t launch_scan_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * L;
+    const int nsteps = a.frames / STEP;
+    *rows_done = nsteps * STEP;
+    if (nsteps == 0) return cudaSuccess;
+    size_t smem = (size_t)NW * 32 * sizeof(float2) * 2 + (size_t)NSEC * L * 32 * sizeof(float2) +
+                  (size_t)NW * L * sizeof(double);
+    auto kern = k_chain_scan<SRC, NSEC, NG, WG, FASTSINE, ALLLP>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((a.C + 31) / 32), block((NW + 1) * 32);
+    kern<<<grid, block, smem, st>>>(a, nsteps);
+    return cudaGetLastError();
+}
+
+template <int SRC, int NSEC, int NG, int WG>
+cudaError_t launch_scan_src(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    bool alllp = true;
+    for (int s = 0; s < a.nsec; ++s) alllp = alllp && a.sec_kind[s] == 0;
+    const bool fast = SRC == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
+    if (SRC == SRC_OSC && fast) {
+        return alllp ? launch_scan_t<SRC_OSC, NSEC, NG, WG, true, true>(a, st, rows_done)
+                     : launch_scan_t<SRC_OSC, NSEC, NG, WG, true, false>(a, st, rows_done);
+    }
+    return alllp ? launch_scan_t<SRC, NSEC, NG, WG, false, true>(a, st, rows_done)
+                 : launch_scan_t<SRC, NSEC, NG, WG, false, false>(a, st, rows_done);
+}
+
+template <int NSEC, int NG, int WG>
+cudaError_t launch_scan_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    switch (a.src_kind) {
+        case SRC_OSC: return launch_scan_src<SRC_OSC, NSEC, NG, WG>(a, st, rows_done);
+        case SRC_BUF: return launch_scan_src<SRC_BUF, NSEC, NG, WG>(a, st, rows_done);
+        default: return launch_scan_src<SRC_CONST, NSEC, NG, WG>(a, st, rows_done);
+    }
+}
+
+}  // namespace
+
+// scan geometry: (groups, worker warps per group).  Deep cascades keep the block at 512 threads
+// so the scanner's fp64 transition matrices stay in registers.
+static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
+    if (nsec > 2) { *ng = 2; *wg = 7; return; }
+    switch (variant) {
+        case 1: *ng = 2; *wg = 15; break;
+        case 2: *ng = 4; *wg = 7; break;
+        case 3: *ng = 2; *wg = 7; break;
+        default: *ng = 1; *wg = 31; break;
+    }
+}
+
+extern "C" int sigb_scan_rows_per_step(int nsec, int variant) {
+    int ng, wg;
+    scan_geometry(nsec, variant, &ng, &wg);
+    return wg * L;
+}
+
+extern "C" int sigb_launch_chain_seq(const ChainDev* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0 || a->C <= 0) return 0;
+    switch (a->src_kind) {
+        case SRC_OSC: return (int)launch_seq_src<SRC_OSC>(*a, st);
+        case SRC_BUF: return (int)launch_seq_src<SRC_BUF>(*a, st);
+        default: return (int)launch_seq_src<SRC_CONST>(*a, st);
+    }
+}
+
+// Renders the leading whole steps of `a` with the time-parallel kernel; *rows_done tells the
+// caller how many rows were covered (the tail goes through k_chain_seq).
+extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stream, int* rows_done) {
+    cudaStream_t st = (cudaStream_t)stream;
+    *rows_done = 0;
+    if (a->frames <= 0 || a->C <= 0 || a->nsec < 1 || a->nsec > 8) return 0;
+    int ng, wg;
+    scan_geometry(a->nsec, variant, &ng, &wg);
+    if (a->nsec > 2) {
+        if (a->nsec <= 4) return (int)launch_scan_n<4, 2, 7>(*a, st, rows_done);
+        return (int)launch_scan_n<8, 2, 7>(*a, st, rows_done);
+    }
+#define SCAN_DISPATCH(NG, WG)                                                        \
+    do {                                                                             \
+        if (a->nsec == 1) return (int)launch_scan_n<1, NG, WG>(*a, st, rows_done);   \
+        return (int)launch_scan_n<2, NG, WG>(*a, st, rows_done);                     \
+    } while (0)
+    if (ng == 2 && wg == 15) SCAN_DISPATCH(2, 15);
+    if (ng == 4) SCAN_DISPATCH(4, 7);
+    if (ng == 2) SCAN_DISPATCH(2, 7);
+    SCAN_DISPATCH(1, 31);
+#undef SCAN_DISPATCH
+}
+
+extern "C" int sigb_launch_ewise(const EwiseDev* a, void* stream) {
+    if (a->frames <= 0 || a->C <= 0) return 0;
+    const int64_t total = (int64_t)a->frames * a->C;
+    int blocks = (int)min((int64_t)148 * 16, (total + 255) / 256);
+    k_ewise<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sigb_launch_reduce(const ReduceDev* a, void* stream) {
+    if (a->frames <= 0 || a->C <= 0) return 0;
+    const int64_t items = (int64_t)a->frames * (a->pan ? 1 : a->groups);
+    int blocks = (int)min((int64_t)148 * 8, (items + 7) / 8);
+    k_reduce<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream) {
+    k_probe_sin<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(r, n, out, variant);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,1069 @@
+// libsigb200 host runtime: graph records -> fused launch plan -> render.
+//
+// The reference evaluates its node graph by Python recursion, one numpy temporary per edge per
+// block (/root/reference/src/signals/chain/__init__.py:245-315).  Here the host compiles the
+// topologically sorted node records once into a short list of kernel launches:
+//   * every maximal linear run  Osc|block -> {Gain, LowPass, HighPass}*  becomes ONE chain launch
+//     (all gains folded into one per-channel factor: the filters are linear and time-invariant),
+//   * Mix / RingMod / Amp / Merge / GroupSum / PanSum run on materialised float32 blocks,
+//   * filter state lives in the plan and is carried from one render call to the next.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "sigb200.h"
+#include "sigb_design.h"
+#include "sigb_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(SIGB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+enum ValKind { VK_NONE = 0, VK_CONST, VK_BUF, VK_EXT };
+
+struct Val {
+    ValKind kind = VK_NONE;
+    int channels = 1;
+    std::vector<double> cv;   // VK_CONST
+    int buf = -1;             // VK_BUF: index into Plan::bufs (-1 = the caller's `out`)
+    int64_t const_off = -1;   // VK_CONST: float offset in the arena once staged
+};
+
+struct BufInfo {
+    int channels = 0;
+    float* ptr = nullptr;
+    int64_t cap_rows = 0;
+};
+
+struct ExtBinding {
+    const float* ptr = nullptr;
+    int64_t rows = 0;
+};
+
+// A table staged in the arena: byte offset + size; resolved to a device pointer after upload.
+struct Table {
+    int64_t off = -1;
+    template <class T> const T* dev(const unsigned char* base) const {
+        return off < 0 ? nullptr : reinterpret_cast<const T*>(base + off);
+    }
+};
+
+struct ChainSpec {
+    int C = 0;
+    int src_kind = SRC_CONST;
+    int wave = 0;
+    int nsec = 0;                // padded section count the kernels run
+    int nsec_real = 0;
+    uint8_t sec_kind[SIGB_MAX_SEC] = {0};
+    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, ztab;
+    int src_node = -1;           // SRC_BUF: node whose value is read
+    int64_t state_off = 0;       // doubles into the state arena
+    int dst_node = -1;
+};
+
+struct EwiseSpec {
+    int op = EW_COPY;
+    int C = 0;
+    int a_node = -1, b_node = -1;   // -1 = zeros(1,1)
+    Table p;
+    int dst_node = -1;
+    int dst_coff = 0;
+};
+
+struct ReduceSpec {
+    int C = 0, groups = 0, pan = 0;
+    int in_node = -1;
+    Table w;
+    int dst_node = -1;
+};
+
+enum LaunchKind { LK_CHAIN, LK_EWISE, LK_REDUCE };
+struct Launch {
+    LaunchKind kind;
+    int idx;
+};
+
+}  // namespace
+
+struct sigb_plan {
+    int channels = 0, rate = 0, root = -1;
+    std::vector<sigb_node> nodes;
+    std::vector<double> data;
+    std::vector<Val> vals;
+    std::vector<int> uses;
+    std::vector<int> node_ctx;      // warm-up frames a seek needs at this node (fx.py:82-83, summed down a cascade)
+    std::vector<BufInfo> bufs;
+    std::vector<ExtBinding> ext;        // per node
+    std::vector<ChainSpec> chains;
+    std::vector<EwiseSpec> ewises;
+    std::vector<ReduceSpec> reduces;
+    std::vector<Launch> launches;
+    std::vector<unsigned char> arena;   // host image of all parameter tables
+    unsigned char* d_arena = nullptr;
+    int64_t n_state = 0;
+    double* d_state = nullptr;
+    int context = 0;
+    int zero_const_node = -1;
+    Val zero_val;
+    // options
+    int64_t opt_scan_variant = 2;
+    int64_t opt_force_seq = 0;
+    int64_t opt_scan_max_tiles = 148 * 6;
+    int64_t opt_slab_frames = 0;
+    int64_t opt_host_slab_bytes = 64ll << 20;
+    int64_t opt_buffer_budget = 6ll << 30;
+    // runtime
+    bool uploaded = false;
+    bool have_pos = false;
+    int64_t next_pos = 0;
+    int64_t launch_count = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    float* scratch = nullptr;
+    int64_t scratch_floats = 0;
+    // host-render resources
+    cudaStream_t s_render = nullptr, s_copy = nullptr;
+    float* stage[2] = {nullptr, nullptr};
+    int64_t stage_floats = 0;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int64_t arena_put(sigb_plan* p, const void* src, size_t bytes) {
+    size_t off = (p->arena.size() + 255) & ~size_t(255);
+    p->arena.resize(off + bytes);
+    std::memcpy(p->arena.data() + off, src, bytes);
+    return (int64_t)off;
+}
+
+template <class T>
+Table put_vec(sigb_plan* p, const std::vector<T>& v) {
+    Table t;
+    t.off = arena_put(p, v.data(), v.size() * sizeof(T));
+    return t;
+}
+
+bool is_chain_kind(int kind) { return kind == SIGB_NODE_OSC || kind == SIGB_NODE_GAIN || kind == SIGB_NODE_FILTER; }
+
+// value of a block-rate / constant port: nullptr when the node is not a compile-time constant
+const std::vector<double>* const_of(sigb_plan* p, int idx) {
+    if (idx < 0) return &p->zero_val.cv;
+    const Val& v = p->vals[idx];
+    return v.kind == VK_CONST ? &v.cv : nullptr;
+}
+
+// replicate a (1,1)/(1,C) constant row to C entries; false when not broadcast-compatible
+bool rep(const std::vector<double>& v, int C, std::vector<double>* out) {
+    if ((int)v.size() == C) { *out = v; return true; }
+    if (v.size() == 1) { out->assign(C, v[0]); return true; }
+    return false;
+}
+
+int section_count(int order) { return order / 2 + (order & 1); }
+
+int pad_sections(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return n == 0 ? 0 : p;
+}
+
+unsigned long long frac_q64(double x) {
+    // frac(x) in Q0.64 for finite x (float64 has at most 53 significant bits, so this is exact
+    // whenever x - floor(x) is; a tiny negative x rounds to 1.0 == 0 cycles)
+    if (!std::isfinite(x)) return 0ull;
+    const double f = x - std::floor(x);
+    if (!(f < 1.0)) return 0ull;
+    const double scaled = std::ldexp(f, 32);
+    const double hi = std::floor(scaled);
+    const double lo = scaled - hi;              // exact, in [0,1)
+    return ((unsigned long long)hi << 32) | (unsigned long long)std::floor(std::ldexp(lo, 32));
+}
+
+// floor(frac(hertz / rate) * 2^64), exact integer arithmetic on the float64 mantissa.
+// Negative frequencies map to the two's-complement (phase runs backwards).
+unsigned long long ratio_q64(double hertz, int rate) {
+    if (!std::isfinite(hertz) || rate <= 0 || hertz == 0.0) return 0ull;
+    int e;
+    const double m = std::frexp(std::fabs(hertz), &e);                        // |hertz| = m 2^e
+    const unsigned long long mant = (unsigned long long)std::ldexp(m, 53);    // 53-bit integer
+    e -= 53;                                                                  // |hertz| = mant 2^e
+    const unsigned __int128 R = (unsigned __int128)(unsigned)rate;
+    unsigned long long q;
+    if (e >= 0) {
+        unsigned __int128 r = (unsigned __int128)mant % R;                    // whole cycles drop out
+        for (int i = 0; i < e; ++i) r = (r << 1) % R;
+        q = (unsigned long long)((r << 64) / R);
+    } else {
+        const int k = -e;
+        unsigned __int128 num;
+        if (k <= 64) num = (unsigned __int128)mant << (64 - k);
+        else num = (k - 64 >= 64) ? 0 : ((unsigned __int128)mant >> (k - 64));
+        q = (unsigned long long)(num / R);                                    // low 64 bits = mod 2^64
+    }
+    return hertz < 0.0 ? (0ull - q) : q;
+}
+
+struct Builder {
+    sigb_plan* p;
+    int err = SIGB_OK;
+
+    int node_C(int i) const { return i == p->root ? p->channels : p->nodes[i].channels; }
+
+    int ensure(int i);            // materialise node i's value (emits launches); returns status
+    int build_chain(int i);
+    int build_ewise(int i);
+    int build_merge(int i);
+    int build_reduce(int i);
+    int new_buf(int i) {
+        if (i == p->root) return -1;
+        BufInfo b;
+        b.channels = p->nodes[i].channels;
+        p->bufs.push_back(b);
+        return (int)p->bufs.size() - 1;
+    }
+};
+
+int Builder::ensure(int i) {
+    if (i < 0) return SIGB_OK;
+    if (p->vals[i].kind != VK_NONE) return SIGB_OK;
+    const sigb_node& n = p->nodes[i];
+    switch (n.kind) {
+        case SIGB_NODE_OSC:
+        case SIGB_NODE_GAIN:
+        case SIGB_NODE_FILTER: return build_chain(i);
+        case SIGB_NODE_MIX:
+        case SIGB_NODE_RINGMOD:
+        case SIGB_NODE_AMP: return build_ewise(i);
+        case SIGB_NODE_MERGE: return build_merge(i);
+        case SIGB_NODE_GROUPSUM:
+        case SIGB_NODE_PANSUM: return build_reduce(i);
+        default: return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": unexpected kind");
+    }
+}
+
+int Builder::build_chain(int i) {
+    ChainSpec ch;
+    const int C = node_C(i);
+    ch.C = C;
+    ch.dst_node = i;
+    std::vector<double> gain(C, 1.0);
+    bool has_gain = false;
+    std::vector<int> filters;     // sink-to-source order
+    int nsec = 0;
+    int cur = i;
+    std::vector<double> tmp;
+    for (;;) {
+        const sigb_node& n = p->nodes[cur];
+        if (n.kind == SIGB_NODE_OSC) {
+            const std::vector<double>* hz = const_of(p, n.in[0]);
+            const std::vector<double>* ph = const_of(p, n.in[1]);
+            if (!hz || !ph)
+                return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(cur) + ": oscillator hertz/phase driven by a non-constant emitter");
+            std::vector<double> hzv, phv;
+            if (!rep(*hz, C, &hzv) || !rep(*ph, C, &phv))
+                return fail(SIGB_ESHAPE, "node " + std::to_string(cur) + ": hertz/phase channels incompatible with " + std::to_string(C));
+            ch.src_kind = SRC_OSC;
+            ch.wave = n.subtype;
+            ch.hertz = put_vec(p, hzv);
+            ch.phase = put_vec(p, phv);
+            if (n.subtype == SIGB_WAVE_SINE) {
+                std::vector<unsigned long long> t0(C), dt(C);
+                for (int c = 0; c < C; ++c) {
+                    t0[c] = frac_q64(phv[c]);
+                    dt[c] = ratio_q64(hzv[c], p->rate);
+                }
+                ch.theta0 = put_vec(p, t0);
+                ch.dtheta = put_vec(p, dt);
+            }
+            break;
+        }
+        int up;
+        if (n.kind == SIGB_NODE_GAIN) {
+            const std::vector<double>* g = const_of(p, n.in[1]);
+            if (!g) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(cur) + ": Gain.right driven by a non-constant emitter");
+            if (!rep(*g, C, &tmp)) return fail(SIGB_ESHAPE, "node " + std::to_string(cur) + ": gain channels incompatible");
+            for (int c = 0; c < C; ++c) gain[c] *= tmp[c];
+            has_gain = true;
+            up = n.in[0];
+        } else {   // FILTER
+            if (n.subtype != SIGB_FILT_LOWPASS && n.subtype != SIGB_FILT_HIGHPASS)
+                return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(cur) + ": band filters are unreachable in the reference (fx.py:99)");
+            if (n.order < 1) return fail(SIGB_EINVAL, "node " + std::to_string(cur) + ": filter order < 1");
+            filters.push_back(cur);
+            nsec += section_count(n.order);
+            up = n.in[0];
+        }
+        if (up < 0) {
+            if (!filters.empty() && C > 1)
+                return fail(SIGB_EINDEX, "node " + std::to_string(cur) + ": filter input narrower than the request (fx.py:105)");
+            ch.src_kind = SRC_CONST;
+            ch.constv = put_vec(p, std::vector<float>(C, 0.0f));
+            break;
+        }
+        const sigb_node& u = p->nodes[up];
+        bool fusable = is_chain_kind(u.kind) && p->uses[up] == 1 && p->vals[up].kind == VK_NONE;
+        if (fusable && u.kind == SIGB_NODE_FILTER && nsec + section_count(u.order) > SIGB_MAX_SEC) fusable = false;
+        // a filter needs its input at full width (fx.py:105 indexes input_[:, i])
+        if (n.kind == SIGB_NODE_FILTER && C > 1 && u.channels != C)
+            return fail(SIGB_EINDEX, "node " + std::to_string(cur) + ": filter input narrower than the request (fx.py:105)");
+        if (fusable) {
+            cur = up;
+            continue;
+        }
+        int st = ensure(up);
+        if (st != SIGB_OK) return st;
+        const Val& uv = p->vals[up];
+        if (uv.channels != 1 && uv.channels != C)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(up) + ": block with " + std::to_string(uv.channels) + " channels incompatible with requested " + std::to_string(C));
+        if (uv.kind == VK_CONST) {
+            std::vector<double> cvd;
+            rep(uv.cv, C, &cvd);
+            std::vector<float> cvf(cvd.begin(), cvd.end());
+            ch.src_kind = SRC_CONST;
+            ch.constv = put_vec(p, cvf);
+        } else {
+            ch.src_kind = SRC_BUF;
+            ch.src_node = up;
+        }
+        break;
+    }
+    // sections, source-to-sink
+    std::reverse(filters.begin(), filters.end());
+    ch.nsec_real = nsec;
+    ch.nsec = pad_sections(nsec);
+    if (ch.nsec > SIGB_MAX_SEC) return fail(SIGB_EUNSUPPORTED, "filter cascade longer than 16 sections in one node");
+    if (ch.nsec > 0) {
+        std::vector<float> coef((size_t)ch.nsec * 3 * C, 0.0f);
+        std::vector<double> apow((size_t)ch.nsec * 4 * C, 0.0);
+        std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * C, 0.0f);
+        for (int s = 0; s < ch.nsec; ++s) {   // identity padding: high-pass with g = 0 passes x through
+            ch.sec_kind[s] = SEC_HP;
+            for (int c = 0; c < C; ++c) {
+                coef[((size_t)s * 3 + 2) * C + c] = 1.0f;
+                apow[((size_t)s * 4 + 0) * C + c] = 1.0;
+                apow[((size_t)s * 4 + 3) * C + c] = 1.0;
+            }
+        }
+        int s0 = 0;
+        for (int f : filters) {
+            const sigb_node& n = p->nodes[f];
+            const std::vector<double>* cut = const_of(p, n.in[1]);
+            if (!cut) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(f) + ": filter cutoff driven by a non-constant emitter");
+            if ((int)cut->size() != C)   // crit_1[0, i] is not broadcast (fx.py:99)
+                return fail(SIGB_EINDEX, "node " + std::to_string(f) + ": cutoff has " + std::to_string(cut->size()) + " channels, request has " + std::to_string(C));
+            const int ns = section_count(n.order);
+            float tab[SIGB_SCAN_L * 2];
+            for (int c = 0; c < C; ++c) {
+                double wn = (*cut)[c] / (p->rate / 2.0);
+                wn = std::min(std::max(wn, 0.0), 1.0);   // fx.py:100-101
+                if (!(wn > 0.0 && wn < 1.0))              // scipy.signal.butter: "0 < Wn < 1"
+                    return fail(SIGB_ECRIT, "node " + std::to_string(f) + ": Digital filter critical frequencies must be 0 < Wn < 1");
+                std::vector<SvfSection> secs = sigb_butter_sections(n.subtype == SIGB_FILT_HIGHPASS, n.order, wn);
+                for (int k = 0; k < ns; ++k) {
+                    float cf[3];
+                    double m[4];
+                    sigb_section_coef(secs[k], cf);
+                    sigb_section_transition(secs[k], SIGB_SCAN_L, m);
+                    sigb_section_zero_input(secs[k], SIGB_SCAN_L, tab);
+                    const int s = s0 + k;
+                    ch.sec_kind[s] = (uint8_t)secs[k].kind;
+                    for (int j = 0; j < 3; ++j) coef[((size_t)s * 3 + j) * C + c] = cf[j];
+                    for (int j = 0; j < 4; ++j) apow[((size_t)s * 4 + j) * C + c] = m[j];
+                    for (int r = 0; r < SIGB_SCAN_L; ++r)
+                        for (int j = 0; j < 2; ++j)
+                            ztab[(((size_t)s * SIGB_SCAN_L + r) * 2 + j) * C + c] = tab[r * 2 + j];
+                }
+            }
+            s0 += ns;
+        }
+        ch.coef = put_vec(p, coef);
+        ch.apow = put_vec(p, apow);
+        ch.ztab = put_vec(p, ztab);
+        ch.state_off = p->n_state;
+        p->n_state += (int64_t)ch.nsec * 2 * C;
+    }
+    if (has_gain) {
+        std::vector<float> gf(gain.begin(), gain.end());
+        ch.gain = put_vec(p, gf);
+    }
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = C;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    p->vals[i] = v;
+    p->chains.push_back(ch);
+    p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+    return SIGB_OK;
+}
+
+int Builder::build_ewise(int i) {
+    const sigb_node& n = p->nodes[i];
+    const int C = node_C(i);
+    EwiseSpec e;
+    e.C = C;
+    e.dst_node = i;
+    e.a_node = n.in[0];
+    e.b_node = n.in[1];
+    std::vector<double> pv;
+    if (n.kind == SIGB_NODE_MIX) {
+        e.op = EW_MIX;
+        const std::vector<double>* m = const_of(p, n.in[2]);
+        if (!m) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": Mix.mix driven by a non-constant emitter");
+        if (!rep(*m, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": mix channels incompatible");
+    } else if (n.kind == SIGB_NODE_RINGMOD) {
+        e.op = EW_RINGMOD;
+    } else {
+        e.op = EW_AMP;
+        e.b_node = -1;
+        const std::vector<double>* x = const_of(p, n.in[1]);
+        if (!x) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": Amp.right driven by a non-constant emitter");
+        if (!rep(*x, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": exponent channels incompatible");
+    }
+    for (int opnd : {e.a_node, e.b_node}) {
+        if (opnd < 0) continue;
+        int st = ensure(opnd);
+        if (st != SIGB_OK) return st;
+        const int oc = p->vals[opnd].channels;
+        if (oc != 1 && oc != C)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(opnd) + ": block with " + std::to_string(oc) + " channels incompatible with requested " + std::to_string(C));
+    }
+    if (!pv.empty()) {
+        std::vector<float> pf(pv.begin(), pv.end());
+        e.p = put_vec(p, pf);
+    }
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = C;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    p->vals[i] = v;
+    p->ewises.push_back(e);
+    p->launches.push_back({LK_EWISE, (int)p->ewises.size() - 1});
+    return SIGB_OK;
+}
+
+int Builder::build_merge(int i) {
+    const sigb_node& n = p->nodes[i];
+    if (n.in[0] < 0 || n.in[1] < 0)
+        return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": Merge with an unplugged input (shape.py:69-72)");
+    const int cl = p->nodes[n.in[0]].channels, cr = p->nodes[n.in[1]].channels;
+    const int C = cl + cr;
+    if (i == p->root && C != p->channels)
+        return fail(SIGB_ESHAPE, "Merge yields " + std::to_string(C) + " channels, request has " + std::to_string(p->channels));
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = C;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    int coff = 0;
+    for (int side = 0; side < 2; ++side) {
+        const int src = n.in[side];
+        int st = ensure(src);
+        if (st != SIGB_OK) return st;
+        EwiseSpec e;
+        e.op = EW_COPY;
+        e.C = side == 0 ? cl : cr;
+        if (p->vals[src].channels != 1 && p->vals[src].channels != e.C)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(src) + ": channels incompatible with Merge slot");
+        e.a_node = src;
+        e.dst_node = i;
+        e.dst_coff = coff;
+        coff += e.C;
+        p->ewises.push_back(e);
+        p->launches.push_back({LK_EWISE, (int)p->ewises.size() - 1});
+    }
+    p->vals[i] = v;
+    return SIGB_OK;
+}
+
+int Builder::build_reduce(int i) {
+    const sigb_node& n = p->nodes[i];
+    if (n.in[0] < 0) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": reduction without input");
+    int st = ensure(n.in[0]);
+    if (st != SIGB_OK) return st;
+    ReduceSpec r;
+    r.in_node = n.in[0];
+    r.C = p->nodes[n.in[0]].channels;
+    r.dst_node = i;
+    const int vc = p->vals[n.in[0]].channels;
+    if (vc != 1 && vc != r.C) return fail(SIGB_ESHAPE, "reduction input channels inconsistent");
+    int outC;
+    if (n.kind == SIGB_NODE_PANSUM) {
+        r.pan = 1;
+        r.groups = 2;
+        outC = 2;
+        const std::vector<double>* pan = const_of(p, n.in[1]);
+        if (!pan) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": pan driven by a non-constant emitter");
+        std::vector<double> pv;
+        if (!rep(*pan, r.C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
+        std::vector<float> pf(pv.begin(), pv.end());
+        r.w = put_vec(p, pf);
+    } else {
+        r.groups = n.order;
+        outC = n.order;
+        if (r.groups < 1 || r.C % r.groups != 0)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": " + std::to_string(r.C) + " channels do not split into " + std::to_string(r.groups) + " groups");
+    }
+    if (i == p->root && outC != p->channels)
+        return fail(SIGB_ESHAPE, "reduction yields " + std::to_string(outC) + " channels, request has " + std::to_string(p->channels));
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = outC;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = outC;
+    p->vals[i] = v;
+    p->reduces.push_back(r);
+    p->launches.push_back({LK_REDUCE, (int)p->reduces.size() - 1});
+    return SIGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// runtime
+// ---------------------------------------------------------------------------------------------
+
+int upload(sigb_plan* p) {
+    if (p->uploaded) return SIGB_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SIGB_ECUDA, "no CUDA device: libsigb200 has no CPU fallback");
+    // constants read at frame rate live in the arena as float rows
+    for (size_t i = 0; i < p->vals.size(); ++i) {
+        Val& v = p->vals[i];
+        if (v.kind == VK_CONST && v.const_off < 0) {
+            std::vector<float> f(v.cv.begin(), v.cv.end());
+            v.const_off = arena_put(p, f.data(), f.size() * sizeof(float));
+        }
+    }
+    {
+        std::vector<float> z(1, 0.0f);
+        p->zero_val.const_off = arena_put(p, z.data(), sizeof(float));
+    }
+    CUDA_TRY(cudaMalloc(&p->d_arena, std::max<size_t>(p->arena.size(), 256)));
+    CUDA_TRY(cudaMemcpy(p->d_arena, p->arena.data(), p->arena.size(), cudaMemcpyHostToDevice));
+    if (p->n_state > 0) {
+        CUDA_TRY(cudaMalloc(&p->d_state, p->n_state * sizeof(double)));
+        CUDA_TRY(cudaMemset(p->d_state, 0, p->n_state * sizeof(double)));
+    }
+    CUDA_TRY(cudaEventCreate(&p->ev0));
+    CUDA_TRY(cudaEventCreate(&p->ev1));
+    p->uploaded = true;
+    return SIGB_OK;
+}
+
+struct Operand {
+    const float* ptr;
+    int64_t ld;
+    int cs;
+    int64_t rows;   // <0: unlimited
+};
+
+// where node `idx`'s value for the current slab can be read
+Operand operand_of(sigb_plan* p, int idx, int64_t abs_row0, const float* out, int64_t ld_out) {
+    Operand o{nullptr, 0, 0, -1};
+    if (idx < 0) {
+        o.ptr = reinterpret_cast<const float*>(p->d_arena + p->zero_val.const_off);
+        return o;
+    }
+    const Val& v = p->vals[idx];
+    if (v.kind == VK_CONST) {
+        o.ptr = reinterpret_cast<const float*>(p->d_arena + v.const_off);
+        o.cs = v.channels == 1 ? 0 : 1;
+    } else if (v.kind == VK_EXT) {
+        const ExtBinding& e = p->ext[idx];
+        o.ld = v.channels;
+        o.cs = v.channels == 1 ? 0 : 1;
+        o.rows = std::max<int64_t>(0, e.rows - abs_row0);
+        o.ptr = e.ptr ? e.ptr + std::min(abs_row0, e.rows) * o.ld : nullptr;
+        if (!e.ptr) o.rows = 0;
+    } else if (v.buf < 0) {   // the root itself (only read by Merge-into-root bookkeeping; not expected)
+        o.ptr = out;
+        o.ld = ld_out;
+        o.cs = 1;
+    } else {
+        o.ptr = p->bufs[v.buf].ptr;
+        o.ld = v.channels;
+        o.cs = v.channels == 1 ? 0 : 1;
+    }
+    return o;
+}
+
+int ensure_bufs(sigb_plan* p, int64_t rows) {
+    for (BufInfo& b : p->bufs) {
+        if (b.cap_rows >= rows) continue;
+        if (b.ptr) cudaFree(b.ptr);
+        b.ptr = nullptr;
+        CUDA_TRY(cudaMalloc(&b.ptr, (size_t)rows * b.channels * sizeof(float)));
+        b.cap_rows = rows;
+    }
+    return SIGB_OK;
+}
+
+// run every launch of the plan for rows [abs_row0, abs_row0 + rows) into `out`
+int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_out, cudaStream_t st) {
+    const unsigned char* base = p->d_arena;
+    for (const Launch& l : p->launches) {
+        if (l.kind == LK_CHAIN) {
+            const ChainSpec& ch = p->chains[l.idx];
+            ChainDev a;
+            std::memset(&a, 0, sizeof(a));
+            a.C = ch.C;
+            a.src_kind = ch.src_kind;
+            a.wave = ch.wave;
+            a.nsec = ch.nsec;
+            a.rate = p->rate;
+            a.frames = rows;
+            a.position = abs_row0;
+            std::memcpy(a.sec_kind, ch.sec_kind, sizeof(a.sec_kind));
+            a.hertz = ch.hertz.dev<double>(base);
+            a.phase = ch.phase.dev<double>(base);
+            a.theta0 = ch.theta0.dev<unsigned long long>(base);
+            a.dtheta = ch.dtheta.dev<unsigned long long>(base);
+            a.constv = ch.constv.dev<float>(base);
+            a.coef = ch.coef.dev<float>(base);
+            a.gain = ch.gain.dev<float>(base);
+            a.apow = ch.apow.dev<double>(base);
+            a.ztab = ch.ztab.dev<float>(base);
+            a.state = p->d_state ? p->d_state + ch.state_off : nullptr;
+            a.src_rows = INT64_MAX;
+            if (ch.src_kind == SRC_BUF) {
+                Operand o = operand_of(p, ch.src_node, abs_row0, out, ld_out);
+                a.src = o.ptr;
+                a.src_ld = o.ld;
+                a.src_cs = o.cs;
+                a.src_rows = o.rows < 0 ? INT64_MAX : o.rows;
+            }
+            const Val& dv = p->vals[ch.dst_node];
+            if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
+            else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
+            int done = 0;
+            const int tiles = (ch.C + 31) / 32;
+            const bool scan_ok = !p->opt_force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
+            if (scan_ok) {
+                int e = sigb_launch_chain_scan(&a, (int)p->opt_scan_variant, st, &done);
+                if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
+                if (done > 0) p->launch_count++;
+            }
+            if (done < rows) {
+                ChainDev t = a;
+                t.frames = rows - done;
+                t.position = abs_row0 + done;
+                t.out = a.out + (int64_t)done * a.ld_out;
+                if (ch.src_kind == SRC_BUF) {
+                    t.src = a.src + (int64_t)done * a.src_ld;
+                    t.src_rows = a.src_rows == INT64_MAX ? INT64_MAX : std::max<int64_t>(0, a.src_rows - done);
+                }
+                int e = sigb_launch_chain_seq(&t, st);
+                if (e) return fail(SIGB_ECUDA, std::string("k_chain_seq: ") + cudaGetErrorString((cudaError_t)e));
+                p->launch_count++;
+            }
+        } else if (l.kind == LK_EWISE) {
+            const EwiseSpec& e = p->ewises[l.idx];
+            EwiseDev a;
+            std::memset(&a, 0, sizeof(a));
+            a.op = e.op;
+            a.C = e.C;
+            a.frames = rows;
+            const Val& dv = p->vals[e.dst_node];
+            if (dv.buf < 0) { a.out = out + e.dst_coff; a.ld_out = ld_out; }
+            else { a.out = p->bufs[dv.buf].ptr + e.dst_coff; a.ld_out = dv.channels; }
+            Operand oa = operand_of(p, e.a_node, abs_row0, out, ld_out);
+            Operand ob = operand_of(p, e.b_node, abs_row0, out, ld_out);
+            a.a = oa.ptr; a.lda = oa.ld; a.acs = oa.cs; a.a_rows = oa.rows;
+            a.b = ob.ptr; a.ldb = ob.ld; a.bcs = ob.cs; a.b_rows = ob.rows;
+            a.p = e.p.dev<float>(base);
+            int err = sigb_launch_ewise(&a, st);
+            if (err) return fail(SIGB_ECUDA, std::string("k_ewise: ") + cudaGetErrorString((cudaError_t)err));
+            p->launch_count++;
+        } else {
+            const ReduceSpec& r = p->reduces[l.idx];
+            ReduceDev a;
+            std::memset(&a, 0, sizeof(a));
+            a.C = r.C;
+            a.groups = r.groups;
+            a.frames = rows;
+            a.pan = r.pan;
+            Operand oi = operand_of(p, r.in_node, abs_row0, out, ld_out);
+            a.in = oi.ptr; a.ld_in = oi.ld; a.ics = oi.cs; a.in_rows = oi.rows;
+            a.w = r.w.dev<float>(base);
+            const Val& dv = p->vals[r.dst_node];
+            if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
+            else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
+            int err = sigb_launch_reduce(&a, st);
+            if (err) return fail(SIGB_ECUDA, std::string("k_reduce: ") + cudaGetErrorString((cudaError_t)err));
+            p->launch_count++;
+        }
+    }
+    return SIGB_OK;
+}
+
+int64_t slab_rows(sigb_plan* p, int64_t frames) {
+    if (p->opt_slab_frames > 0) return std::min<int64_t>(frames, p->opt_slab_frames);
+    int64_t chsum = 0;
+    for (const BufInfo& b : p->bufs) chsum += b.channels;
+    if (chsum == 0) return frames;
+    int64_t rows = p->opt_buffer_budget / (4 * chsum);
+    const int64_t step = 7 * SIGB_SCAN_L * 4;    // keep slabs a multiple of every scan step size
+    rows = std::max<int64_t>(step, rows / step * step);
+    return std::min(frames, rows);
+}
+
+// the body of sigb_render: seek handling + slab loop, all on `st`
+int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
+    if (!p->have_pos || p->next_pos != position) {
+        // seek: zero state, then warm the filters up on `context` frames (fx.py:93-105)
+        if (p->d_state) CUDA_TRY(cudaMemsetAsync(p->d_state, 0, p->n_state * sizeof(double), st));
+        int64_t pre = std::min<int64_t>(p->context, position);
+        if (pre > 0 && p->n_state > 0) {
+            int st_ = ensure_bufs(p, slab_rows(p, std::max(pre, frames)));
+            if (st_ != SIGB_OK) return st_;
+            const int64_t need = pre * p->channels;
+            if (p->scratch_floats < need) {
+                if (p->scratch) cudaFree(p->scratch);
+                p->scratch = nullptr;
+                CUDA_TRY(cudaMalloc(&p->scratch, need * sizeof(float)));
+                p->scratch_floats = need;
+            }
+            int e = run_slab(p, position - pre, (int)pre, p->scratch, p->channels, st);
+            if (e != SIGB_OK) return e;
+        }
+    }
+    const int64_t slab = slab_rows(p, frames);
+    int e = ensure_bufs(p, slab);
+    if (e != SIGB_OK) return e;
+    for (int64_t r = 0; r < frames; r += slab) {
+        const int rows = (int)std::min(slab, frames - r);
+        e = run_slab(p, position + r, rows, out + r * ld_out, ld_out, st);
+        if (e != SIGB_OK) return e;
+    }
+    p->have_pos = true;
+    p->next_pos = position + frames;
+    return SIGB_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int sigb_abi_version(void) { return SIGB_ABI_VERSION; }
+
+extern "C" const char* sigb_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char* sigb_strerror(int status) {
+    switch (status) {
+        case SIGB_OK: return "ok";
+        case SIGB_EINVAL: return "invalid argument";
+        case SIGB_ESHAPE: return "block shape incompatible with the requested shape";
+        case SIGB_EINDEX: return "filter cutoff/input narrower than the requested channels";
+        case SIGB_ECRIT: return "Digital filter critical frequencies must be 0 < Wn < 1";
+        case SIGB_EUNSUPPORTED: return "graph not supported by the B200 evaluator";
+        case SIGB_ECUDA: return "CUDA failure";
+        case SIGB_ENOMEM: return "out of memory";
+        case SIGB_ESTATE: return "plan in invalid state";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int sigb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t root, const double* data,
+                                int64_t n_data, int32_t channels, int32_t rate, sigb_plan** out_plan) {
+    if (!nodes || !out_plan || n_nodes <= 0 || root < 0 || root >= n_nodes || channels < 1 || rate < 1)
+        return fail(SIGB_EINVAL, "sigb_plan_create: bad arguments");
+    std::unique_ptr<sigb_plan> p(new sigb_plan());
+    p->channels = channels;
+    p->rate = rate;
+    p->root = root;
+    p->nodes.assign(nodes, nodes + n_nodes);
+    if (data && n_data > 0) p->data.assign(data, data + n_data);
+    p->vals.resize(n_nodes);
+    p->uses.assign(n_nodes, 0);
+    p->node_ctx.assign(n_nodes, 0);
+    p->ext.resize(n_nodes);
+    p->zero_val.kind = VK_CONST;
+    p->zero_val.channels = 1;
+    p->zero_val.cv.assign(1, 0.0);
+    for (int i = 0; i < n_nodes; ++i) {
+        const sigb_node& n = p->nodes[i];
+        if (n.kind < SIGB_NODE_ZERO || n.kind > SIGB_NODE_BUFFER) return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": unknown kind");
+        if (n.channels < 1) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": channels < 1");
+        for (int k = 0; k < 3; ++k)
+            if (n.in[k] >= i || n.in[k] < -1) return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": inputs must precede the node (topological order)");
+        Val& v = p->vals[i];
+        if (n.kind == SIGB_NODE_ZERO) {
+            v = p->zero_val;
+        } else if (n.kind == SIGB_NODE_FIXED) {
+            if (n.rows != 1)
+                return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": Fixed with " + std::to_string(n.rows) + " rows (frame-rate tables go through a Buffer node)");
+            if (n.data_off < 0 || n.data_off + n.channels > (int64_t)p->data.size())
+                return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": data_off out of range");
+            v.kind = VK_CONST;
+            v.channels = n.channels;
+            v.cv.assign(p->data.begin() + n.data_off, p->data.begin() + n.data_off + n.channels);
+        } else if (n.kind == SIGB_NODE_BUFFER) {
+            v.kind = VK_EXT;
+            v.channels = n.channels;
+        }
+        // frame-rate edges (block-rate parameter ports are constants and never materialise)
+        int nsig = 0;
+        switch (n.kind) {
+            case SIGB_NODE_GAIN: case SIGB_NODE_AMP: case SIGB_NODE_FILTER:
+            case SIGB_NODE_GROUPSUM: case SIGB_NODE_PANSUM: nsig = 1; break;
+            case SIGB_NODE_MIX: case SIGB_NODE_RINGMOD: case SIGB_NODE_MERGE: nsig = 2; break;
+            default: break;
+        }
+        int ctx = 0;
+        for (int k = 0; k < nsig; ++k)
+            if (n.in[k] >= 0) {
+                p->uses[n.in[k]]++;
+                ctx = std::max(ctx, p->node_ctx[n.in[k]]);
+            }
+        p->node_ctx[i] = ctx + (n.kind == SIGB_NODE_FILTER ? std::max(0, n.context) : 0);
+    }
+    p->context = p->node_ctx[root];
+    p->uses[root]++;
+    const sigb_node& rn = p->nodes[root];
+    if (rn.channels != 1 && rn.channels != channels)
+        return fail(SIGB_ESHAPE, "root block with " + std::to_string(rn.channels) + " channels incompatible with requested " + std::to_string(channels));
+    Builder b{p.get()};
+    if (p->vals[root].kind == VK_NONE) {
+        int st = b.ensure(root);
+        if (st != SIGB_OK) return st;
+    } else {
+        // constant or external root: broadcast-copy it into the output
+        EwiseSpec e;
+        e.op = EW_COPY;
+        e.C = channels;
+        e.a_node = root;
+        e.dst_node = root;
+        p->ewises.push_back(e);
+        p->launches.push_back({LK_EWISE, (int)p->ewises.size() - 1});
+    }
+    *out_plan = p.release();
+    return SIGB_OK;
+}
+
+extern "C" int sigb_plan_bind_buffer(sigb_plan* plan, int32_t node, const float* dev_ptr, int64_t rows) {
+    if (!plan || node < 0 || node >= (int)plan->nodes.size() || plan->nodes[node].kind != SIGB_NODE_BUFFER)
+        return fail(SIGB_EINVAL, "sigb_plan_bind_buffer: not a Buffer node");
+    plan->ext[node].ptr = dev_ptr;
+    plan->ext[node].rows = rows;
+    return SIGB_OK;
+}
+
+extern "C" int sigb_render(sigb_plan* plan, int64_t position, int32_t frames, float* out, int64_t ld_out, void* stream) {
+    if (!plan || !out || frames < 0 || position < 0 || ld_out < plan->channels)
+        return fail(SIGB_EINVAL, "sigb_render: bad arguments");
+    int e = upload(plan);
+    if (e != SIGB_OK) return e;
+    if (frames == 0) return SIGB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaEventRecord(plan->ev0, st));
+    e = render_range(plan, position, frames, out, ld_out, st);
+    if (e != SIGB_OK) return e;
+    CUDA_TRY(cudaEventRecord(plan->ev1, st));
+    plan->ev_valid = true;
+    return SIGB_OK;
+}
+
+extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out) {
+    if (!plan || !out_host || frames < 0 || position < 0 || ld_out < plan->channels)
+        return fail(SIGB_EINVAL, "sigb_render_host: bad arguments");
+    int e = upload(plan);
+    if (e != SIGB_OK) return e;
+    if (frames == 0) return SIGB_OK;
+    if (!plan->s_render) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_render, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_rendered[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const int C = plan->channels;
+    int64_t rows = std::max<int64_t>(1, plan->opt_host_slab_bytes / (4ll * C));
+    const int64_t step = 7 * SIGB_SCAN_L * 4;
+    if (rows > step) rows = rows / step * step;
+    rows = std::min<int64_t>(rows, frames);
+    if (plan->stage_floats < rows * C) {
+        for (int i = 0; i < 2; ++i) {
+            if (plan->stage[i]) cudaFree(plan->stage[i]);
+            plan->stage[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&plan->stage[i], (size_t)rows * C * sizeof(float)));
+        }
+        plan->stage_floats = rows * C;
+    }
+    int slot = 0;
+    int64_t n_slabs = 0;
+    for (int64_t r = 0; r < frames; r += rows, slot ^= 1, ++n_slabs) {
+        const int64_t nr = std::min(rows, frames - r);
+        if (n_slabs >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_render, plan->ev_copied[slot], 0));
+        e = render_range(plan, position + r, nr, plan->stage[slot], C, plan->s_render);
+        if (e != SIGB_OK) return e;
+        CUDA_TRY(cudaEventRecord(plan->ev_rendered[slot], plan->s_render));
+        CUDA_TRY(cudaStreamWaitEvent(plan->s_copy, plan->ev_rendered[slot], 0));
+        if (ld_out == C) {
+            CUDA_TRY(cudaMemcpyAsync(out_host + r * ld_out, plan->stage[slot], (size_t)nr * C * sizeof(float),
+                                     cudaMemcpyDeviceToHost, plan->s_copy));
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(out_host + r * ld_out, ld_out * sizeof(float), plan->stage[slot],
+                                       (size_t)C * sizeof(float), (size_t)C * sizeof(float), nr,
+                                       cudaMemcpyDeviceToHost, plan->s_copy));
+        }
+        CUDA_TRY(cudaEventRecord(plan->ev_copied[slot], plan->s_copy));
+    }
+    CUDA_TRY(cudaStreamSynchronize(plan->s_copy));
+    CUDA_TRY(cudaStreamSynchronize(plan->s_render));
+    return SIGB_OK;
+}
+
+extern "C" int sigb_state_reset(sigb_plan* plan) {
+    if (!plan) return fail(SIGB_EINVAL, "null plan");
+    plan->have_pos = false;
+    return SIGB_OK;
+}
+
+extern "C" int sigb_plan_destroy(sigb_plan* plan) {
+    if (!plan) return SIGB_OK;
+    if (plan->uploaded) cudaDeviceSynchronize();
+    for (BufInfo& b : plan->bufs)
+        if (b.ptr) cudaFree(b.ptr);
+    if (plan->d_arena) cudaFree(plan->d_arena);
+    if (plan->d_state) cudaFree(plan->d_state);
+    if (plan->scratch) cudaFree(plan->scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (plan->stage[i]) cudaFree(plan->stage[i]);
+        if (plan->ev_rendered[i]) cudaEventDestroy(plan->ev_rendered[i]);
+        if (plan->ev_copied[i]) cudaEventDestroy(plan->ev_copied[i]);
+    }
+    if (plan->ev0) cudaEventDestroy(plan->ev0);
+    if (plan->ev1) cudaEventDestroy(plan->ev1);
+    if (plan->s_render) cudaStreamDestroy(plan->s_render);
+    if (plan->s_copy) cudaStreamDestroy(plan->s_copy);
+    delete plan;
+    return SIGB_OK;
+}
+
+extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap) {
+    if (!plan) return 0;
+    static const char* src_names[] = {"osc", "block", "const"};
+    static const char* wave_names[] = {"sine", "square", "sawtooth", "triangle"};
+    static const char* ew_names[] = {"copy", "gain", "mix", "ringmod", "amp"};
+    std::string s = "{\"channels\": " + std::to_string(plan->channels) + ", \"rate\": " + std::to_string(plan->rate) +
+                    ", \"context\": " + std::to_string(plan->context) + ", \"buffers\": " + std::to_string(plan->bufs.size()) +
+                    ", \"state_doubles\": " + std::to_string(plan->n_state) + ", \"param_bytes\": " + std::to_string(plan->arena.size()) +
+                    ", \"launches\": [";
+    bool first = true;
+    for (const Launch& l : plan->launches) {
+        if (!first) s += ", ";
+        first = false;
+        if (l.kind == LK_CHAIN) {
+            const ChainSpec& c = plan->chains[l.idx];
+            s += "{\"kind\": \"chain\", \"node\": " + std::to_string(c.dst_node) + ", \"channels\": " + std::to_string(c.C) +
+                 ", \"source\": \"" + src_names[c.src_kind] + "\"";
+            if (c.src_kind == SRC_OSC) s += std::string(", \"wave\": \"") + wave_names[c.wave & 3] + "\"";
+            s += ", \"sections\": " + std::to_string(c.nsec_real) + ", \"sections_padded\": " + std::to_string(c.nsec) +
+                 ", \"gain\": " + (c.gain.off >= 0 ? "true" : "false") + "}";
+        } else if (l.kind == LK_EWISE) {
+            const EwiseSpec& e = plan->ewises[l.idx];
+            s += "{\"kind\": \"ewise\", \"node\": " + std::to_string(e.dst_node) + ", \"op\": \"" + ew_names[e.op] +
+                 "\", \"channels\": " + std::to_string(e.C) + ", \"column\": " + std::to_string(e.dst_coff) + "}";
+        } else {
+            const ReduceSpec& r = plan->reduces[l.idx];
+            s += "{\"kind\": \"reduce\", \"node\": " + std::to_string(r.dst_node) + ", \"op\": \"" +
+                 (r.pan ? "pansum" : "groupsum") + "\", \"channels\": " + std::to_string(r.C) +
+                 ", \"groups\": " + std::to_string(r.groups) + "}";
+        }
+    }
+    s += "]}";
+    if (buf && cap > 0) {
+        const int64_t n = std::min<int64_t>(cap - 1, (int64_t)s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t value) {
+    if (!plan || !key) return fail(SIGB_EINVAL, "null");
+    const std::string k(key);
+    if (k == "scan_variant") plan->opt_scan_variant = value;
+    else if (k == "force_seq") plan->opt_force_seq = value;
+    else if (k == "scan_max_tiles") plan->opt_scan_max_tiles = value;
+    else if (k == "slab_frames") plan->opt_slab_frames = value;
+    else if (k == "host_slab_bytes") plan->opt_host_slab_bytes = value;
+    else if (k == "buffer_budget") plan->opt_buffer_budget = value;
+    else return fail(SIGB_EINVAL, "unknown option " + k);
+    return SIGB_OK;
+}
+
+extern "C" int64_t sigb_plan_launch_count(const sigb_plan* plan) { return plan ? plan->launch_count : 0; }
+
+extern "C" int sigb_plan_last_kernel_ms(sigb_plan* plan, float* ms) {
+    if (!plan || !ms || !plan->ev_valid) return fail(SIGB_ESTATE, "no render recorded");
+    CUDA_TRY(cudaEventElapsedTime(ms, plan->ev0, plan->ev1));
+    return SIGB_OK;
+}
+
+extern "C" int sigb_design_butter(int32_t subtype, int32_t order, double wn, double* coef, int32_t cap_sections) {
+    if (!coef || order < 1) return fail(SIGB_EINVAL, "sigb_design_butter: bad arguments");
+    if (!(wn > 0.0 && wn < 1.0)) return fail(SIGB_ECRIT, "Digital filter critical frequencies must be 0 < Wn < 1");
+    std::vector<SvfSection> secs = sigb_butter_sections(subtype == SIGB_FILT_HIGHPASS, order, wn);
+    if ((int)secs.size() > cap_sections) return fail(SIGB_EINVAL, "sigb_design_butter: buffer too small");
+    for (size_t i = 0; i < secs.size(); ++i) {
+        coef[i * 4 + 0] = secs[i].g;
+        coef[i * 4 + 1] = secs[i].r2;
+        coef[i * 4 + 2] = (double)secs[i].kind;
+        coef[i * 4 + 3] = 0.0;
+    }
+    return (int)secs.size();
+}
+
+extern "C" int sigb_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(SIGB_EINVAL, "sigb_host_alloc: bad arguments");
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return SIGB_OK;
+}
+
+extern "C" int sigb_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return SIGB_OK;
+}
+
+// test hooks -----------------------------------------------------------------------------------
+extern "C" int sigb_probe_sin(const double* r_dev, int32_t n, float* out_dev, int32_t variant, void* stream) {
+    int e = sigb_launch_probe_sin(r_dev, n, out_dev, variant, stream);
+    if (e) return fail(SIGB_ECUDA, cudaGetErrorString((cudaError_t)e));
+    return SIGB_OK;
+}
+
+extern "C" uint64_t sigb_probe_ratio_q64(double hertz, int32_t rate) { return ratio_q64(hertz, rate); }
+extern "C" uint64_t sigb_probe_frac_q64(double x) { return frac_q64(x); }

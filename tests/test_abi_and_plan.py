@@ -1,0 +1,196 @@
+"""CPU: the C-ABI library loads and exports every symbol include/sigb200.h declares; the host
+planner (graph -> records -> fused launches) and the reference's error behaviour.  No compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.signal
+
+from conftest import ROOT
+from oracle import cases
+from signals_b200 import _lib, engine as engine_mod, plan as plan_mod
+from signals_b200 import chain
+from signals_b200.chain import ext, fx, osc, shape
+
+
+def test_header_symbols_are_exported():
+    text = open(os.path.join(ROOT, 'include', 'sigb200.h')).read()
+    declared = set(re.findall(r'\b(sigb_[a-z0-9_]+)\s*\(', text))
+    assert len(declared) >= 17
+    lib = _lib.lib()
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+    assert lib.sigb_abi_version() == 1
+
+
+def test_no_fallback_without_gpu(ns, engine):
+    """Without a CUDA device a render raises; it never silently computes on the CPU."""
+    if _lib.lib().sigb_device_count() > 0:
+        pytest.skip('GPU present')
+    g = cases.CASES_BY_NAME['sine_basic'].build(ns)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        engine_mod.render(g, 0, 16, 4)
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle or scipy (no CPU fallback)."""
+    pkg = os.path.join(ROOT, 'signals_b200')
+    pat = re.compile(r'^\s*(import|from)\s+(oracle|scipy)\b', re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+@pytest.mark.parametrize('case', cases.CASES, ids=lambda c: c.name)
+def test_every_case_compiles(case, ns, engine):
+    compiled = engine.compile(case.build(ns), case.channels, case.rate, case.frames)
+    d = compiled.describe()
+    assert d['channels'] == case.channels and d['launches']
+    compiled.close()
+
+
+def test_voice_chain_fuses_into_one_launch(ns, engine):
+    """Sine<-Fixed -> LowPass<-Fixed -> Gain<-Fixed (config C2) is ONE chain launch with 1 section."""
+    d = engine.compile(cases.CASES_BY_NAME['lowpass_c2_8v'].build(ns), 8, 48000).describe()
+    assert d['launches'] == [dict(kind='chain', node=d['launches'][0]['node'], channels=8, source='osc', wave='sine',
+                                  sections=1, sections_padded=1, gain=True)]
+    assert d['buffers'] == 0 and d['context'] == 100
+
+
+def test_cascade_fuses_sections(ns, engine):
+    d = engine.compile(cases.CASES_BY_NAME['cascade8'].build(ns), 4, 48000).describe()
+    assert len(d['launches']) == 1 and d['launches'][0]['sections'] == 8 and d['context'] == 800
+    d = engine.compile(cases.CASES_BY_NAME['highpass_order3'].build(ns), 2, 48000).describe()
+    assert d['launches'][0]['sections'] == 2 and d['launches'][0]['sections_padded'] == 2
+
+
+def test_fanout_materialises_shared_node(ns, engine):
+    d = engine.compile(cases.CASES_BY_NAME['fanout'].build(ns), 4, 48000).describe()
+    kinds = [l['kind'] for l in d['launches']]
+    assert kinds.count('chain') == 3 and d['buffers'] >= 3
+
+
+@pytest.mark.parametrize('name,build,frames,channels,exc', cases.ERROR_CASES, ids=lambda v: v if isinstance(v, str) else '')
+def test_error_cases_raise_like_the_reference(name, build, frames, channels, exc, ns, engine):
+    with pytest.raises(Exception) as info:
+        engine.compile(build(ns), channels, 48000, frames)
+    assert any(k.__name__ == exc for k in type(info.value).__mro__), type(info.value).__mro__
+    assert isinstance(info.value, chain.ChainLayerError)
+
+
+def test_bad_shape_when_block_wider_than_request(ns, engine):
+    g = cases.osc(ns, 'Sine', [[1.0, 2.0, 3.0, 4.0]])
+    with pytest.raises(chain.BadShape):
+        engine.compile(g, 2, 48000, 16)
+
+
+def test_band_filters_are_unrenderable_like_the_reference(ns, engine):
+    f = fx.BandPass()
+    f.input = cases.osc(ns, 'Sine', [[100.0]])
+    f.low = cases.fixed(ns, [[100.0]])
+    f.high = cases.fixed(ns, [[200.0]])
+    with pytest.raises(TypeError):
+        engine.compile(f, 1, 48000, 16)
+
+
+def test_unsupported_nodes_raise_at_compile_time(ns, engine):
+    f = shape.Flatten()
+    f.input = cases.osc(ns, 'Sine', [[100.0, 200.0]])
+    with pytest.raises(chain.UnsupportedGraph):
+        engine.compile(f, 1, 48000, 16)
+
+
+def test_modulated_parameter_is_rejected_for_now(ns, engine):
+    lfo = cases.osc(ns, 'Sine', [[2.0]])
+    car = osc.Sine()
+    car.hertz = lfo
+    with pytest.raises(chain.UnsupportedGraph):
+        engine.compile(car, 1, 48000, 16)
+
+
+def test_api_surface_mirrors_reference():
+    s = chain.Shape(frames=10, channels=2)
+    assert s == (10, 2) and (1, 1) <= chain.Shape(10, 1) <= s and not (chain.Shape(3, 2) <= s) and (10, 1) <= s
+    loc = chain.BlockLoc(position=150, rate=48000, shape=s)
+    assert loc.end_position == 160 and loc.resize(1).shape == (1, 2) and loc.reslice(5).shape == (10, 5)
+    assert loc.before(100).position == 50 and loc.before(100).shape == (100, 2)
+    assert loc.before(1000).position == 0 and loc.before(1000).shape == (150, 2)
+    assert loc.after(7).position == 160 and loc.after(7).shape == (7, 2)
+    assert loc.resize(4) <= loc and not (loc.after(1) <= loc)
+    assert np.array_equal(loc.frame_range, np.arange(150, 160).reshape(-1, 1))
+    sine = osc.Sine()
+    assert sorted(sine.port_names()) == ['hertz', 'phase'] and sine.inputs_by_port == {}
+    f = cases.b200_namespace().Fixed()
+    f.get_state().value = np.array([[1.0, 2.0]])
+    sine.hertz = f
+    assert sine.inputs_by_port == {'hertz': f} and sine.channels == 2 and ('hertz', sine) in f.outputs_with_ports
+    del sine.hertz
+    assert not sine.hertz and f.outputs_with_ports == set()
+    with pytest.raises(chain.BadStateValue):
+        f.get_state().value = np.zeros(3)
+    with pytest.raises(chain.BadStateSchema):
+        f.set_state(sine.get_state())
+    assert osc.Sine.cls_name() == 'signals_b200.chain.osc.Sine'
+    assert fx.LowPass().type() == 'lp' and fx.LowPass.order == 2 and fx.LowPass().context_frames() == 100
+    assert sine.state_attrs() == {'enabled'} and f.state_attrs() == {'enabled', 'value'}
+
+
+def test_upstream_is_post_order_of_receivers(ns):
+    g = cases.CASES_BY_NAME['lowpass_c2_8v'].build(ns)
+    names = [type(n).__name__ for n in g.upstream()]
+    assert names == ['Sine', 'LowPass', 'Gain']
+
+
+@pytest.mark.parametrize('subtype,btype', [(_lib.FILT_LOWPASS, 'lp'), (_lib.FILT_HIGHPASS, 'hp')])
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 8, 16])
+@pytest.mark.parametrize('wn', [100 / 24000, 0.05, 0.5, 0.95])
+def test_library_filter_design_equals_scipy_butter(subtype, btype, order, wn):
+    """The state-variable sections libsigb200 designs have the transfer function of
+    scipy.signal.butter (what chain/fx.py:115-121 calls): compare frequency responses."""
+    lib = _lib.lib()
+    coef = (ctypes.c_double * (4 * 16))()
+    n = lib.sigb_design_butter(subtype, order, wn, coef, 16)
+    assert n == order // 2 + order % 2
+    w = np.linspace(1e-3, np.pi - 1e-3, 257)
+    z = np.exp(1j * w)
+    s = (z - 1) / (z + 1)            # bilinear variable (2*fs factor folded into g)
+    h = np.ones_like(z)
+    for k in range(n):
+        g, r2, kind = coef[4 * k], coef[4 * k + 1], int(coef[4 * k + 2])
+        sn = s / g
+        if kind & 2:
+            h *= (sn if kind & 1 else 1) / (sn + 1)
+        else:
+            h *= (sn * sn if kind & 1 else 1) / (sn * sn + r2 * sn + 1)
+    _, want = scipy.signal.sosfreqz(scipy.signal.butter(order, wn, btype, output='sos'), worN=w)
+    assert np.abs(h - want).max() < 1e-9
+
+
+def test_signature_changes_with_state_and_topology(ns):
+    g = cases.CASES_BY_NAME['lowpass_c2_8v'].build(ns)
+    s0 = plan_mod.signature(g)
+    assert plan_mod.signature(g) == s0
+    g.inputs_by_port['right'].get_state().value = np.full((1, 8), 0.5)
+    s1 = plan_mod.signature(g)
+    assert s1 != s0
+    g.inputs_by_port['left'].get_state().enabled = False
+    assert plan_mod.signature(g) != s1
+
+
+def test_plan_walker_accepts_reference_objects():
+    """Drop-in boundary: the same lowering runs on the reference's OWN node objects."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip('reference sources only exist in the build container')
+    ref = ref_harness.load()
+    rns = cases.ref_namespace(ref)
+    for name in ('lowpass_c2_8v', 'lowpass_test_sigs', 'mix', 'cascade8', 'disabled_osc', 'unconnected'):
+        case = cases.CASES_BY_NAME[name]
+        a = plan_mod.lower(case.build(rns), case.channels, case.rate, case.frames)
+        b = plan_mod.lower(case.build(cases.b200_namespace()), case.channels, case.rate, case.frames)
+        assert len(a.nodes) == len(b.nodes) and np.array_equal(a.data, b.data)
+        for x, y in zip(a.nodes, b.nodes):
+            assert bytes(x) == bytes(y)

@@ -1,0 +1,222 @@
+"""GPU: parity of the CUDA path (through the C ABI) against golden vectors minted from the
+reference, against the numpy oracle on seeded inputs, and size-independent properties at the
+BASELINE sizes.  Tolerances are the north-star's: 1e-6 max-abs for oscillators / gain / mix,
+1e-4 for cascaded IIR output (each case carries its own in oracle/cases.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, max_abs_err
+from oracle import cases, np_oracle
+
+pytestmark = pytest.mark.gpu
+
+RATE = 48000
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def render_case(engine, ns, case, **options):
+    compiled = engine.compile(case.build(ns), case.channels, case.rate, case.frames)
+    for k, v in options.items():
+        compiled.set_option(k, v)
+    out = compiled.render_device(case.position, case.frames).cpu().numpy()
+    launches = compiled.launch_count
+    compiled.close()
+    assert launches > 0, 'no CUDA kernel was launched'
+    return out
+
+
+FILTER_CASES = [c for c in cases.CASES if c.tol > 1e-6]
+PLAIN_CASES = [c for c in cases.CASES if c.tol <= 2e-6]
+
+
+@pytest.mark.parametrize('case', cases.CASES, ids=lambda c: c.name)
+def test_cuda_matches_reference_golden(case, ns, engine):
+    got = render_case(engine, ns, case)[::case.stride]
+    want = load_golden(case.name)
+    assert got.shape == want.shape and got.dtype == np.float32
+    err = max_abs_err(got, want)
+    assert err <= case.tol, f'{case.name}: max-abs {err:.3e} > {case.tol:.1e}'
+
+
+@pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3'])
+def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
+    """k_chain_seq and each geometry of the time-parallel k_chain_scan agree with the reference."""
+    opts = dict(force_seq=1) if mode == 'seq' else dict(scan_variant=int(mode[-1]))
+    got = render_case(engine, ns, case, **opts)[::case.stride]
+    err = max_abs_err(got, load_golden(case.name))
+    assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
+
+
+def test_sine_error_budget(ns, engine):
+    """Oscillator budget: <= 1e-6 full scale; report how much of it each sin2pi variant uses."""
+    torch = _torch()
+    from signals_b200 import _lib
+    lib = _lib.lib()
+    r = np.concatenate([np.linspace(-0.5, 0.5, 2_000_001), np.random.default_rng(0).uniform(-0.5, 0.5, 1_000_000)])
+    want = np.sin(2 * np.pi * r.astype(np.float32).astype(np.float64))
+    d_r = torch.from_numpy(r).cuda()
+    d_o = torch.empty(r.size, dtype=torch.float32, device='cuda')
+    errs = {}
+    for variant in (0, 1, 2):
+        st = lib.sigb_probe_sin(ctypes.c_void_p(d_r.data_ptr()), r.size, ctypes.c_void_p(d_o.data_ptr()), variant, None)
+        assert st == 0
+        torch.cuda.synchronize()
+        errs[variant] = float(np.abs(d_o.cpu().numpy().astype(np.float64) - want).max())
+    print('sin2pi max-abs error by variant (0=MUFU, 1=folded MUFU, 2=folded polynomial):', errs)
+    assert errs[1] < 5e-7 and errs[2] < 3e-7
+
+
+def test_oscillators_are_block_invariant_bitwise(ns, engine):
+    """Rendering [0,F) in one call equals rendering it in unequal calls, bit for bit."""
+    for wave in ('Sine', 'Square', 'Sawtooth', 'Triangle'):
+        g = cases.osc(ns, wave, [[440.0, 439.99, 12000.0, 27.5]], [[0.0, 0.1, 0.2, 0.3]])
+        compiled = engine.compile(g, 4, RATE)
+        whole = compiled.render_device(0, 10000).cpu().numpy()
+        cuts = [0, 1, 48, 1000, 1001, 4097, 10000]
+        parts = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+        assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32)), wave
+        compiled.close()
+
+
+def test_filter_state_is_carried_across_calls(ns, engine):
+    """Streaming a filter chain in ragged chunks == one request (the reference cannot do this:
+    it restarts from zero state every block)."""
+    case = cases.CASES_BY_NAME['lowpass_c2_8v']
+    want = load_golden(case.name)
+    compiled = engine.compile(case.build(ns), case.channels, RATE)
+    cuts = [0, 1, 7, 512, 513, 5000, 20000, 20112, 48000]
+    parts = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+    assert max_abs_err(parts, want) <= 1e-5
+    compiled.close()
+
+
+def test_seek_restarts_with_context_like_the_reference(ns, engine):
+    """After a seek the plan zeroes state and warms up on context_frames() frames, which is
+    exactly what the reference does for every block (fx.py:93-105)."""
+    case = cases.CASES_BY_NAME['lowpass_blockwise']
+    compiled = engine.compile(case.build(ns), case.channels, RATE)
+    compiled.render_device(0, 1000)                       # some unrelated history
+    got = compiled.render_device(case.position, case.frames).cpu().numpy()
+    assert max_abs_err(got, load_golden(case.name)) <= 1e-5
+    compiled.close()
+
+
+def test_render_host_equals_render_device(ns, engine):
+    case = cases.CASES_BY_NAME['lowpass_c2_8v']
+    compiled = engine.compile(case.build(ns), case.channels, RATE)
+    compiled.set_option('host_slab_bytes', 8 * 4 * 1000)   # force many slabs
+    dev = compiled.render_device(0, case.frames).cpu().numpy()
+    host = compiled.render_host(0, case.frames)
+    assert max_abs_err(host, dev) <= 2e-6
+    assert max_abs_err(host, load_golden(case.name)) <= 1e-5
+    compiled.close()
+
+
+@pytest.mark.parametrize('voices,frames,wave,cls', [
+    (64, 48000, 'Sine', 'LowPass'), (200, 9999, 'Sawtooth', 'HighPass'), (33, 12345, 'Triangle', 'LowPass'),
+    (1, 4800, 'Square', 'LowPass'), (1000, 4999, 'Sine', 'LowPass')])
+def test_voice_chain_vs_oracle(voices, frames, wave, cls, ns, engine):
+    """Config C2 shape on seeded inputs, ragged sizes (voices not a multiple of 32, frames not a
+    multiple of the scan step)."""
+    hertz, phase, cutoff, g = cases.voice_params(1234 + voices, voices)
+    graph = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, wave, [hertz], [phase]), [cutoff], cls), [g])
+    want = np_oracle.render_voice_chain(0, frames, RATE, hertz, phase, cutoff, g, wave=wave,
+                                        btype=np_oracle.FILTER_TYPES[cls])
+    compiled = engine.compile(graph, voices, RATE)
+    got = compiled.render_device(0, frames).cpu().numpy()
+    compiled.close()
+    err = max_abs_err(got, want)
+    assert err <= 1e-4, err
+    print(f'C2-shape {voices}x{frames} {wave}->{cls}: max-abs {err:.3e}')
+
+
+def test_low_cutoff_iir_stays_inside_budget(ns, engine):
+    """Direct-form float32 biquads lose 1e-3 at 20-100 Hz cutoffs; the state-variable sections must not."""
+    v = 16
+    hertz = np.linspace(20.0, 200.0, v)
+    cutoff = np.geomspace(20.0, 300.0, v)
+    graph = cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz]), [cutoff])
+    frames = 10 * RATE
+    want = np_oracle.render_voice_chain(0, frames, RATE, hertz, np.zeros(v), cutoff, np.ones(v))
+    for opts in (dict(force_seq=1), dict(scan_variant=2)):
+        compiled = engine.compile(graph, v, RATE)
+        for k, val in opts.items():
+            compiled.set_option(k, val)
+        got = compiled.render_device(0, frames).cpu().numpy()
+        compiled.close()
+        err = max_abs_err(got, want)
+        assert err <= 2e-5, (opts, err)
+
+
+def test_group_sum_and_pan_sum_vs_numpy(ns, engine):
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(3)
+    p, groups, frames = 4096, 8, 4800
+    hertz = rng.uniform(27.5, 12000.0, p)
+    phase = rng.uniform(0, 1, p)
+    amp = rng.uniform(0, 1, p) / (p // groups)
+    bank = cases.gain(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [amp])
+    gs = ext.GroupSum()
+    gs.get_state().groups = groups
+    gs.input = bank
+    x = np_oracle.gain(np_oracle.sine(np_oracle.osc_cycles(0, frames, RATE, hertz[None], phase[None])), amp[None])
+    got = engine.compile(gs, groups, RATE).render_device(0, frames).cpu().numpy()
+    assert max_abs_err(got, np_oracle.group_sum(x, groups)) <= 1e-6
+    ps = ext.PanSum()
+    ps.input = bank
+    pan = rng.uniform(0, 1, p)
+    ps.pan = cases.fixed(ns, [pan])
+    got = engine.compile(ps, 2, RATE).render_device(0, frames).cpu().numpy()
+    assert max_abs_err(got, np_oracle.pan_sum(x, pan[None])) <= 1e-6
+
+
+def test_buffer_source_through_cascade(ns, engine):
+    """Config C4 shape: an HBM-resident noise block through 8 chained LowPass nodes, streamed in
+    chunks with carried state, vs scipy's sosfilt cascade."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(4)
+    ch, frames = 96, 20000
+    x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
+    cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (8, ch)))
+    node = ext.Buffer(x)
+    for s in range(8):
+        node = cases.lowpass(ns, node, [cut[s]])
+    want, _ = np_oracle.render_cascade(x.astype(np.float64), cut, RATE)
+    compiled = engine.compile(node, ch, RATE)
+    cuts = [0, 4800, 4801, 12000, 20000]
+    got = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+    past_end = compiled.render_device(frames, 64).cpu().numpy()
+    compiled.close()
+    assert max_abs_err(got, want) <= 1e-4
+    assert np.isfinite(past_end).all()
+
+
+def test_full_size_voice_bank_properties(ns, engine):
+    """BASELINE config C2 at full size (4096 voices x 10 s, 7.9 GB): spot-check 12 voices against
+    the oracle over all 480000 frames, exact gain linearity, and finiteness of everything."""
+    torch = _torch()
+    v, frames = 4096, 10 * RATE
+    hertz, phase, cutoff, g = cases.voice_params(2, v)
+    graph = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff]), [g])
+    compiled = engine.compile(graph, v, RATE)
+    out = compiled.render_device(0, frames)
+    assert bool(torch.isfinite(out).all())
+    pick = np.concatenate([np.argsort(cutoff)[:4], np.argsort(hertz)[:4], np.random.default_rng(0).choice(v, 4)])
+    got = out[:, torch.from_numpy(pick).cuda()].cpu().numpy()
+    want = np_oracle.render_voice_chain(0, frames, RATE, hertz[pick], phase[pick], cutoff[pick], g[pick])
+    err = max_abs_err(got, want)
+    print(f'C2 full size: max-abs over 12 voices x 480000 frames = {err:.3e}')
+    assert err <= 1e-4
+    compiled.close()
+    graph2 = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff]), [2.0 * g])
+    compiled2 = engine.compile(graph2, v, RATE)
+    out2 = compiled2.render_device(0, frames)
+    assert bool(torch.equal(out2, out * 2.0))          # power-of-two gain is exact in float32
+    compiled2.close()
