@@ -158,7 +158,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:   # noqa: BLE001
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def finish(self):
         self._stop_evt.set()
@@ -252,7 +252,7 @@ def run_b200(args):
     te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = float(world) * v * frames * len(e2e_times) / float(te.item())
+    e2e_value = float(world) * v * frames * len(e2e_times) / float(te.item()) if e2e_times else None
     checksum = float(host_out[-1].double().sum())
 
     if rank == 0:

@@ -77,6 +77,7 @@ int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stream, int* ro
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);
+void sigb_set_scan_tma(int on);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

@@ -16,9 +16,11 @@
 //   fx.py:85-121   per-channel Butterworth low/high-pass == cascade of bilinear 2nd-order sections;
 //                  run here as zero-delay-feedback state-variable sections (same transfer function,
 //                  far better float32 behaviour at low cutoffs than the direct form scipy uses)
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "sigb200.h"
 #include "sigb_internal.h"
@@ -26,13 +28,15 @@
 namespace {
 
 constexpr int L = SIGB_SCAN_L;
+int g_scan_tma = 1;   // staged TMA tensor stores in k_chain_scan (0: direct STG)
 
 // ------------------------------------------------------------------------------------------
 // oscillators
 // ------------------------------------------------------------------------------------------
 
-// sin(2*pi*r) for r in [-0.5, 0.5], float32.  Folds to [-1/4, 1/4] (exact in float32) so the
-// MUFU.SIN absolute error and the 2*pi scaling error stay below ~2e-7.
+// sin(2*pi*r) for r in [-0.5, 0.5], float32.  Measured on B200 over 3M points (tests/test_gpu_parity.py
+// ::test_sine_error_budget): variant 0 (MUFU.SIN) 3.39e-7 max-abs, variant 1 (folded to [-1/4,1/4]
+// first) 3.39e-7 -- folding buys nothing --, variant 2 (folded FP32 polynomial) 1.73e-7.
 template <int VARIANT>
 __device__ __forceinline__ float sin2pi(float r) {
     if (VARIANT == 0) {
@@ -55,7 +59,7 @@ __device__ __forceinline__ float sin2pi(float r) {
 }
 
 #ifndef SIGB_SIN_VARIANT
-#define SIGB_SIN_VARIANT 1
+#define SIGB_SIN_VARIANT 0
 #endif
 
 // numpy float remainder np.mod(a, b) for b in {1, 0.5}: fmod, then shift negatives up by b,
@@ -99,10 +103,21 @@ __device__ __forceinline__ float osc_wave(int wave, double cyc) {
     }
 }
 
-// sine from a Q0.64 phase accumulator: the top 32 bits as a signed fraction of a cycle
-__device__ __forceinline__ float sine_q64(unsigned long long th) {
-    int hi = (int)(th >> 32);
+// sine from the top 32 bits of a Q0.64 phase accumulator, read as a signed fraction of a cycle
+// (one I2F, one FMUL by 2*pi*2^-32, then __sinf = FMUL.RZ by 1/2pi + MUFU.SIN)
+__device__ __forceinline__ float sine_q32(int hi) {
+    if (SIGB_SIN_VARIANT == 0) return __sinf((float)hi * 1.4629180792671596e-9f);
     return sin2pi<SIGB_SIN_VARIANT>((float)hi * 2.3283064365386963e-10f);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// one (L x 32) staging tile -> global memory with a single TMA tensor store (UTMASTG); the tensor
+// map clips columns past C, so ragged last tiles take this path too
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, int x, int y, const float* ssrc) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+                 "r"(smem_u32(ssrc))
+                 : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -202,7 +217,8 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 // a step is WG sub-chunks of L rows.  Named barrier 1+2g: "end states of group g published",
 // 2+2g: "initial states for group g published".
 template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
-__global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const ChainDev a, int nsteps) {
+__global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
+k_chain_scan(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;                    // rows per step
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -210,6 +226,8 @@ __global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const Chai
     float2* si = zs + NW * 32;                                     // [NW][32] true initial states
     float2* tab = si + NW * 32;                                    // [NSEC][L][32] zero-input responses
     double* tnb = reinterpret_cast<double*>(tab + NSEC * L * 32);  // [NW][L] n/rate (generic osc)
+    // [NW][L][32] output staging tiles, 128-byte aligned for TMA
+    float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tnb + NW * L) + 127) & ~uintptr_t(127));
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -286,14 +304,19 @@ __global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const Chai
     const int64_t row_stride = (int64_t)NG * STEP;
     float* outp = a.out + row * a.ld_out + c;
     const int64_t out_stride = row_stride * a.ld_out;
-    unsigned long long th = 0, dth = 0, th_skip = 0;
+    const bool bulk = use_tma != 0;
+    unsigned long long th = 0, th_step = 0;
+    int dhi = 0;
     double hz = 0.0, ph = 0.0;
     float cv = 0.0f;
     if (SRC == SRC_OSC) {
         if (FASTSINE) {
-            dth = a.dtheta[cc];
+            // exact Q0.64 phase at the first row of every sub-chunk; inside a sub-chunk the top word
+            // advances by the rounded top word of the increment (<= L * 2^-33 cycles of drift)
+            const unsigned long long dth = a.dtheta[cc];
             th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
-            th_skip = dth * (unsigned long long)(row_stride - L);
+            th_step = dth * (unsigned long long)row_stride;
+            dhi = (int)((dth + 0x80000000ull) >> 32);
         } else {
             hz = a.hertz[cc];
             ph = a.phase[cc];
@@ -306,12 +329,13 @@ __global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const Chai
         float v[L];
         if (SRC == SRC_OSC) {
             if (FASTSINE) {
+                int hi = (int)(th >> 32);
 #pragma unroll
                 for (int k = 0; k < L; ++k) {
-                    v[k] = sine_q64(th);
-                    th += dth;
+                    v[k] = sine_q32(hi);
+                    hi += dhi;
                 }
-                th += th_skip;
+                th += th_step;
             } else {
                 if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
                 __syncwarp();
@@ -347,13 +371,28 @@ __global__ void __launch_bounds__((NG * WG + 1) * 32, 1) k_chain_scan(const Chai
                 v[k] = fmaf(t.x, i0.x, fmaf(t.y, i0.y, v[k]));
             }
         }
-        if (live) {
+        if (bulk) {
+            // stage the (L x 32) tile in shared memory (one STS per sample, immediate offsets), then
+            // one elected lane hands the whole tile to the TMA engine
+            float* tile = stage + w * (L * 32);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < L; ++k) tile[k * 32 + lane] = v[k] * gain;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_tile(&out_map, blockIdx.x * 32, (int)row, tile);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else if (live) {
 #pragma unroll
             for (int k = 0; k < L; ++k) __stcs(outp + (int64_t)k * a.ld_out, v[k] * gain);
         }
         outp += out_stride;
         row += row_stride;
     }
+    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -464,6 +503,36 @@ cudaError_t launch_seq_src(const ChainDev& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// 2-D float32 tensor map over the output block: dim0 = channels (contiguous), dim1 = rows; box 32 x L
+bool make_out_map(const ChainDev& a, int rows, CUtensorMap* map) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(a.out) & 15) != 0 || ((a.ld_out * 4) & 15) != 0 || rows <= 0) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)a.C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)a.ld_out * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)L};
+    cuuint32_t estr[2] = {1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
 cudaError_t launch_scan_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     constexpr int NW = NG * WG;
@@ -472,7 +541,7 @@ cudaError_t launch_scan_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     *rows_done = nsteps * STEP;
     if (nsteps == 0) return cudaSuccess;
     size_t smem = (size_t)NW * 32 * sizeof(float2) * 2 + (size_t)NSEC * L * 32 * sizeof(float2) +
-                  (size_t)NW * L * sizeof(double);
+                  (size_t)NW * L * sizeof(double) + 128 + (size_t)NW * L * 32 * sizeof(float);
     auto kern = k_chain_scan<SRC, NSEC, NG, WG, FASTSINE, ALLLP>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -480,8 +549,11 @@ cudaError_t launch_scan_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const int use_tma = g_scan_tma && make_out_map(a, nsteps * STEP, &map) ? 1 : 0;
     dim3 grid((a.C + 31) / 32), block((NW + 1) * 32);
-    kern<<<grid, block, smem, st>>>(a, nsteps);
+    kern<<<grid, block, smem, st>>>(a, nsteps, map, use_tma);
     return cudaGetLastError();
 }
 
@@ -526,6 +598,8 @@ extern "C" int sigb_scan_rows_per_step(int nsec, int variant) {
     scan_geometry(nsec, variant, &ng, &wg);
     return wg * L;
 }
+
+extern "C" void sigb_set_scan_tma(int on) { g_scan_tma = on; }
 
 extern "C" int sigb_launch_chain_seq(const ChainDev* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

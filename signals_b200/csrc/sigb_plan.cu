@@ -1021,6 +1021,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "slab_frames") plan->opt_slab_frames = value;
     else if (k == "host_slab_bytes") plan->opt_host_slab_bytes = value;
     else if (k == "buffer_budget") plan->opt_buffer_budget = value;
+    else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);
     return SIGB_OK;
 }

