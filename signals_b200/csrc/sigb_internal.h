@@ -44,6 +44,8 @@ struct ChainDev {
     // output response of each state over one sub-chunk
     const double* apow;             // [(s*4+k)*C + c], row-major 2x2
     const float* ztab;              // [((s*L + k)*2 + j)*C + c]
+    const float* m8;                // [(s*4+k)*C + c]  float32 A^(L/2) (packed kernel: stitches the two halves)
+    const float* hrec;              // [(s*2+k)*C + c]  k: 0 = tr(A), 1 = -det(A) (zero-input output recurrence)
     float* out;
     int64_t ld_out;
 };

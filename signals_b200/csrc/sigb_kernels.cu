@@ -221,13 +221,12 @@ __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;                    // rows per step
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* zs = reinterpret_cast<float2*>(smem_raw);             // [NW][32] sub-chunk end states
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);            // [NW][L][32] output staging tiles (TMA source)
+    float2* zs = reinterpret_cast<float2*>(stage + NW * L * 32);  // [NW][32] sub-chunk end states
     float2* si = zs + NW * 32;                                     // [NW][32] true initial states
     float2* tab = si + NW * 32;                                    // [NSEC][L][32] zero-input responses
     double* tnb = reinterpret_cast<double*>(tab + NSEC * L * 32);  // [NW][L] n/rate (generic osc)
-    // [NW][L][32] output staging tiles, 128-byte aligned for TMA
-    float* stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tnb + NW * L) + 127) & ~uintptr_t(127));
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -388,6 +387,280 @@ k_chain_scan(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap o
         } else if (live) {
 #pragma unroll
             for (int k = 0; k < L; ++k) __stcs(outp + (int64_t)k * a.ld_out, v[k] * gain);
+        }
+        outp += out_stride;
+        row += row_stride;
+    }
+    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// k_chain_scan2: the packed (f32x2) time-parallel kernel
+//
+// Same decomposition as k_chain_scan, but every worker thread renders its 16-row sub-chunk as TWO
+// independent 8-row halves from zero state, carried in the two lanes of packed float2 registers, so
+// the state-variable section, the zero-input correction and the gain run as FFMA2/FMUL2/FADD2 (one
+// issue slot per two samples).  The halves are stitched inside the thread with the fp32 transition
+// A^8; the scanner warp still chains whole sub-chunks with the fp64 transition A^16.  The
+// zero-input response is advanced with its own 2-term recurrence h[k] = tr(A) h[k-1] - det(A) h[k-2]
+// (Cayley-Hamilton on the section's transition), so the correction needs no table traffic.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 pk(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }
+
+struct SecPar {            // per-thread parameters of one section (packed where the math is packed)
+    float2 g, nc, d;       // (g,g) (-c,-c) (d,d); first-order: g = (G,G)
+    float2 al, be;         // zero-input recurrence coefficients
+    float m8[4];           // A^8, row-major
+    float p0, r0, p1, r1;  // zero-input output at samples 0 and 1 of a half, per unit state
+};
+
+template <int H, bool HP>
+__device__ __forceinline__ void svf2_second_order(const SecPar& c, float2 (&v)[H], float2& s1, float2& s2) {
+    const float2 neg1 = pk1(-1.0f);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float2 t = __ffma2_rn(c.nc, s1, v[k]);
+        float2 u = __ffma2_rn(s2, neg1, t);
+        float2 hp = __fmul2_rn(u, c.d);
+        float2 bp = __ffma2_rn(c.g, hp, s1);
+        s1 = __ffma2_rn(c.g, hp, bp);
+        float2 lp = __ffma2_rn(c.g, bp, s2);
+        s2 = __ffma2_rn(c.g, bp, lp);
+        v[k] = HP ? hp : lp;
+    }
+}
+
+template <int H, bool HP>
+__device__ __forceinline__ void svf2_first_order(const SecPar& c, float2 (&v)[H], float2& s1) {
+    const float2 neg1 = pk1(-1.0f);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float2 t = __ffma2_rn(s1, neg1, v[k]);        // x - s1
+        float2 w = __fmul2_rn(t, c.g);
+        float2 lp = __fadd2_rn(w, s1);
+        s1 = __fadd2_rn(lp, w);
+        v[k] = HP ? __ffma2_rn(lp, neg1, v[k]) : lp;
+    }
+}
+
+// the section kind is uniform over the launch: branch once per block of samples, not per sample
+template <int H>
+__device__ __forceinline__ void svf2_block(int kind, const SecPar& c, float2 (&v)[H], float2& s1, float2& s2) {
+    if (kind == 0) svf2_second_order<H, false>(c, v, s1, s2);
+    else if (kind == SEC_HP) svf2_second_order<H, true>(c, v, s1, s2);
+    else if (kind == SEC_FIRST_ORDER) svf2_first_order<H, false>(c, v, s1);
+    else svf2_first_order<H, true>(c, v, s1);
+}
+
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE>
+__global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
+k_chain_scan2(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * L;
+    constexpr int H = L / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                        // [NW][L][32] output tiles (TMA source)
+    float2* zs = reinterpret_cast<float2*>(stage + NW * L * 32);             // [NW][32]
+    float2* si = zs + NW * 32;                                                // [NW][32]
+    float4* par = reinterpret_cast<float4*>(si + NW * 32);                    // [NSEC][4][32]
+    double* tnb = reinterpret_cast<double*>(par + NSEC * 4 * 32);             // [NW][L]
+
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const bool live = c < a.C;
+    const int cc = live ? c : a.C - 1;
+    const size_t C = (size_t)a.C;
+
+    // per-channel section parameters -> shared memory (read back per section, or once when NSEC == 1)
+    for (int i = threadIdx.x; i < NSEC * 32; i += blockDim.x) {
+        const int l = i & 31, s = i >> 5;
+        const int ch = min(blockIdx.x * 32 + l, a.C - 1);
+        par[(s * 4 + 0) * 32 + l] = make_float4(a.coef[(size_t)(s * 3 + 0) * C + ch], a.coef[(size_t)(s * 3 + 1) * C + ch],
+                                                a.coef[(size_t)(s * 3 + 2) * C + ch], 0.0f);
+        par[(s * 4 + 1) * 32 + l] = make_float4(a.m8[(size_t)(s * 4 + 0) * C + ch], a.m8[(size_t)(s * 4 + 1) * C + ch],
+                                                a.m8[(size_t)(s * 4 + 2) * C + ch], a.m8[(size_t)(s * 4 + 3) * C + ch]);
+        par[(s * 4 + 2) * 32 + l] = make_float4(a.hrec[(size_t)(s * 2 + 0) * C + ch], a.hrec[(size_t)(s * 2 + 1) * C + ch], 0.0f, 0.0f);
+        // zero-input output at samples 0 and 1: rows 0,1 of the response table
+        par[(s * 4 + 3) * 32 + l] = make_float4(a.ztab[((size_t)(s * L + 0) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 0) * 2 + 1) * C + ch],
+                                                a.ztab[((size_t)(s * L + 1) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 1) * 2 + 1) * C + ch]);
+    }
+    __syncthreads();
+
+    if (w == NW) {
+        // ---------------- scanner warp ----------------
+        double m[NSEC][4], c1[NSEC], c2[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) m[s][k] = a.apow[(size_t)(s * 4 + k) * C + cc];
+            c1[s] = a.state[(size_t)(s * 2 + 0) * C + cc];
+            c2[s] = a.state[(size_t)(s * 2 + 1) * C + cc];
+        }
+        for (int step = 0; step < nsteps; ++step) {
+            const int grp = step % NG;
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                const float f00 = (float)m[s][0], f01 = (float)m[s][1], f10 = (float)m[s][2], f11 = (float)m[s][3];
+                bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                float2 z[WG];
+#pragma unroll
+                for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
+                // fast float32 chain releases the workers; the exact float64 carry follows off the critical path
+                float f1 = (float)c1[s], f2 = (float)c2[s];
+#pragma unroll
+                for (int q = 0; q < WG; ++q) {
+                    si[(grp * WG + q) * 32 + lane] = make_float2(f1, f2);
+                    const float n1 = fmaf(f00, f1, fmaf(f01, f2, z[q].x));
+                    const float n2 = fmaf(f10, f1, fmaf(f11, f2, z[q].y));
+                    f1 = n1;
+                    f2 = n2;
+                }
+                bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+#pragma unroll
+                for (int q = 0; q < WG; ++q) {
+                    const double n1 = fma(m[s][0], c1[s], fma(m[s][1], c2[s], (double)z[q].x));
+                    const double n2 = fma(m[s][2], c1[s], fma(m[s][3], c2[s], (double)z[q].y));
+                    c1[s] = n1;
+                    c2[s] = n2;
+                }
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                a.state[(size_t)(s * 2 + 0) * C + c] = c1[s];
+                a.state[(size_t)(s * 2 + 1) * C + c] = c2[s];
+            }
+        }
+        return;
+    }
+
+    // ---------------- worker warps ----------------
+    const int grp = w / WG, q = w % WG;
+    const float gain = a.gain ? a.gain[cc] : 1.0f;
+    const float2 gain2 = pk1(gain);
+    int64_t row = (int64_t)grp * STEP + (int64_t)q * L;
+    const int64_t row_stride = (int64_t)NG * STEP;
+    float* outp = a.out + row * a.ld_out + c;
+    const int64_t out_stride = row_stride * a.ld_out;
+    const bool bulk = use_tma != 0;
+    float* tile = stage + w * (L * 32);
+
+    unsigned long long th = 0, th_step = 0;
+    int dhi = 0, dhi_h = 0;
+    double hz = 0.0, ph = 0.0;
+    float cv = 0.0f;
+    if (SRC == SRC_OSC) {
+        if (FASTSINE) {
+            const unsigned long long dth = a.dtheta[cc];
+            th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
+            th_step = dth * (unsigned long long)row_stride;
+            dhi = (int)((dth + 0x80000000ull) >> 32);
+            dhi_h = (int)((dth * (unsigned long long)H + 0x80000000ull) >> 32);   // half-chunk jump, rounded once
+        } else {
+            hz = a.hertz[cc];
+            ph = a.phase[cc];
+        }
+    }
+    if (SRC == SRC_CONST) cv = a.constv[cc];
+    const double rate = (double)a.rate;
+
+    auto load_par = [&](int s, SecPar& p) {
+        const float4 c0 = par[(s * 4 + 0) * 32 + lane], c1 = par[(s * 4 + 1) * 32 + lane];
+        const float4 c2 = par[(s * 4 + 2) * 32 + lane], c3 = par[(s * 4 + 3) * 32 + lane];
+        p.g = pk1(c0.x); p.nc = pk1(-c0.y); p.d = pk1(c0.z);
+        p.m8[0] = c1.x; p.m8[1] = c1.y; p.m8[2] = c1.z; p.m8[3] = c1.w;
+        p.al = pk1(c2.x); p.be = pk1(c2.y);
+        p.p0 = c3.x; p.r0 = c3.y; p.p1 = c3.z; p.r1 = c3.w;
+    };
+    SecPar p0;
+    if (NSEC == 1) load_par(0, p0);
+
+    for (int step = grp; step < nsteps; step += NG) {
+        float2 v[H];          // v[k] = (row k of the first half, row k of the second half)
+        if (SRC == SRC_OSC) {
+            if (FASTSINE) {
+                int ha = (int)(th >> 32);
+                int hb = ha + dhi_h;
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    // (I2F, I2F) -> one FMUL2 by 2*pi*2^-32 -> two __sinf (FMUL.RZ by 1/2pi + MUFU.SIN)
+                    const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
+                    v[k] = pk(__sinf(r.x), __sinf(r.y));
+                    ha += dhi;
+                    hb += dhi;
+                }
+                th += th_step;
+            } else {
+                if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < H; ++k)
+                    v[k] = pk(osc_wave(a.wave, osc_cycles(tnb[w * L + k], hz, ph)),
+                              osc_wave(a.wave, osc_cycles(tnb[w * L + H + k], hz, ph)));
+                __syncwarp();
+            }
+        } else if (SRC == SRC_BUF) {
+#pragma unroll
+            for (int k = 0; k < H; ++k)
+                v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
+        } else {
+#pragma unroll
+            for (int k = 0; k < H; ++k) v[k] = pk1(cv);
+        }
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            SecPar ps;
+            if (NSEC == 1) ps = p0; else load_par(s, ps);
+            const int kind = a.sec_kind[s];
+            float2 s1 = pk1(0.0f), s2 = pk1(0.0f);
+            svf2_block<H>(kind, ps, v, s1, s2);
+            // end state of the whole 16-row sub-chunk from zero state: A^8 * z_a + z_b
+            const float zx = fmaf(ps.m8[0], s1.x, fmaf(ps.m8[1], s2.x, s1.y));
+            const float zy = fmaf(ps.m8[2], s1.x, fmaf(ps.m8[3], s2.x, s2.y));
+            zs[w * 32 + lane] = make_float2(zx, zy);
+            bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+            bar_sync(2 + 2 * grp, (WG + 1) * 32);
+            const float2 ia = si[w * 32 + lane];                         // true state entering the first half
+            const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, s1.x));   // ... and the second half
+            const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, s2.x));
+            // zero-input response of both halves, advanced by its 2-term recurrence
+            float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
+            float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
+            v[0] = __fadd2_rn(v[0], h0);
+            v[1] = __fadd2_rn(v[1], h1);
+#pragma unroll
+            for (int k = 2; k < H; ++k) {
+                const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
+                v[k] = __fadd2_rn(v[k], hn);
+                h0 = h1;
+                h1 = hn;
+            }
+        }
+        if (bulk) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float2 o = __fmul2_rn(v[k], gain2);
+                tile[k * 32 + lane] = o.x;
+                tile[(H + k) * 32 + lane] = o.y;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_tile(&out_map, blockIdx.x * 32, (int)row, tile);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else if (live) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const float2 o = __fmul2_rn(v[k], gain2);
+                __stcs(outp + (int64_t)k * a.ld_out, o.x);
+                __stcs(outp + (int64_t)(H + k) * a.ld_out, o.y);
+            }
         }
         outp += out_stride;
         row += row_stride;
@@ -579,11 +852,57 @@ cudaError_t launch_scan_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     }
 }
 
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE>
+cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * L;
+    const int nsteps = a.frames / STEP;
+    *rows_done = nsteps * STEP;
+    if (nsteps == 0) return cudaSuccess;
+    size_t smem = (size_t)NW * L * 32 * sizeof(float) + (size_t)NW * 32 * sizeof(float2) * 2 +
+                  (size_t)NSEC * 4 * 32 * sizeof(float4) + (size_t)NW * L * sizeof(double);
+    auto kern = k_chain_scan2<SRC, NSEC, NG, WG, FASTSINE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const int use_tma = g_scan_tma && make_out_map(a, nsteps * STEP, &map) ? 1 : 0;
+    dim3 grid((a.C + 31) / 32), block((NW + 1) * 32);
+    kern<<<grid, block, smem, st>>>(a, nsteps, map, use_tma);
+    return cudaGetLastError();
+}
+
+template <int NSEC, int NG, int WG>
+cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    const bool fast = a.src_kind == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
+    switch (a.src_kind) {
+        case SRC_OSC:
+            return fast ? launch_scan2_t<SRC_OSC, NSEC, NG, WG, true>(a, st, rows_done)
+                        : launch_scan2_t<SRC_OSC, NSEC, NG, WG, false>(a, st, rows_done);
+        case SRC_BUF: return launch_scan2_t<SRC_BUF, NSEC, NG, WG, false>(a, st, rows_done);
+        default: return launch_scan2_t<SRC_CONST, NSEC, NG, WG, false>(a, st, rows_done);
+    }
+}
+
 }  // namespace
 
 // scan geometry: (groups, worker warps per group).  Deep cascades keep the block at 512 threads
 // so the scanner's fp64 transition matrices stay in registers.
 static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
+    if (variant >= 4) {               // packed kernel k_chain_scan2
+        if (nsec > 2) { *ng = 2; *wg = 7; return; }
+        switch (variant) {
+            case 5: *ng = 7; *wg = 4; break;
+            case 6: *ng = 2; *wg = 15; break;
+            case 7: *ng = 5; *wg = 6; break;
+            default: *ng = 4; *wg = 7; break;
+        }
+        return;
+    }
     if (nsec > 2) { *ng = 2; *wg = 7; return; }
     switch (variant) {
         case 1: *ng = 2; *wg = 15; break;
@@ -619,6 +938,22 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     if (a->frames <= 0 || a->C <= 0 || a->nsec < 1 || a->nsec > 8) return 0;
     int ng, wg;
     scan_geometry(a->nsec, variant, &ng, &wg);
+    if (variant >= 4) {
+        if (a->nsec > 2) {
+            if (a->nsec <= 4) return (int)launch_scan2_n<4, 2, 7>(*a, st, rows_done);
+            return (int)launch_scan2_n<8, 2, 7>(*a, st, rows_done);
+        }
+#define SCAN2_DISPATCH(NG, WG)                                                        \
+    do {                                                                              \
+        if (a->nsec == 1) return (int)launch_scan2_n<1, NG, WG>(*a, st, rows_done);   \
+        return (int)launch_scan2_n<2, NG, WG>(*a, st, rows_done);                     \
+    } while (0)
+        if (ng == 7) SCAN2_DISPATCH(7, 4);
+        if (ng == 2) SCAN2_DISPATCH(2, 15);
+        if (ng == 5) SCAN2_DISPATCH(5, 6);
+        SCAN2_DISPATCH(4, 7);
+#undef SCAN2_DISPATCH
+    }
     if (a->nsec > 2) {
         if (a->nsec <= 4) return (int)launch_scan_n<4, 2, 7>(*a, st, rows_done);
         return (int)launch_scan_n<8, 2, 7>(*a, st, rows_done);

@@ -73,7 +73,7 @@ struct ChainSpec {
     int nsec = 0;                // padded section count the kernels run
     int nsec_real = 0;
     uint8_t sec_kind[SIGB_MAX_SEC] = {0};
-    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, ztab;
+    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, ztab, m8, hrec;
     int src_node = -1;           // SRC_BUF: node whose value is read
     int64_t state_off = 0;       // doubles into the state arena
     int dst_node = -1;
@@ -124,7 +124,7 @@ struct sigb_plan {
     int zero_const_node = -1;
     Val zero_val;
     // options
-    int64_t opt_scan_variant = 2;
+    int64_t opt_scan_variant = 4;
     int64_t opt_force_seq = 0;
     int64_t opt_scan_max_tiles = 148 * 6;
     int64_t opt_slab_frames = 0;
@@ -355,12 +355,16 @@ int Builder::build_chain(int i) {
         std::vector<float> coef((size_t)ch.nsec * 3 * C, 0.0f);
         std::vector<double> apow((size_t)ch.nsec * 4 * C, 0.0);
         std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * C, 0.0f);
+        std::vector<float> m8((size_t)ch.nsec * 4 * C, 0.0f);
+        std::vector<float> hrec((size_t)ch.nsec * 2 * C, 0.0f);
         for (int s = 0; s < ch.nsec; ++s) {   // identity padding: high-pass with g = 0 passes x through
             ch.sec_kind[s] = SEC_HP;
             for (int c = 0; c < C; ++c) {
                 coef[((size_t)s * 3 + 2) * C + c] = 1.0f;
                 apow[((size_t)s * 4 + 0) * C + c] = 1.0;
                 apow[((size_t)s * 4 + 3) * C + c] = 1.0;
+                m8[((size_t)s * 4 + 0) * C + c] = 1.0f;
+                m8[((size_t)s * 4 + 3) * C + c] = 1.0f;
             }
         }
         int s0 = 0;
@@ -388,6 +392,12 @@ int Builder::build_chain(int i) {
                     ch.sec_kind[s] = (uint8_t)secs[k].kind;
                     for (int j = 0; j < 3; ++j) coef[((size_t)s * 3 + j) * C + c] = cf[j];
                     for (int j = 0; j < 4; ++j) apow[((size_t)s * 4 + j) * C + c] = m[j];
+                    double mh[4], m1[4];
+                    sigb_section_transition(secs[k], SIGB_SCAN_L / 2, mh);
+                    sigb_section_transition(secs[k], 1, m1);
+                    for (int j = 0; j < 4; ++j) m8[((size_t)s * 4 + j) * C + c] = (float)mh[j];
+                    hrec[((size_t)s * 2 + 0) * C + c] = (float)(m1[0] + m1[3]);                     // tr(A)
+                    hrec[((size_t)s * 2 + 1) * C + c] = (float)(-(m1[0] * m1[3] - m1[1] * m1[2]));  // -det(A)
                     for (int r = 0; r < SIGB_SCAN_L; ++r)
                         for (int j = 0; j < 2; ++j)
                             ztab[(((size_t)s * SIGB_SCAN_L + r) * 2 + j) * C + c] = tab[r * 2 + j];
@@ -398,6 +408,8 @@ int Builder::build_chain(int i) {
         ch.coef = put_vec(p, coef);
         ch.apow = put_vec(p, apow);
         ch.ztab = put_vec(p, ztab);
+        ch.m8 = put_vec(p, m8);
+        ch.hrec = put_vec(p, hrec);
         ch.state_off = p->n_state;
         p->n_state += (int64_t)ch.nsec * 2 * C;
     }
@@ -643,6 +655,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.gain = ch.gain.dev<float>(base);
             a.apow = ch.apow.dev<double>(base);
             a.ztab = ch.ztab.dev<float>(base);
+            a.m8 = ch.m8.dev<float>(base);
+            a.hrec = ch.hrec.dev<float>(base);
             a.state = p->d_state ? p->d_state + ch.state_off : nullptr;
             a.src_rows = INT64_MAX;
             if (ch.src_kind == SRC_BUF) {

@@ -51,7 +51,7 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq and each geometry of the time-parallel k_chain_scan agree with the reference."""
     opts = dict(force_seq=1) if mode == 'seq' else dict(scan_variant=int(mode[-1]))
