@@ -72,3 +72,15 @@ void sigb_section_zero_input(const SvfSection& s, int len, float* tab) {
         tab[k * 2 + 1] = (float)sigb_section_step(s, 0.0, b1, b2);
     }
 }
+
+double sigb_section_decay_rows(const double m1[4]) {
+    const double tr = m1[0] + m1[3], det = m1[0] * m1[3] - m1[1] * m1[2];
+    const double disc = tr * tr - 4.0 * det;
+    double rho;
+    if (disc < 0.0) rho = std::sqrt(std::fabs(det));
+    else rho = std::max(std::fabs(tr + std::sqrt(disc)), std::fabs(tr - std::sqrt(disc))) / 2.0;
+    if (!(rho < 1.0)) return 1e9;
+    if (rho < 1e-12) return 2.0;
+    // 2^-40 decay, doubled: a near-defective pair decays like k rho^k
+    return 2.0 * (40.0 * std::log(2.0) / -std::log(rho)) + 16.0;
+}

@@ -31,3 +31,7 @@ void sigb_section_transition(const SvfSection& s, int len, double m[4]);
 
 // Zero-input output response: tab[k*2+j] = output at sample k (k < len) when state j starts at 1.
 void sigb_section_zero_input(const SvfSection& s, int len, float* tab);
+
+// Rows after which the section's zero-input response has decayed below 2^-40 of the initial state,
+// from the spectral radius of the one-sample transition m1 (row-major 2x2); 1e9 if not contractive.
+double sigb_section_decay_rows(const double m1[4]);

@@ -21,6 +21,7 @@ struct ChainDev {
     int32_t nsec;
     int32_t rate;
     int32_t frames;                 // rows this launch covers
+    int32_t warm_rows;              // rows after which the filters forget their initial state (< 2^-40); -1: unknown
     int64_t position;               // absolute index of row 0
     uint8_t sec_kind[SIGB_MAX_SEC];
     // SRC_OSC
@@ -40,6 +41,7 @@ struct ChainDev {
     const float* coef;
     const float* gain;              // [C] or nullptr
     double* state;                  // [(s*2+k)*C + c] integrator states (carried across launches)
+    double* state_out;              // k_chain_scan2 writes end states here (a piece of another CTA may still read `state`)
     // scan helpers (time-parallel kernel): transition A^L per section, and the zero-input
     // output response of each state over one sub-chunk
     const double* apow;             // [(s*4+k)*C + c], row-major 2x2
@@ -80,6 +82,7 @@ int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);
 void sigb_set_scan_tma(int on);
+void sigb_set_scan_split(int on);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

@@ -29,6 +29,16 @@ namespace {
 
 constexpr int L = SIGB_SCAN_L;
 int g_scan_tma = 1;   // staged TMA tensor stores in k_chain_scan (0: direct STG)
+int g_scan_split = 1; // k_chain_scan2: split tiles along time across SMs (decay warm-up)
+
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
 
 // ------------------------------------------------------------------------------------------
 // oscillators
@@ -455,7 +465,7 @@ __device__ __forceinline__ void svf2_block(int kind, const SecPar& c, float2 (&v
 
 template <int SRC, int NSEC, int NG, int WG, bool FASTSINE>
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
-k_chain_scan2(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
+k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;
     constexpr int H = L / 2;
@@ -468,204 +478,239 @@ k_chain_scan2(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap 
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
-    const bool live = c < a.C;
-    const int cc = live ? c : a.C - 1;
     const size_t C = (size_t)a.C;
+    const bool bulk = use_tma != 0;
+    const double rate = (double)a.rate;
 
-    // per-channel section parameters -> shared memory (read back per section, or once when NSEC == 1)
-    for (int i = threadIdx.x; i < NSEC * 32; i += blockDim.x) {
-        const int l = i & 31, s = i >> 5;
-        const int ch = min(blockIdx.x * 32 + l, a.C - 1);
-        par[(s * 4 + 0) * 32 + l] = make_float4(a.coef[(size_t)(s * 3 + 0) * C + ch], a.coef[(size_t)(s * 3 + 1) * C + ch],
-                                                a.coef[(size_t)(s * 3 + 2) * C + ch], 0.0f);
-        par[(s * 4 + 1) * 32 + l] = make_float4(a.m8[(size_t)(s * 4 + 0) * C + ch], a.m8[(size_t)(s * 4 + 1) * C + ch],
-                                                a.m8[(size_t)(s * 4 + 2) * C + ch], a.m8[(size_t)(s * 4 + 3) * C + ch]);
-        par[(s * 4 + 2) * 32 + l] = make_float4(a.hrec[(size_t)(s * 2 + 0) * C + ch], a.hrec[(size_t)(s * 2 + 1) * C + ch], 0.0f, 0.0f);
-        // zero-input output at samples 0 and 1: rows 0,1 of the response table
-        par[(s * 4 + 3) * 32 + l] = make_float4(a.ztab[((size_t)(s * L + 0) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 0) * 2 + 1) * C + ch],
-                                                a.ztab[((size_t)(s * L + 1) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 1) * 2 + 1) * C + ch]);
-    }
-    __syncthreads();
+    // Work = (tile, step) pairs in tile-major order, cut into gridDim.x equal contiguous pieces, so a
+    // launch with fewer tiles than SMs (C2: 128 tiles, 148 SMs) still fills the machine.  A piece that
+    // starts inside a tile first re-renders `warm_steps` steps from zero state without storing: the
+    // host sizes them so the filters' memory of the unknown true state has decayed below 2^-40.
+    const int tiles = (a.C + 31) / 32;
+    const long long total = (long long)tiles * nsteps;
+    const long long quota = (total + gridDim.x - 1) / gridDim.x;
+    long long lin = (long long)blockIdx.x * quota;
+    const long long lin_end = min(total, lin + quota);
 
-    if (w == NW) {
-        // ---------------- scanner warp ----------------
-        double m[NSEC][4], c1[NSEC], c2[NSEC];
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m[s][k] = a.apow[(size_t)(s * 4 + k) * C + cc];
-            c1[s] = a.state[(size_t)(s * 2 + 0) * C + cc];
-            c2[s] = a.state[(size_t)(s * 2 + 1) * C + cc];
+    while (lin < lin_end) {
+        const int tile_idx = (int)(lin / nsteps);
+        const int s0 = (int)(lin - (long long)tile_idx * nsteps);
+        const int s1 = (int)min((long long)nsteps, s0 + (lin_end - lin));
+        const int w0 = max(0, s0 - warm_steps);
+        lin += s1 - s0;
+
+        const int c = tile_idx * 32 + lane;
+        const bool live = c < a.C;
+        const int cc = live ? c : a.C - 1;
+
+        // per-channel section parameters -> shared memory
+        for (int i = threadIdx.x; i < NSEC * 32; i += blockDim.x) {
+            const int l = i & 31, s = i >> 5;
+            const int ch = min(tile_idx * 32 + l, a.C - 1);
+            par[(s * 4 + 0) * 32 + l] = make_float4(a.coef[(size_t)(s * 3 + 0) * C + ch], a.coef[(size_t)(s * 3 + 1) * C + ch],
+                                                    a.coef[(size_t)(s * 3 + 2) * C + ch], 0.0f);
+            par[(s * 4 + 1) * 32 + l] = make_float4(a.m8[(size_t)(s * 4 + 0) * C + ch], a.m8[(size_t)(s * 4 + 1) * C + ch],
+                                                    a.m8[(size_t)(s * 4 + 2) * C + ch], a.m8[(size_t)(s * 4 + 3) * C + ch]);
+            par[(s * 4 + 2) * 32 + l] = make_float4(a.hrec[(size_t)(s * 2 + 0) * C + ch], a.hrec[(size_t)(s * 2 + 1) * C + ch], 0.0f, 0.0f);
+            // zero-input output at samples 0 and 1: rows 0,1 of the response table
+            par[(s * 4 + 3) * 32 + l] = make_float4(a.ztab[((size_t)(s * L + 0) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 0) * 2 + 1) * C + ch],
+                                                    a.ztab[((size_t)(s * L + 1) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 1) * 2 + 1) * C + ch]);
         }
-        for (int step = 0; step < nsteps; ++step) {
-            const int grp = step % NG;
+        __syncthreads();
+
+        if (w == NW) {
+            // ---------------- scanner warp: lane = channel ----------------
+            // Per event (one step of one group, one section) the only work on the step-to-step critical
+            // path is the float64 carry update c' = A^(16 WG) c + P_WG (two dependent DFMAs).  The prefix
+            // offsets P_q = sum_{j<q} A^(16 (q-1-j)) z_j do not depend on the carry, and the initial states
+            // s_q = A^(16 q) c + P_q of all sub-chunks are independent of each other.
+            double mg[NSEC][4], c1[NSEC], c2[NSEC];   // A^(16 WG) in float64, carries
+            float mq[NSEC][WG][4];                     // A^(16 q), q = 0..WG-1, float32
 #pragma unroll
             for (int s = 0; s < NSEC; ++s) {
-                const float f00 = (float)m[s][0], f01 = (float)m[s][1], f10 = (float)m[s][2], f11 = (float)m[s][3];
-                bar_sync(1 + 2 * grp, (WG + 1) * 32);
-                float2 z[WG];
+                double m0[4], acc[4] = {1.0, 0.0, 0.0, 1.0};
 #pragma unroll
-                for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
-                // fast float32 chain releases the workers; the exact float64 carry follows off the critical path
-                float f1 = (float)c1[s], f2 = (float)c2[s];
+                for (int k = 0; k < 4; ++k) m0[k] = a.apow[(size_t)(s * 4 + k) * C + cc];
 #pragma unroll
                 for (int q = 0; q < WG; ++q) {
-                    si[(grp * WG + q) * 32 + lane] = make_float2(f1, f2);
-                    const float n1 = fmaf(f00, f1, fmaf(f01, f2, z[q].x));
-                    const float n2 = fmaf(f10, f1, fmaf(f11, f2, z[q].y));
-                    f1 = n1;
-                    f2 = n2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mq[s][q][k] = (float)acc[k];
+                    const double n0 = m0[0] * acc[0] + m0[1] * acc[2], n1 = m0[0] * acc[1] + m0[1] * acc[3];
+                    const double n2 = m0[2] * acc[0] + m0[3] * acc[2], n3 = m0[2] * acc[1] + m0[3] * acc[3];
+                    acc[0] = n0; acc[1] = n1; acc[2] = n2; acc[3] = n3;
                 }
-                bar_arrive(2 + 2 * grp, (WG + 1) * 32);
 #pragma unroll
-                for (int q = 0; q < WG; ++q) {
-                    const double n1 = fma(m[s][0], c1[s], fma(m[s][1], c2[s], (double)z[q].x));
-                    const double n2 = fma(m[s][2], c1[s], fma(m[s][3], c2[s], (double)z[q].y));
+                for (int k = 0; k < 4; ++k) mg[s][k] = acc[k];
+                // a piece that starts at the beginning of a tile continues the carried state
+                c1[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 0) * C + cc] : 0.0;
+                c2[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 1) * C + cc] : 0.0;
+            }
+            for (int step = w0; step < s1; ++step) {
+                const int grp = (step - w0) % NG;
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s) {
+                    const float f1 = (float)c1[s], f2 = (float)c2[s];
+                    bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                    float2 z[WG];
+#pragma unroll
+                    for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
+                    float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < WG; ++q) {
+                        si[(grp * WG + q) * 32 + lane] = make_float2(fmaf(mq[s][q][0], f1, fmaf(mq[s][q][1], f2, p1)),
+                                                                     fmaf(mq[s][q][2], f1, fmaf(mq[s][q][3], f2, p2)));
+                        const float n1 = fmaf(mq[s][1][0], p1, fmaf(mq[s][1][1], p2, z[q].x));
+                        const float n2 = fmaf(mq[s][1][2], p1, fmaf(mq[s][1][3], p2, z[q].y));
+                        p1 = n1;
+                        p2 = n2;
+                    }
+                    bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+                    const double n1 = fma(mg[s][0], c1[s], fma(mg[s][1], c2[s], (double)p1));
+                    const double n2 = fma(mg[s][2], c1[s], fma(mg[s][3], c2[s], (double)p2));
                     c1[s] = n1;
                     c2[s] = n2;
                 }
             }
-        }
-        if (live) {
+            if (live && s1 == nsteps) {   // the piece that finishes a tile hands its state to the next launch
 #pragma unroll
-            for (int s = 0; s < NSEC; ++s) {
-                a.state[(size_t)(s * 2 + 0) * C + c] = c1[s];
-                a.state[(size_t)(s * 2 + 1) * C + c] = c2[s];
-            }
-        }
-        return;
-    }
-
-    // ---------------- worker warps ----------------
-    const int grp = w / WG, q = w % WG;
-    const float gain = a.gain ? a.gain[cc] : 1.0f;
-    const float2 gain2 = pk1(gain);
-    int64_t row = (int64_t)grp * STEP + (int64_t)q * L;
-    const int64_t row_stride = (int64_t)NG * STEP;
-    float* outp = a.out + row * a.ld_out + c;
-    const int64_t out_stride = row_stride * a.ld_out;
-    const bool bulk = use_tma != 0;
-    float* tile = stage + w * (L * 32);
-
-    unsigned long long th = 0, th_step = 0;
-    int dhi = 0, dhi_h = 0;
-    double hz = 0.0, ph = 0.0;
-    float cv = 0.0f;
-    if (SRC == SRC_OSC) {
-        if (FASTSINE) {
-            const unsigned long long dth = a.dtheta[cc];
-            th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
-            th_step = dth * (unsigned long long)row_stride;
-            dhi = (int)((dth + 0x80000000ull) >> 32);
-            dhi_h = (int)((dth * (unsigned long long)H + 0x80000000ull) >> 32);   // half-chunk jump, rounded once
-        } else {
-            hz = a.hertz[cc];
-            ph = a.phase[cc];
-        }
-    }
-    if (SRC == SRC_CONST) cv = a.constv[cc];
-    const double rate = (double)a.rate;
-
-    auto load_par = [&](int s, SecPar& p) {
-        const float4 c0 = par[(s * 4 + 0) * 32 + lane], c1 = par[(s * 4 + 1) * 32 + lane];
-        const float4 c2 = par[(s * 4 + 2) * 32 + lane], c3 = par[(s * 4 + 3) * 32 + lane];
-        p.g = pk1(c0.x); p.nc = pk1(-c0.y); p.d = pk1(c0.z);
-        p.m8[0] = c1.x; p.m8[1] = c1.y; p.m8[2] = c1.z; p.m8[3] = c1.w;
-        p.al = pk1(c2.x); p.be = pk1(c2.y);
-        p.p0 = c3.x; p.r0 = c3.y; p.p1 = c3.z; p.r1 = c3.w;
-    };
-    SecPar p0;
-    if (NSEC == 1) load_par(0, p0);
-
-    for (int step = grp; step < nsteps; step += NG) {
-        float2 v[H];          // v[k] = (row k of the first half, row k of the second half)
-        if (SRC == SRC_OSC) {
-            if (FASTSINE) {
-                int ha = (int)(th >> 32);
-                int hb = ha + dhi_h;
-#pragma unroll
-                for (int k = 0; k < H; ++k) {
-                    // (I2F, I2F) -> one FMUL2 by 2*pi*2^-32 -> two __sinf (FMUL.RZ by 1/2pi + MUFU.SIN)
-                    const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
-                    v[k] = pk(__sinf(r.x), __sinf(r.y));
-                    ha += dhi;
-                    hb += dhi;
+                for (int s = 0; s < NSEC; ++s) {
+                    a.state_out[(size_t)(s * 2 + 0) * C + c] = c1[s];
+                    a.state_out[(size_t)(s * 2 + 1) * C + c] = c2[s];
                 }
-                th += th_step;
-            } else {
-                if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < H; ++k)
-                    v[k] = pk(osc_wave(a.wave, osc_cycles(tnb[w * L + k], hz, ph)),
-                              osc_wave(a.wave, osc_cycles(tnb[w * L + H + k], hz, ph)));
-                __syncwarp();
             }
-        } else if (SRC == SRC_BUF) {
-#pragma unroll
-            for (int k = 0; k < H; ++k)
-                v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
         } else {
+            // ---------------- worker warps: lane = channel, warp = sub-chunk ----------------
+            const int grp = w / WG, q = w % WG;
+            const float gain = a.gain ? a.gain[cc] : 1.0f;
+            const float2 gain2 = pk1(gain);
+            int64_t row = ((int64_t)w0 + grp) * STEP + (int64_t)q * L;
+            const int64_t row_stride = (int64_t)NG * STEP;
+            float* outp = a.out + row * a.ld_out + c;
+            const int64_t out_stride = row_stride * a.ld_out;
+            float* tile = stage + w * (L * 32);
+
+            unsigned long long th = 0, th_step = 0;
+            int dhi = 0, dhi_h = 0;
+            double hz = 0.0, ph = 0.0;
+            float cv = 0.0f;
+            if (SRC == SRC_OSC) {
+                if (FASTSINE) {
+                    const unsigned long long dth = a.dtheta[cc];
+                    th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
+                    th_step = dth * (unsigned long long)row_stride;
+                    dhi = (int)((dth + 0x80000000ull) >> 32);
+                    dhi_h = (int)((dth * (unsigned long long)H + 0x80000000ull) >> 32);   // half-chunk jump, rounded once
+                } else {
+                    hz = a.hertz[cc];
+                    ph = a.phase[cc];
+                }
+            }
+            if (SRC == SRC_CONST) cv = a.constv[cc];
+
+            auto load_par = [&](int s, SecPar& p) {
+                const float4 q0 = par[(s * 4 + 0) * 32 + lane], q1 = par[(s * 4 + 1) * 32 + lane];
+                const float4 q2 = par[(s * 4 + 2) * 32 + lane], q3 = par[(s * 4 + 3) * 32 + lane];
+                p.g = pk1(q0.x); p.nc = pk1(-q0.y); p.d = pk1(q0.z);
+                p.m8[0] = q1.x; p.m8[1] = q1.y; p.m8[2] = q1.z; p.m8[3] = q1.w;
+                p.al = pk1(q2.x); p.be = pk1(q2.y);
+                p.p0 = q3.x; p.r0 = q3.y; p.p1 = q3.z; p.r1 = q3.w;
+            };
+            SecPar p0;
+            if (NSEC == 1) load_par(0, p0);
+
+            for (int step = w0 + grp; step < s1; step += NG) {
+                float2 v[H];          // v[k] = (row k of the first half, row k of the second half)
+                if (SRC == SRC_OSC) {
+                    if (FASTSINE) {
+                        int ha = (int)(th >> 32);
+                        int hb = ha + dhi_h;
 #pragma unroll
-            for (int k = 0; k < H; ++k) v[k] = pk1(cv);
-        }
+                        for (int k = 0; k < H; ++k) {
+                            // (I2F, I2F) -> one FMUL2 by 2*pi*2^-32 -> two __sinf (FMUL.RZ by 1/2pi + MUFU.SIN)
+                            const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
+                            v[k] = pk(__sinf(r.x), __sinf(r.y));
+                            ha += dhi;
+                            hb += dhi;
+                        }
+                        th += th_step;
+                    } else {
+                        if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
+                        __syncwarp();
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-            SecPar ps;
-            if (NSEC == 1) ps = p0; else load_par(s, ps);
-            const int kind = a.sec_kind[s];
-            float2 s1 = pk1(0.0f), s2 = pk1(0.0f);
-            svf2_block<H>(kind, ps, v, s1, s2);
-            // end state of the whole 16-row sub-chunk from zero state: A^8 * z_a + z_b
-            const float zx = fmaf(ps.m8[0], s1.x, fmaf(ps.m8[1], s2.x, s1.y));
-            const float zy = fmaf(ps.m8[2], s1.x, fmaf(ps.m8[3], s2.x, s2.y));
-            zs[w * 32 + lane] = make_float2(zx, zy);
-            bar_arrive(1 + 2 * grp, (WG + 1) * 32);
-            bar_sync(2 + 2 * grp, (WG + 1) * 32);
-            const float2 ia = si[w * 32 + lane];                         // true state entering the first half
-            const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, s1.x));   // ... and the second half
-            const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, s2.x));
-            // zero-input response of both halves, advanced by its 2-term recurrence
-            float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
-            float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
-            v[0] = __fadd2_rn(v[0], h0);
-            v[1] = __fadd2_rn(v[1], h1);
+                        for (int k = 0; k < H; ++k)
+                            v[k] = pk(osc_wave(a.wave, osc_cycles(tnb[w * L + k], hz, ph)),
+                                      osc_wave(a.wave, osc_cycles(tnb[w * L + H + k], hz, ph)));
+                        __syncwarp();
+                    }
+                } else if (SRC == SRC_BUF) {
 #pragma unroll
-            for (int k = 2; k < H; ++k) {
-                const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
-                v[k] = __fadd2_rn(v[k], hn);
-                h0 = h1;
-                h1 = hn;
+                    for (int k = 0; k < H; ++k)
+                        v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < H; ++k) v[k] = pk1(cv);
+                }
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s) {
+                    SecPar ps;
+                    if (NSEC == 1) ps = p0; else load_par(s, ps);
+                    const int kind = a.sec_kind[s];
+                    float2 s1v = pk1(0.0f), s2v = pk1(0.0f);
+                    svf2_block<H>(kind, ps, v, s1v, s2v);
+                    // end state of the whole 16-row sub-chunk from zero state: A^8 * z_a + z_b
+                    const float zx = fmaf(ps.m8[0], s1v.x, fmaf(ps.m8[1], s2v.x, s1v.y));
+                    const float zy = fmaf(ps.m8[2], s1v.x, fmaf(ps.m8[3], s2v.x, s2v.y));
+                    zs[w * 32 + lane] = make_float2(zx, zy);
+                    bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+                    bar_sync(2 + 2 * grp, (WG + 1) * 32);
+                    const float2 ia = si[w * 32 + lane];                         // true state entering the first half
+                    const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, s1v.x));   // ... and the second half
+                    const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, s2v.x));
+                    // zero-input response of both halves, advanced by its 2-term recurrence
+                    float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
+                    float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
+                    v[0] = __fadd2_rn(v[0], h0);
+                    v[1] = __fadd2_rn(v[1], h1);
+#pragma unroll
+                    for (int k = 2; k < H; ++k) {
+                        const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
+                        v[k] = __fadd2_rn(v[k], hn);
+                        h0 = h1;
+                        h1 = hn;
+                    }
+                }
+                if (step >= s0) {           // warm-up steps only advance the state
+                    if (bulk) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < H; ++k) {
+                            const float2 o = __fmul2_rn(v[k], gain2);
+                            tile[k * 32 + lane] = o.x;
+                            tile[(H + k) * 32 + lane] = o.y;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_tile(&out_map, tile_idx * 32, (int)row, tile);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else if (live) {
+#pragma unroll
+                        for (int k = 0; k < H; ++k) {
+                            const float2 o = __fmul2_rn(v[k], gain2);
+                            __stcs(outp + (int64_t)k * a.ld_out, o.x);
+                            __stcs(outp + (int64_t)(H + k) * a.ld_out, o.y);
+                        }
+                    }
+                }
+                outp += out_stride;
+                row += row_stride;
             }
         }
-        if (bulk) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const float2 o = __fmul2_rn(v[k], gain2);
-                tile[k * 32 + lane] = o.x;
-                tile[(H + k) * 32 + lane] = o.y;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_tile(&out_map, blockIdx.x * 32, (int)row, tile);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else if (live) {
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const float2 o = __fmul2_rn(v[k], gain2);
-                __stcs(outp + (int64_t)k * a.ld_out, o.x);
-                __stcs(outp + (int64_t)(H + k) * a.ld_out, o.y);
-            }
-        }
-        outp += out_stride;
-        row += row_stride;
+        __syncthreads();     // piece boundary: shared parameters and the barrier protocol restart
     }
-    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (bulk && w < NW && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -871,8 +916,22 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     const int use_tma = g_scan_tma && make_out_map(a, nsteps * STEP, &map) ? 1 : 0;
-    dim3 grid((a.C + 31) / 32), block((NW + 1) * 32);
-    kern<<<grid, block, smem, st>>>(a, nsteps, map, use_tma);
+    // one persistent CTA per SM, each taking an equal share of the (tile, step) work, when a mid-tile
+    // start costs little warm-up; otherwise one CTA per tile
+    const int tiles = (a.C + 31) / 32;
+    const int sms = sm_count();
+    int grid_x = tiles, warm_steps = 0;
+    if (g_scan_split && a.warm_rows >= 0) {
+        const int ws = (a.warm_rows + STEP - 1) / STEP;
+        const long long total = (long long)tiles * nsteps;
+        const long long quota = (total + sms - 1) / sms;
+        if (tiles % sms != 0 && quota >= 8ll * ws && quota >= 4) {
+            grid_x = (int)((total + quota - 1) / quota);
+            warm_steps = ws;
+        }
+    }
+    dim3 grid(grid_x), block((NW + 1) * 32);
+    kern<<<grid, block, smem, st>>>(a, nsteps, warm_steps, map, use_tma);
     return cudaGetLastError();
 }
 
@@ -919,6 +978,7 @@ extern "C" int sigb_scan_rows_per_step(int nsec, int variant) {
 }
 
 extern "C" void sigb_set_scan_tma(int on) { g_scan_tma = on; }
+extern "C" void sigb_set_scan_split(int on) { g_scan_split = on; }
 
 extern "C" int sigb_launch_chain_seq(const ChainDev* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -76,6 +76,8 @@ struct ChainSpec {
     Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, ztab, m8, hrec;
     int src_node = -1;           // SRC_BUF: node whose value is read
     int64_t state_off = 0;       // doubles into the state arena
+    int state_cur = 0;           // which copy of the state arena holds the live state
+    int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     int dst_node = -1;
 };
 
@@ -119,12 +121,12 @@ struct sigb_plan {
     std::vector<unsigned char> arena;   // host image of all parameter tables
     unsigned char* d_arena = nullptr;
     int64_t n_state = 0;
-    double* d_state = nullptr;
+    double* d_state = nullptr;          // two copies of the state arena: [0, n_state) and [n_state, 2 n_state)
     int context = 0;
     int zero_const_node = -1;
     Val zero_val;
     // options
-    int64_t opt_scan_variant = 4;
+    int64_t opt_scan_variant = 7;
     int64_t opt_force_seq = 0;
     int64_t opt_scan_max_tiles = 148 * 6;
     int64_t opt_slab_frames = 0;
@@ -368,6 +370,7 @@ int Builder::build_chain(int i) {
             }
         }
         int s0 = 0;
+        double warm = 0.0;
         for (int f : filters) {
             const sigb_node& n = p->nodes[f];
             const std::vector<double>* cut = const_of(p, n.in[1]);
@@ -376,6 +379,7 @@ int Builder::build_chain(int i) {
                 return fail(SIGB_EINDEX, "node " + std::to_string(f) + ": cutoff has " + std::to_string(cut->size()) + " channels, request has " + std::to_string(C));
             const int ns = section_count(n.order);
             float tab[SIGB_SCAN_L * 2];
+            std::vector<double> sec_warm(ns, 0.0);
             for (int c = 0; c < C; ++c) {
                 double wn = (*cut)[c] / (p->rate / 2.0);
                 wn = std::min(std::max(wn, 0.0), 1.0);   // fx.py:100-101
@@ -398,16 +402,19 @@ int Builder::build_chain(int i) {
                     for (int j = 0; j < 4; ++j) m8[((size_t)s * 4 + j) * C + c] = (float)mh[j];
                     hrec[((size_t)s * 2 + 0) * C + c] = (float)(m1[0] + m1[3]);                     // tr(A)
                     hrec[((size_t)s * 2 + 1) * C + c] = (float)(-(m1[0] * m1[3] - m1[1] * m1[2]));  // -det(A)
+                    sec_warm[k] = std::max(sec_warm[k], sigb_section_decay_rows(m1));
                     for (int r = 0; r < SIGB_SCAN_L; ++r)
                         for (int j = 0; j < 2; ++j)
                             ztab[(((size_t)s * SIGB_SCAN_L + r) * 2 + j) * C + c] = tab[r * 2 + j];
                 }
             }
             s0 += ns;
+            for (double wv : sec_warm) warm += wv;   // sections in series: budget the decays one after another
         }
         ch.coef = put_vec(p, coef);
         ch.apow = put_vec(p, apow);
         ch.ztab = put_vec(p, ztab);
+        ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
         ch.m8 = put_vec(p, m8);
         ch.hrec = put_vec(p, hrec);
         ch.state_off = p->n_state;
@@ -573,8 +580,8 @@ int upload(sigb_plan* p) {
     CUDA_TRY(cudaMalloc(&p->d_arena, std::max<size_t>(p->arena.size(), 256)));
     CUDA_TRY(cudaMemcpy(p->d_arena, p->arena.data(), p->arena.size(), cudaMemcpyHostToDevice));
     if (p->n_state > 0) {
-        CUDA_TRY(cudaMalloc(&p->d_state, p->n_state * sizeof(double)));
-        CUDA_TRY(cudaMemset(p->d_state, 0, p->n_state * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&p->d_state, 2 * p->n_state * sizeof(double)));
+        CUDA_TRY(cudaMemset(p->d_state, 0, 2 * p->n_state * sizeof(double)));
     }
     CUDA_TRY(cudaEventCreate(&p->ev0));
     CUDA_TRY(cudaEventCreate(&p->ev1));
@@ -635,7 +642,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
     const unsigned char* base = p->d_arena;
     for (const Launch& l : p->launches) {
         if (l.kind == LK_CHAIN) {
-            const ChainSpec& ch = p->chains[l.idx];
+            ChainSpec& ch = p->chains[l.idx];
             ChainDev a;
             std::memset(&a, 0, sizeof(a));
             a.C = ch.C;
@@ -644,6 +651,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.nsec = ch.nsec;
             a.rate = p->rate;
             a.frames = rows;
+            a.warm_rows = ch.warm_rows;
             a.position = abs_row0;
             std::memcpy(a.sec_kind, ch.sec_kind, sizeof(a.sec_kind));
             a.hertz = ch.hertz.dev<double>(base);
@@ -657,7 +665,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.ztab = ch.ztab.dev<float>(base);
             a.m8 = ch.m8.dev<float>(base);
             a.hrec = ch.hrec.dev<float>(base);
-            a.state = p->d_state ? p->d_state + ch.state_off : nullptr;
+            a.state = p->d_state ? p->d_state + ch.state_cur * p->n_state + ch.state_off : nullptr;
+            a.state_out = p->d_state ? p->d_state + (ch.state_cur ^ 1) * p->n_state + ch.state_off : nullptr;
             a.src_rows = INT64_MAX;
             if (ch.src_kind == SRC_BUF) {
                 Operand o = operand_of(p, ch.src_node, abs_row0, out, ld_out);
@@ -675,7 +684,13 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             if (scan_ok) {
                 int e = sigb_launch_chain_scan(&a, (int)p->opt_scan_variant, st, &done);
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
-                if (done > 0) p->launch_count++;
+                if (done > 0) {
+                    p->launch_count++;
+                    if (p->opt_scan_variant >= 4) {   // the packed kernel wrote the other copy
+                        ch.state_cur ^= 1;
+                        std::swap(a.state, a.state_out);
+                    }
+                }
             }
             if (done < rows) {
                 ChainDev t = a;
@@ -745,7 +760,7 @@ int64_t slab_rows(sigb_plan* p, int64_t frames) {
 int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
     if (!p->have_pos || p->next_pos != position) {
         // seek: zero state, then warm the filters up on `context` frames (fx.py:93-105)
-        if (p->d_state) CUDA_TRY(cudaMemsetAsync(p->d_state, 0, p->n_state * sizeof(double), st));
+        if (p->d_state) CUDA_TRY(cudaMemsetAsync(p->d_state, 0, 2 * p->n_state * sizeof(double), st));
         int64_t pre = std::min<int64_t>(p->context, position);
         if (pre > 0 && p->n_state > 0) {
             int st_ = ensure_bufs(p, slab_rows(p, std::max(pre, frames)));
@@ -1036,6 +1051,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "host_slab_bytes") plan->opt_host_slab_bytes = value;
     else if (k == "buffer_budget") plan->opt_buffer_budget = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
+    else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);
     return SIGB_OK;
 }
