@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--scan-variant', type=int, default=None)
+    ap.add_argument('--plan-opt', action='append', default=[], help='key=value passed to sigb_plan_set_option (A/B testing)')
     return ap.parse_args()
 
 
@@ -203,6 +204,9 @@ def run_b200(args):
     compiled = eng.compile(build_graph(), v, RATE, frames)
     if args.scan_variant is not None:
         compiled.set_option('scan_variant', args.scan_variant)
+    for kv in args.plan_opt:
+        k, val = kv.split('=')
+        compiled.set_option(k, int(val))
     out = torch.empty((frames, v), dtype=torch.float32, device='cuda')
 
     for _ in range(max(args.warmup, 3)):
