@@ -93,6 +93,10 @@ int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t root,
 
 /* Attach device memory to a SIGB_NODE_BUFFER node (caller keeps ownership). */
 int sigb_plan_bind_buffer(sigb_plan* plan, int32_t node, const float* dev_ptr, int64_t rows);
+/* Streaming variant: the bound memory holds frames [first_row, first_row + rows) of the source (a
+ * FileReader-style window, chain/files.py:70-87); frames outside the window read as zero.  Re-bind
+ * before each sigb_render call of a stream; filter state is carried as usual. */
+int sigb_plan_bind_buffer_window(sigb_plan* plan, int32_t node, const float* dev_ptr, int64_t first_row, int64_t rows);
 
 /* Render frames [position, position+frames) into `out` (device, row-major, leading dimension
  * `ld_out` floats >= channels).  Filter state is carried when `position` continues the previous
@@ -115,6 +119,10 @@ int sigb_plan_destroy(sigb_plan* plan);
 int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
 /* Tuning knobs: "scan_min_tiles", "slab_frames", "force_seq", ... ; unknown key -> SIGB_EINVAL */
 int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t value);
+/* Defaults for plans created AFTERWARDS (decisions taken while the plan is built):
+ * "fuse_reduce" (1: GroupSum / PanSum over oscillator chains run as one fused render+reduce kernel,
+ * 0: always on materialised blocks), "voices_m" (0 auto, 1 or 4 voices per thread in the fused kernel). */
+int sigb_set_default_option(const char* key, int64_t value);
 /* Kernels launched by this plan since creation (bench.py's gpu_launches claim). */
 int64_t sigb_plan_launch_count(const sigb_plan* plan);
 /* Device time (ms) of the kernels of the most recent sigb_render call, measured with CUDA events

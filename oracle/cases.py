@@ -247,3 +247,69 @@ ERROR_CASES = [
     ('mono_input_multichannel_filter',
      lambda ns: lowpass(ns, osc(ns, 'Sine', [[100.0]]), [[500.0, 600.0]]), 256, 2, 'IndexError'),
 ]
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE configs C3 (additive bank) and C5 (randomised voice-bank instances), SURVEY 8d
+# ----------------------------------------------------------------------------------------------
+
+def bank_params(seed: int, partials: int, per_group: int = 1024):
+    """C3: hertz~U(27.5, 12000), phase~U(0,1), amp~U(0,1)/per_group; group g = p // per_group."""
+    rng = np.random.default_rng(seed)
+    hertz = rng.uniform(27.5, 12000.0, partials)
+    phase = rng.uniform(0.0, 1.0, partials)
+    amp = rng.uniform(0.0, 1.0, partials) / per_group
+    return hertz, phase, amp
+
+
+def build_bank(ns, ext, hertz, phase, amp, groups: int):
+    """GroupSum(Gain(Sine(hertz, phase), amp)) -> (frames, groups)."""
+    gs = ext.GroupSum()
+    gs.get_state().groups = groups
+    gs.input = gain(ns, osc(ns, 'Sine', [hertz], [phase]), [amp])
+    return gs
+
+
+WAVES = ('Sine', 'Square', 'Sawtooth', 'Triangle')
+FILTERS = (None, 'LowPass', 'HighPass')
+
+
+def instance_params(seed: int, n_total: int, rank: int = 0, world: int = 1) -> dict:
+    """C5: n_total randomised osc -> (filter) -> gain -> pan instances; instance i lives on rank
+    i % world.  Returns this rank's shard as arrays (global draw, so every world size sees the same bank)."""
+    rng = np.random.default_rng(seed)
+    wave = rng.integers(0, 4, n_total)
+    filt = rng.integers(0, 3, n_total)
+    hertz = rng.uniform(27.5, 4186.0, n_total)
+    phase = rng.uniform(0.0, 1.0, n_total)
+    cutoff = np.exp(rng.uniform(np.log(100.0), np.log(8000.0), n_total))
+    g = rng.uniform(0.05, 1.0, n_total) / np.sqrt(n_total)
+    pan = rng.uniform(0.0, 1.0, n_total)
+    mine = slice(rank, n_total, world)
+    return dict(wave=wave[mine], filt=filt[mine], hertz=hertz[mine], phase=phase[mine], cutoff=cutoff[mine],
+                gain=g[mine], pan=pan[mine], n_total=n_total)
+
+
+def build_instances(ns, ext, prm: dict):
+    """One homogeneous chain per (wave, filter) kind, merged channel-wise, under one PanSum."""
+    chains, pans = [], []
+    for w, wname in enumerate(WAVES):
+        for f, fname in enumerate(FILTERS):
+            sel = np.flatnonzero((prm['wave'] == w) & (prm['filt'] == f))
+            if sel.size == 0:
+                continue
+            x = osc(ns, wname, [prm['hertz'][sel]], [prm['phase'][sel]])
+            if fname is not None:
+                x = lowpass(ns, x, [prm['cutoff'][sel]], fname)
+            chains.append(gain(ns, x, [prm['gain'][sel]]))
+            pans.append(prm['pan'][sel])
+    node = chains[0]
+    for nxt in chains[1:]:
+        m = ns.Merge()
+        m.left = node
+        m.right = nxt
+        node = m
+    ps = ext.PanSum()
+    ps.input = node
+    ps.pan = fixed(ns, [np.concatenate(pans)])
+    return ps

@@ -338,3 +338,36 @@ def render_cascade(x: np.ndarray, cutoffs: np.ndarray, rate: int, btype: str = '
             z0 = np.zeros((n_sec, 2)) if zi is None else zi[s, i]
             y[:, i], zf[s, i] = scipy.signal.sosfilt(sos, y[:, i], axis=0, zi=z0)
     return y, zf
+
+
+def render_bank(position: int, frames: int, rate: int, hertz, phase, amp, groups: int, chunk: int = 256) -> np.ndarray:
+    """Config C3 as arrays: group_sum(gain(sine(cycles), amp)) accumulated in float64, partials
+    processed `chunk` at a time to bound the (frames, chunk) float64 temporaries."""
+    hertz, phase, amp = (np.asarray(a, dtype=float) for a in (hertz, phase, amp))
+    p = hertz.size
+    per = p // groups
+    out = np.zeros((frames, groups))
+    for g in range(groups):
+        for a in range(g * per, (g + 1) * per, chunk):
+            b = min(a + chunk, (g + 1) * per)
+            x = gain(sine(osc_cycles(position, frames, rate, hertz[None, a:b], phase[None, a:b])), amp[None, a:b])
+            out[:, g] += x.sum(-1)
+    return out
+
+
+def render_instances(prm: dict, position: int, frames: int, rate: int, chunk: int = 256) -> np.ndarray:
+    """Config C5 as arrays: per instance osc(wave) -> (LowPass | HighPass | none) -> gain, then
+    pan_sum; single request from zero state (position must be 0 when any instance has a filter)."""
+    waves = ('Sine', 'Square', 'Sawtooth', 'Triangle')
+    out = np.zeros((frames, 2))
+    n = prm['hertz'].size
+    for a in range(0, n, chunk):
+        b = min(a + chunk, n)
+        y = np.empty((frames, b - a))
+        for j in range(a, b):
+            btype = (None, 'lp', 'hp')[int(prm['filt'][j])]
+            y[:, j - a] = render_voice_chain(position, frames, rate, prm['hertz'][j:j + 1], prm['phase'][j:j + 1],
+                                             prm['cutoff'][j:j + 1], prm['gain'][j:j + 1],
+                                             wave=waves[int(prm['wave'][j])], btype=btype)[:, 0]
+        out += pan_sum(y, prm['pan'][None, a:b])
+    return out

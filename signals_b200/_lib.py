@@ -58,6 +58,8 @@ def lib() -> ctypes.CDLL:
     L.sigb_plan_create.restype = ctypes.c_int
     L.sigb_plan_bind_buffer.argtypes = [vp, i32, vp, i64]
     L.sigb_plan_bind_buffer.restype = ctypes.c_int
+    L.sigb_plan_bind_buffer_window.argtypes = [vp, i32, vp, i64, i64]
+    L.sigb_plan_bind_buffer_window.restype = ctypes.c_int
     L.sigb_render.argtypes = [vp, i64, i32, vp, i64, vp]
     L.sigb_render.restype = ctypes.c_int
     L.sigb_render_host.argtypes = [vp, i64, i32, vp, i64]
@@ -70,6 +72,8 @@ def lib() -> ctypes.CDLL:
     L.sigb_plan_describe.restype = i64
     L.sigb_plan_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     L.sigb_plan_set_option.restype = ctypes.c_int
+    L.sigb_set_default_option.argtypes = [ctypes.c_char_p, i64]
+    L.sigb_set_default_option.restype = ctypes.c_int
     L.sigb_plan_launch_count.argtypes = [vp]
     L.sigb_plan_launch_count.restype = i64
     L.sigb_plan_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]

@@ -1,0 +1,290 @@
+// Fused render + mix-down kernels of libsigb200.so (sm_100a): the voice / partial blocks of these
+// configurations are never materialised in HBM.
+//
+//   k_bank          oscillator bank under a GroupSum (BASELINE config C3: 65,536 sine partials -> 64
+//                   channels).  Lane = time sample; the partials of a group are walked from a shared
+//                   memory tile of {phase word, phase increment, amplitude}.  Bound: the MUFU pipe.
+//   k_voices        voice bank under a PanSum (config C5: 1M osc -> filter -> gain -> pan instances ->
+//                   stereo).  Thread = M voices with phase, filter state and weights in registers,
+//                   walking time in 16-row tiles; per tile the CTA reduces its voices to one (16, 2)
+//                   partial in a fixed order.
+//   k_voices_finish fixed-order sum of the per-CTA partials into the (frames, 2) output.
+//
+// Reference semantics (file:line under /root/reference/src/signals/chain): osc.py:26-62 (phase from the
+// absolute frame index, four waveforms), fx.py:49-52 (Gain), fx.py:85-151 (order <= 2 Butterworth
+// low/high-pass).  The reference has no working N -> 1 mix-down (shape.py:32-57 is broken); GroupSum /
+// PanSum are defined by oracle/np_oracle.py::group_sum / pan_sum.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sigb200.h"
+#include "sigb_internal.h"
+#include "sigb_device.cuh"
+
+namespace {
+
+using namespace sigb_dev;
+
+constexpr float kTwoPiQ32 = 1.4629180792671596e-9f;   // 2*pi*2^-32
+
+// ------------------------------------------------------------------------------------------
+// k_bank
+// ------------------------------------------------------------------------------------------
+constexpr int BANK_THREADS = 256;
+constexpr int BANK_WARPS = BANK_THREADS / 32;
+constexpr int BANK_TN = 256;       // rows per tile: 8 per lane
+constexpr int BANK_J = BANK_TN / 32;
+constexpr int BANK_GB = 8;         // groups per work item (one 32-byte sector of an output row)
+constexpr int BANK_PCHUNK = 1024;  // partials staged in shared memory at a time
+
+__global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n_items, int gblocks) {
+    __shared__ int4 par[BANK_PCHUNK];                         // {B - 128 D, D, amplitude bits, 0}
+    __shared__ float red[BANK_WARPS][BANK_TN];
+    __shared__ float outtile[BANK_TN][BANK_GB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = a.P / a.groups;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / gblocks, gb = item - tile * gblocks;
+        const int n0 = tile * BANK_TN;
+        const int g_first = gb * BANK_GB;
+        const int g_count = min(BANK_GB, a.groups - g_first);
+        // the phase word is exact at the centre row of the tile; rows are +-128 away, so the rounded
+        // increment drifts by at most 128 * 2^-33 cycles (9.4e-8 rad)
+        const unsigned long long n_mid = (unsigned long long)(a.position + n0 + BANK_TN / 2);
+
+        for (int gi = 0; gi < g_count; ++gi) {
+            const int g = g_first + gi;
+            float2 acc[BANK_J / 2];
+#pragma unroll
+            for (int j = 0; j < BANK_J / 2; ++j) acc[j] = make_float2(0.0f, 0.0f);
+
+            for (int p0 = 0; p0 < per; p0 += BANK_PCHUNK) {
+                const int cnt = min(BANK_PCHUNK, per - p0);
+                __syncthreads();                              // previous chunk fully consumed
+                for (int q = tid; q < cnt; q += BANK_THREADS) {
+                    const int p = g * per + p0 + q;
+                    const unsigned long long dth = a.dtheta[p];
+                    const unsigned long long th = a.theta0[p] + n_mid * dth;      // exact mod 2^64
+                    const int B = (int)((th + 0x80000000ull) >> 32);
+                    const int D = (int)((dth + 0x80000000ull) >> 32);
+                    const float amp = a.gain ? a.gain[p] : 1.0f;
+                    par[q] = make_int4(B - (BANK_TN / 2) * D, D, __float_as_int(amp), 0);
+                }
+                __syncthreads();
+                for (int q = warp; q < cnt; q += BANK_WARPS) {
+                    const int4 e = par[q];                    // broadcast read
+                    int w = e.x + lane * e.y;
+                    const int step = e.y << 5;
+                    const float amp = __int_as_float(e.z);
+                    const float2 amp2 = make_float2(amp, amp);
+#pragma unroll
+                    for (int j = 0; j < BANK_J / 2; ++j) {
+                        const float2 r = __fmul2_rn(make_float2((float)w, (float)(w + step)), make_float2(kTwoPiQ32, kTwoPiQ32));
+                        w += 2 * step;
+                        acc[j] = __ffma2_rn(amp2, make_float2(__sinf(r.x), __sinf(r.y)), acc[j]);
+                    }
+                }
+            }
+            // cross-warp sum in a fixed order
+#pragma unroll
+            for (int j = 0; j < BANK_J / 2; ++j) {
+                red[warp][lane + 32 * (2 * j)] = acc[j].x;
+                red[warp][lane + 32 * (2 * j + 1)] = acc[j].y;
+            }
+            __syncthreads();
+            {
+                float s = 0.0f;
+#pragma unroll
+                for (int wv = 0; wv < BANK_WARPS; ++wv) s += red[wv][tid];
+                outtile[tid][gi] = s;
+            }
+        }
+        __syncthreads();
+        const int rows = min(BANK_TN, a.frames - n0);
+        for (int i = tid; i < rows * g_count; i += BANK_THREADS) {
+            const int r = i / g_count, gi = i - r * g_count;
+            a.out[(int64_t)(n0 + r) * a.ld_out + g_first + gi] = outtile[r][gi];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_voices
+// ------------------------------------------------------------------------------------------
+constexpr int VK = SIGB_VOICE_K;
+constexpr int VT = SIGB_VOICE_THREADS;
+
+// waveform from the signed top word of the Q0.64 phase (fraction of a cycle in [-1/2, 1/2) after the
+// two's-complement reading): osc.py:43, 49, 55, 61-62 away from their discontinuities
+template <int WAVE>
+__device__ __forceinline__ float wave_q32(int w) {
+    if (WAVE == SIGB_WAVE_SINE) return __sinf((float)w * kTwoPiQ32);
+    if (WAVE == SIGB_WAVE_SQUARE) return w >= 0 ? 1.0f : -1.0f;                    // frac < 1/2 -> +1
+    if (WAVE == SIGB_WAVE_SAWTOOTH) return (float)w * 4.656612873077393e-10f;      // 2 frac (- 2 past 1/2)
+    return fmaf(-fabsf((float)(w - 0x40000000)), 9.313225746154785e-10f, 1.0f);    // 1 - 4 |frac - 1/4|
+}
+
+template <int WAVE>
+__device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[VK]) {
+    unsigned near = 0u;
+#pragma unroll
+    for (int k = 0; k < VK; ++k) {
+        x[k] = wave_q32<WAVE>(w);
+        if (WAVE == SIGB_WAVE_SQUARE) near |= (((unsigned)(w + guard) & 0x7fffffffu) < 2u * (unsigned)guard);   // edges at 0 and 1/2
+        if (WAVE == SIGB_WAVE_SAWTOOTH) near |= (((unsigned)w ^ 0x80000000u) + (unsigned)guard < 2u * (unsigned)guard);   // wrap at 1/2
+        w += dhi;
+    }
+    return near != 0u;
+}
+
+template <int KIND>
+__device__ __forceinline__ void filt_tile(float (&x)[VK], float g, float c, float d, float& s1, float& s2, int kmax) {
+#pragma unroll
+    for (int k = 0; k < VK; ++k)
+        if (k < kmax) x[k] = svf_any(KIND, x[k], g, c, d, s1, s2);
+}
+
+template <int M>
+__global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_constant__ VoicesDev a) {
+    __shared__ float2 red[VK * VT];
+    const int tid = threadIdx.x;
+    int si = 0;
+    for (int i = 1; i < a.nseg; ++i)
+        if ((int)blockIdx.x >= a.seg[i].cta0) si = i;
+    const VoiceSeg& sg = a.seg[si];
+    const int cta = blockIdx.x - sg.cta0;
+    const int wave = sg.wave, guard = sg.guard;
+    const int fk = sg.nsec == 0 ? -1 : sg.sec_kind;
+    const size_t C = (size_t)sg.C;
+
+    unsigned long long th[M], dK[M];
+    int dhi[M], chan[M];
+    float g[M], cf[M], d[M], s1[M], s2[M];
+    float2 wt[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int c = (cta * M + m) * VT + tid;
+        const bool live = c < sg.C;
+        const int cc = live ? c : sg.C - 1;
+        chan[m] = live ? c : -1;
+        const unsigned long long dth = sg.dtheta[cc];
+        th[m] = sg.theta0[cc] + (unsigned long long)a.position * dth + 0x80000000ull;   // + 1/2 ulp of the top word
+        dK[m] = dth * (unsigned long long)VK;
+        dhi[m] = (int)((dth + 0x80000000ull) >> 32);
+        wt[m] = live ? make_float2(sg.wl[cc], sg.wr[cc]) : make_float2(0.0f, 0.0f);
+        g[m] = cf[m] = d[m] = s1[m] = s2[m] = 0.0f;
+        if (fk >= 0) {
+            g[m] = sg.coef[0 * C + cc];
+            cf[m] = sg.coef[1 * C + cc];
+            d[m] = sg.coef[2 * C + cc];
+            s1[m] = (float)sg.state[0 * C + cc];
+            s2[m] = (float)sg.state[1 * C + cc];
+        }
+    }
+    float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)blockIdx.x * a.frames;
+    const double rate = (double)a.rate;
+
+    for (int n0 = 0; n0 < a.frames; n0 += VK) {
+        const int kmax = min(VK, a.frames - n0);
+        float2 acc[VK];
+#pragma unroll
+        for (int k = 0; k < VK; ++k) acc[k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float x[VK];
+            const int w = (int)(th[m] >> 32);
+            th[m] += dK[m];
+            bool near;
+            switch (wave) {
+                case SIGB_WAVE_SINE: near = gen_tile<SIGB_WAVE_SINE>(w, dhi[m], guard, x); break;
+                case SIGB_WAVE_SQUARE: near = gen_tile<SIGB_WAVE_SQUARE>(w, dhi[m], guard, x); break;
+                case SIGB_WAVE_SAWTOOTH: near = gen_tile<SIGB_WAVE_SAWTOOTH>(w, dhi[m], guard, x); break;
+                default: near = gen_tile<SIGB_WAVE_TRIANGLE>(w, dhi[m], guard, x); break;
+            }
+            if (near && chan[m] >= 0) {
+                // a sample within `guard` of a discontinuity: redo the tile with the reference's own
+                // float64 arithmetic (osc.py:32), so the jump lands on the same sample as in numpy
+                const double hz = sg.hertz[chan[m]], ph = sg.phase[chan[m]];
+                for (int k = 0; k < VK; ++k)
+                    x[k] = osc_wave(wave, osc_cycles(__ddiv_rn((double)(a.position + n0 + k), rate), hz, ph));
+            }
+            switch (fk) {
+                case 0: filt_tile<0>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
+                case SEC_HP: filt_tile<SEC_HP>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
+                case SEC_FIRST_ORDER: filt_tile<SEC_FIRST_ORDER>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
+                case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
+                default: break;
+            }
+#pragma unroll
+            for (int k = 0; k < VK; ++k) acc[k] = __ffma2_rn(wt[m], make_float2(x[k], x[k]), acc[k]);
+        }
+        // CTA reduction in a fixed order: 16 rows x 256 threads -> 16 float2
+#pragma unroll
+        for (int k = 0; k < VK; ++k) red[k * VT + tid] = acc[k];
+        __syncthreads();
+        {
+            const int k = tid >> 4, part = tid & 15;
+            float2 s = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < VT / 16; ++i) s = __fadd2_rn(s, red[k * VT + i * 16 + part]);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+                s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+            }
+            if (part == 0 && k < kmax) part_out[n0 + k] = s;
+        }
+        __syncthreads();
+    }
+    if (fk >= 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (chan[m] >= 0) {
+                sg.state[0 * C + chan[m]] = (double)s1[m];
+                sg.state[1 * C + chan[m]] = (double)s2[m];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_voices_finish(const float* __restrict__ partial, int nparts, int frames,
+                                                       float* __restrict__ out, int64_t ld_out) {
+    const int64_t total = (int64_t)frames * 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int p = 0; p < nparts; ++p) s += (double)__ldg(partial + (int64_t)p * total + i);
+        out[(i >> 1) * ld_out + (i & 1)] = (float)s;
+    }
+}
+
+}  // namespace
+
+extern "C" int sigb_launch_bank(const BankDev* a, void* stream) {
+    if (a->frames <= 0 || a->P <= 0 || a->groups <= 0) return 0;
+    const int tiles = (a->frames + BANK_TN - 1) / BANK_TN;
+    const int gblocks = (a->groups + BANK_GB - 1) / BANK_GB;
+    const long long items = (long long)tiles * gblocks;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(items < (long long)sms * 4 ? items : (long long)sms * 4);
+    k_bank<<<grid, BANK_THREADS, 0, (cudaStream_t)stream>>>(*a, (int)items, gblocks);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sigb_voices_ctas(int channels, int M) { return (channels + VT * M - 1) / (VT * M); }
+
+extern "C" int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream) {
+    if (a->frames <= 0 || nparts <= 0) return 0;
+    if (a->M == 4) k_voices<4><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
+    else k_voices<1><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sigb_launch_voices_finish(const float* partial, int nparts, int frames, float* out, int64_t ld_out, void* stream) {
+    if (frames <= 0) return 0;
+    const int64_t total = (int64_t)frames * 2;
+    const int blocks = (int)(total + 255) / 256 < 148 * 8 ? (int)((total + 255) / 256) : 148 * 8;
+    k_voices_finish<<<blocks, 256, 0, (cudaStream_t)stream>>>(partial, nparts, frames, out, ld_out);
+    return (int)cudaGetLastError();
+}

@@ -72,6 +72,54 @@ struct ReduceDev {
     float* out; int64_t ld_out;
 };
 
+
+// Oscillator bank fused with GroupSum (config C3): out[n][g] = sum_{p in group g} gain[p] * sin(2 pi theta_p(n)),
+// theta_p(n) = theta0[p] + (position + n) * dtheta[p] in Q0.64.
+struct BankDev {
+    int32_t P;                          // partials = input channels
+    int32_t groups;                     // output channels; partial p belongs to group p / (P/groups)
+    int32_t frames;
+    int64_t position;
+    const unsigned long long* theta0;   // [P]
+    const unsigned long long* dtheta;   // [P]
+    const float* gain;                  // [P] or nullptr (unit amplitude)
+    float* out;
+    int64_t ld_out;
+};
+
+// One homogeneous segment of a voice bank fused with PanSum (config C5): per channel
+// osc(wave) -> at most one filter section -> gain -> (L, R) weights; channels are summed.
+struct VoiceSeg {
+    int32_t C;
+    int32_t wave;                       // SIGB_WAVE_*
+    int32_t nsec;                       // 0 or 1
+    int32_t sec_kind;                   // SEC_* bits of the section
+    int32_t cta0;                       // first CTA (= partial index) of this segment in the launch
+    int32_t guard;                      // phase-word guard band around waveform discontinuities
+    const unsigned long long* theta0;   // [C] Q0.64 phase / increment (all waves)
+    const unsigned long long* dtheta;
+    const double* hertz;                // [C] reference float64 path near discontinuities
+    const double* phase;
+    const float* coef;                  // [(k)*C + c], k: g c d
+    const float* wl;                    // [C] gain * (1 - pan)
+    const float* wr;                    // [C] gain * pan
+    double* state;                      // [(k)*C + c]
+};
+
+#define SIGB_VOICE_SEGS 24              // segments per k_voices launch
+#define SIGB_VOICE_K 16                 // rows per tile
+#define SIGB_VOICE_THREADS 256
+
+struct VoicesDev {
+    int32_t nseg;
+    int32_t rate;
+    int32_t frames;
+    int32_t M;                          // channels per thread (1 or 4)
+    int64_t position;
+    float* partial;                     // [nparts][frames][2]
+    VoiceSeg seg[SIGB_VOICE_SEGS];
+};
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -83,6 +131,10 @@ int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);
 void sigb_set_scan_tma(int on);
 void sigb_set_scan_split(int on);
+int sigb_launch_bank(const BankDev* a, void* stream);
+int sigb_voices_ctas(int channels, int M);                         // CTAs (= partials) a segment of `channels` needs
+int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream);
+int sigb_launch_voices_finish(const float* partial, int nparts, int frames, float* out, int64_t ld_out, void* stream);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

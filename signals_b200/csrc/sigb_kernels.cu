@@ -24,8 +24,11 @@
 
 #include "sigb200.h"
 #include "sigb_internal.h"
+#include "sigb_device.cuh"
 
 namespace {
+
+using namespace sigb_dev;
 
 constexpr int L = SIGB_SCAN_L;
 int g_scan_tma = 1;   // staged TMA tensor stores in k_chain_scan (0: direct STG)
@@ -40,86 +43,6 @@ int sm_count() {
     return n;
 }
 
-// ------------------------------------------------------------------------------------------
-// oscillators
-// ------------------------------------------------------------------------------------------
-
-// sin(2*pi*r) for r in [-0.5, 0.5], float32.  Measured on B200 over 3M points (tests/test_gpu_parity.py
-// ::test_sine_error_budget): variant 0 (MUFU.SIN) 3.39e-7 max-abs, variant 1 (folded to [-1/4,1/4]
-// first) 3.39e-7 -- folding buys nothing --, variant 2 (folded FP32 polynomial) 1.73e-7.
-template <int VARIANT>
-__device__ __forceinline__ float sin2pi(float r) {
-    if (VARIANT == 0) {
-        return __sinf(r * 6.2831853071795864f);
-    } else {
-        float f = copysignf(0.5f, r) - r;          // exact (Sterbenz) when |r| >= 1/4
-        r = fabsf(r) > 0.25f ? f : r;
-        if (VARIANT == 1) {
-            return __sinf(r * 6.2831853071795864f);
-        } else {
-            float u = r * r;                        // x * P4(x^2), max error 1.7e-7
-            float p = 39.53670883178711f;
-            p = fmaf(p, u, -76.5497817993164f);
-            p = fmaf(p, u, 81.60100555419922f);
-            p = fmaf(p, u, -41.34165573120117f);
-            p = fmaf(p, u, 6.283185005187988f);
-            return p * r;
-        }
-    }
-}
-
-#ifndef SIGB_SIN_VARIANT
-#define SIGB_SIN_VARIANT 0
-#endif
-
-// numpy float remainder np.mod(a, b) for b in {1, 0.5}: fmod, then shift negatives up by b,
-// and +0.0 for an exact zero (npy_divmod semantics; osc.py:49,55,61-62 rely on them).
-template <int HALF>
-__device__ __forceinline__ double np_mod(double a) {
-    double m = HALF ? a - trunc(a * 2.0) * 0.5 : a - trunc(a);   // == fmod(a, b), exact
-    if (m != 0.0) {
-        if (m < 0.0) m = __dadd_rn(m, HALF ? 0.5 : 1.0);
-    } else {
-        m = 0.0;
-    }
-    return m;
-}
-
-__device__ __forceinline__ double np_sign(double v) {
-    return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : (v == 0.0 ? 0.0 : v));   // NaN stays NaN
-}
-
-// osc.py:32 with the reference's exact float64 op order and no FMA contraction.
-__device__ __forceinline__ double osc_cycles(double tn, double hertz, double phase) {
-    return __dadd_rn(__dmul_rn(tn, hertz), phase);
-}
-
-__device__ __forceinline__ float osc_wave(int wave, double cyc) {
-    switch (wave) {
-        case SIGB_WAVE_SINE: {
-            double r = cyc - rint(cyc);                                   // exact
-            return sin2pi<SIGB_SIN_VARIANT>((float)r);
-        }
-        case SIGB_WAVE_SQUARE:                                           // osc.py:49
-            return (float)np_sign(__dadd_rn(0.5, -np_mod<0>(cyc)));
-        case SIGB_WAVE_SAWTOOTH:                                              // osc.py:55
-            return (float)__dadd_rn(__dmul_rn(2.0, np_mod<0>(__dadd_rn(cyc, -0.5))), -1.0);
-        default: {                                                        // osc.py:61-62
-            double t = __dadd_rn(cyc, -0.25);
-            double a = __dadd_rn(__dmul_rn(4.0, np_mod<1>(t)), -1.0);
-            double s = np_sign(__dadd_rn(np_mod<0>(t), -0.5));
-            return (float)__dmul_rn(a, s);
-        }
-    }
-}
-
-// sine from the top 32 bits of a Q0.64 phase accumulator, read as a signed fraction of a cycle
-// (one I2F, one FMUL by 2*pi*2^-32, then __sinf = FMUL.RZ by 1/2pi + MUFU.SIN)
-__device__ __forceinline__ float sine_q32(int hi) {
-    if (SIGB_SIN_VARIANT == 0) return __sinf((float)hi * 1.4629180792671596e-9f);
-    return sin2pi<SIGB_SIN_VARIANT>((float)hi * 2.3283064365386963e-10f);
-}
-
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 // one (L x 32) staging tile -> global memory with a single TMA tensor store (UTMASTG); the tensor
@@ -128,37 +51,6 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, int x, in
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
                  "r"(smem_u32(ssrc))
                  : "memory");
-}
-
-// ------------------------------------------------------------------------------------------
-// zero-delay-feedback state-variable section (one 2nd-order Butterworth factor)
-//   hp = d (x - c s1 - s2);  bp = g hp + s1;  s1' = g hp + bp;  lp = g bp + s2;  s2' = g bp + lp
-// first-order section: v = G (x - s1); lp = v + s1; s1' = lp + v; hp = x - lp
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float svf_lp2(float x, float g, float c, float d, float& s1, float& s2) {
-    float t = fmaf(-c, s1, x);
-    float hp = (t - s2) * d;
-    float bp = fmaf(g, hp, s1);
-    s1 = fmaf(g, hp, bp);
-    float lp = fmaf(g, bp, s2);
-    s2 = fmaf(g, bp, lp);
-    return lp;
-}
-
-__device__ __forceinline__ float svf_any(int kind, float x, float g, float c, float d, float& s1, float& s2) {
-    if (kind & SEC_FIRST_ORDER) {
-        float v = (x - s1) * g;
-        float lp = v + s1;
-        s1 = lp + v;
-        return (kind & SEC_HP) ? x - lp : lp;
-    }
-    float t = fmaf(-c, s1, x);
-    float hp = (t - s2) * d;
-    float bp = fmaf(g, hp, s1);
-    s1 = fmaf(g, hp, bp);
-    float lp = fmaf(g, bp, s2);
-    s2 = fmaf(g, bp, lp);
-    return (kind & SEC_HP) ? hp : lp;
 }
 
 __device__ __forceinline__ float load_src(const ChainDev& a, int64_t row, int c) {

@@ -25,6 +25,10 @@ namespace {
 
 thread_local std::string g_last_error;
 
+// defaults applied to plans created afterwards (sigb_set_default_option)
+int64_t g_default_fuse_reduce = 1;
+int64_t g_default_voices_m = 0;
+
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
@@ -55,6 +59,7 @@ struct BufInfo {
 
 struct ExtBinding {
     const float* ptr = nullptr;
+    int64_t first_row = 0;      // absolute frame position of row 0 of the bound memory
     int64_t rows = 0;
 };
 
@@ -79,6 +84,8 @@ struct ChainSpec {
     int state_cur = 0;           // which copy of the state arena holds the live state
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     int dst_node = -1;
+    std::vector<double> gain_d;  // folded gain in float64 (fused reductions derive their weights from it)
+    bool has_gain = false;
 };
 
 struct EwiseSpec {
@@ -97,7 +104,28 @@ struct ReduceSpec {
     int dst_node = -1;
 };
 
-enum LaunchKind { LK_CHAIN, LK_EWISE, LK_REDUCE };
+// oscillator bank fused with its GroupSum (k_bank)
+struct BankSpec {
+    ChainSpec ch;
+    int groups = 0;
+    int dst_node = -1;
+};
+
+// voice chains fused with their PanSum (k_voices): one segment per leaf of the Merge tree
+struct VoiceSegSpec {
+    ChainSpec ch;
+    Table wl, wr;
+    double max_abs_hertz = 0.0, max_abs_phase = 0.0;
+};
+struct VoicesSpec {
+    std::vector<VoiceSegSpec> segs;
+    int M = 1;
+    int nparts = 0;
+    int partial_buf = -1;      // index into Plan::bufs (2 * nparts "channels")
+    int dst_node = -1;
+};
+
+enum LaunchKind { LK_CHAIN, LK_EWISE, LK_REDUCE, LK_BANK, LK_VOICES };
 struct Launch {
     LaunchKind kind;
     int idx;
@@ -117,6 +145,8 @@ struct sigb_plan {
     std::vector<ChainSpec> chains;
     std::vector<EwiseSpec> ewises;
     std::vector<ReduceSpec> reduces;
+    std::vector<BankSpec> banks;
+    std::vector<VoicesSpec> voices;
     std::vector<Launch> launches;
     std::vector<unsigned char> arena;   // host image of all parameter tables
     unsigned char* d_arena = nullptr;
@@ -132,6 +162,8 @@ struct sigb_plan {
     int64_t opt_slab_frames = 0;
     int64_t opt_host_slab_bytes = 64ll << 20;
     int64_t opt_buffer_budget = 6ll << 30;
+    int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
+    int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
     bool uploaded = false;
     bool have_pos = false;
@@ -232,6 +264,11 @@ struct Builder {
 
     int ensure(int i);            // materialise node i's value (emits launches); returns status
     int build_chain(int i);
+    int make_chain(int i, ChainSpec& ch, bool scan_tables);
+    bool pure_osc_run(int i, int* nsec, int* wave) const;
+    bool collect_voice_leaves(int idx, std::vector<int>* leaves) const;
+    int build_bank(int i);
+    int build_voices(int i, const std::vector<int>& leaves);
     int build_ewise(int i);
     int build_merge(int i);
     int build_reduce(int i);
@@ -264,6 +301,23 @@ int Builder::ensure(int i) {
 
 int Builder::build_chain(int i) {
     ChainSpec ch;
+    int st = make_chain(i, ch, true);
+    if (st != SIGB_OK) return st;
+    const int C = ch.C;
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = C;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    p->vals[i] = v;
+    p->chains.push_back(ch);
+    p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+    return SIGB_OK;
+}
+
+// Walks the linear run ending at node i down to its source and fills `ch` with the per-channel tables
+// (no launch is recorded).  scan_tables = false skips the tables only the time-parallel kernels read.
+int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
     const int C = node_C(i);
     ch.C = C;
     ch.dst_node = i;
@@ -287,7 +341,7 @@ int Builder::build_chain(int i) {
             ch.wave = n.subtype;
             ch.hertz = put_vec(p, hzv);
             ch.phase = put_vec(p, phv);
-            if (n.subtype == SIGB_WAVE_SINE) {
+            {   // Q0.64 phase / increment: sine fast path of the chain kernels, every wave in k_voices
                 std::vector<unsigned long long> t0(C), dt(C);
                 for (int c = 0; c < C; ++c) {
                     t0[c] = frac_q64(phv[c]);
@@ -354,15 +408,17 @@ int Builder::build_chain(int i) {
     ch.nsec = pad_sections(nsec);
     if (ch.nsec > SIGB_MAX_SEC) return fail(SIGB_EUNSUPPORTED, "filter cascade longer than 16 sections in one node");
     if (ch.nsec > 0) {
+        const size_t CS = scan_tables ? (size_t)C : 0;      // scan-only tables are left empty when unused
         std::vector<float> coef((size_t)ch.nsec * 3 * C, 0.0f);
-        std::vector<double> apow((size_t)ch.nsec * 4 * C, 0.0);
-        std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * C, 0.0f);
-        std::vector<float> m8((size_t)ch.nsec * 4 * C, 0.0f);
-        std::vector<float> hrec((size_t)ch.nsec * 2 * C, 0.0f);
+        std::vector<double> apow((size_t)ch.nsec * 4 * CS, 0.0);
+        std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * CS, 0.0f);
+        std::vector<float> m8((size_t)ch.nsec * 4 * CS, 0.0f);
+        std::vector<float> hrec((size_t)ch.nsec * 2 * CS, 0.0f);
         for (int s = 0; s < ch.nsec; ++s) {   // identity padding: high-pass with g = 0 passes x through
             ch.sec_kind[s] = SEC_HP;
             for (int c = 0; c < C; ++c) {
                 coef[((size_t)s * 3 + 2) * C + c] = 1.0f;
+                if (!scan_tables) continue;
                 apow[((size_t)s * 4 + 0) * C + c] = 1.0;
                 apow[((size_t)s * 4 + 3) * C + c] = 1.0;
                 m8[((size_t)s * 4 + 0) * C + c] = 1.0f;
@@ -390,11 +446,12 @@ int Builder::build_chain(int i) {
                     float cf[3];
                     double m[4];
                     sigb_section_coef(secs[k], cf);
-                    sigb_section_transition(secs[k], SIGB_SCAN_L, m);
-                    sigb_section_zero_input(secs[k], SIGB_SCAN_L, tab);
                     const int s = s0 + k;
                     ch.sec_kind[s] = (uint8_t)secs[k].kind;
                     for (int j = 0; j < 3; ++j) coef[((size_t)s * 3 + j) * C + c] = cf[j];
+                    if (!scan_tables) continue;
+                    sigb_section_transition(secs[k], SIGB_SCAN_L, m);
+                    sigb_section_zero_input(secs[k], SIGB_SCAN_L, tab);
                     for (int j = 0; j < 4; ++j) apow[((size_t)s * 4 + j) * C + c] = m[j];
                     double mh[4], m1[4];
                     sigb_section_transition(secs[k], SIGB_SCAN_L / 2, mh);
@@ -412,11 +469,13 @@ int Builder::build_chain(int i) {
             for (double wv : sec_warm) warm += wv;   // sections in series: budget the decays one after another
         }
         ch.coef = put_vec(p, coef);
-        ch.apow = put_vec(p, apow);
-        ch.ztab = put_vec(p, ztab);
-        ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
-        ch.m8 = put_vec(p, m8);
-        ch.hrec = put_vec(p, hrec);
+        if (scan_tables) {
+            ch.apow = put_vec(p, apow);
+            ch.ztab = put_vec(p, ztab);
+            ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
+            ch.m8 = put_vec(p, m8);
+            ch.hrec = put_vec(p, hrec);
+        }
         ch.state_off = p->n_state;
         p->n_state += (int64_t)ch.nsec * 2 * C;
     }
@@ -424,14 +483,138 @@ int Builder::build_chain(int i) {
         std::vector<float> gf(gain.begin(), gain.end());
         ch.gain = put_vec(p, gf);
     }
+    ch.gain_d = gain;
+    ch.has_gain = has_gain;
+    return SIGB_OK;
+}
+
+// true when the linear run ending at node i consists only of Gain / LowPass / HighPass nodes, each
+// consumed once, down to an oscillator (so the whole run can live inside a fused render+reduce kernel)
+bool Builder::pure_osc_run(int i, int* nsec, int* wave) const {
+    int cur = i;
+    *nsec = 0;
+    for (;;) {
+        if (cur < 0 || p->vals[cur].kind != VK_NONE || p->uses[cur] != 1) return false;
+        const sigb_node& n = p->nodes[cur];
+        if (n.kind == SIGB_NODE_OSC) {
+            *wave = n.subtype;
+            return true;
+        }
+        if (n.kind == SIGB_NODE_FILTER) {
+            if (n.order < 1) return false;
+            *nsec += section_count(n.order);
+        } else if (n.kind != SIGB_NODE_GAIN) {
+            return false;
+        }
+        cur = n.in[0];
+    }
+}
+
+bool Builder::collect_voice_leaves(int idx, std::vector<int>* leaves) const {
+    if (idx < 0 || p->vals[idx].kind != VK_NONE || p->uses[idx] != 1) return false;
+    const sigb_node& n = p->nodes[idx];
+    if (n.kind == SIGB_NODE_MERGE)
+        return collect_voice_leaves(n.in[0], leaves) && collect_voice_leaves(n.in[1], leaves);
+    int nsec = 0, wave = 0;
+    if (!pure_osc_run(idx, &nsec, &wave) || nsec > 1) return false;
+    leaves->push_back(idx);
+    return true;
+}
+
+int Builder::build_bank(int i) {
+    const sigb_node& n = p->nodes[i];
+    BankSpec b;
+    int st = make_chain(n.in[0], b.ch, false);
+    if (st != SIGB_OK) return st;
+    b.groups = n.order;
+    b.dst_node = i;
+    if (b.groups < 1 || b.ch.C % b.groups != 0)
+        return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": " + std::to_string(b.ch.C) + " channels do not split into " + std::to_string(b.groups) + " groups");
+    if (i == p->root && b.groups != p->channels)
+        return fail(SIGB_ESHAPE, "reduction yields " + std::to_string(b.groups) + " channels, request has " + std::to_string(p->channels));
     Val v;
     v.kind = VK_BUF;
-    v.channels = C;
+    v.channels = b.groups;
     v.buf = new_buf(i);
-    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    if (v.buf >= 0) p->bufs[v.buf].channels = b.groups;
     p->vals[i] = v;
-    p->chains.push_back(ch);
-    p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+    p->vals[n.in[0]].kind = VK_BUF;      // consumed inside the fused kernel: never materialised
+    p->vals[n.in[0]].channels = b.ch.C;
+    p->vals[n.in[0]].buf = -2;
+    p->banks.push_back(b);
+    p->launches.push_back({LK_BANK, (int)p->banks.size() - 1});
+    return SIGB_OK;
+}
+
+int Builder::build_voices(int i, const std::vector<int>& leaves) {
+    const sigb_node& n = p->nodes[i];
+    const int Cin = p->nodes[n.in[0]].channels;
+    const std::vector<double>* pan = const_of(p, n.in[1]);
+    if (!pan) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": pan driven by a non-constant emitter");
+    std::vector<double> pv;
+    if (!rep(*pan, Cin, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
+    if (i == p->root && p->channels != 2)
+        return fail(SIGB_ESHAPE, "reduction yields 2 channels, request has " + std::to_string(p->channels));
+    VoicesSpec vs;
+    vs.dst_node = i;
+    int coff = 0;
+    long long total = 0;
+    for (int leaf : leaves) {
+        VoiceSegSpec sg;
+        int st = make_chain(leaf, sg.ch, false);
+        if (st != SIGB_OK) return st;
+        const int C = sg.ch.C;
+        if (coff + C > Cin) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": merged voices exceed the input width");
+        std::vector<float> wl(C), wr(C);
+        for (int c = 0; c < C; ++c) {
+            const double g = sg.ch.has_gain ? sg.ch.gain_d[c] : 1.0;
+            wl[c] = (float)(g * (1.0 - pv[coff + c]));
+            wr[c] = (float)(g * pv[coff + c]);
+        }
+        sg.wl = put_vec(p, wl);
+        sg.wr = put_vec(p, wr);
+        {
+            const double* hz = reinterpret_cast<const double*>(p->arena.data() + sg.ch.hertz.off);
+            const double* ph = reinterpret_cast<const double*>(p->arena.data() + sg.ch.phase.off);
+            for (int c = 0; c < C; ++c) {
+                sg.max_abs_hertz = std::max(sg.max_abs_hertz, std::fabs(hz[c]));
+                sg.max_abs_phase = std::max(sg.max_abs_phase, std::fabs(ph[c]));
+            }
+        }
+        sg.ch.gain_d.clear();
+        coff += C;
+        total += C;
+        vs.segs.push_back(std::move(sg));
+    }
+    if (coff != Cin) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": merged voices do not cover the input width");
+    vs.M = p->opt_voices_m == 1 || p->opt_voices_m == 4 ? (int)p->opt_voices_m
+                                                         : (total >= 148ll * 2 * SIGB_VOICE_THREADS * 2 ? 4 : 1);
+    for (const VoiceSegSpec& sg : vs.segs) vs.nparts += sigb_voices_ctas(sg.ch.C, vs.M);
+    BufInfo pb;
+    pb.channels = 2 * vs.nparts;
+    p->bufs.push_back(pb);
+    vs.partial_buf = (int)p->bufs.size() - 1;
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = 2;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = 2;
+    p->vals[i] = v;
+    // everything below the PanSum lives inside the fused kernel
+    std::vector<int> stack{n.in[0]};
+    while (!stack.empty()) {
+        const int k = stack.back();
+        stack.pop_back();
+        p->vals[k].kind = VK_BUF;
+        p->vals[k].channels = p->nodes[k].channels;
+        p->vals[k].buf = -2;
+        if (p->nodes[k].kind == SIGB_NODE_MERGE) {
+            stack.push_back(p->nodes[k].in[0]);
+            stack.push_back(p->nodes[k].in[1]);
+        }
+    }
+    p->voices.push_back(std::move(vs));
+    p->launches.push_back({LK_VOICES, (int)p->voices.size() - 1});
     return SIGB_OK;
 }
 
@@ -518,6 +701,15 @@ int Builder::build_merge(int i) {
 int Builder::build_reduce(int i) {
     const sigb_node& n = p->nodes[i];
     if (n.in[0] < 0) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": reduction without input");
+    if (p->opt_fuse_reduce) {
+        if (n.kind == SIGB_NODE_GROUPSUM) {
+            int nsec = 0, wave = 0;
+            if (pure_osc_run(n.in[0], &nsec, &wave) && nsec == 0 && wave == SIGB_WAVE_SINE) return build_bank(i);
+        } else {
+            std::vector<int> leaves;
+            if (collect_voice_leaves(n.in[0], &leaves)) return build_voices(i, leaves);
+        }
+    }
     int st = ensure(n.in[0]);
     if (st != SIGB_OK) return st;
     ReduceSpec r;
@@ -611,8 +803,9 @@ Operand operand_of(sigb_plan* p, int idx, int64_t abs_row0, const float* out, in
         const ExtBinding& e = p->ext[idx];
         o.ld = v.channels;
         o.cs = v.channels == 1 ? 0 : 1;
-        o.rows = std::max<int64_t>(0, e.rows - abs_row0);
-        o.ptr = e.ptr ? e.ptr + std::min(abs_row0, e.rows) * o.ld : nullptr;
+        const int64_t rel = abs_row0 - e.first_row;      // rows outside the bound window read as zero
+        o.rows = rel < 0 ? 0 : std::max<int64_t>(0, e.rows - rel);
+        o.ptr = e.ptr ? e.ptr + std::min(std::max<int64_t>(rel, 0), e.rows) * o.ld : nullptr;
         if (!e.ptr) o.rows = 0;
     } else if (v.buf < 0) {   // the root itself (only read by Merge-into-root bookkeeping; not expected)
         o.ptr = out;
@@ -723,6 +916,71 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             int err = sigb_launch_ewise(&a, st);
             if (err) return fail(SIGB_ECUDA, std::string("k_ewise: ") + cudaGetErrorString((cudaError_t)err));
             p->launch_count++;
+        } else if (l.kind == LK_BANK) {
+            const BankSpec& b = p->banks[l.idx];
+            BankDev a;
+            std::memset(&a, 0, sizeof(a));
+            a.P = b.ch.C;
+            a.groups = b.groups;
+            a.frames = rows;
+            a.position = abs_row0;
+            a.theta0 = b.ch.theta0.dev<unsigned long long>(base);
+            a.dtheta = b.ch.dtheta.dev<unsigned long long>(base);
+            a.gain = b.ch.gain.dev<float>(base);
+            const Val& dv = p->vals[b.dst_node];
+            if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
+            else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
+            int err = sigb_launch_bank(&a, st);
+            if (err) return fail(SIGB_ECUDA, std::string("k_bank: ") + cudaGetErrorString((cudaError_t)err));
+            p->launch_count++;
+        } else if (l.kind == LK_VOICES) {
+            const VoicesSpec& vs = p->voices[l.idx];
+            float* partial = p->bufs[vs.partial_buf].ptr;
+            int part0 = 0;
+            for (size_t s0 = 0; s0 < vs.segs.size(); s0 += SIGB_VOICE_SEGS) {
+                VoicesDev a;
+                std::memset(&a, 0, sizeof(a));
+                a.nseg = (int)std::min<size_t>(SIGB_VOICE_SEGS, vs.segs.size() - s0);
+                a.rate = p->rate;
+                a.frames = rows;
+                a.M = vs.M;
+                a.position = abs_row0;
+                a.partial = partial + (int64_t)part0 * rows * 2;
+                int ctas = 0;
+                for (int k = 0; k < a.nseg; ++k) {
+                    const VoiceSegSpec& sg = vs.segs[s0 + k];
+                    VoiceSeg& d = a.seg[k];
+                    d.C = sg.ch.C;
+                    d.wave = sg.ch.wave;
+                    d.nsec = sg.ch.nsec_real;
+                    d.sec_kind = sg.ch.sec_kind[0];
+                    d.cta0 = ctas;
+                    d.theta0 = sg.ch.theta0.dev<unsigned long long>(base);
+                    d.dtheta = sg.ch.dtheta.dev<unsigned long long>(base);
+                    d.hertz = sg.ch.hertz.dev<double>(base);
+                    d.phase = sg.ch.phase.dev<double>(base);
+                    d.coef = sg.ch.coef.dev<float>(base);
+                    d.wl = sg.wl.dev<float>(base);
+                    d.wr = sg.wr.dev<float>(base);
+                    d.state = p->d_state ? p->d_state + sg.ch.state_off : nullptr;
+                    // guard band (units of 2^-32 cycles): in-tile drift of the rounded increment, the
+                    // rounding of the top word, and the float64 rounding of the reference's own phase
+                    const double cyc = sg.max_abs_hertz * (double)(abs_row0 + rows) / p->rate + sg.max_abs_phase + 1.0;
+                    const double g = 16.0 + cyc * 3.0 * 4294967296.0 / 9007199254740992.0;
+                    d.guard = g < 1073741823.0 ? (int)std::ceil(g) : 0x3fffffff;
+                    ctas += sigb_voices_ctas(sg.ch.C, vs.M);
+                }
+                int err = sigb_launch_voices(&a, ctas, st);
+                if (err) return fail(SIGB_ECUDA, std::string("k_voices: ") + cudaGetErrorString((cudaError_t)err));
+                p->launch_count++;
+                part0 += ctas;
+            }
+            const Val& dv = p->vals[vs.dst_node];
+            float* o = dv.buf < 0 ? out : p->bufs[dv.buf].ptr;
+            const int64_t ldo = dv.buf < 0 ? ld_out : dv.channels;
+            int err = sigb_launch_voices_finish(partial, vs.nparts, rows, o, ldo, st);
+            if (err) return fail(SIGB_ECUDA, std::string("k_voices_finish: ") + cudaGetErrorString((cudaError_t)err));
+            p->launch_count++;
         } else {
             const ReduceSpec& r = p->reduces[l.idx];
             ReduceDev a;
@@ -828,6 +1086,8 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
     if (!nodes || !out_plan || n_nodes <= 0 || root < 0 || root >= n_nodes || channels < 1 || rate < 1)
         return fail(SIGB_EINVAL, "sigb_plan_create: bad arguments");
     std::unique_ptr<sigb_plan> p(new sigb_plan());
+    p->opt_fuse_reduce = g_default_fuse_reduce;
+    p->opt_voices_m = g_default_voices_m;
     p->channels = channels;
     p->rate = rate;
     p->root = root;
@@ -904,7 +1164,15 @@ extern "C" int sigb_plan_bind_buffer(sigb_plan* plan, int32_t node, const float*
     if (!plan || node < 0 || node >= (int)plan->nodes.size() || plan->nodes[node].kind != SIGB_NODE_BUFFER)
         return fail(SIGB_EINVAL, "sigb_plan_bind_buffer: not a Buffer node");
     plan->ext[node].ptr = dev_ptr;
+    plan->ext[node].first_row = 0;
     plan->ext[node].rows = rows;
+    return SIGB_OK;
+}
+
+extern "C" int sigb_plan_bind_buffer_window(sigb_plan* plan, int32_t node, const float* dev_ptr, int64_t first_row, int64_t rows) {
+    int e = sigb_plan_bind_buffer(plan, node, dev_ptr, rows);
+    if (e != SIGB_OK) return e;
+    plan->ext[node].first_row = first_row;
     return SIGB_OK;
 }
 
@@ -1025,6 +1293,17 @@ extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t 
             const EwiseSpec& e = plan->ewises[l.idx];
             s += "{\"kind\": \"ewise\", \"node\": " + std::to_string(e.dst_node) + ", \"op\": \"" + ew_names[e.op] +
                  "\", \"channels\": " + std::to_string(e.C) + ", \"column\": " + std::to_string(e.dst_coff) + "}";
+        } else if (l.kind == LK_BANK) {
+            const BankSpec& b = plan->banks[l.idx];
+            s += "{\"kind\": \"bank\", \"node\": " + std::to_string(b.dst_node) + ", \"partials\": " + std::to_string(b.ch.C) +
+                 ", \"groups\": " + std::to_string(b.groups) + ", \"gain\": " + (b.ch.gain.off >= 0 ? "true" : "false") + "}";
+        } else if (l.kind == LK_VOICES) {
+            const VoicesSpec& v = plan->voices[l.idx];
+            long long total = 0;
+            for (const VoiceSegSpec& sg : v.segs) total += sg.ch.C;
+            s += "{\"kind\": \"voices\", \"node\": " + std::to_string(v.dst_node) + ", \"segments\": " + std::to_string(v.segs.size()) +
+                 ", \"channels\": " + std::to_string(total) + ", \"channels_per_thread\": " + std::to_string(v.M) +
+                 ", \"partials\": " + std::to_string(v.nparts) + "}";
         } else {
             const ReduceSpec& r = plan->reduces[l.idx];
             s += "{\"kind\": \"reduce\", \"node\": " + std::to_string(r.dst_node) + ", \"op\": \"" +
@@ -1053,6 +1332,15 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);
+    return SIGB_OK;
+}
+
+extern "C" int sigb_set_default_option(const char* key, int64_t value) {
+    if (!key) return fail(SIGB_EINVAL, "null");
+    const std::string k(key);
+    if (k == "fuse_reduce") g_default_fuse_reduce = value;
+    else if (k == "voices_m") g_default_voices_m = value;
+    else return fail(SIGB_EINVAL, "unknown default option " + k);
     return SIGB_OK;
 }
 

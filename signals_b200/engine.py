@@ -54,6 +54,7 @@ class CompiledPlan:
         self.rate = records.rate
         self._lib = _lib.lib()
         self._keep: list = []
+        self._windows: dict = {}
         handle = ctypes.c_void_p()
         data = records.data
         dptr = data.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if data.size else None
@@ -118,6 +119,21 @@ class CompiledPlan:
             if st != _lib.SIGB_OK:
                 _raise(st, 'sigb_plan_bind_buffer')
         self._bound = True
+
+    def bind_window(self, buffer_node, samples, first_row: int):
+        """Streaming source: ``samples`` (CUDA float32 ``(rows, channels)``) holds frames
+        ``[first_row, first_row + rows)`` of ``buffer_node``; re-bind before each render of a stream."""
+        self._bind_buffers()
+        for idx, node in self.records.buffers.items():
+            if node is buffer_node:
+                assert samples.is_cuda and samples.is_contiguous() and samples.shape[1] == node.channels
+                self._windows[idx] = samples          # keeps the memory alive while it is bound
+                st = self._lib.sigb_plan_bind_buffer_window(self.handle, idx, ctypes.c_void_p(samples.data_ptr()),
+                                                            int(first_row), int(samples.shape[0]))
+                if st != _lib.SIGB_OK:
+                    _raise(st, 'sigb_plan_bind_buffer_window')
+                return
+        raise ValueError('bind_window: not a Buffer node of this plan')
 
     def render_device(self, position: int, frames: int, out=None):
         """Render into a CUDA float32 tensor ``(frames, channels)`` on torch's current stream."""

@@ -1,0 +1,73 @@
+"""Voice sharding across GPUs: one process per GPU, no data-path collective except the final mix.
+
+Every node of the reference graph is per-channel (chain/osc.py:26-62,
+chain/fx.py:35-139); voices only meet in the mix-down.  So a bank of N voices is split by voice --
+voice ``i`` lives on rank ``i % world`` (round-robin balances the random osc/filter kinds) -- each
+rank renders the ``(frames, 2)`` partial mix of its own voices with the fused ``k_voices`` kernel, and
+the ranks' partials are summed with ONE ``torch.distributed`` reduce per render (NCCL over
+NVLink/NVSwitch for CUDA tensors; the same code path runs on gloo with CPU tensors in the tests).
+Time is never sharded: IIR state is per voice, so all chunks of a voice stay on its rank.
+"""
+from __future__ import annotations
+
+import typing
+
+import numpy as np
+
+
+def shard_indices(n_total: int, rank: int, world: int) -> np.ndarray:
+    """Global voice indices owned by ``rank``: i % world == rank."""
+    if not 0 <= rank < world:
+        raise ValueError(f'rank {rank} outside world of {world}')
+    return np.arange(rank, n_total, world)
+
+
+def shard_counts(n_total: int, world: int) -> list[int]:
+    return [len(range(r, n_total, world)) for r in range(world)]
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def reduce_mix(partial, dst: typing.Optional[int] = 0, group=None):
+    """Sum the ranks' partial mixes in place.  ``dst`` = rank that receives the mix (``None``: every
+    rank, all-reduce).  A single-process run (no process group) returns ``partial`` untouched."""
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return partial
+    if dst is None:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(partial, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return partial
+
+
+class ShardedMix:
+    """A voice bank split over the ranks of a process group.
+
+    ``build_shard(rank, world)`` returns this rank's root emitter (a ``PanSum`` over its voices);
+    ``render`` = local fused render + one reduce of the ``(frames, 2)`` block on the render stream.
+    """
+
+    def __init__(self, build_shard: typing.Callable[[int, int], typing.Any], rate: int = 48000, channels: int = 2,
+                 engine=None, group=None):
+        from signals_b200 import engine as engine_mod
+        dist = _dist()
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.engine = engine or engine_mod.Engine()
+        self.channels = channels
+        self.rate = rate
+        self.compiled = self.engine.compile(build_shard(self.rank, self.world), channels, rate)
+
+    def render(self, position: int, frames: int, out=None, dst: typing.Optional[int] = 0):
+        """Returns the CUDA ``(frames, channels)`` mix (complete on ``dst``, or on every rank when
+        ``dst`` is None; other ranks hold their own partial)."""
+        out = self.compiled.render_device(position, frames, out)
+        return reduce_mix(out, dst=dst, group=self.group)
+
+    def close(self):
+        self.compiled.close()

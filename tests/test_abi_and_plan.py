@@ -194,3 +194,69 @@ def test_plan_walker_accepts_reference_objects():
         assert len(a.nodes) == len(b.nodes) and np.array_equal(a.data, b.data)
         for x, y in zip(a.nodes, b.nodes):
             assert bytes(x) == bytes(y)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused render + mix-down lowering (configs C3 / C5)
+# ------------------------------------------------------------------------------------------------
+
+def _set_default(key, value):
+    assert _lib.lib().sigb_set_default_option(key.encode(), int(value)) == 0
+
+
+def test_bank_lowers_to_one_fused_launch(ns, engine):
+    hertz, phase, amp = cases.bank_params(3, 2048, 256)
+    d = engine.compile(cases.build_bank(ns, ext, hertz, phase, amp, 8), 8, 48000).describe()
+    assert d['launches'] == [dict(kind='bank', node=d['launches'][0]['node'], partials=2048, groups=8, gain=True)]
+    assert d['buffers'] == 0 and d['state_doubles'] == 0
+
+
+def test_non_sine_bank_and_filtered_bank_fall_back_to_materialised_blocks(ns, engine):
+    gs = ext.GroupSum()
+    gs.get_state().groups = 2
+    gs.input = cases.osc(ns, 'Square', [[100.0, 200.0, 300.0, 400.0]])
+    kinds = [l['kind'] for l in engine.compile(gs, 2, 48000).describe()['launches']]
+    assert kinds == ['chain', 'reduce']
+    gs.input = cases.lowpass(ns, cases.osc(ns, 'Sine', [[100.0, 200.0, 300.0, 400.0]]), [[500.0] * 4])
+    kinds = [l['kind'] for l in engine.compile(gs, 2, 48000).describe()['launches']]
+    assert kinds == ['chain', 'reduce']
+
+
+def test_instances_lower_to_one_voices_launch(ns, engine):
+    prm = cases.instance_params(5, 600)
+    d = engine.compile(cases.build_instances(ns, ext, prm), 2, 48000).describe()
+    (l,) = d['launches']
+    assert l['kind'] == 'voices' and l['segments'] == 12 and l['channels'] == 600 and l['channels_per_thread'] == 1
+    assert d['context'] == 100          # LowPass / HighPass context (fx.py:82-83) survives the fusion
+    # filter state: one section (2 doubles) per filtered instance
+    assert d['state_doubles'] == 2 * int((prm['filt'] > 0).sum())
+
+
+def test_fan_out_below_a_pansum_disables_the_fusion(ns, engine):
+    """A chain consumed twice must be materialised once (the block cache's job, chain/__init__.py:424-457)."""
+    o = cases.gain(ns, cases.osc(ns, 'Sine', [[100.0, 200.0]]), [[0.5, 0.5]])
+    m = ns.Merge()
+    m.left = o
+    m.right = o
+    ps = ext.PanSum()
+    ps.input = m
+    ps.pan = cases.fixed(ns, [[0.1, 0.2, 0.3, 0.4]])
+    kinds = [l['kind'] for l in engine.compile(ps, 2, 48000).describe()['launches']]
+    assert 'voices' not in kinds and kinds[-1] == 'reduce'
+
+
+def test_fuse_reduce_default_option(ns, engine):
+    hertz, phase, amp = cases.bank_params(3, 64, 32)
+    _set_default('fuse_reduce', 0)
+    try:
+        kinds = [l['kind'] for l in engine.compile(cases.build_bank(ns, ext, hertz, phase, amp, 2), 2, 48000).describe()['launches']]
+    finally:
+        _set_default('fuse_reduce', 1)
+    assert kinds == ['chain', 'reduce']
+    assert _lib.lib().sigb_set_default_option(b'nope', 1) == _lib.SIGB_EINVAL
+
+
+def test_pansum_shape_errors(ns, engine):
+    prm = cases.instance_params(5, 40)
+    with pytest.raises(chain.BadShape):
+        engine.compile(cases.build_instances(ns, ext, prm), 3, 48000)      # PanSum yields 2 channels

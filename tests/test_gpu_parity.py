@@ -252,3 +252,124 @@ def test_time_split_pieces_match_oracle(ns, engine):
     compiled.set_option('scan_split', 1)
     assert float((whole - first).abs().max()) <= 2e-6
     compiled.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# fused render + mix-down kernels (configs C3 and C5)
+# ------------------------------------------------------------------------------------------------
+
+def _set_default(key, value):
+    from signals_b200 import _lib
+    assert _lib.lib().sigb_set_default_option(key.encode(), int(value)) == 0
+
+
+@pytest.mark.parametrize('partials,groups,frames,position', [
+    (4096, 8, 4800, 0),            # C3 in miniature: 512 partials per group
+    (4096, 4, 5000, 12345),        # ragged last tile, 1024 per group, position > 0
+    (300, 3, 777, 2 ** 31 + 5),    # groups not a multiple of 8, 100 per group, huge position
+    (9000, 2, 600, 47999),         # 4500 per group: more than one shared-memory chunk
+])
+def test_bank_fused_vs_oracle(partials, groups, frames, position, ns, engine):
+    """k_bank (oscillator bank fused with GroupSum) against the float64 numpy oracle."""
+    from signals_b200.chain import ext
+    hertz, phase, amp = cases.bank_params(3, partials, partials // groups)
+    compiled = engine.compile(cases.build_bank(ns, ext, hertz, phase, amp, groups), groups, RATE)
+    assert [l['kind'] for l in compiled.describe()['launches']] == ['bank']
+    got = compiled.render_device(position, frames).cpu().numpy()
+    compiled.close()
+    want = np_oracle.render_bank(position, frames, RATE, hertz, phase, amp, groups)
+    err = max_abs_err(got, want)
+    print(f'bank {partials}->{groups}: max-abs {err:.3e}')
+    assert err <= (2e-6 if position > 2 ** 31 else 1e-6)
+
+
+def test_bank_full_scale_partials_stay_inside_budget(ns, engine):
+    """Two partials of amplitude 0.5 per group: the per-partial error budget (phase-word drift + MUFU)
+    must itself stay under 1e-6 of full scale, not only its average over 1024 small partials."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(33)
+    hertz = rng.uniform(27.5, 12000.0, 8)
+    phase = rng.uniform(0, 1, 8)
+    amp = np.full(8, 0.5)
+    compiled = engine.compile(cases.build_bank(ns, ext, hertz, phase, amp, 4), 4, RATE)
+    got = compiled.render_device(0, 96000).cpu().numpy()
+    compiled.close()
+    assert max_abs_err(got, np_oracle.render_bank(0, 96000, RATE, hertz, phase, amp, 4)) <= 1e-6
+
+
+def test_bank_fused_equals_materialised_path(ns, engine):
+    from signals_b200.chain import ext
+    hertz, phase, amp = cases.bank_params(31, 2048, 256)
+    graph = lambda: cases.build_bank(ns, ext, hertz, phase, amp, 8)   # noqa: E731
+    fused = engine.compile(graph(), 8, RATE)
+    a = fused.render_device(100, 3000).cpu().numpy()
+    fused.close()
+    _set_default('fuse_reduce', 0)
+    try:
+        plain = engine.compile(graph(), 8, RATE)
+        assert [l['kind'] for l in plain.describe()['launches']] == ['chain', 'reduce']
+        b = plain.render_device(100, 3000).cpu().numpy()
+        plain.close()
+    finally:
+        _set_default('fuse_reduce', 1)
+    assert max_abs_err(a, b) <= 5e-7
+
+
+@pytest.mark.parametrize('m', [1, 4])
+def test_instances_fused_vs_oracle(m, ns, engine):
+    """k_voices (config C5 in miniature): 3000 randomised osc/filter/gain/pan instances -> stereo."""
+    from signals_b200.chain import ext
+    prm = cases.instance_params(5, 3000)
+    frames = 4800
+    _set_default('voices_m', m)
+    try:
+        compiled = engine.compile(cases.build_instances(ns, ext, prm), 2, RATE)
+    finally:
+        _set_default('voices_m', 0)
+    d = compiled.describe()
+    assert [l['kind'] for l in d['launches']] == ['voices'] and d['launches'][0]['channels_per_thread'] == m
+    cuts = [0, 1000, 1001, 1017, frames]                       # ragged calls: state and phase are carried
+    got = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+    compiled.close()
+    want = np_oracle.render_instances(prm, 0, frames, RATE)
+    err = max_abs_err(got, want)
+    print(f'instances M={m}: max-abs {err:.3e}, mix peak {np.abs(want).max():.3f}')
+    assert err <= 1e-6
+
+
+def test_instances_discontinuities_land_on_the_reference_sample(ns, engine):
+    """Rational hertz/rate puts samples exactly ON the Square/Sawtooth jumps: the phase-word
+    fast path must hand those tiles to the float64 path, or single samples are off by 1-2 full scale."""
+    from signals_b200.chain import ext
+    hz = np.array([440.0, 1000.0, 12000.0, 6000.0, 439.99, 100.0])
+    n = hz.size
+    for wave in (1, 2, 3):
+        prm = dict(wave=np.full(n, wave), filt=np.zeros(n, dtype=int), hertz=hz, phase=np.array([0, 0, 0, 0, 0.3, -0.75]),
+                   cutoff=np.full(n, 1000.0), gain=np.full(n, 1.0 / n), pan=np.linspace(0.1, 0.9, n))
+        compiled = engine.compile(cases.build_instances(ns, ext, prm), 2, RATE)
+        got = compiled.render_device(0, 48000).cpu().numpy()
+        compiled.close()
+        want = np_oracle.render_instances(prm, 0, 48000, RATE)
+        assert max_abs_err(got, want) <= 1e-6, wave
+
+
+def test_instances_seek_and_materialised_path_agree(ns, engine):
+    """position > 0 on a fresh plan: zero state + context warm-up (fx.py:93-105), same as the graph
+    oracle; and the fused kernel equals the chain + merge + reduce launches it replaces."""
+    from signals_b200.chain import ext
+    prm = cases.instance_params(55, 96)
+    graph = lambda: cases.build_instances(ns, ext, prm)   # noqa: E731
+    compiled = engine.compile(graph(), 2, RATE)
+    got = compiled.render_device(4800, 512).cpu().numpy()
+    compiled.close()
+    want = np_oracle.GraphOracle(RATE).render(graph(), 4800, 512, 2)
+    assert max_abs_err(got, want) <= 1e-6
+    _set_default('fuse_reduce', 0)
+    try:
+        plain = engine.compile(graph(), 2, RATE)
+        assert 'voices' not in [l['kind'] for l in plain.describe()['launches']]
+        b = plain.render_device(4800, 512).cpu().numpy()
+        plain.close()
+    finally:
+        _set_default('fuse_reduce', 1)
+    assert max_abs_err(got, b) <= 1e-6
