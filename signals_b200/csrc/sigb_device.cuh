@@ -122,4 +122,45 @@ __device__ __forceinline__ float svf_any(int kind, float x, float g, float c, fl
     return (kind & SEC_HP) ? hp : lp;
 }
 
+constexpr float kTwoPiQ32 = 1.4629180792671596e-9f;   // 2*pi*2^-32
+
+// waveform from the signed top word of the Q0.64 phase (fraction of a cycle in [-1/2, 1/2) after the
+// two's-complement reading): osc.py:43, 49, 55, 61-62 away from their discontinuities
+template <int WAVE>
+__device__ __forceinline__ float wave_q32(int w) {
+    if (WAVE == SIGB_WAVE_SINE) return __sinf((float)w * kTwoPiQ32);
+    if (WAVE == SIGB_WAVE_SQUARE) return w >= 0 ? 1.0f : -1.0f;                    // frac < 1/2 -> +1
+    if (WAVE == SIGB_WAVE_SAWTOOTH) return (float)w * 4.656612873077393e-10f;      // 2 frac (- 2 past 1/2)
+    return fmaf(-fabsf((float)(w - 0x40000000)), 9.313225746154785e-10f, 1.0f);    // 1 - 4 |frac - 1/4|
+}
+
+// true when phase word w lies within `guard` (units of 2^-32 cycles) of a point where wave_q32 may
+// disagree with the reference's float64 evaluation: the jumps of Square (frac 0 and 1/2) and Sawtooth
+// (1/2), and Triangle's trough (3/4), where the reference yields -0.0 instead of -1 (sign(0) = 0, osc.py:62)
+template <int WAVE>
+__device__ __forceinline__ bool wave_near_edge(int w, int guard) {
+    if (WAVE == SIGB_WAVE_SQUARE) return ((unsigned)(w + guard) & 0x7fffffffu) < 2u * (unsigned)guard;
+    if (WAVE == SIGB_WAVE_SAWTOOTH) return ((unsigned)w ^ 0x80000000u) + (unsigned)guard < 2u * (unsigned)guard;
+    if (WAVE == SIGB_WAVE_TRIANGLE) return (unsigned)w - 0xC0000000u + (unsigned)guard < 2u * (unsigned)guard;
+    return false;
+}
+
+// K consecutive samples from phase word w advancing by dhi; returns true when any of them needs the
+// float64 path
+template <int WAVE, int K>
+__device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[K]) {
+    bool near = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        x[k] = wave_q32<WAVE>(w);
+        near |= wave_near_edge<WAVE>(w, guard);
+        w += dhi;
+    }
+    return near;
+}
+
+// guard band for wave_near_edge, in units of 2^-32 cycles (host and device agree on the formula):
+// in-tile drift of the rounded increment (<= K/2), rounding of the top word (1), and the float64
+// rounding of the reference's own phase (3 roundings of relative size 2^-53 on `cycles` cycles)
+
 }  // namespace sigb_dev

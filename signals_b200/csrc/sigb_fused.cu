@@ -25,7 +25,6 @@ namespace {
 
 using namespace sigb_dev;
 
-constexpr float kTwoPiQ32 = 1.4629180792671596e-9f;   // 2*pi*2^-32
 
 // ------------------------------------------------------------------------------------------
 // k_bank
@@ -115,29 +114,6 @@ __global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n
 constexpr int VK = SIGB_VOICE_K;
 constexpr int VT = SIGB_VOICE_THREADS;
 
-// waveform from the signed top word of the Q0.64 phase (fraction of a cycle in [-1/2, 1/2) after the
-// two's-complement reading): osc.py:43, 49, 55, 61-62 away from their discontinuities
-template <int WAVE>
-__device__ __forceinline__ float wave_q32(int w) {
-    if (WAVE == SIGB_WAVE_SINE) return __sinf((float)w * kTwoPiQ32);
-    if (WAVE == SIGB_WAVE_SQUARE) return w >= 0 ? 1.0f : -1.0f;                    // frac < 1/2 -> +1
-    if (WAVE == SIGB_WAVE_SAWTOOTH) return (float)w * 4.656612873077393e-10f;      // 2 frac (- 2 past 1/2)
-    return fmaf(-fabsf((float)(w - 0x40000000)), 9.313225746154785e-10f, 1.0f);    // 1 - 4 |frac - 1/4|
-}
-
-template <int WAVE>
-__device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[VK]) {
-    unsigned near = 0u;
-#pragma unroll
-    for (int k = 0; k < VK; ++k) {
-        x[k] = wave_q32<WAVE>(w);
-        if (WAVE == SIGB_WAVE_SQUARE) near |= (((unsigned)(w + guard) & 0x7fffffffu) < 2u * (unsigned)guard);   // edges at 0 and 1/2
-        if (WAVE == SIGB_WAVE_SAWTOOTH) near |= (((unsigned)w ^ 0x80000000u) + (unsigned)guard < 2u * (unsigned)guard);   // wrap at 1/2
-        w += dhi;
-    }
-    return near != 0u;
-}
-
 template <int KIND>
 __device__ __forceinline__ void filt_tile(float (&x)[VK], float g, float c, float d, float& s1, float& s2, int kmax) {
 #pragma unroll
@@ -197,10 +173,10 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             th[m] += dK[m];
             bool near;
             switch (wave) {
-                case SIGB_WAVE_SINE: near = gen_tile<SIGB_WAVE_SINE>(w, dhi[m], guard, x); break;
-                case SIGB_WAVE_SQUARE: near = gen_tile<SIGB_WAVE_SQUARE>(w, dhi[m], guard, x); break;
-                case SIGB_WAVE_SAWTOOTH: near = gen_tile<SIGB_WAVE_SAWTOOTH>(w, dhi[m], guard, x); break;
-                default: near = gen_tile<SIGB_WAVE_TRIANGLE>(w, dhi[m], guard, x); break;
+                case SIGB_WAVE_SINE: near = gen_tile<SIGB_WAVE_SINE, VK>(w, dhi[m], guard, x); break;
+                case SIGB_WAVE_SQUARE: near = gen_tile<SIGB_WAVE_SQUARE, VK>(w, dhi[m], guard, x); break;
+                case SIGB_WAVE_SAWTOOTH: near = gen_tile<SIGB_WAVE_SAWTOOTH, VK>(w, dhi[m], guard, x); break;
+                default: near = gen_tile<SIGB_WAVE_TRIANGLE, VK>(w, dhi[m], guard, x); break;
             }
             if (near && chan[m] >= 0) {
                 // a sample within `guard` of a discontinuity: redo the tile with the reference's own

@@ -22,6 +22,7 @@ struct ChainDev {
     int32_t rate;
     int32_t frames;                 // rows this launch covers
     int32_t warm_rows;              // rows after which the filters forget their initial state (< 2^-40); -1: unknown
+    int32_t guard;                  // phase-word guard band around waveform discontinuities (pipelined kernel)
     int64_t position;               // absolute index of row 0
     uint8_t sec_kind[SIGB_MAX_SEC];
     // SRC_OSC
@@ -126,6 +127,8 @@ extern "C" {
 // launch wrappers implemented in sigb_kernels.cu; return cudaError_t as int
 int sigb_launch_chain_seq(const ChainDev* a, void* stream);
 int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stream, int* rows_done);
+int sigb_cascade_pipe_ok(const ChainDev* a);
+int sigb_launch_cascade_pipe(const ChainDev* a, void* stream);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);

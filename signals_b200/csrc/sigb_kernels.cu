@@ -367,6 +367,10 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
     float2* si = zs + NW * 32;                                                // [NW][32]
     float4* par = reinterpret_cast<float4*>(si + NW * 32);                    // [NSEC][4][32]
     double* tnb = reinterpret_cast<double*>(par + NSEC * 4 * 32);             // [NW][L]
+    // deep cascades: the scanner's transition tables live in shared memory (in registers they spill)
+    constexpr bool SMEM_SCAN = NSEC > 2;
+    double* smg = tnb + NW * L;                                               // [NSEC][4][32]  A^(16 WG), float64
+    float4* smq = reinterpret_cast<float4*>(smg + (SMEM_SCAN ? NSEC * 4 * 32 : 0));   // [NSEC][WG][32] A^(16 q), float32
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -416,7 +420,63 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             // path is the float64 carry update c' = A^(16 WG) c + P_WG (two dependent DFMAs).  The prefix
             // offsets P_q = sum_{j<q} A^(16 (q-1-j)) z_j do not depend on the carry, and the initial states
             // s_q = A^(16 q) c + P_q of all sub-chunks are independent of each other.
-            double mg[NSEC][4], c1[NSEC], c2[NSEC];   // A^(16 WG) in float64, carries
+            double c1[NSEC], c2[NSEC];                 // carries
+            if (SMEM_SCAN) {
+#pragma unroll 1
+                for (int s = 0; s < NSEC; ++s) {
+                    double m0[4], acc[4] = {1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m0[k] = a.apow[(size_t)(s * 4 + k) * C + cc];
+#pragma unroll
+                    for (int q = 0; q < WG; ++q) {
+                        smq[(s * WG + q) * 32 + lane] = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
+                        const double n0 = m0[0] * acc[0] + m0[1] * acc[2], n1 = m0[0] * acc[1] + m0[1] * acc[3];
+                        const double n2 = m0[2] * acc[0] + m0[3] * acc[2], n3 = m0[2] * acc[1] + m0[3] * acc[3];
+                        acc[0] = n0; acc[1] = n1; acc[2] = n2; acc[3] = n3;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) smg[(s * 4 + k) * 32 + lane] = acc[k];
+                }
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s) {
+                    c1[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 0) * C + cc] : 0.0;
+                    c2[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 1) * C + cc] : 0.0;
+                }
+                __syncwarp();
+                // events in (round, section, group) order: all NG groups advance section by section, so a
+                // group never waits for another group's whole 8-section chain
+                for (int base = w0; base < s1; base += NG) {
+#pragma unroll
+                    for (int s = 0; s < NSEC; ++s) {
+#pragma unroll 1
+                      for (int grp = 0; grp < NG; ++grp) {
+                        if (base + grp >= s1) break;
+                        const float f1 = (float)c1[s], f2 = (float)c2[s];
+                        const float4 a16 = smq[(s * WG + 1) * 32 + lane];
+                        const double g0 = smg[(s * 4 + 0) * 32 + lane], g1 = smg[(s * 4 + 1) * 32 + lane];
+                        const double g2 = smg[(s * 4 + 2) * 32 + lane], g3 = smg[(s * 4 + 3) * 32 + lane];
+                        bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                        float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+                        for (int q = 0; q < WG; ++q) {
+                            const float4 m = smq[(s * WG + q) * 32 + lane];
+                            const float2 z = zs[(grp * WG + q) * 32 + lane];
+                            si[(grp * WG + q) * 32 + lane] = make_float2(fmaf(m.x, f1, fmaf(m.y, f2, p1)), fmaf(m.z, f1, fmaf(m.w, f2, p2)));
+                            const float n1 = fmaf(a16.x, p1, fmaf(a16.y, p2, z.x));
+                            const float n2 = fmaf(a16.z, p1, fmaf(a16.w, p2, z.y));
+                            p1 = n1;
+                            p2 = n2;
+                        }
+                        bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+                        const double n1 = fma(g0, c1[s], fma(g1, c2[s], (double)p1));
+                        const double n2 = fma(g2, c1[s], fma(g3, c2[s], (double)p2));
+                        c1[s] = n1;
+                        c2[s] = n2;
+                      }
+                    }
+                }
+            } else {
+            double mg[NSEC][4];                        // A^(16 WG) in float64
             float mq[NSEC][WG][4];                     // A^(16 q), q = 0..WG-1, float32
 #pragma unroll
             for (int s = 0; s < NSEC; ++s) {
@@ -437,10 +497,12 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 c1[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 0) * C + cc] : 0.0;
                 c2[s] = w0 == 0 ? a.state[(size_t)(s * 2 + 1) * C + cc] : 0.0;
             }
-            for (int step = w0; step < s1; ++step) {
-                const int grp = (step - w0) % NG;
+            for (int base = w0; base < s1; base += NG) {
 #pragma unroll
                 for (int s = 0; s < NSEC; ++s) {
+#pragma unroll 1
+                  for (int grp = 0; grp < NG; ++grp) {
+                    if (base + grp >= s1) break;
                     const float f1 = (float)c1[s], f2 = (float)c2[s];
                     bar_sync(1 + 2 * grp, (WG + 1) * 32);
                     float2 z[WG];
@@ -461,7 +523,9 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     const double n2 = fma(mg[s][2], c1[s], fma(mg[s][3], c2[s], (double)p2));
                     c1[s] = n1;
                     c2[s] = n2;
+                  }
                 }
+            }
             }
             if (live && s1 == nsteps) {   // the piece that finishes a tile hands its state to the next launch
 #pragma unroll
@@ -535,9 +599,15 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                         __syncwarp();
                     }
                 } else if (SRC == SRC_BUF) {
+                    if (live && row + L <= a.src_rows) {          // whole sub-chunk inside the source: plain loads
+                        const float* sp = a.src + row * a.src_ld + (int64_t)c * a.src_cs;
 #pragma unroll
-                    for (int k = 0; k < H; ++k)
-                        v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
+                        for (int k = 0; k < H; ++k) v[k] = pk(__ldg(sp + (int64_t)k * a.src_ld), __ldg(sp + (int64_t)(H + k) * a.src_ld));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < H; ++k)
+                            v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < H; ++k) v[k] = pk1(cv);
@@ -797,7 +867,8 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     *rows_done = nsteps * STEP;
     if (nsteps == 0) return cudaSuccess;
     size_t smem = (size_t)NW * L * 32 * sizeof(float) + (size_t)NW * 32 * sizeof(float2) * 2 +
-                  (size_t)NSEC * 4 * 32 * sizeof(float4) + (size_t)NW * L * sizeof(double);
+                  (size_t)NSEC * 4 * 32 * sizeof(float4) + (size_t)NW * L * sizeof(double) +
+                  (NSEC > 2 ? (size_t)NSEC * 4 * 32 * sizeof(double) + (size_t)NSEC * WG * 32 * sizeof(float4) : 0);
     auto kern = k_chain_scan2<SRC, NSEC, NG, WG, FASTSINE>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -845,7 +916,7 @@ cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
 // so the scanner's fp64 transition matrices stay in registers.
 static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
     if (variant >= 4) {               // packed kernel k_chain_scan2
-        if (nsec > 2) { *ng = 2; *wg = 7; return; }
+        if (nsec > 2) { *ng = 4; *wg = 7; return; }
         switch (variant) {
             case 5: *ng = 7; *wg = 4; break;
             case 6: *ng = 2; *wg = 15; break;
@@ -892,8 +963,8 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     scan_geometry(a->nsec, variant, &ng, &wg);
     if (variant >= 4) {
         if (a->nsec > 2) {
-            if (a->nsec <= 4) return (int)launch_scan2_n<4, 2, 7>(*a, st, rows_done);
-            return (int)launch_scan2_n<8, 2, 7>(*a, st, rows_done);
+            if (a->nsec <= 4) return (int)launch_scan2_n<4, 4, 7>(*a, st, rows_done);
+            return (int)launch_scan2_n<8, 4, 7>(*a, st, rows_done);
         }
 #define SCAN2_DISPATCH(NG, WG)                                                        \
     do {                                                                              \

@@ -86,6 +86,7 @@ struct ChainSpec {
     int dst_node = -1;
     std::vector<double> gain_d;  // folded gain in float64 (fused reductions derive their weights from it)
     bool has_gain = false;
+    double max_abs_hertz = 0.0, max_abs_phase = 0.0;   // SRC_OSC: sizes the phase-word guard band
 };
 
 struct EwiseSpec {
@@ -115,7 +116,6 @@ struct BankSpec {
 struct VoiceSegSpec {
     ChainSpec ch;
     Table wl, wr;
-    double max_abs_hertz = 0.0, max_abs_phase = 0.0;
 };
 struct VoicesSpec {
     std::vector<VoiceSegSpec> segs;
@@ -162,6 +162,7 @@ struct sigb_plan {
     int64_t opt_slab_frames = 0;
     int64_t opt_host_slab_bytes = 64ll << 20;
     int64_t opt_buffer_budget = 6ll << 30;
+    int64_t opt_cascade_pipe = -1;      // -1: section-pipelined kernel for cascades of >= 3 sections; 0 never; 1: from 2 sections
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
@@ -213,6 +214,15 @@ bool rep(const std::vector<double>& v, int C, std::vector<double>* out) {
 }
 
 int section_count(int order) { return order / 2 + (order & 1); }
+
+// guard band (units of 2^-32 cycles) around waveform discontinuities for the phase-word fast paths:
+// in-tile drift of the rounded increment, the rounding of the top word, and the float64 rounding of
+// the reference's own phase (3 roundings of relative size 2^-53 on `cycles` cycles)
+int phase_guard(double max_abs_hertz, double max_abs_phase, int64_t last_row, int rate) {
+    const double cyc = max_abs_hertz * (double)last_row / rate + max_abs_phase + 1.0;
+    const double g = 16.0 + cyc * 3.0 * 4294967296.0 / 9007199254740992.0;
+    return g < 1073741823.0 ? (int)std::ceil(g) : 0x3fffffff;
+}
 
 int pad_sections(int n) {
     int p = 1;
@@ -341,6 +351,10 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
             ch.wave = n.subtype;
             ch.hertz = put_vec(p, hzv);
             ch.phase = put_vec(p, phv);
+            for (int c = 0; c < C; ++c) {
+                ch.max_abs_hertz = std::max(ch.max_abs_hertz, std::fabs(hzv[c]));
+                ch.max_abs_phase = std::max(ch.max_abs_phase, std::fabs(phv[c]));
+            }
             {   // Q0.64 phase / increment: sine fast path of the chain kernels, every wave in k_voices
                 std::vector<unsigned long long> t0(C), dt(C);
                 for (int c = 0; c < C; ++c) {
@@ -573,14 +587,7 @@ int Builder::build_voices(int i, const std::vector<int>& leaves) {
         }
         sg.wl = put_vec(p, wl);
         sg.wr = put_vec(p, wr);
-        {
-            const double* hz = reinterpret_cast<const double*>(p->arena.data() + sg.ch.hertz.off);
-            const double* ph = reinterpret_cast<const double*>(p->arena.data() + sg.ch.phase.off);
-            for (int c = 0; c < C; ++c) {
-                sg.max_abs_hertz = std::max(sg.max_abs_hertz, std::fabs(hz[c]));
-                sg.max_abs_phase = std::max(sg.max_abs_phase, std::fabs(ph[c]));
-            }
-        }
+
         sg.ch.gain_d.clear();
         coff += C;
         total += C;
@@ -872,6 +879,18 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
             int done = 0;
+            if (ch.src_kind == SRC_OSC) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
+            const int pipe_min = p->opt_cascade_pipe < 0 ? 3 : (p->opt_cascade_pipe == 0 ? 1 << 30 : 2);
+            if (!p->opt_force_seq && ch.nsec_real >= pipe_min && ch.nsec_real <= 8) {
+                ChainDev t = a;
+                t.nsec = ch.nsec_real;           // identity padding sections are not run
+                if (sigb_cascade_pipe_ok(&t)) {
+                    int e = sigb_launch_cascade_pipe(&t, st);
+                    if (e) return fail(SIGB_ECUDA, std::string("k_cascade_pipe: ") + cudaGetErrorString((cudaError_t)e));
+                    p->launch_count++;
+                    continue;
+                }
+            }
             const int tiles = (ch.C + 31) / 32;
             const bool scan_ok = !p->opt_force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
             if (scan_ok) {
@@ -965,9 +984,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     d.state = p->d_state ? p->d_state + sg.ch.state_off : nullptr;
                     // guard band (units of 2^-32 cycles): in-tile drift of the rounded increment, the
                     // rounding of the top word, and the float64 rounding of the reference's own phase
-                    const double cyc = sg.max_abs_hertz * (double)(abs_row0 + rows) / p->rate + sg.max_abs_phase + 1.0;
-                    const double g = 16.0 + cyc * 3.0 * 4294967296.0 / 9007199254740992.0;
-                    d.guard = g < 1073741823.0 ? (int)std::ceil(g) : 0x3fffffff;
+                    d.guard = phase_guard(sg.ch.max_abs_hertz, sg.ch.max_abs_phase, abs_row0 + rows, p->rate);
                     ctas += sigb_voices_ctas(sg.ch.C, vs.M);
                 }
                 int err = sigb_launch_voices(&a, ctas, st);
@@ -1329,6 +1346,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "slab_frames") plan->opt_slab_frames = value;
     else if (k == "host_slab_bytes") plan->opt_host_slab_bytes = value;
     else if (k == "buffer_budget") plan->opt_buffer_budget = value;
+    else if (k == "cascade_pipe") plan->opt_cascade_pipe = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);

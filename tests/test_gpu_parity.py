@@ -51,10 +51,11 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'pipe'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
-    """k_chain_seq and each geometry of the time-parallel k_chain_scan agree with the reference."""
-    opts = dict(force_seq=1) if mode == 'seq' else dict(scan_variant=int(mode[-1]))
+    """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
+    the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""
+    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(scan_variant=int(mode[-1]), cascade_pipe=0)
     got = render_case(engine, ns, case, **opts)[::case.stride]
     err = max_abs_err(got, load_golden(case.name))
     assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
@@ -373,3 +374,49 @@ def test_instances_seek_and_materialised_path_agree(ns, engine):
     finally:
         _set_default('fuse_reduce', 1)
     assert max_abs_err(got, b) <= 1e-6
+
+
+def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
+    """k_cascade_pipe: channel counts that are not a multiple of the 64-channel tile (odd, so the last
+    lane holds one live channel), rows that are not a multiple of the 16-row chunk, state carried across
+    ragged calls, against scipy's float64 sosfilt cascade; and bit-agreement of a streamed render with the
+    single-request render."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(44)
+    for ch, nsec in [(200, 8), (68, 5), (4, 3)]:
+        frames = 6000
+        x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
+        cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (nsec, ch)))
+        node = ext.Buffer(x)
+        for s in range(nsec):
+            node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if s == 1 else 'LowPass')
+        want = x.astype(np.float64)
+        for s in range(nsec):
+            want, _ = np_oracle.render_cascade(want, cut[s:s + 1], RATE, btype='hp' if s == 1 else 'lp')
+        compiled = engine.compile(node, ch, RATE)
+        whole = compiled.render_device(0, frames).cpu().numpy()
+        compiled.reset()
+        cuts = [0, 1, 17, 1000, 1016, 4803, frames]
+        parts = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+        compiled.close()
+        err = max_abs_err(whole, want)
+        print(f'cascade pipe {ch} ch x {nsec} sections: max-abs {err:.3e}')
+        assert err <= 1e-4
+        assert np.array_equal(parts, whole)      # sequential in time: chunking cannot change a single bit
+    # odd channel count (one live channel in the last lane) from an oscillator source, into a padded block
+    torch = _torch()
+    ch = 67
+    hertz = rng.uniform(55.0, 880.0, ch)
+    node = cases.osc(ns, 'Sawtooth', [hertz], [rng.uniform(0, 1, ch)])
+    cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (3, ch)))
+    for s in range(3):
+        node = cases.lowpass(ns, node, [cut[s]])
+    compiled = engine.compile(node, ch, RATE)
+    assert compiled.describe()['launches'][0]['sections'] == 3
+    big = torch.full((3000, 68), 7.0, dtype=torch.float32, device='cuda')
+    compiled.render_device(0, 3000, big[:, :ch])
+    compiled.close()
+    got = big.cpu().numpy()
+    assert (got[:, ch:] == 7.0).all()            # the padding column is untouched
+    want = np_oracle.GraphOracle(RATE).render(node, 0, 3000, ch)
+    assert max_abs_err(got[:, :ch], want) <= 1e-4
