@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument('--voices', type=int, default=None, help='voices / partials / channels / instances (config default if omitted)')
     ap.add_argument('--seconds', type=float, default=None)
     ap.add_argument('--e2e-steps', type=int, default=None)
+    ap.add_argument('--slab-seconds', type=float, default=5.0, help='c4: seconds of audio per streamed slab')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--scan-variant', type=int, default=None)
     ap.add_argument('--plan-opt', action='append', default=[], help='key=value passed to sigb_plan_set_option (A/B testing)')
@@ -153,16 +154,16 @@ class C3(Workload):
 
 
 class C4(Workload):
-    name = 'C4: 8-biquad low-pass cascade on %d channels x %g s @ 48 kHz per GPU, streamed in 1 s slabs with carried state'
-    kernel = 'k_chain_scan2<SRC_BUF, 8 sections>'
+    name = 'C4: 8-biquad low-pass cascade on %d channels x %g s @ 48 kHz per GPU, streamed in %g s slabs with carried state'
+    kernel = 'k_cascade_pipe<SRC_BUF> (8 section warps per 64-channel tile)'
     bound = 'hbm'
     bytes_per_unit = 8.0
-    slab_frames = RATE
 
     def __init__(self, args, rank, world):
         super().__init__(args, rank, world)
         self.ch = args.voices
         self.out_channels = self.ch
+        self.slab_frames = min(self.frames, int(args.slab_seconds * RATE))
         rng = np.random.default_rng(4 + rank)
         self.cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (8, self.ch)))
         self.seed = 4 + rank
@@ -181,9 +182,9 @@ class C4(Workload):
         return node
 
     def describe(self):
-        return {'workload': self.name % (self.ch, self.args.seconds), 'channels_per_gpu': self.ch, 'frames': self.frames, 'rate': RATE,
+        return {'workload': self.name % (self.ch, self.args.seconds, self.slab_frames / RATE), 'channels_per_gpu': self.ch, 'frames': self.frames, 'rate': RATE,
                 'slab_frames': self.slab_frames, 'sharding': 'channels across %d rank(s), no collective' % self.world,
-                'l2': 'slab in + out = %.2f GB >> 126 MB L2; the same 1 s of U(-1,1) noise is re-bound at each slab position'
+                'l2': 'slab in + out = %.2f GB >> 126 MB L2; the same slab of U(-1,1) noise is re-bound at each slab position' 
                       % (2 * self.ch * self.slab_frames * 4 / 1e9)}
 
     def units_per_step(self):

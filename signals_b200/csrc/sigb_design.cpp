@@ -84,3 +84,40 @@ double sigb_section_decay_rows(const double m1[4]) {
     // 2^-40 decay, doubled: a near-defective pair decays like k rho^k
     return 2.0 * (40.0 * std::log(2.0) / -std::log(rho)) + 16.0;
 }
+
+double sigb_section_radius(const double m1[4]) {
+    const double tr = m1[0] + m1[3], det = m1[0] * m1[3] - m1[1] * m1[2];
+    const double disc = tr * tr - 4.0 * det;
+    if (disc < 0.0) return std::sqrt(std::fabs(det));
+    return std::max(std::fabs(tr + std::sqrt(disc)), std::fabs(tr - std::sqrt(disc))) / 2.0;
+}
+
+int sigb_cascade_decay_rows(const std::vector<SvfSection>& secs, int bits, int max_rows) {
+    const int S = (int)secs.size();
+    const double eps = std::ldexp(1.0, -bits);
+    int worst = 0;
+    std::vector<double> s1(S), s2(S);
+    for (int j = 0; j < 2 * S; ++j) {
+        std::fill(s1.begin(), s1.end(), 0.0);
+        std::fill(s2.begin(), s2.end(), 0.0);
+        if (j & 1) {
+            if (secs[j / 2].kind & SEC_FIRST_ORDER) continue;     // no second state
+            s2[j / 2] = 1.0;
+        } else {
+            s1[j / 2] = 1.0;
+        }
+        int last = 0, quiet = 0;
+        for (int k = 0; k < max_rows; ++k) {
+            double x = 0.0, big = 0.0;
+            for (int s = 0; s < S; ++s) {
+                x = sigb_section_step(secs[s], x, s1[s], s2[s]);
+                big = std::max(big, std::max(std::fabs(x), std::max(std::fabs(s1[s]), std::fabs(s2[s]))));
+            }
+            if (big >= eps) { last = k + 1; quiet = 0; }
+            else if (++quiet > 256) break;                        // below the threshold for good
+            if (k + 1 == max_rows) return -1;
+        }
+        worst = std::max(worst, last);
+    }
+    return worst;
+}

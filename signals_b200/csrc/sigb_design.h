@@ -35,3 +35,10 @@ void sigb_section_zero_input(const SvfSection& s, int len, float* tab);
 // Rows after which the section's zero-input response has decayed below 2^-40 of the initial state,
 // from the spectral radius of the one-sample transition m1 (row-major 2x2); 1e9 if not contractive.
 double sigb_section_decay_rows(const double m1[4]);
+
+// Spectral radius of a one-sample transition.
+double sigb_section_radius(const double m1[4]);
+
+// Rows after which the zero-input response of the whole cascade (every state and the output, from every
+// unit initial state) stays below 2^-bits: simulated in float64.  -1 when it has not decayed by max_rows.
+int sigb_cascade_decay_rows(const std::vector<SvfSection>& secs, int bits, int max_rows);

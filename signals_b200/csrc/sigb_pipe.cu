@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "sigb200.h"
 #include "sigb_internal.h"
 #include "sigb_device.cuh"
@@ -31,8 +33,7 @@ using namespace sigb_dev;
 
 constexpr int PR = 16;          // rows per chunk
 constexpr int PC = 64;          // channels per tile (2 per lane)
-constexpr int PRE = 6;          // cp.async chunks in flight per CTA (6 x 4 KB)
-constexpr int NSLOT = PRE + 2;     // a slot is rewritten two iterations after it was read (one barrier in between)
+constexpr int PRE = 4;          // cp.async chunks in flight per CTA (4 x 4 KB; 4 CTAs per SM)
 constexpr int CHUNK_FLOATS = PR * PC;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -43,10 +44,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct SecReg {
-    float2 g, nc, d;      // second order: (g) (-c) (d); first order: g = G
+    float2 nc, a2, al, g, g2;   // second order: (-c) (2 g d) (g d) (g) (2 g); first order: g = G; d kept in a2 for HP
+    float2 d;                   // high-pass output scale
     float2 s1, s2;
 };
 
+// One sample (two channels) of a zero-delay-feedback state-variable section.  With e = x - c s1 - s2:
+//   hp = d e;  bp = s1 + g d e;  s1' = s1 + 2 g d e;  lp = s2 + g bp;  s2' = s2 + 2 g bp
+// -- six packed FP32 instructions for a low-pass section (seven for high-pass), and only two of them
+// (e, s1') on the s1 -> s1' dependency chain.
 template <int KIND>
 __device__ __forceinline__ float2 pipe_step(float2 x, SecReg& r) {
     const float2 neg1 = make_float2(-1.0f, -1.0f);
@@ -57,58 +63,44 @@ __device__ __forceinline__ float2 pipe_step(float2 x, SecReg& r) {
         r.s1 = __fadd2_rn(lp, w);
         return (KIND & SEC_HP) ? __ffma2_rn(lp, neg1, x) : lp;
     }
-    const float2 t = __ffma2_rn(r.nc, r.s1, x);
-    const float2 u = __ffma2_rn(r.s2, neg1, t);
-    const float2 hp = __fmul2_rn(u, r.d);
-    const float2 bp = __ffma2_rn(r.g, hp, r.s1);
-    r.s1 = __ffma2_rn(r.g, hp, bp);
+    const float2 xs = __ffma2_rn(r.s2, neg1, x);          // x - s2 (off the s1 chain)
+    const float2 e = __ffma2_rn(r.nc, r.s1, xs);
+    const float2 bp = __ffma2_rn(r.al, e, r.s1);
+    r.s1 = __ffma2_rn(r.a2, e, r.s1);
     const float2 lp = __ffma2_rn(r.g, bp, r.s2);
-    r.s2 = __ffma2_rn(r.g, bp, lp);
-    return (KIND & SEC_HP) ? hp : lp;
+    r.s2 = __ffma2_rn(r.g2, bp, r.s2);
+    return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
 }
 
-// one chunk of one section: in -> (section) -> smem out, or -> gain -> global rows when LAST
-template <int KIND, bool LAST>
-__device__ __forceinline__ void pipe_chunk(const float* in, float* out_s, float* out_g, int64_t ld_out, int rows, int lane,
-                                           bool live0, bool live1, float2 gain, SecReg& r) {
+// one chunk of one section, in place in the shared-memory slot (a lane owns its two channels of every
+// row, so there is no cross-thread hazard inside a section)
+template <int KIND>
+__device__ __forceinline__ void pipe_chunk(float* __restrict__ slot, int rows, int lane, SecReg& r) {
+    float2* __restrict__ p = reinterpret_cast<float2*>(slot) + lane;
     if (rows == PR) {
+        constexpr int HR = PR / 2;                 // two half-chunks of 8 rows keep the kernel at 64 registers
 #pragma unroll
-        for (int k = 0; k < PR; ++k) {
-            const float2 x = *reinterpret_cast<const float2*>(in + k * PC + 2 * lane);
-            float2 y = pipe_step<KIND>(x, r);
-            if (LAST) {
-                y = __fmul2_rn(y, gain);
-                float* o = out_g + (int64_t)k * ld_out;
-                if (live1) *reinterpret_cast<float2*>(o) = y;
-                else if (live0) *o = y.x;
-            } else {
-                *reinterpret_cast<float2*>(out_s + k * PC + 2 * lane) = y;
-            }
+        for (int h = 0; h < 2; ++h) {
+            float2 x[HR];
+#pragma unroll
+            for (int k = 0; k < HR; ++k) x[k] = p[(h * HR + k) * (PC / 2)];
+#pragma unroll
+            for (int k = 0; k < HR; ++k) x[k] = pipe_step<KIND>(x[k], r);
+#pragma unroll
+            for (int k = 0; k < HR; ++k) p[(h * HR + k) * (PC / 2)] = x[k];
         }
     } else {
-        for (int k = 0; k < rows; ++k) {     // ragged last chunk: state must stop at the last real row
-            const float2 x = *reinterpret_cast<const float2*>(in + k * PC + 2 * lane);
-            float2 y = pipe_step<KIND>(x, r);
-            if (LAST) {
-                y = __fmul2_rn(y, gain);
-                float* o = out_g + (int64_t)k * ld_out;
-                if (live1) *reinterpret_cast<float2*>(o) = y;
-                else if (live0) *o = y.x;
-            } else {
-                *reinterpret_cast<float2*>(out_s + k * PC + 2 * lane) = y;
-            }
-        }
+        for (int k = 0; k < rows; ++k)       // ragged last chunk: state must stop at the last real row
+            p[k * (PC / 2)] = pipe_step<KIND>(p[k * (PC / 2)], r);
     }
 }
 
-template <bool LAST>
-__device__ __forceinline__ void pipe_chunk_kind(int kind, const float* in, float* out_s, float* out_g, int64_t ld_out, int rows,
-                                                int lane, bool live0, bool live1, float2 gain, SecReg& r) {
+__device__ __forceinline__ void pipe_chunk_kind(int kind, float* slot, int rows, int lane, SecReg& r) {
     switch (kind) {
-        case 0: pipe_chunk<0, LAST>(in, out_s, out_g, ld_out, rows, lane, live0, live1, gain, r); break;
-        case SEC_HP: pipe_chunk<SEC_HP, LAST>(in, out_s, out_g, ld_out, rows, lane, live0, live1, gain, r); break;
-        case SEC_FIRST_ORDER: pipe_chunk<SEC_FIRST_ORDER, LAST>(in, out_s, out_g, ld_out, rows, lane, live0, live1, gain, r); break;
-        default: pipe_chunk<SEC_FIRST_ORDER | SEC_HP, LAST>(in, out_s, out_g, ld_out, rows, lane, live0, live1, gain, r); break;
+        case 0: pipe_chunk<0>(slot, rows, lane, r); break;
+        case SEC_HP: pipe_chunk<SEC_HP>(slot, rows, lane, r); break;
+        case SEC_FIRST_ORDER: pipe_chunk<SEC_FIRST_ORDER>(slot, rows, lane, r); break;
+        default: pipe_chunk<SEC_FIRST_ORDER | SEC_HP>(slot, rows, lane, r); break;
     }
 }
 
@@ -145,132 +137,229 @@ __device__ __noinline__ void pipe_source_chunk(const ChainDev& a, int tile, int 
     }
 }
 
+// Work item = (tile of 64 channels, time segment).  Segment j > 0 starts `warm_chunks` chunks early from
+// zero state without storing: the host sizes the warm-up so that the cascade's memory of the unknown true
+// state has decayed below 2^-40 (same contract as the time-split pieces of k_chain_scan2).  Segment 0
+// continues the carried state exactly; the last segment hands its state to the next launch.
+//
+// Iteration t of an item:  every thread issues its 16-byte granule of source chunk t + PRE (cp.async) and
+// stores its granule of finished chunk t - nsec (x gain) to global memory; warp w filters chunk t - w in
+// place.  All section warps do identical work, so nobody waits at the barrier for a straggler.
 template <bool BUF>
-__global__ void __launch_bounds__(288, 2) k_cascade_pipe(const ChainDev a, int nchunks, int tiles) {
-    extern __shared__ __align__(16) float psm[];
+__global__ void __launch_bounds__(BUF ? 256 : 288, BUF ? 4 : 3)
+k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunks, int warm_chunks, int nslot, int src_fast, int out_fast) {
+    extern __shared__ __align__(16) float ring[];        // [nslot] chunks of (PR x PC); a chunk stays in its slot
+                                                         // from its load until its rows have been stored
     const int nsec = a.nsec;
-    float* ring = psm;                                              // BUF: [NSLOT] chunks; else [2] chunks
-    float* stage = psm + (BUF ? NSLOT : 2) * CHUNK_FLOATS;          // [nsec - 1][2] chunks: inputs of sections 1..
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t C = (size_t)a.C;
+    const int nthreads = blockDim.x;
+    constexpr int GRAN = PR * (PC / 4);                   // 16-byte granules per chunk (256)
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned ring_end = ring_base + (unsigned)nslot * CHUNK_FLOATS * 4u;
 
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < tiles * nseg; item += gridDim.x) {
+        const int tile = item / nseg, seg = item - tile * nseg;
+        const int c_store = seg * seg_chunks;                            // first chunk this item stores
+        const int c_end = min(nchunks, c_store + seg_chunks);
+        const int c_first = max(0, c_store - (seg > 0 ? warm_chunks : 0));
         const int c0 = tile * PC + 2 * lane;
         const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
         SecReg r;
-        r.g = r.nc = r.d = r.s1 = r.s2 = make_float2(0.0f, 0.0f);
+        r.nc = r.a2 = r.al = r.g = r.g2 = r.d = r.s1 = r.s2 = make_float2(0.0f, 0.0f);
         int kind = 0;
-        float2 gain = make_float2(1.0f, 1.0f);
         if (w < nsec) {
             const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
             kind = a.sec_kind[w];
-            r.g = make_float2(a.coef[(size_t)(w * 3 + 0) * C + ca], a.coef[(size_t)(w * 3 + 0) * C + cb]);
+            const float ga = a.coef[(size_t)(w * 3 + 0) * C + ca], gb = a.coef[(size_t)(w * 3 + 0) * C + cb];
+            const float da = a.coef[(size_t)(w * 3 + 2) * C + ca], db = a.coef[(size_t)(w * 3 + 2) * C + cb];
+            r.g = make_float2(ga, gb);
+            r.g2 = make_float2(2.0f * ga, 2.0f * gb);
             r.nc = make_float2(-a.coef[(size_t)(w * 3 + 1) * C + ca], -a.coef[(size_t)(w * 3 + 1) * C + cb]);
-            r.d = make_float2(a.coef[(size_t)(w * 3 + 2) * C + ca], a.coef[(size_t)(w * 3 + 2) * C + cb]);
-            r.s1 = make_float2((float)a.state[(size_t)(w * 2 + 0) * C + ca], (float)a.state[(size_t)(w * 2 + 0) * C + cb]);
-            r.s2 = make_float2((float)a.state[(size_t)(w * 2 + 1) * C + ca], (float)a.state[(size_t)(w * 2 + 1) * C + cb]);
-            if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
+            r.d = make_float2(da, db);
+            r.al = make_float2(ga * da, gb * db);
+            r.a2 = make_float2(2.0f * (ga * da), 2.0f * (gb * db));
+            if (c_first == 0) {
+                r.s1 = make_float2((float)a.state[(size_t)(w * 2 + 0) * C + ca], (float)a.state[(size_t)(w * 2 + 0) * C + cb]);
+                r.s2 = make_float2((float)a.state[(size_t)(w * 2 + 1) * C + ca], (float)a.state[(size_t)(w * 2 + 1) * C + cb]);
+            }
         }
-        float* out_g = a.out + c0;
 
-        // 16-byte granule `i` of chunk c: row i / 16, channels 4 (i % 16) .. +3 of the tile
-        auto issue_chunk = [&](int c) {
-            if (c < nchunks) {
-                float* slot = ring + (c % NSLOT) * CHUNK_FLOATS;
-                for (int i = tid; i < PR * (PC / 4); i += blockDim.x) {
+        // ---- per-thread granule: row g_k, channels g_ch .. g_ch + 3 (hoisted out of the time loop)
+        const int g_k = tid >> 4, g_col = (tid & 15) * 4;
+        const int g_ch = tile * PC + g_col;
+        const bool g_in = g_ch + 3 < a.C;
+        const unsigned g_off = (unsigned)(g_k * PC + g_col) * 4u;
+        const int64_t full_rows = min(a.src_rows, (int64_t)a.frames);
+        const bool one_granule = nthreads == GRAN;
+        // source side
+        const int fast_end = (BUF && src_fast && one_granule && g_in) ? min(c_end, (int)min(full_rows / PR, (int64_t)nchunks)) : c_first;
+        const float* g_src = BUF ? a.src + ((int64_t)c_first * PR + g_k) * a.src_ld + g_ch : nullptr;
+        const int64_t src_step = (int64_t)PR * a.src_ld;
+        int issue_c = c_first;
+        unsigned issue_addr = ring_base;
+        auto issue_chunk = [&]() {
+            if (issue_c < fast_end) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off), "l"(g_src) : "memory");
+            } else if (issue_c < c_end) {
+                float* slot = ring + (issue_addr - ring_base) / 4u;
+                const int64_t row0 = (int64_t)issue_c * PR;
+                for (int i = tid; i < GRAN; i += nthreads) {
                     const int k = i >> 4, col = (i & 15) * 4;
-                    const int64_t row = (int64_t)c * PR + k;
                     const int ch = tile * PC + col;
                     float* dst = slot + k * PC + col;
-                    if (row < a.src_rows && row < a.frames && ch + 3 < a.C) {
+                    const int64_t row = row0 + k;
+                    if (src_fast && row < full_rows && ch + 3 < a.C) {
                         cp_async16(dst, a.src + row * a.src_ld + ch);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            dst[j] = (row < a.src_rows && row < a.frames && ch + j < a.C) ? __ldg(a.src + row * a.src_ld + ch + j) : 0.0f;
+                            dst[j] = (row < full_rows && ch + j < a.C) ? __ldg(a.src + row * a.src_ld + (int64_t)(ch + j) * a.src_cs) : 0.0f;
                     }
                 }
             }
             cp_async_commit();
+            ++issue_c;
+            g_src += src_step;
+            issue_addr += CHUNK_FLOATS * 4u;
+            if (issue_addr == ring_end) issue_addr = ring_base;
+        };
+        // sink side: chunk d = c_first + t - nsec leaves the ring at iteration t
+        float4 gain4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        if (a.gain && one_granule) {
+            gain4.x = a.gain[min(g_ch, a.C - 1)];
+            gain4.y = a.gain[min(g_ch + 1, a.C - 1)];
+            gain4.z = a.gain[min(g_ch + 2, a.C - 1)];
+            gain4.w = a.gain[min(g_ch + 3, a.C - 1)];
+        }
+        const bool sink_fast = out_fast && one_granule && g_in;
+        int drain_c = c_first - nsec;
+        float* g_dst = a.out + ((int64_t)drain_c * PR + g_k) * a.ld_out + g_ch;
+        const int64_t dst_step = (int64_t)PR * a.ld_out;
+        unsigned drain_addr = ring_base;
+        auto drain_chunk = [&]() {
+            if (drain_c >= c_store) {
+                if (sink_fast && (drain_c + 1) * PR <= a.frames) {
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off) : "memory");
+                    v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
+                    __stcs(reinterpret_cast<float4*>(g_dst), v);
+                } else {
+                    const float* slot = ring + (drain_addr - ring_base) / 4u;
+                    for (int i = tid; i < GRAN; i += nthreads) {
+                        const int k = i >> 4, col = (i & 15) * 4;
+                        const int64_t row = (int64_t)drain_c * PR + k;
+                        if (row >= a.frames) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ch = tile * PC + col + j;
+                            if (ch < a.C) a.out[row * a.ld_out + ch] = slot[k * PC + col + j] * (a.gain ? a.gain[ch] : 1.0f);
+                        }
+                    }
+                }
+            }
+            if (drain_c >= c_first) {
+                drain_addr += CHUNK_FLOATS * 4u;
+                if (drain_addr == ring_end) drain_addr = ring_base;
+            }
+            ++drain_c;
+            g_dst += dst_step;
         };
 
         if (BUF) {
-            for (int c = 0; c < PRE; ++c) issue_chunk(c);
+            for (int c = 0; c < PRE; ++c) issue_chunk();
         } else if (w == nsec) {
-            pipe_source_chunk(a, tile, 0, lane, ring);
+            pipe_source_chunk(a, tile, c_first, lane, ring);
         }
 
-        const int iters = nchunks + nsec - 1;
-        for (int t = 0; t < iters; ++t) {
+        // warp w handles chunk c_first + t - w at iteration t; its slot pointer advances with it
+        float* my_slot = ring;
+        float* const ring_last = ring + (size_t)nslot * CHUNK_FLOATS;
+        int c = c_first - w;                              // this warp's chunk at iteration t
+        const int iters = (c_end - c_first) + nsec;       // one extra iteration drains the last chunk
+        for (int t = 0; t < iters; ++t, ++c) {
             if (BUF) {
-                issue_chunk(t + PRE);
-                cp_async_wait<PRE>();            // this thread's granules of chunk t have landed
+                issue_chunk();                   // chunk c_first + t + PRE
+                cp_async_wait<PRE>();            // this thread's granules of chunk c_first + t have landed
             }
             __syncthreads();
+            drain_chunk();                       // chunk c_first + t - nsec: every section finished it last iteration
             if (w < nsec) {
-                const int c = t - w;
-                if (c >= 0 && c < nchunks) {
-                    const int rows = min(PR, a.frames - c * PR);
-                    const float* in = w == 0 ? ring + (BUF ? (c % NSLOT) : (c & 1)) * CHUNK_FLOATS
-                                             : stage + ((w - 1) * 2 + (c & 1)) * CHUNK_FLOATS;
-                    if (w == nsec - 1)
-                        pipe_chunk_kind<true>(kind, in, nullptr, out_g + (int64_t)c * PR * a.ld_out, a.ld_out, rows, lane, live0, live1, gain, r);
-                    else
-                        pipe_chunk_kind<false>(kind, in, stage + (w * 2 + (c & 1)) * CHUNK_FLOATS, nullptr, 0, rows, lane, live0, live1, gain, r);
+                if (c >= c_first && c < c_end) {
+                    pipe_chunk_kind(kind, my_slot, min(PR, a.frames - c * PR), lane, r);
+                    my_slot += CHUNK_FLOATS;
+                    if (my_slot == ring_last) my_slot = ring;
                 }
-            } else if (!BUF && t + 1 < nchunks) {
-                pipe_source_chunk(a, tile, t + 1, lane, ring + ((t + 1) & 1) * CHUNK_FLOATS);
+            } else if (!BUF && c_first + t + 1 < c_end) {
+                pipe_source_chunk(a, tile, c_first + t + 1, lane, ring + ((t + 1) % nslot) * CHUNK_FLOATS);
             }
         }
         if (BUF) cp_async_wait<0>();
-        if (w < nsec) {
+        if (w < nsec && c_end == nchunks) {       // the segment that finishes the launch carries the state on
             if (live0) {
-                a.state[(size_t)(w * 2 + 0) * C + c0] = (double)r.s1.x;
-                a.state[(size_t)(w * 2 + 1) * C + c0] = (double)r.s2.x;
+                a.state_out[(size_t)(w * 2 + 0) * C + c0] = (double)r.s1.x;
+                a.state_out[(size_t)(w * 2 + 1) * C + c0] = (double)r.s2.x;
             }
             if (live1) {
-                a.state[(size_t)(w * 2 + 0) * C + c0 + 1] = (double)r.s1.y;
-                a.state[(size_t)(w * 2 + 1) * C + c0 + 1] = (double)r.s2.y;
+                a.state_out[(size_t)(w * 2 + 0) * C + c0 + 1] = (double)r.s1.y;
+                a.state_out[(size_t)(w * 2 + 1) * C + c0 + 1] = (double)r.s2.y;
             }
         }
-        __syncthreads();       // tile boundary: the ring and the stage buffers restart
+        __syncthreads();       // item boundary: the ring restarts
     }
 }
 
 }  // namespace
 
-// Whether the pipelined kernel can take this chain (alignment of the packed 8-byte stores and the
-// 16-byte cp.async granules); the planner falls back to the scan kernel otherwise.
+// Whether the pipelined kernel can take this chain: a static property of the chain (never of a
+// particular call's pointers), so a stream keeps one kernel -- and one state convention -- for its life.
 extern "C" int sigb_cascade_pipe_ok(const ChainDev* a) {
-    if (a->nsec < 2 || a->nsec > 8 || a->frames <= 0 || a->C <= 0) return 0;
-    if ((reinterpret_cast<uintptr_t>(a->out) & 7) != 0 || (a->ld_out & 1) != 0) return 0;
-    if (a->src_kind == SRC_BUF) {
-        if (a->src_cs != 1 || (reinterpret_cast<uintptr_t>(a->src) & 15) != 0 || (a->src_ld & 3) != 0) return 0;
-    } else if (a->src_kind == SRC_OSC) {
-        if (!a->theta0 || !a->dtheta) return 0;
-    }
+    if (a->nsec < 2 || a->nsec > 8 || a->C <= 0) return 0;
+    if (a->src_kind == SRC_OSC && (!a->theta0 || !a->dtheta)) return 0;
     return 1;
 }
 
-extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, void* stream) {
+extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
     const int nchunks = (a->frames + PR - 1) / PR;
     const int tiles = (a->C + PC - 1) / PC;
     const bool buf = a->src_kind == SRC_BUF;
     const int warps = a->nsec + (buf ? 0 : 1);
-    const size_t smem = ((buf ? NSLOT : 2) + (size_t)(a->nsec - 1) * 2) * CHUNK_FLOATS * sizeof(float);
+    // a chunk occupies its slot while it is in flight (PRE), while each section works on it (nsec) and while
+    // it is stored (1), plus one iteration of slack so a slot is never rewritten right after its last read
+    const int nslot = (buf ? PRE : 1) + a->nsec + 2;
+    const size_t smem = (size_t)nslot * CHUNK_FLOATS * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        const int max_smem = (NSLOT + 7 * 2) * CHUNK_FLOATS * (int)sizeof(float);
+        const int max_smem = (PRE + 8 + 2) * CHUNK_FLOATS * (int)sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(k_cascade_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cascade_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
+    // fast paths: 16-byte cp.async granules of the source, 16-byte stores of the output
+    const int src_fast = buf && a->src_cs == 1 && (reinterpret_cast<uintptr_t>(a->src) & 15) == 0 && (a->src_ld & 3) == 0;
+    const int out_fast = (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ld_out & 3) == 0;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = tiles < sms * 2 ? tiles : sms * 2;
-    if (buf) k_cascade_pipe<true><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles);
-    else k_cascade_pipe<false><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles);
+    // time segments: as many as it takes to fill 3 CTAs per SM, as long as the warm-up stays below 1/4 of a segment
+    int nseg = 1, warm_chunks = 0;
+    if (max_segments > 1 && a->warm_rows >= 0) {
+        warm_chunks = (a->warm_rows + PR - 1) / PR;
+        const int per_sm = buf ? 4 : 3;
+        const int want = std::max(1, sms * per_sm / tiles);          // whole items must fit in one wave
+        const int fit = warm_chunks > 0 ? nchunks / (4 * warm_chunks) : nchunks;
+        nseg = want < fit ? want : fit;
+        if (nseg > max_segments) nseg = max_segments;
+        if (nseg < 1) nseg = 1;
+    }
+    const int seg_chunks = (nchunks + nseg - 1) / nseg;
+    nseg = (nchunks + seg_chunks - 1) / seg_chunks;
+    const long long items = (long long)tiles * nseg;
+    const long long slots = (long long)sms * (buf ? 4 : 3);
+    const int grid = (int)(items < slots ? items : slots);
+    if (buf) k_cascade_pipe<true><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);
+    else k_cascade_pipe<false><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);
     return (int)cudaGetLastError();
 }

@@ -163,6 +163,7 @@ struct sigb_plan {
     int64_t opt_host_slab_bytes = 64ll << 20;
     int64_t opt_buffer_budget = 6ll << 30;
     int64_t opt_cascade_pipe = -1;      // -1: section-pipelined kernel for cascades of >= 3 sections; 0 never; 1: from 2 sections
+    int64_t opt_pipe_segments = 16;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
@@ -441,6 +442,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
         }
         int s0 = 0;
         double warm = 0.0;
+        std::vector<double> rho_max(scan_tables ? C : 0, 0.0), tau_sum(scan_tables ? C : 0, 0.0);
         for (int f : filters) {
             const sigb_node& n = p->nodes[f];
             const std::vector<double>* cut = const_of(p, n.in[1]);
@@ -474,6 +476,9 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
                     hrec[((size_t)s * 2 + 0) * C + c] = (float)(m1[0] + m1[3]);                     // tr(A)
                     hrec[((size_t)s * 2 + 1) * C + c] = (float)(-(m1[0] * m1[3] - m1[1] * m1[2]));  // -det(A)
                     sec_warm[k] = std::max(sec_warm[k], sigb_section_decay_rows(m1));
+                    const double rho = sigb_section_radius(m1);
+                    rho_max[c] = std::max(rho_max[c], rho);
+                    tau_sum[c] += rho < 1.0 ? 1.0 / (1.0 - rho) : 1e12;
                     for (int r = 0; r < SIGB_SCAN_L; ++r)
                         for (int j = 0; j < 2; ++j)
                             ztab[(((size_t)s * SIGB_SCAN_L + r) * 2 + j) * C + c] = tab[r * 2 + j];
@@ -487,6 +492,33 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
             ch.apow = put_vec(p, apow);
             ch.ztab = put_vec(p, ztab);
             ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
+            if (nsec >= 2 && ch.warm_rows >= 0) {
+                // Cascades: the per-section budgets add up far too conservatively.  Simulate, in float64, the
+                // zero-input decay (to 2^-44) of the slowest channels -- largest pole radius, largest sum of
+                // section time constants -- and keep a 10 % margin over the worst of them.
+                std::vector<int> cand;
+                for (int pass = 0; pass < 2; ++pass) {
+                    const std::vector<double>& key = pass == 0 ? rho_max : tau_sum;
+                    std::vector<int> idx(C);
+                    for (int c = 0; c < C; ++c) idx[c] = c;
+                    const int top = std::min(C, 4);
+                    std::partial_sort(idx.begin(), idx.begin() + top, idx.end(), [&](int x, int y) { return key[x] > key[y]; });
+                    cand.insert(cand.end(), idx.begin(), idx.begin() + top);
+                }
+                int worst = 0;
+                for (int c : cand) {
+                    std::vector<SvfSection> all;
+                    for (int f : filters) {
+                        const sigb_node& n = p->nodes[f];
+                        double wn = (*const_of(p, n.in[1]))[c] / (p->rate / 2.0);
+                        std::vector<SvfSection> secs = sigb_butter_sections(n.subtype == SIGB_FILT_HIGHPASS, n.order, wn);
+                        all.insert(all.end(), secs.begin(), secs.end());
+                    }
+                    const int rows = sigb_cascade_decay_rows(all, 44, 1 << 20);
+                    worst = rows < 0 ? (1 << 30) : std::max(worst, rows);
+                }
+                if (worst < (1 << 30)) ch.warm_rows = std::min(ch.warm_rows, (int)(worst * 1.1) + 64);
+            }
             ch.m8 = put_vec(p, m8);
             ch.hrec = put_vec(p, hrec);
         }
@@ -885,9 +917,10 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 ChainDev t = a;
                 t.nsec = ch.nsec_real;           // identity padding sections are not run
                 if (sigb_cascade_pipe_ok(&t)) {
-                    int e = sigb_launch_cascade_pipe(&t, st);
+                    int e = sigb_launch_cascade_pipe(&t, (int)p->opt_pipe_segments, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_cascade_pipe: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;
+                    ch.state_cur ^= 1;           // the kernel wrote the other copy of the state
                     continue;
                 }
             }
@@ -1305,6 +1338,7 @@ extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t 
                  ", \"source\": \"" + src_names[c.src_kind] + "\"";
             if (c.src_kind == SRC_OSC) s += std::string(", \"wave\": \"") + wave_names[c.wave & 3] + "\"";
             s += ", \"sections\": " + std::to_string(c.nsec_real) + ", \"sections_padded\": " + std::to_string(c.nsec) +
+                 ", \"warm_rows\": " + std::to_string(c.warm_rows) +
                  ", \"gain\": " + (c.gain.off >= 0 ? "true" : "false") + "}";
         } else if (l.kind == LK_EWISE) {
             const EwiseSpec& e = plan->ewises[l.idx];
@@ -1347,6 +1381,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "host_slab_bytes") plan->opt_host_slab_bytes = value;
     else if (k == "buffer_budget") plan->opt_buffer_budget = value;
     else if (k == "cascade_pipe") plan->opt_cascade_pipe = value;
+    else if (k == "pipe_segments") plan->opt_pipe_segments = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);

@@ -383,7 +383,7 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     single-request render."""
     from signals_b200.chain import ext
     rng = np.random.default_rng(44)
-    for ch, nsec in [(200, 8), (68, 5), (4, 3)]:
+    for ch, nsec in [(200, 8), (68, 5), (67, 4), (4, 3)]:
         frames = 6000
         x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
         cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (nsec, ch)))
@@ -420,3 +420,32 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert (got[:, ch:] == 7.0).all()            # the padding column is untouched
     want = np_oracle.GraphOracle(RATE).render(node, 0, 3000, ch)
     assert max_abs_err(got[:, :ch], want) <= 1e-4
+
+
+def test_cascade_pipe_time_segments_match_oracle(ns, engine):
+    """k_cascade_pipe cuts long renders into time segments that warm up from zero state (decayed below
+    2^-40); every segment must match the float64 cascade, the segmented render must agree with the
+    unsegmented one, and the state handed to the next call must be the true one."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(45)
+    ch, nsec, frames = 192, 8, 60000
+    x = rng.uniform(-1, 1, (frames + 4000, ch)).astype(np.float32)
+    cut = np.exp(rng.uniform(np.log(600.0), np.log(8000.0), (nsec, ch)))
+    node = ext.Buffer(x)
+    for s in range(nsec):
+        node = cases.lowpass(ns, node, [cut[s]])
+    compiled = engine.compile(node, ch, RATE)
+    warm = compiled.describe()['launches'][0]['warm_rows']
+    assert 0 < warm < frames // 8, warm                       # so that the launch really is segmented
+    first = compiled.render_device(0, frames).cpu().numpy()
+    second = compiled.render_device(frames, 4000).cpu().numpy()          # continues from the carried state
+    compiled.set_option('pipe_segments', 1)
+    compiled.reset()
+    whole = compiled.render_device(0, frames).cpu().numpy()
+    compiled.close()
+    pick = rng.choice(ch, 24, replace=False)
+    want, _ = np_oracle.render_cascade(x[:, pick].astype(np.float64), cut[:, pick], RATE)
+    err = max_abs_err(np.concatenate([first, second])[:, pick], want)
+    print(f'pipe segments: warm_rows {warm}, max-abs over 24 channels x {frames + 4000} frames = {err:.3e}')
+    assert err <= 1e-4
+    assert max_abs_err(first, whole) <= 1e-6
