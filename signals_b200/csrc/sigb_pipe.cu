@@ -33,7 +33,7 @@ using namespace sigb_dev;
 
 constexpr int PR = 16;          // rows per chunk
 constexpr int PC = 64;          // channels per tile (2 per lane)
-constexpr int PRE = 4;          // cp.async chunks in flight per CTA (4 x 4 KB; 4 CTAs per SM)
+constexpr int PRE = 3;          // cp.async chunks in flight per CTA (3 x 4 KB; 4 CTAs per SM at 8 sections)
 constexpr int CHUNK_FLOATS = PR * PC;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -63,6 +63,29 @@ __device__ __forceinline__ float2 pipe_step(float2 x, SecReg& r) {
         r.s1 = __fadd2_rn(lp, w);
         return (KIND & SEC_HP) ? __ffma2_rn(lp, neg1, x) : lp;
     }
+#ifdef SIGB_PIPE_SCALAR
+    // two independent scalar chains (4-cycle FFMA latency each) instead of one packed chain
+    float2 y;
+    {
+        const float xs = x.x - r.s2.x;
+        const float e = fmaf(r.nc.x, r.s1.x, xs);
+        const float bp = fmaf(r.al.x, e, r.s1.x);
+        r.s1.x = fmaf(r.a2.x, e, r.s1.x);
+        const float lp = fmaf(r.g.x, bp, r.s2.x);
+        r.s2.x = fmaf(r.g2.x, bp, r.s2.x);
+        y.x = (KIND & SEC_HP) ? e * r.d.x : lp;
+    }
+    {
+        const float xs = x.y - r.s2.y;
+        const float e = fmaf(r.nc.y, r.s1.y, xs);
+        const float bp = fmaf(r.al.y, e, r.s1.y);
+        r.s1.y = fmaf(r.a2.y, e, r.s1.y);
+        const float lp = fmaf(r.g.y, bp, r.s2.y);
+        r.s2.y = fmaf(r.g2.y, bp, r.s2.y);
+        y.y = (KIND & SEC_HP) ? e * r.d.y : lp;
+    }
+    return y;
+#else
     const float2 xs = __ffma2_rn(r.s2, neg1, x);          // x - s2 (off the s1 chain)
     const float2 e = __ffma2_rn(r.nc, r.s1, xs);
     const float2 bp = __ffma2_rn(r.al, e, r.s1);
@@ -70,6 +93,7 @@ __device__ __forceinline__ float2 pipe_step(float2 x, SecReg& r) {
     const float2 lp = __ffma2_rn(r.g, bp, r.s2);
     r.s2 = __ffma2_rn(r.g2, bp, r.s2);
     return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
+#endif
 }
 
 // one chunk of one section, in place in the shared-memory slot (a lane owns its two channels of every
@@ -105,35 +129,48 @@ __device__ __forceinline__ void pipe_chunk_kind(int kind, float* slot, int rows,
 }
 
 // source warp: chunk c of an oscillator / constant source for the tile's 64 channels -> smem
-__device__ __noinline__ void pipe_source_chunk(const ChainDev& a, int tile, int c, int lane, float* dst) {
-    const int64_t n0 = a.position + (int64_t)c * PR;
-#pragma unroll 1
+template <int WAVE>
+__device__ __forceinline__ void pipe_source_wave(const ChainDev& a, int tile, int64_t n0, int lane, float2* dst) {
+    float x[2][PR];
+    bool near[2];
+#pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int ch = tile * PC + 2 * lane + h;
-        const int cc = min(ch, a.C - 1);
-        float x[PR];
-        if (a.src_kind == SRC_CONST) {
-            const float v = a.constv[cc];
+        const int cc = min(tile * PC + 2 * lane + h, a.C - 1);
+        const unsigned long long dth = a.dtheta[cc];
+        const unsigned long long th = a.theta0[cc] + (unsigned long long)n0 * dth + 0x80000000ull;
+        const int w = (int)(th >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
+        near[h] = gen_tile<WAVE, PR>(w, dhi, a.guard, x[h]);
+    }
 #pragma unroll
-            for (int k = 0; k < PR; ++k) x[k] = v;
-        } else {
-            const unsigned long long dth = a.dtheta[cc];
-            const unsigned long long th = a.theta0[cc] + (unsigned long long)n0 * dth + 0x80000000ull;
-            const int w = (int)(th >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
-            bool near;
-            switch (a.wave) {
-                case SIGB_WAVE_SINE: near = gen_tile<SIGB_WAVE_SINE, PR>(w, dhi, a.guard, x); break;
-                case SIGB_WAVE_SQUARE: near = gen_tile<SIGB_WAVE_SQUARE, PR>(w, dhi, a.guard, x); break;
-                case SIGB_WAVE_SAWTOOTH: near = gen_tile<SIGB_WAVE_SAWTOOTH, PR>(w, dhi, a.guard, x); break;
-                default: near = gen_tile<SIGB_WAVE_TRIANGLE, PR>(w, dhi, a.guard, x); break;
-            }
-            if (near) {   // within the guard band of a discontinuity: the reference's float64 arithmetic (osc.py:32)
-                const double hz = a.hertz[cc], ph = a.phase[cc], rate = (double)a.rate;
-                for (int k = 0; k < PR; ++k) x[k] = osc_wave(a.wave, osc_cycles(__ddiv_rn((double)(n0 + k), rate), hz, ph));
-            }
+    for (int k = 0; k < PR; ++k) dst[k * (PC / 2) + lane] = make_float2(x[0][k], x[1][k]);
+    if (WAVE != SIGB_WAVE_SINE && (near[0] || near[1])) {
+        // within the guard band of a discontinuity: redo the lane's column with the reference's float64
+        // arithmetic (osc.py:32), written straight to shared memory (keeps x[] in registers)
+        float* col = reinterpret_cast<float*>(dst + lane);
+        for (int h = 0; h < 2; ++h) {
+            if (!near[h]) continue;
+            const int cc = min(tile * PC + 2 * lane + h, a.C - 1);
+            const double hz = a.hertz[cc], ph = a.phase[cc], rate = (double)a.rate;
+            for (int k = 0; k < PR; ++k)
+                col[k * PC + h] = osc_wave(WAVE, osc_cycles(__ddiv_rn((double)(n0 + k), rate), hz, ph));
         }
+    }
+}
+
+__device__ __forceinline__ void pipe_source_chunk(const ChainDev& a, int tile, int c, int lane, float* dstf) {
+    const int64_t n0 = a.position + (int64_t)c * PR;
+    float2* dst = reinterpret_cast<float2*>(dstf);
+    if (a.src_kind == SRC_CONST) {
+        const float2 v = make_float2(a.constv[min(tile * PC + 2 * lane, a.C - 1)], a.constv[min(tile * PC + 2 * lane + 1, a.C - 1)]);
 #pragma unroll
-        for (int k = 0; k < PR; ++k) dst[k * PC + 2 * lane + h] = x[k];
+        for (int k = 0; k < PR; ++k) dst[k * (PC / 2) + lane] = v;
+        return;
+    }
+    switch (a.wave) {
+        case SIGB_WAVE_SINE: pipe_source_wave<SIGB_WAVE_SINE>(a, tile, n0, lane, dst); break;
+        case SIGB_WAVE_SQUARE: pipe_source_wave<SIGB_WAVE_SQUARE>(a, tile, n0, lane, dst); break;
+        case SIGB_WAVE_SAWTOOTH: pipe_source_wave<SIGB_WAVE_SAWTOOTH>(a, tile, n0, lane, dst); break;
+        default: pipe_source_wave<SIGB_WAVE_TRIANGLE>(a, tile, n0, lane, dst); break;
     }
 }
 
@@ -146,7 +183,7 @@ __device__ __noinline__ void pipe_source_chunk(const ChainDev& a, int tile, int 
 // stores its granule of finished chunk t - nsec (x gain) to global memory; warp w filters chunk t - w in
 // place.  All section warps do identical work, so nobody waits at the barrier for a straggler.
 template <bool BUF>
-__global__ void __launch_bounds__(BUF ? 256 : 288, BUF ? 4 : 3)
+__global__ void __launch_bounds__(BUF ? 256 : 288, BUF ? 4 : 2)
 k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunks, int warm_chunks, int nslot, int src_fast, int out_fast) {
     extern __shared__ __align__(16) float ring[];        // [nslot] chunks of (PR x PC); a chunk stays in its slot
                                                          // from its load until its rows have been stored
@@ -191,7 +228,11 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         const bool g_in = g_ch + 3 < a.C;
         const unsigned g_off = (unsigned)(g_k * PC + g_col) * 4u;
         const int64_t full_rows = min(a.src_rows, (int64_t)a.frames);
-        const bool one_granule = nthreads == GRAN;
+        // a thread owns gpt granules of every chunk: rows g_k, g_k + nthreads/16, ... (same channels)
+        const int gpt = (GRAN % nthreads == 0 && nthreads % 16 == 0) ? GRAN / nthreads : 0;
+        const bool one_granule = gpt > 0;
+        const unsigned row_skip_smem = (unsigned)(nthreads / 16) * PC * 4u;
+        const int64_t row_skip_src = (int64_t)(nthreads / 16) * a.src_ld, row_skip_dst = (int64_t)(nthreads / 16) * a.ld_out;
         // source side
         const int fast_end = (BUF && src_fast && one_granule && g_in) ? min(c_end, (int)min(full_rows / PR, (int64_t)nchunks)) : c_first;
         const float* g_src = BUF ? a.src + ((int64_t)c_first * PR + g_k) * a.src_ld + g_ch : nullptr;
@@ -200,7 +241,8 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         unsigned issue_addr = ring_base;
         auto issue_chunk = [&]() {
             if (issue_c < fast_end) {
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off), "l"(g_src) : "memory");
+                for (int j = 0; j < gpt; ++j)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off + j * row_skip_smem), "l"(g_src + j * row_skip_src) : "memory");
             } else if (issue_c < c_end) {
                 float* slot = ring + (issue_addr - ring_base) / 4u;
                 const int64_t row0 = (int64_t)issue_c * PR;
@@ -240,10 +282,12 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         auto drain_chunk = [&]() {
             if (drain_c >= c_store) {
                 if (sink_fast && (drain_c + 1) * PR <= a.frames) {
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off) : "memory");
-                    v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
-                    __stcs(reinterpret_cast<float4*>(g_dst), v);
+                    for (int j = 0; j < gpt; ++j) {
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off + j * row_skip_smem) : "memory");
+                        v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
+                        __stcs(reinterpret_cast<float4*>(g_dst + j * row_skip_dst), v);
+                    }
                 } else {
                     const float* slot = ring + (drain_addr - ring_base) / 4u;
                     for (int i = tid; i < GRAN; i += nthreads) {
@@ -274,6 +318,7 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
 
         // warp w handles chunk c_first + t - w at iteration t; its slot pointer advances with it
         float* my_slot = ring;
+        float* src_slot = ring;                           // source warp: slot of the chunk it rendered last
         float* const ring_last = ring + (size_t)nslot * CHUNK_FLOATS;
         int c = c_first - w;                              // this warp's chunk at iteration t
         const int iters = (c_end - c_first) + nsec;       // one extra iteration drains the last chunk
@@ -291,7 +336,9 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
                     if (my_slot == ring_last) my_slot = ring;
                 }
             } else if (!BUF && c_first + t + 1 < c_end) {
-                pipe_source_chunk(a, tile, c_first + t + 1, lane, ring + ((t + 1) % nslot) * CHUNK_FLOATS);
+                src_slot += CHUNK_FLOATS;
+                if (src_slot == ring_last) src_slot = ring;
+                pipe_source_chunk(a, tile, c_first + t + 1, lane, src_slot);
             }
         }
         if (BUF) cp_async_wait<0>();
@@ -314,9 +361,32 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
 // Whether the pipelined kernel can take this chain: a static property of the chain (never of a
 // particular call's pointers), so a stream keeps one kernel -- and one state convention -- for its life.
 extern "C" int sigb_cascade_pipe_ok(const ChainDev* a) {
-    if (a->nsec < 2 || a->nsec > 8 || a->C <= 0) return 0;
+    if (a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
     if (a->src_kind == SRC_OSC && (!a->theta0 || !a->dtheta)) return 0;
     return 1;
+}
+
+// resident CTAs per SM the launch is sized for: limited by warps (48 of 64 slots), shared memory and 16 CTAs
+static int ctas_per_sm(int warps, size_t smem) {
+    int n = 48 / warps;
+    const int by_smem = (int)((size_t)220 * 1024 / (smem + 1024));
+    if (n > by_smem) n = by_smem;
+    if (n > 16) n = 16;
+    return n < 1 ? 1 : n;
+}
+
+// Work items (tiles x time segments) the launch would run: the planner prefers the scan kernel for
+// shallow chains when this cannot fill the machine.
+extern "C" int sigb_cascade_pipe_items(const ChainDev* a, int max_segments) {
+    const int nchunks = (a->frames + PR - 1) / PR;
+    const int tiles = (a->C + PC - 1) / PC;
+    int nseg = 1;
+    if (max_segments > 1 && a->warm_rows >= 0) {
+        const int warm_chunks = (a->warm_rows + PR - 1) / PR;
+        const int fit = warm_chunks > 0 ? nchunks / (4 * warm_chunks) : nchunks;
+        nseg = std::max(1, std::min(fit, max_segments));
+    }
+    return tiles * nseg;
 }
 
 extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, void* stream) {
@@ -343,11 +413,11 @@ extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, voi
     const int out_fast = (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 && (a->ld_out & 3) == 0;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // time segments: as many as it takes to fill 3 CTAs per SM, as long as the warm-up stays below 1/4 of a segment
+    // time segments: enough items to fill the machine in one wave, as long as the warm-up stays below 1/4 of a segment
+    const int per_sm = ctas_per_sm(warps, smem);
     int nseg = 1, warm_chunks = 0;
     if (max_segments > 1 && a->warm_rows >= 0) {
         warm_chunks = (a->warm_rows + PR - 1) / PR;
-        const int per_sm = buf ? 4 : 3;
         const int want = std::max(1, sms * per_sm / tiles);          // whole items must fit in one wave
         const int fit = warm_chunks > 0 ? nchunks / (4 * warm_chunks) : nchunks;
         nseg = want < fit ? want : fit;
@@ -357,7 +427,7 @@ extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, voi
     const int seg_chunks = (nchunks + nseg - 1) / nseg;
     nseg = (nchunks + seg_chunks - 1) / seg_chunks;
     const long long items = (long long)tiles * nseg;
-    const long long slots = (long long)sms * (buf ? 4 : 3);
+    const long long slots = (long long)sms * per_sm;
     const int grid = (int)(items < slots ? items : slots);
     if (buf) k_cascade_pipe<true><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);
     else k_cascade_pipe<false><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);

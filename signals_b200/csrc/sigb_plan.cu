@@ -162,8 +162,8 @@ struct sigb_plan {
     int64_t opt_slab_frames = 0;
     int64_t opt_host_slab_bytes = 64ll << 20;
     int64_t opt_buffer_budget = 6ll << 30;
-    int64_t opt_cascade_pipe = -1;      // -1: section-pipelined kernel for cascades of >= 3 sections; 0 never; 1: from 2 sections
-    int64_t opt_pipe_segments = 16;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
+    int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
+    int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
@@ -912,11 +912,16 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
             int done = 0;
             if (ch.src_kind == SRC_OSC) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
-            const int pipe_min = p->opt_cascade_pipe < 0 ? 3 : (p->opt_cascade_pipe == 0 ? 1 << 30 : 2);
-            if (!p->opt_force_seq && ch.nsec_real >= pipe_min && ch.nsec_real <= 8) {
+            // kernel choice: cascades of >= 3 sections run section-pipelined (k_cascade_pipe); shallower
+            // chains stay on the time-parallel scan kernel, which measured faster for them (C2: 1.07e12 vs
+            // 0.82e12 voice-samples/s) unless "cascade_pipe" forces the pipeline from n sections
+            if (!p->opt_force_seq && p->opt_cascade_pipe != 0 && ch.nsec_real >= 1 && ch.nsec_real <= 8) {
                 ChainDev t = a;
                 t.nsec = ch.nsec_real;           // identity padding sections are not run
-                if (sigb_cascade_pipe_ok(&t)) {
+                const bool deep = ch.nsec_real >= 3;
+                const bool forced = p->opt_cascade_pipe > 0 && ch.nsec_real >= (int)p->opt_cascade_pipe;
+                if (sigb_cascade_pipe_ok(&t) &&
+                    (deep || forced)) {
                     int e = sigb_launch_cascade_pipe(&t, (int)p->opt_pipe_segments, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_cascade_pipe: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;

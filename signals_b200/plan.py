@@ -29,8 +29,9 @@ from signals_b200.chain import BadShape, ChainLayerError, FilterIndexError, Unsu
 _OSC = {'Sine': _lib.WAVE_SINE, 'Square': _lib.WAVE_SQUARE, 'Sawtooth': _lib.WAVE_SAWTOOTH,
         'Triangle': _lib.WAVE_TRIANGLE}
 _FILTER = {'LowPass': _lib.FILT_LOWPASS, 'HighPass': _lib.FILT_HIGHPASS}
+_TAPS = ('Wave', 'Spec', 'FileWriter')     # pass-through side-effect nodes (chain/vis.py:61-64, chain/files.py:89-102)
 _KNOWN = ('Fixed', *_OSC, 'Mix', 'RingMod', 'Gain', 'Amp', *_FILTER, 'BandPass', 'BandStop', 'Merge',
-          'GroupSum', 'PanSum', 'Buffer')
+          'GroupSum', 'PanSum', 'Buffer', *_TAPS)
 
 
 def node_kind(node) -> str:
@@ -127,6 +128,10 @@ class _Lowering:
                 return self.port(node, 'input', creq, self.frames)
             return self.emit(node, _lib.NODE_ZERO, 1), 1
         F = self.frames
+        if kind in _TAPS:
+            # the tap's audio result IS its input (PassThroughResult.forward, chain/__init__.py:409-417);
+            # queueing blocks for the GUI / writing the file is host-side work outside the render
+            return self.port(node, 'input', creq, F)
         if kind == 'Fixed':
             value = np.asarray(st.value, dtype=np.float64)
             rows, ch = value.shape

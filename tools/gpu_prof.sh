@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for spec in $1; do
   c=${spec%%:*}; k=${spec##*:}
   case $c in
-    c2) A="--config c2 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
+    c2) A="--config c2 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline $C2_EXTRA";;
     c3) A="--config c3 --seconds 2 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
     c4) A="--config c4 --seconds 5 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
     c5) A="--config c5 --seconds 1 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
