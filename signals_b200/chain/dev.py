@@ -24,6 +24,8 @@ from signals_b200.chain import (BlockLoc, ChainLayerError, ExplicitChannels, Rec
 def _sd():
     try:
         import sounddevice as sd
+        if not callable(getattr(sd, 'query_devices', None)) or not isinstance(getattr(sd, 'CallbackStop', None), type):
+            raise ImportError('not a usable sounddevice module')
     except (ImportError, OSError):
         from signals_b200 import sounddevice_shim as sd
     return sd
