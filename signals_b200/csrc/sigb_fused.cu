@@ -264,3 +264,18 @@ extern "C" int sigb_launch_voices_finish(const float* partial, int nparts, int f
     k_voices_finish<<<blocks, 256, 0, (cudaStream_t)stream>>>(partial, nparts, frames, out, ld_out);
     return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// probe: write-only streaming fill (the practical HBM ceiling of a store-only kernel such as C2's)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_probe_fill(float4* __restrict__ out, int64_t n4, float v) {
+    const float4 val = make_float4(v, v, v, v);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) __stcs(out + i, val);
+}
+}  // namespace
+
+extern "C" int sigb_probe_fill(float* out_dev, int64_t n_floats, float value, int32_t blocks, void* stream) {
+    k_probe_fill<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(out_dev), n_floats / 4, value);
+    return (int)cudaGetLastError();
+}

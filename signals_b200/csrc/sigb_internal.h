@@ -3,7 +3,9 @@
 #include <stdint.h>
 
 #define SIGB_MAX_SEC 16       // sections per fused chain launch (longer cascades are split)
+#ifndef SIGB_SCAN_L
 #define SIGB_SCAN_L 16        // rows per sub-chunk in the time-parallel scan kernel
+#endif
 
 enum { SRC_OSC = 0, SRC_BUF = 1, SRC_CONST = 2 };
 

@@ -312,24 +312,26 @@ __device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }
 
 struct SecPar {            // per-thread parameters of one section (packed where the math is packed)
     float2 g, nc, d;       // (g,g) (-c,-c) (d,d); first-order: g = (G,G)
+    float2 gd, gd2, g2;    // (g d) (2 g d) (2 g): six-instruction low-pass form
     float2 al, be;         // zero-input recurrence coefficients
     float m8[4];           // A^8, row-major
     float p0, r0, p1, r1;  // zero-input output at samples 0 and 1 of a half, per unit state
 };
 
+// With e = x - c s1 - s2:  hp = d e;  bp = s1 + g d e;  s1' = s1 + 2 g d e;  lp = s2 + g bp;  s2' = s2 + 2 g bp
+// (the same section as svf_lp2, regrouped: six packed instructions for low-pass, seven for high-pass).
 template <int H, bool HP>
 __device__ __forceinline__ void svf2_second_order(const SecPar& c, float2 (&v)[H], float2& s1, float2& s2) {
     const float2 neg1 = pk1(-1.0f);
 #pragma unroll
     for (int k = 0; k < H; ++k) {
-        float2 t = __ffma2_rn(c.nc, s1, v[k]);
-        float2 u = __ffma2_rn(s2, neg1, t);
-        float2 hp = __fmul2_rn(u, c.d);
-        float2 bp = __ffma2_rn(c.g, hp, s1);
-        s1 = __ffma2_rn(c.g, hp, bp);
-        float2 lp = __ffma2_rn(c.g, bp, s2);
-        s2 = __ffma2_rn(c.g, bp, lp);
-        v[k] = HP ? hp : lp;
+        const float2 xs = __ffma2_rn(s2, neg1, v[k]);
+        const float2 e = __ffma2_rn(c.nc, s1, xs);
+        const float2 bp = __ffma2_rn(c.gd, e, s1);
+        s1 = __ffma2_rn(c.gd2, e, s1);
+        const float2 lp = __ffma2_rn(c.g, bp, s2);
+        s2 = __ffma2_rn(c.g2, bp, s2);
+        v[k] = HP ? __fmul2_rn(e, c.d) : lp;
     }
 }
 
@@ -355,7 +357,7 @@ __device__ __forceinline__ void svf2_block(int kind, const SecPar& c, float2 (&v
     else svf2_first_order<H, true>(c, v, s1);
 }
 
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE>
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool PIPE = false>
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
@@ -534,7 +536,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     a.state_out[(size_t)(s * 2 + 1) * C + c] = c2[s];
                 }
             }
-        } else {
+        } else if (w < NW) {
             // ---------------- worker warps: lane = channel, warp = sub-chunk ----------------
             const int grp = w / WG, q = w % WG;
             const float gain = a.gain ? a.gain[cc] : 1.0f;
@@ -567,6 +569,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 const float4 q0 = par[(s * 4 + 0) * 32 + lane], q1 = par[(s * 4 + 1) * 32 + lane];
                 const float4 q2 = par[(s * 4 + 2) * 32 + lane], q3 = par[(s * 4 + 3) * 32 + lane];
                 p.g = pk1(q0.x); p.nc = pk1(-q0.y); p.d = pk1(q0.z);
+                p.gd = pk1(q0.x * q0.z); p.gd2 = pk1(2.0f * (q0.x * q0.z)); p.g2 = pk1(2.0f * q0.x);
                 p.m8[0] = q1.x; p.m8[1] = q1.y; p.m8[2] = q1.z; p.m8[3] = q1.w;
                 p.al = pk1(q2.x); p.be = pk1(q2.y);
                 p.p0 = q3.x; p.r0 = q3.y; p.p1 = q3.z; p.r1 = q3.w;
@@ -574,8 +577,8 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             SecPar p0;
             if (NSEC == 1) load_par(0, p0);
 
-            for (int step = w0 + grp; step < s1; step += NG) {
-                float2 v[H];          // v[k] = (row k of the first half, row k of the second half)
+            // source samples of the sub-chunk starting at row `grow`: v[k] = (row k of the first half, row k of the second half)
+            auto gen = [&](float2 (&v)[H], int64_t grow) {
                 if (SRC == SRC_OSC) {
                     if (FASTSINE) {
                         int ha = (int)(th >> 32);
@@ -590,7 +593,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                         }
                         th += th_step;
                     } else {
-                        if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
+                        if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + grow + lane), rate);
                         __syncwarp();
 #pragma unroll
                         for (int k = 0; k < H; ++k)
@@ -599,19 +602,101 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                         __syncwarp();
                     }
                 } else if (SRC == SRC_BUF) {
-                    if (live && row + L <= a.src_rows) {          // whole sub-chunk inside the source: plain loads
-                        const float* sp = a.src + row * a.src_ld + (int64_t)c * a.src_cs;
+                    if (live && grow + L <= a.src_rows) {          // whole sub-chunk inside the source: plain loads
+                        const float* sp = a.src + grow * a.src_ld + (int64_t)c * a.src_cs;
 #pragma unroll
                         for (int k = 0; k < H; ++k) v[k] = pk(__ldg(sp + (int64_t)k * a.src_ld), __ldg(sp + (int64_t)(H + k) * a.src_ld));
                     } else {
 #pragma unroll
                         for (int k = 0; k < H; ++k)
-                            v[k] = live ? pk(load_src(a, row + k, c), load_src(a, row + H + k, c)) : pk1(0.0f);
+                            v[k] = live ? pk(load_src(a, grow + k, c), load_src(a, grow + H + k, c)) : pk1(0.0f);
                     }
                 } else {
 #pragma unroll
                     for (int k = 0; k < H; ++k) v[k] = pk1(cv);
                 }
+            };
+            // add the zero-input response of the true initial state `ia` (both halves; the second half's
+            // initial state follows from the first half's zero-state end state (za1, za2))
+            auto correct = [&](const SecPar& ps, float2 (&v)[H], float2 ia, float za1, float za2) {
+                const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, za1));
+                const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, za2));
+                float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
+                float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
+                v[0] = __fadd2_rn(v[0], h0);
+                v[1] = __fadd2_rn(v[1], h1);
+#pragma unroll
+                for (int k = 2; k < H; ++k) {       // advanced by its 2-term recurrence
+                    const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
+                    v[k] = __fadd2_rn(v[k], hn);
+                    h0 = h1;
+                    h1 = hn;
+                }
+            };
+            auto store = [&](float2 (&v)[H], int64_t srow, float* soutp) {
+                if (bulk) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        const float2 o = __fmul2_rn(v[k], gain2);
+                        tile[k * 32 + lane] = o.x;
+                        tile[(H + k) * 32 + lane] = o.y;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_tile(&out_map, tile_idx * 32, (int)srow, tile);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else if (live) {
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        const float2 o = __fmul2_rn(v[k], gain2);
+                        __stcs(soutp + (int64_t)k * a.ld_out, o.x);
+                        __stcs(soutp + (int64_t)(H + k) * a.ld_out, o.y);
+                    }
+                }
+            };
+
+            if (PIPE && NSEC == 1) {
+                // Software-pipelined single-section loop: the zero-state render of the NEXT step is issued between
+                // publishing this step's end state and waiting for its true initial state, so the scanner's
+                // turn-around is hidden behind useful work instead of stalling the warp at the barrier.
+                const int kind = a.sec_kind[0];
+                int step = w0 + grp;
+                float2 vn[H];
+                float2 s1n = pk1(0.0f), s2n = pk1(0.0f);
+                if (step < s1) {
+                    gen(vn, row);
+                    svf2_block<H>(kind, p0, vn, s1n, s2n);
+                }
+                while (step < s1) {
+                    zs[w * 32 + lane] = make_float2(fmaf(p0.m8[0], s1n.x, fmaf(p0.m8[1], s2n.x, s1n.y)),
+                                                    fmaf(p0.m8[2], s1n.x, fmaf(p0.m8[3], s2n.x, s2n.y)));
+                    bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+                    float2 v[H];
+#pragma unroll
+                    for (int k = 0; k < H; ++k) v[k] = vn[k];
+                    const float za1 = s1n.x, za2 = s2n.x;
+                    const int next = step + NG;
+                    if (next < s1) {
+                        s1n = pk1(0.0f);
+                        s2n = pk1(0.0f);
+                        gen(vn, row + row_stride);
+                        svf2_block<H>(kind, p0, vn, s1n, s2n);
+                    }
+                    bar_sync(2 + 2 * grp, (WG + 1) * 32);
+                    correct(p0, v, si[w * 32 + lane], za1, za2);
+                    if (step >= s0) store(v, row, outp);
+                    outp += out_stride;
+                    row += row_stride;
+                    step = next;
+                }
+            } else {
+            for (int step = w0 + grp; step < s1; step += NG) {
+                float2 v[H];
+                gen(v, row);
 #pragma unroll
                 for (int s = 0; s < NSEC; ++s) {
                     SecPar ps;
@@ -625,49 +710,12 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     zs[w * 32 + lane] = make_float2(zx, zy);
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
                     bar_sync(2 + 2 * grp, (WG + 1) * 32);
-                    const float2 ia = si[w * 32 + lane];                         // true state entering the first half
-                    const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, s1v.x));   // ... and the second half
-                    const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, s2v.x));
-                    // zero-input response of both halves, advanced by its 2-term recurrence
-                    float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
-                    float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
-                    v[0] = __fadd2_rn(v[0], h0);
-                    v[1] = __fadd2_rn(v[1], h1);
-#pragma unroll
-                    for (int k = 2; k < H; ++k) {
-                        const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
-                        v[k] = __fadd2_rn(v[k], hn);
-                        h0 = h1;
-                        h1 = hn;
-                    }
+                    correct(ps, v, si[w * 32 + lane], s1v.x, s2v.x);
                 }
-                if (step >= s0) {           // warm-up steps only advance the state
-                    if (bulk) {
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
-#pragma unroll
-                        for (int k = 0; k < H; ++k) {
-                            const float2 o = __fmul2_rn(v[k], gain2);
-                            tile[k * 32 + lane] = o.x;
-                            tile[(H + k) * 32 + lane] = o.y;
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_tile(&out_map, tile_idx * 32, (int)row, tile);
-                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        }
-                    } else if (live) {
-#pragma unroll
-                        for (int k = 0; k < H; ++k) {
-                            const float2 o = __fmul2_rn(v[k], gain2);
-                            __stcs(outp + (int64_t)k * a.ld_out, o.x);
-                            __stcs(outp + (int64_t)(H + k) * a.ld_out, o.y);
-                        }
-                    }
-                }
+                if (step >= s0) store(v, row, outp);           // warm-up steps only advance the state
                 outp += out_stride;
                 row += row_stride;
+            }
             }
         }
         __syncthreads();     // piece boundary: shared parameters and the barrier protocol restart
@@ -859,7 +907,7 @@ cudaError_t launch_scan_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     }
 }
 
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE>
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool PIPE = false>
 cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;
@@ -869,7 +917,7 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     size_t smem = (size_t)NW * L * 32 * sizeof(float) + (size_t)NW * 32 * sizeof(float2) * 2 +
                   (size_t)NSEC * 4 * 32 * sizeof(float4) + (size_t)NW * L * sizeof(double) +
                   (NSEC > 2 ? (size_t)NSEC * 4 * 32 * sizeof(double) + (size_t)NSEC * WG * 32 * sizeof(float4) : 0);
-    auto kern = k_chain_scan2<SRC, NSEC, NG, WG, FASTSINE>;
+    auto kern = k_chain_scan2<SRC, NSEC, NG, WG, FASTSINE, PIPE>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -898,15 +946,15 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     return cudaGetLastError();
 }
 
-template <int NSEC, int NG, int WG>
+template <int NSEC, int NG, int WG, bool PIPE = false>
 cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const bool fast = a.src_kind == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
     switch (a.src_kind) {
         case SRC_OSC:
-            return fast ? launch_scan2_t<SRC_OSC, NSEC, NG, WG, true>(a, st, rows_done)
-                        : launch_scan2_t<SRC_OSC, NSEC, NG, WG, false>(a, st, rows_done);
-        case SRC_BUF: return launch_scan2_t<SRC_BUF, NSEC, NG, WG, false>(a, st, rows_done);
-        default: return launch_scan2_t<SRC_CONST, NSEC, NG, WG, false>(a, st, rows_done);
+            return fast ? launch_scan2_t<SRC_OSC, NSEC, NG, WG, true, PIPE>(a, st, rows_done)
+                        : launch_scan2_t<SRC_OSC, NSEC, NG, WG, false, PIPE>(a, st, rows_done);
+        case SRC_BUF: return launch_scan2_t<SRC_BUF, NSEC, NG, WG, false, PIPE>(a, st, rows_done);
+        default: return launch_scan2_t<SRC_CONST, NSEC, NG, WG, false, PIPE>(a, st, rows_done);
     }
 }
 
@@ -921,6 +969,11 @@ static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
             case 5: *ng = 7; *wg = 4; break;
             case 6: *ng = 2; *wg = 15; break;
             case 7: *ng = 5; *wg = 6; break;
+            case 8: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;     // single section: software-pipelined workers
+            case 9: *ng = (nsec == 1 ? 3 : 5); *wg = 8; break;
+            case 10: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;
+            case 11: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 12 : 6); break;
+            case 12: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 10 : 6); break;
             default: *ng = 4; *wg = 7; break;
         }
         return;
@@ -971,6 +1024,11 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
         if (a->nsec == 1) return (int)launch_scan2_n<1, NG, WG>(*a, st, rows_done);   \
         return (int)launch_scan2_n<2, NG, WG>(*a, st, rows_done);                     \
     } while (0)
+        if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, true>(*a, st, rows_done);
+        if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, true>(*a, st, rows_done);
+        if (variant == 10 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 9, true>(*a, st, rows_done);
+        if (variant == 11 && a->nsec == 1) return (int)launch_scan2_n<1, 2, 12, true>(*a, st, rows_done);
+        if (variant == 12 && a->nsec == 1) return (int)launch_scan2_n<1, 2, 10, true>(*a, st, rows_done);
         if (ng == 7) SCAN2_DISPATCH(7, 4);
         if (ng == 2) SCAN2_DISPATCH(2, 15);
         if (ng == 5) SCAN2_DISPATCH(5, 6);

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Write-only HBM ceiling on this GPU: a streaming fill of the C2 output block (7.86 GB) with plain
+128-bit stores, and torch's own fill for comparison.  Usage (GPU box): python tools/probe_fill.py"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from signals_b200 import _lib
+L = _lib.lib()
+L.sigb_probe_fill.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p]
+n = 480000 * 4096
+out = torch.empty(n, dtype=torch.float32, device='cuda')
+st = torch.cuda.current_stream().cuda_stream
+def timed(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+for blocks in (148 * 2, 148 * 4, 148 * 8, 148 * 16, 148 * 32):
+    ms = timed(lambda: L.sigb_probe_fill(ctypes.c_void_p(out.data_ptr()), n, 1.0, blocks, ctypes.c_void_p(st)))
+    print(f'k_probe_fill {blocks:5d} CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+ms = timed(lambda: out.fill_(2.0))
+print(f'torch fill_: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+src = torch.empty(n // 2, dtype=torch.float32, device='cuda'); dst = torch.empty_like(src)
+ms = timed(lambda: dst.copy_(src))
+print(f'torch copy_ (read+write bytes): {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
