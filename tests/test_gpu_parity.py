@@ -449,3 +449,99 @@ def test_cascade_pipe_time_segments_match_oracle(ns, engine):
     print(f'pipe segments: warm_rows {warm}, max-abs over 24 channels x {frames + 4000} frames = {err:.3e}')
     assert err <= 1e-4
     assert max_abs_err(first, whole) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE full sizes of C3 / C4 / C5: size-independent properties + spot checks against the oracle
+# ------------------------------------------------------------------------------------------------
+
+def test_full_size_bank_properties(ns, engine):
+    """Config C3 at full size (65,536 partials -> 64 channels x 10 s): windows at the start, middle and end
+    of the render against the float64 oracle for four groups, and exact linearity in the amplitudes."""
+    from signals_b200.chain import ext
+    torch = _torch()
+    p, groups, frames = 65536, 64, 10 * RATE
+    hertz, phase, amp = cases.bank_params(3, p, p // groups)
+    compiled = engine.compile(cases.build_bank(ns, ext, hertz, phase, amp, groups), groups, RATE)
+    out = compiled.render_device(0, frames)
+    compiled.close()
+    assert bool(torch.isfinite(out).all())
+    per = p // groups
+    for g in (0, 17, 40, 63):
+        sl = slice(g * per, (g + 1) * per)
+        for pos in (0, 240000 - 128, frames - 1000):
+            want = np_oracle.render_bank(pos, 1000, RATE, hertz[sl], phase[sl], amp[sl], 1)
+            got = out[pos:pos + 1000, g].cpu().numpy()[:, None]
+            assert max_abs_err(got, want) <= 1e-6, (g, pos)
+    doubled = engine.compile(cases.build_bank(ns, ext, hertz, phase, 2.0 * amp, groups), groups, RATE)
+    out2 = doubled.render_device(0, frames)
+    doubled.close()
+    assert bool(torch.equal(out2, out * 2.0))          # power-of-two amplitude scaling is exact in float32
+
+
+def test_full_size_cascade_properties(ns, engine):
+    """Config C4 at full size (16,384 channels x 8 low-pass sections x 60 s, streamed in 5 s slabs with carried
+    state, as bench.py --config c4 does): six channels over the whole minute against scipy's float64 cascade."""
+    from signals_b200.chain import ext
+    torch = _torch()
+    ch, slab, n_slabs = 16384, 5 * RATE, 12
+    rng = np.random.default_rng(4)
+    cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (8, ch)))
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(4)
+    noise = torch.rand((slab, ch), generator=gen, device='cuda', dtype=torch.float32) * 2 - 1
+    buf = ext.Buffer(noise)
+    node = buf
+    for s in range(8):
+        node = cases.lowpass(ns, node, [cut[s]])
+    compiled = engine.compile(node, ch, RATE, slab)
+    assert [l['kind'] for l in compiled.describe()['launches']] == ['chain']
+    pick = np.concatenate([np.argsort(cut.min(0))[:3], rng.choice(ch, 3, replace=False)])
+    idx = torch.from_numpy(pick).cuda()
+    out = torch.empty((slab, ch), dtype=torch.float32, device='cuda')
+    got = []
+    for k in range(n_slabs):
+        compiled.bind_window(buf, noise, k * slab)
+        compiled.render_device(k * slab, slab, out)
+        got.append(out[:, idx].cpu().numpy())
+    assert bool(torch.isfinite(out).all())
+    compiled.close()
+    got = np.concatenate(got)
+    x = np.tile(noise[:, idx].cpu().numpy().astype(np.float64), (n_slabs, 1))
+    want, _ = np_oracle.render_cascade(x, cut[:, pick], RATE)
+    err = max_abs_err(got, want)
+    print(f'C4 full size: max-abs over 6 channels x {n_slabs * slab} frames = {err:.3e}')
+    assert err <= 1e-4
+
+
+def test_full_size_instances_properties(ns, engine):
+    """Config C5 at full size (1,048,576 instances): (i) the mix of the four rank shards (instance i on rank
+    i % 4) summed equals the mix of the whole bank -- sharding does not change the result; (ii) with every gain
+    but 64 picked instances' set to zero the million-voice render must equal the oracle mix of those 64."""
+    from signals_b200.chain import ext
+    n, frames = 1 << 20, RATE // 2
+    whole_prm = cases.instance_params(5, n)
+    compiled = engine.compile(cases.build_instances(ns, ext, whole_prm), 2, RATE)
+    assert compiled.describe()['launches'][0]['channels_per_thread'] == 4
+    whole = compiled.render_device(0, frames).cpu().numpy().astype(np.float64)
+    compiled.close()
+    parts = np.zeros_like(whole)
+    for r in range(4):
+        c = engine.compile(cases.build_instances(ns, ext, cases.instance_params(5, n, r, 4)), 2, RATE)
+        parts += c.render_device(0, frames).cpu().numpy()
+        c.close()
+    assert np.isfinite(whole).all() and np.abs(whole).max() > 0.05
+    assert max_abs_err(parts, whole) <= 1e-6
+    rng = np.random.default_rng(9)
+    pick = np.sort(rng.choice(n, 64, replace=False))
+    prm = dict(whole_prm)
+    prm['gain'] = np.zeros(n)
+    prm['gain'][pick] = whole_prm['gain'][pick] * 256.0          # lift the 64 voices to a measurable level
+    c = engine.compile(cases.build_instances(ns, ext, prm), 2, RATE)
+    got = c.render_device(0, frames).cpu().numpy()
+    c.close()
+    sub = {k: (v[pick] if isinstance(v, np.ndarray) else v) for k, v in prm.items()}
+    want = np_oracle.render_instances(sub, 0, frames, RATE)
+    err = max_abs_err(got, want)
+    print(f'C5 full size, 64 live voices of 1M: max-abs {err:.3e} (mix peak {np.abs(want).max():.3f})')
+    assert err <= 1e-6
