@@ -111,17 +111,34 @@ __global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n
 // ------------------------------------------------------------------------------------------
 // k_voices
 // ------------------------------------------------------------------------------------------
-constexpr int VK = SIGB_VOICE_K;
 constexpr int VT = SIGB_VOICE_THREADS;
 
-template <int KIND>
-__device__ __forceinline__ void filt_tile(float (&x)[VK], float g, float c, float d, float& s1, float& s2, int kmax) {
+// filter one tile of M voices: the M recurrences are independent, so they are written interleaved
+// (row-major over k, then m) and the scheduler overlaps their dependency chains
+template <int KIND, int M, int VK>
+__device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M], const float (&c)[M], const float (&d)[M],
+                                          float (&s1)[M], float (&s2)[M], int kmax) {
 #pragma unroll
-    for (int k = 0; k < VK; ++k)
-        if (k < kmax) x[k] = svf_any(KIND, x[k], g, c, d, s1, s2);
+    for (int k = 0; k < VK; ++k) {
+        if (k < kmax) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) x[m][k] = svf_any(KIND, x[m][k], g[m], c[m], d[m], s1[m], s2[m]);
+        }
+    }
 }
 
-template <int M>
+template <int WAVE, int M, int VK>
+__device__ __forceinline__ unsigned gen_tiles(const int (&w)[M], const int (&dhi)[M], int guard, float (&x)[M][VK]) {
+    unsigned near = 0u;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+        if (gen_tile<WAVE, VK>(w[m], dhi[m], guard, x[m])) near |= 1u << m;
+    return near;
+}
+
+// M voices per thread, VK rows per tile (M = 4: VK = 8 keeps x[M][VK], the accumulators and the voices'
+// phase / filter / weight registers inside 128 registers)
+template <int M, int VK>
 __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_constant__ VoicesDev a) {
     __shared__ float2 red[VK * VT];
     const int tid = threadIdx.x;
@@ -160,52 +177,60 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
     }
     float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)blockIdx.x * a.frames;
     const double rate = (double)a.rate;
+    constexpr int PARTS = VT / VK;          // threads that share one row in the CTA reduction
 
     for (int n0 = 0; n0 < a.frames; n0 += VK) {
         const int kmax = min(VK, a.frames - n0);
-        float2 acc[VK];
-#pragma unroll
-        for (int k = 0; k < VK; ++k) acc[k] = make_float2(0.0f, 0.0f);
+        float x[M][VK];
+        int w[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            float x[VK];
-            const int w = (int)(th[m] >> 32);
+            w[m] = (int)(th[m] >> 32);
             th[m] += dK[m];
-            bool near;
-            switch (wave) {
-                case SIGB_WAVE_SINE: near = gen_tile<SIGB_WAVE_SINE, VK>(w, dhi[m], guard, x); break;
-                case SIGB_WAVE_SQUARE: near = gen_tile<SIGB_WAVE_SQUARE, VK>(w, dhi[m], guard, x); break;
-                case SIGB_WAVE_SAWTOOTH: near = gen_tile<SIGB_WAVE_SAWTOOTH, VK>(w, dhi[m], guard, x); break;
-                default: near = gen_tile<SIGB_WAVE_TRIANGLE, VK>(w, dhi[m], guard, x); break;
-            }
-            if (near && chan[m] >= 0) {
-                // a sample within `guard` of a discontinuity: redo the tile with the reference's own
-                // float64 arithmetic (osc.py:32), so the jump lands on the same sample as in numpy
-                const double hz = sg.hertz[chan[m]], ph = sg.phase[chan[m]];
-                for (int k = 0; k < VK; ++k)
-                    x[k] = osc_wave(wave, osc_cycles(__ddiv_rn((double)(a.position + n0 + k), rate), hz, ph));
-            }
-            switch (fk) {
-                case 0: filt_tile<0>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
-                case SEC_HP: filt_tile<SEC_HP>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
-                case SEC_FIRST_ORDER: filt_tile<SEC_FIRST_ORDER>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
-                case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP>(x, g[m], cf[m], d[m], s1[m], s2[m], kmax); break;
-                default: break;
-            }
-#pragma unroll
-            for (int k = 0; k < VK; ++k) acc[k] = __ffma2_rn(wt[m], make_float2(x[k], x[k]), acc[k]);
         }
-        // CTA reduction in a fixed order: 16 rows x 256 threads -> 16 float2
+        unsigned near;
+        switch (wave) {
+            case SIGB_WAVE_SINE: near = gen_tiles<SIGB_WAVE_SINE, M, VK>(w, dhi, guard, x); break;
+            case SIGB_WAVE_SQUARE: near = gen_tiles<SIGB_WAVE_SQUARE, M, VK>(w, dhi, guard, x); break;
+            case SIGB_WAVE_SAWTOOTH: near = gen_tiles<SIGB_WAVE_SAWTOOTH, M, VK>(w, dhi, guard, x); break;
+            default: near = gen_tiles<SIGB_WAVE_TRIANGLE, M, VK>(w, dhi, guard, x); break;
+        }
+        if (near) {
+            // a sample within `guard` of a discontinuity: redo that voice's tile with the reference's own
+            // float64 arithmetic (osc.py:32), so the jump lands on the same sample as in numpy
 #pragma unroll
-        for (int k = 0; k < VK; ++k) red[k * VT + tid] = acc[k];
+            for (int m = 0; m < M; ++m) {
+                if (((near >> m) & 1u) && chan[m] >= 0) {
+                    const double hz = sg.hertz[chan[m]], ph = sg.phase[chan[m]];
+#pragma unroll
+                    for (int k = 0; k < VK; ++k)
+                        x[m][k] = osc_wave(wave, osc_cycles(__ddiv_rn((double)(a.position + n0 + k), rate), hz, ph));
+                }
+            }
+        }
+        switch (fk) {
+            case 0: filt_tile<0, M, VK>(x, g, cf, d, s1, s2, kmax); break;
+            case SEC_HP: filt_tile<SEC_HP, M, VK>(x, g, cf, d, s1, s2, kmax); break;
+            case SEC_FIRST_ORDER: filt_tile<SEC_FIRST_ORDER, M, VK>(x, g, cf, d, s1, s2, kmax); break;
+            case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP, M, VK>(x, g, cf, d, s1, s2, kmax); break;
+            default: break;
+        }
+        // CTA reduction in a fixed order: VK rows x 256 threads -> VK float2
+#pragma unroll
+        for (int k = 0; k < VK; ++k) {
+            float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int m = 0; m < M; ++m) acc = __ffma2_rn(wt[m], make_float2(x[m][k], x[m][k]), acc);
+            red[k * VT + tid] = acc;
+        }
         __syncthreads();
         {
-            const int k = tid >> 4, part = tid & 15;
+            const int k = tid / PARTS, part = tid % PARTS;
             float2 s = make_float2(0.0f, 0.0f);
 #pragma unroll
-            for (int i = 0; i < VT / 16; ++i) s = __fadd2_rn(s, red[k * VT + i * 16 + part]);
+            for (int i = 0; i < VT / PARTS; ++i) s = __fadd2_rn(s, red[k * VT + i * PARTS + part]);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = PARTS / 2; o > 0; o >>= 1) {
                 s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
                 s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
             }
@@ -252,8 +277,8 @@ extern "C" int sigb_voices_ctas(int channels, int M) { return (channels + VT * M
 
 extern "C" int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream) {
     if (a->frames <= 0 || nparts <= 0) return 0;
-    if (a->M == 4) k_voices<4><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
-    else k_voices<1><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
+    if (a->M == 4) k_voices<4, 8><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
+    else k_voices<1, 16><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 

@@ -357,7 +357,7 @@ __device__ __forceinline__ void svf2_block(int kind, const SecPar& c, float2 (&v
     else svf2_first_order<H, true>(c, v, s1);
 }
 
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool PIPE = false>
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, int PIPE = 0>
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
@@ -907,7 +907,7 @@ cudaError_t launch_scan_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     }
 }
 
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool PIPE = false>
+template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, int PIPE = 0>
 cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;
@@ -946,7 +946,7 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     return cudaGetLastError();
 }
 
-template <int NSEC, int NG, int WG, bool PIPE = false>
+template <int NSEC, int NG, int WG, int PIPE = 0>
 cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const bool fast = a.src_kind == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
     switch (a.src_kind) {
@@ -971,9 +971,6 @@ static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
             case 7: *ng = 5; *wg = 6; break;
             case 8: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;     // single section: software-pipelined workers
             case 9: *ng = (nsec == 1 ? 3 : 5); *wg = 8; break;
-            case 10: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;
-            case 11: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 12 : 6); break;
-            case 12: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 10 : 6); break;
             default: *ng = 4; *wg = 7; break;
         }
         return;
@@ -1024,11 +1021,8 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
         if (a->nsec == 1) return (int)launch_scan2_n<1, NG, WG>(*a, st, rows_done);   \
         return (int)launch_scan2_n<2, NG, WG>(*a, st, rows_done);                     \
     } while (0)
-        if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, true>(*a, st, rows_done);
-        if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, true>(*a, st, rows_done);
-        if (variant == 10 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 9, true>(*a, st, rows_done);
-        if (variant == 11 && a->nsec == 1) return (int)launch_scan2_n<1, 2, 12, true>(*a, st, rows_done);
-        if (variant == 12 && a->nsec == 1) return (int)launch_scan2_n<1, 2, 10, true>(*a, st, rows_done);
+        if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, 1>(*a, st, rows_done);
+        if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, 1>(*a, st, rows_done);
         if (ng == 7) SCAN2_DISPATCH(7, 4);
         if (ng == 2) SCAN2_DISPATCH(2, 15);
         if (ng == 5) SCAN2_DISPATCH(5, 6);

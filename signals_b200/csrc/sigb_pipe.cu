@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "sigb200.h"
 #include "sigb_internal.h"
@@ -322,7 +323,8 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         float* const ring_last = ring + (size_t)nslot * CHUNK_FLOATS;
         int c = c_first - w;                              // this warp's chunk at iteration t
         const int iters = (c_end - c_first) + nsec;       // one extra iteration drains the last chunk
-        for (int t = 0; t < iters; ++t, ++c) {
+        // one generic iteration: every path (ragged rows, slow granules, idle warps at the pipeline's ends)
+        auto iteration = [&](int t) {
             if (BUF) {
                 issue_chunk();                   // chunk c_first + t + PRE
                 cp_async_wait<PRE>();            // this thread's granules of chunk c_first + t have landed
@@ -340,7 +342,62 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
                 if (src_slot == ring_last) src_slot = ring;
                 pipe_source_chunk(a, tile, c_first + t + 1, lane, src_slot);
             }
+            ++c;
+        };
+        // Steady state [t_lo, t_hi): every warp holds a full chunk, the chunk being issued takes the cp.async
+        // fast path and the chunk being drained is a stored, full one -- a branch-free body with the section
+        // kind resolved outside the loop.
+        int t_lo = iters, t_hi = iters;
+        const bool tile_in = (tile + 1) * PC <= a.C;                        // CTA-uniform: no ragged channels in this tile
+        if (BUF && gpt == 1 && src_fast && out_fast && tile_in) {
+            const int full_end = min(c_end, a.frames / PR);                 // chunks with all PR rows
+            t_lo = max(nsec, (c_store - c_first) + nsec);
+            t_hi = min(fast_end - c_first - PRE, full_end - c_first);
+            if (t_hi <= t_lo) t_lo = t_hi = iters;
         }
+        int t = 0;
+        for (; t < t_lo && t < iters; ++t) iteration(t);
+        if (t_lo < t_hi) {
+            auto steady = [&](auto kind_tag) {
+                constexpr int KIND = decltype(kind_tag)::value;
+                unsigned my_addr = ring_base + (unsigned)(my_slot - ring) * 4u;
+                for (; t < t_hi; ++t) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off), "l"(g_src) : "memory");
+                    cp_async_commit();
+                    g_src += src_step;
+                    issue_addr += CHUNK_FLOATS * 4u;
+                    if (issue_addr == ring_end) issue_addr = ring_base;
+                    cp_async_wait<PRE>();
+                    __syncthreads();
+                    {
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off) : "memory");
+                        v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
+                        __stcs(reinterpret_cast<float4*>(g_dst), v);
+                        g_dst += dst_step;
+                        drain_addr += CHUNK_FLOATS * 4u;
+                        if (drain_addr == ring_end) drain_addr = ring_base;
+                    }
+                    if (w < nsec) {
+                        pipe_chunk<KIND>(ring + (my_addr - ring_base) / 4u, PR, lane, r);
+                        my_addr += CHUNK_FLOATS * 4u;
+                        if (my_addr == ring_end) my_addr = ring_base;
+                    }
+                }
+                const int done = t_hi - t_lo;
+                issue_c += done;
+                drain_c += done;
+                c += done;
+                my_slot = ring + (my_addr - ring_base) / 4u;
+            };
+            switch (kind) {
+                case 0: steady(std::integral_constant<int, 0>{}); break;
+                case SEC_HP: steady(std::integral_constant<int, SEC_HP>{}); break;
+                case SEC_FIRST_ORDER: steady(std::integral_constant<int, SEC_FIRST_ORDER>{}); break;
+                default: steady(std::integral_constant<int, SEC_FIRST_ORDER | SEC_HP>{}); break;
+            }
+        }
+        for (; t < iters; ++t) iteration(t);
         if (BUF) cp_async_wait<0>();
         if (w < nsec && c_end == nchunks) {       // the segment that finishes the launch carries the state on
             if (live0) {

@@ -55,7 +55,7 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
     the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""
-    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(scan_variant=int(mode[-1]), cascade_pipe=0)
+    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(scan_variant=int(mode[4:]), cascade_pipe=0)
     got = render_case(engine, ns, case, **opts)[::case.stride]
     err = max_abs_err(got, load_golden(case.name))
     assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
