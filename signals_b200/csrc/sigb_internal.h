@@ -131,7 +131,7 @@ int sigb_launch_chain_seq(const ChainDev* a, void* stream);
 int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stream, int* rows_done);
 int sigb_cascade_pipe_ok(const ChainDev* a);
 int sigb_cascade_pipe_items(const ChainDev* a, int max_segments);
-int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, void* stream);
+int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, int sections_per_warp, void* stream);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);

@@ -34,7 +34,7 @@ using namespace sigb_dev;
 
 constexpr int PR = 16;          // rows per chunk
 constexpr int PC = 64;          // channels per tile (2 per lane)
-constexpr int PRE = 3;          // cp.async chunks in flight per CTA (3 x 4 KB; 4 CTAs per SM at 8 sections)
+__host__ __device__ constexpr int pre_chunks(int spw) { return spw == 2 ? 2 : 3; }   // cp.async chunks in flight per CTA (4 KB each)
 constexpr int CHUNK_FLOATS = PR * PC;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -97,10 +97,12 @@ __device__ __forceinline__ float2 pipe_step(float2 x, SecReg& r) {
 #endif
 }
 
-// one chunk of one section, in place in the shared-memory slot (a lane owns its two channels of every
-// row, so there is no cross-thread hazard inside a section)
-template <int KIND>
-__device__ __forceinline__ void pipe_chunk(float* __restrict__ slot, int rows, int lane, SecReg& r) {
+// one chunk through SPW consecutive sections of the same kind, in place in the shared-memory slot (a lane owns
+// its two channels of every row, so there is no cross-thread hazard inside a stage).  Two sections per warp
+// halve the shared-memory traffic of the pipeline (the binding resource at one section per warp) and give the
+// scheduler two dependency chains to overlap.
+template <int KIND, int SPW>
+__device__ __forceinline__ void pipe_chunk(float* __restrict__ slot, int rows, int lane, SecReg (&r)[2]) {
     float2* __restrict__ p = reinterpret_cast<float2*>(slot) + lane;
     if (rows == PR) {
         constexpr int HR = PR / 2;                 // two half-chunks of 8 rows keep the kernel at 64 registers
@@ -110,22 +112,29 @@ __device__ __forceinline__ void pipe_chunk(float* __restrict__ slot, int rows, i
 #pragma unroll
             for (int k = 0; k < HR; ++k) x[k] = p[(h * HR + k) * (PC / 2)];
 #pragma unroll
-            for (int k = 0; k < HR; ++k) x[k] = pipe_step<KIND>(x[k], r);
+            for (int k = 0; k < HR; ++k) {
+                x[k] = pipe_step<KIND>(x[k], r[0]);
+                if (SPW == 2) x[k] = pipe_step<KIND>(x[k], r[1]);
+            }
 #pragma unroll
             for (int k = 0; k < HR; ++k) p[(h * HR + k) * (PC / 2)] = x[k];
         }
     } else {
-        for (int k = 0; k < rows; ++k)       // ragged last chunk: state must stop at the last real row
-            p[k * (PC / 2)] = pipe_step<KIND>(p[k * (PC / 2)], r);
+        for (int k = 0; k < rows; ++k) {     // ragged last chunk: state must stop at the last real row
+            float2 y = pipe_step<KIND>(p[k * (PC / 2)], r[0]);
+            if (SPW == 2) y = pipe_step<KIND>(y, r[1]);
+            p[k * (PC / 2)] = y;
+        }
     }
 }
 
-__device__ __forceinline__ void pipe_chunk_kind(int kind, float* slot, int rows, int lane, SecReg& r) {
+template <int SPW>
+__device__ __forceinline__ void pipe_chunk_kind(int kind, float* slot, int rows, int lane, SecReg (&r)[2]) {
     switch (kind) {
-        case 0: pipe_chunk<0>(slot, rows, lane, r); break;
-        case SEC_HP: pipe_chunk<SEC_HP>(slot, rows, lane, r); break;
-        case SEC_FIRST_ORDER: pipe_chunk<SEC_FIRST_ORDER>(slot, rows, lane, r); break;
-        default: pipe_chunk<SEC_FIRST_ORDER | SEC_HP>(slot, rows, lane, r); break;
+        case 0: pipe_chunk<0, SPW>(slot, rows, lane, r); break;
+        case SEC_HP: pipe_chunk<SEC_HP, SPW>(slot, rows, lane, r); break;
+        case SEC_FIRST_ORDER: pipe_chunk<SEC_FIRST_ORDER, SPW>(slot, rows, lane, r); break;
+        default: pipe_chunk<SEC_FIRST_ORDER | SEC_HP, SPW>(slot, rows, lane, r); break;
     }
 }
 
@@ -183,12 +192,13 @@ __device__ __forceinline__ void pipe_source_chunk(const ChainDev& a, int tile, i
 // Iteration t of an item:  every thread issues its 16-byte granule of source chunk t + PRE (cp.async) and
 // stores its granule of finished chunk t - nsec (x gain) to global memory; warp w filters chunk t - w in
 // place.  All section warps do identical work, so nobody waits at the barrier for a straggler.
-template <bool BUF>
-__global__ void __launch_bounds__(BUF ? 256 : 288, BUF ? 4 : 2)
+template <bool BUF, int SPW>
+__global__ void __launch_bounds__(BUF ? 256 : 288, BUF ? (SPW == 2 ? 3 : 4) : 2)
 k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunks, int warm_chunks, int nslot, int src_fast, int out_fast) {
     extern __shared__ __align__(16) float ring[];        // [nslot] chunks of (PR x PC); a chunk stays in its slot
                                                          // from its load until its rows have been stored
-    const int nsec = a.nsec;
+    constexpr int PRE = pre_chunks(SPW);
+    const int nsec = a.nsec / SPW;          // pipeline stages (warps): SPW sections each
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const size_t C = (size_t)a.C;
     const int nthreads = blockDim.x;
@@ -203,23 +213,28 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         const int c_first = max(0, c_store - (seg > 0 ? warm_chunks : 0));
         const int c0 = tile * PC + 2 * lane;
         const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
-        SecReg r;
-        r.nc = r.a2 = r.al = r.g = r.g2 = r.d = r.s1 = r.s2 = make_float2(0.0f, 0.0f);
+        SecReg r[2];
         int kind = 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) r[j].nc = r[j].a2 = r[j].al = r[j].g = r[j].g2 = r[j].d = r[j].s1 = r[j].s2 = make_float2(0.0f, 0.0f);
         if (w < nsec) {
             const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
-            kind = a.sec_kind[w];
-            const float ga = a.coef[(size_t)(w * 3 + 0) * C + ca], gb = a.coef[(size_t)(w * 3 + 0) * C + cb];
-            const float da = a.coef[(size_t)(w * 3 + 2) * C + ca], db = a.coef[(size_t)(w * 3 + 2) * C + cb];
-            r.g = make_float2(ga, gb);
-            r.g2 = make_float2(2.0f * ga, 2.0f * gb);
-            r.nc = make_float2(-a.coef[(size_t)(w * 3 + 1) * C + ca], -a.coef[(size_t)(w * 3 + 1) * C + cb]);
-            r.d = make_float2(da, db);
-            r.al = make_float2(ga * da, gb * db);
-            r.a2 = make_float2(2.0f * (ga * da), 2.0f * (gb * db));
-            if (c_first == 0) {
-                r.s1 = make_float2((float)a.state[(size_t)(w * 2 + 0) * C + ca], (float)a.state[(size_t)(w * 2 + 0) * C + cb]);
-                r.s2 = make_float2((float)a.state[(size_t)(w * 2 + 1) * C + ca], (float)a.state[(size_t)(w * 2 + 1) * C + cb]);
+            kind = a.sec_kind[w * SPW];
+#pragma unroll
+            for (int j = 0; j < SPW; ++j) {
+                const int sx = w * SPW + j;
+                const float ga = a.coef[(size_t)(sx * 3 + 0) * C + ca], gb = a.coef[(size_t)(sx * 3 + 0) * C + cb];
+                const float da = a.coef[(size_t)(sx * 3 + 2) * C + ca], db = a.coef[(size_t)(sx * 3 + 2) * C + cb];
+                r[j].g = make_float2(ga, gb);
+                r[j].g2 = make_float2(2.0f * ga, 2.0f * gb);
+                r[j].nc = make_float2(-a.coef[(size_t)(sx * 3 + 1) * C + ca], -a.coef[(size_t)(sx * 3 + 1) * C + cb]);
+                r[j].d = make_float2(da, db);
+                r[j].al = make_float2(ga * da, gb * db);
+                r[j].a2 = make_float2(2.0f * (ga * da), 2.0f * (gb * db));
+                if (c_first == 0) {
+                    r[j].s1 = make_float2((float)a.state[(size_t)(sx * 2 + 0) * C + ca], (float)a.state[(size_t)(sx * 2 + 0) * C + cb]);
+                    r[j].s2 = make_float2((float)a.state[(size_t)(sx * 2 + 1) * C + ca], (float)a.state[(size_t)(sx * 2 + 1) * C + cb]);
+                }
             }
         }
 
@@ -333,7 +348,7 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
             drain_chunk();                       // chunk c_first + t - nsec: every section finished it last iteration
             if (w < nsec) {
                 if (c >= c_first && c < c_end) {
-                    pipe_chunk_kind(kind, my_slot, min(PR, a.frames - c * PR), lane, r);
+                    pipe_chunk_kind<SPW>(kind, my_slot, min(PR, a.frames - c * PR), lane, r);
                     my_slot += CHUNK_FLOATS;
                     if (my_slot == ring_last) my_slot = ring;
                 }
@@ -349,7 +364,7 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         // kind resolved outside the loop.
         int t_lo = iters, t_hi = iters;
         const bool tile_in = (tile + 1) * PC <= a.C;                        // CTA-uniform: no ragged channels in this tile
-        if (BUF && gpt == 1 && src_fast && out_fast && tile_in) {
+        if (BUF && gpt >= 1 && src_fast && out_fast && tile_in) {
             const int full_end = min(c_end, a.frames / PR);                 // chunks with all PR rows
             t_lo = max(nsec, (c_store - c_first) + nsec);
             t_hi = min(fast_end - c_first - PRE, full_end - c_first);
@@ -362,24 +377,25 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
                 constexpr int KIND = decltype(kind_tag)::value;
                 unsigned my_addr = ring_base + (unsigned)(my_slot - ring) * 4u;
                 for (; t < t_hi; ++t) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off), "l"(g_src) : "memory");
+                    for (int j = 0; j < gpt; ++j)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off + j * row_skip_smem), "l"(g_src + j * row_skip_src) : "memory");
                     cp_async_commit();
                     g_src += src_step;
                     issue_addr += CHUNK_FLOATS * 4u;
                     if (issue_addr == ring_end) issue_addr = ring_base;
                     cp_async_wait<PRE>();
                     __syncthreads();
-                    {
+                    for (int j = 0; j < gpt; ++j) {
                         float4 v;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off) : "memory");
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off + j * row_skip_smem) : "memory");
                         v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
-                        __stcs(reinterpret_cast<float4*>(g_dst), v);
-                        g_dst += dst_step;
-                        drain_addr += CHUNK_FLOATS * 4u;
-                        if (drain_addr == ring_end) drain_addr = ring_base;
+                        __stcs(reinterpret_cast<float4*>(g_dst + j * row_skip_dst), v);
                     }
+                    g_dst += dst_step;
+                    drain_addr += CHUNK_FLOATS * 4u;
+                    if (drain_addr == ring_end) drain_addr = ring_base;
                     if (w < nsec) {
-                        pipe_chunk<KIND>(ring + (my_addr - ring_base) / 4u, PR, lane, r);
+                        pipe_chunk<KIND, SPW>(ring + (my_addr - ring_base) / 4u, PR, lane, r);
                         my_addr += CHUNK_FLOATS * 4u;
                         if (my_addr == ring_end) my_addr = ring_base;
                     }
@@ -400,13 +416,17 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         for (; t < iters; ++t) iteration(t);
         if (BUF) cp_async_wait<0>();
         if (w < nsec && c_end == nchunks) {       // the segment that finishes the launch carries the state on
-            if (live0) {
-                a.state_out[(size_t)(w * 2 + 0) * C + c0] = (double)r.s1.x;
-                a.state_out[(size_t)(w * 2 + 1) * C + c0] = (double)r.s2.x;
-            }
-            if (live1) {
-                a.state_out[(size_t)(w * 2 + 0) * C + c0 + 1] = (double)r.s1.y;
-                a.state_out[(size_t)(w * 2 + 1) * C + c0 + 1] = (double)r.s2.y;
+#pragma unroll
+            for (int j = 0; j < SPW; ++j) {
+                const int sx = w * SPW + j;
+                if (live0) {
+                    a.state_out[(size_t)(sx * 2 + 0) * C + c0] = (double)r[j].s1.x;
+                    a.state_out[(size_t)(sx * 2 + 1) * C + c0] = (double)r[j].s2.x;
+                }
+                if (live1) {
+                    a.state_out[(size_t)(sx * 2 + 0) * C + c0 + 1] = (double)r[j].s1.y;
+                    a.state_out[(size_t)(sx * 2 + 1) * C + c0 + 1] = (double)r[j].s2.y;
+                }
             }
         }
         __syncthreads();       // item boundary: the ring restarts
@@ -446,22 +466,30 @@ extern "C" int sigb_cascade_pipe_items(const ChainDev* a, int max_segments) {
     return tiles * nseg;
 }
 
-extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, void* stream) {
+extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, int sections_per_warp, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->frames <= 0) return 0;
     const int nchunks = (a->frames + PR - 1) / PR;
     const int tiles = (a->C + PC - 1) / PC;
     const bool buf = a->src_kind == SRC_BUF;
-    const int warps = a->nsec + (buf ? 0 : 1);
+    // two sections per warp when the cascade is an even number of sections of one kind
+    bool same = true;
+    for (int k = 1; k < a->nsec; ++k) same = same && a->sec_kind[k] == a->sec_kind[0];
+    // (measured on C4: 3.30e11 vs 3.35e11 channel-samples/s with one section per warp -- kept selectable)
+    const int spw = (sections_per_warp == 2 && a->nsec % 2 == 0 && same && !(a->sec_kind[0] & SEC_FIRST_ORDER)) ? 2 : 1;
+    const int nstage = a->nsec / spw;
+    const int warps = nstage + (buf ? 0 : 1);
     // a chunk occupies its slot while it is in flight (PRE), while each section works on it (nsec) and while
     // it is stored (1), plus one iteration of slack so a slot is never rewritten right after its last read
-    const int nslot = (buf ? PRE : 1) + a->nsec + 2;
+    const int nslot = (buf ? pre_chunks(spw) : 1) + nstage + 2;
     const size_t smem = (size_t)nslot * CHUNK_FLOATS * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        const int max_smem = (PRE + 8 + 2) * CHUNK_FLOATS * (int)sizeof(float);
-        cudaError_t e = cudaFuncSetAttribute(k_cascade_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cascade_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        const int max_smem = (3 + 8 + 2) * CHUNK_FLOATS * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(k_cascade_pipe<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cascade_pipe<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cascade_pipe<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cascade_pipe<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) return (int)e;
         attr_done = true;
     }
@@ -486,7 +514,9 @@ extern "C" int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, voi
     const long long items = (long long)tiles * nseg;
     const long long slots = (long long)sms * per_sm;
     const int grid = (int)(items < slots ? items : slots);
-    if (buf) k_cascade_pipe<true><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);
-    else k_cascade_pipe<false><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast);
+#define PIPE_LAUNCH(B, S) k_cascade_pipe<B, S><<<grid, warps * 32, smem, st>>>(*a, nchunks, tiles, nseg, seg_chunks, warm_chunks, nslot, src_fast, out_fast)
+    if (buf) { if (spw == 2) PIPE_LAUNCH(true, 2); else PIPE_LAUNCH(true, 1); }
+    else { if (spw == 2) PIPE_LAUNCH(false, 2); else PIPE_LAUNCH(false, 1); }
+#undef PIPE_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -163,6 +163,7 @@ struct sigb_plan {
     int64_t opt_host_slab_bytes = 64ll << 20;
     int64_t opt_buffer_budget = 6ll << 30;
     int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
+    int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
@@ -922,7 +923,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 const bool forced = p->opt_cascade_pipe > 0 && ch.nsec_real >= (int)p->opt_cascade_pipe;
                 if (sigb_cascade_pipe_ok(&t) &&
                     (deep || forced)) {
-                    int e = sigb_launch_cascade_pipe(&t, (int)p->opt_pipe_segments, st);
+                    int e = sigb_launch_cascade_pipe(&t, (int)p->opt_pipe_segments, (int)p->opt_pipe_spw, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_cascade_pipe: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;
                     ch.state_cur ^= 1;           // the kernel wrote the other copy of the state
@@ -1387,6 +1388,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "buffer_budget") plan->opt_buffer_budget = value;
     else if (k == "cascade_pipe") plan->opt_cascade_pipe = value;
     else if (k == "pipe_segments") plan->opt_pipe_segments = value;
+    else if (k == "pipe_spw") plan->opt_pipe_spw = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);

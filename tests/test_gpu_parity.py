@@ -51,11 +51,11 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'pipe'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'pipe', 'pipe2'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
     the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""
-    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(scan_variant=int(mode[4:]), cascade_pipe=0)
+    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(cascade_pipe=1, pipe_spw=2) if mode == 'pipe2' else dict(scan_variant=int(mode[4:]), cascade_pipe=0)
     got = render_case(engine, ns, case, **opts)[::case.stride]
     err = max_abs_err(got, load_golden(case.name))
     assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
@@ -545,3 +545,45 @@ def test_full_size_instances_properties(ns, engine):
     err = max_abs_err(got, want)
     print(f'C5 full size, 64 live voices of 1M: max-abs {err:.3e} (mix peak {np.abs(want).max():.3f})')
     assert err <= 1e-6
+
+
+@pytest.mark.parametrize('name', ['sine_basic', 'square_edges', 'lowpass_c2_8v', 'highpass_order3', 'cascade8', 'mix', 'fanout'])
+@pytest.mark.parametrize('frames', [1, 17, 1000])
+def test_renders_stay_inside_their_block(name, frames, ns, engine):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are caught with canaries: the block
+    is a window (rows 3.., columns ..C) of a larger tensor whose every other element must stay untouched;
+    also covers ragged row counts (1, 17) through every kernel family."""
+    torch = _torch()
+    case = cases.CASES_BY_NAME[name]
+    c = case.channels
+    big = torch.full((frames + 8, c + 5), -777.0, dtype=torch.float32, device='cuda')
+    window = big[3:3 + frames, :c]
+    compiled = engine.compile(case.build(ns), c, case.rate, frames)
+    compiled.render_device(case.position, frames, window)
+    compiled.close()
+    host = big.cpu().numpy()
+    inside = host[3:3 + frames, :c].copy()
+    host[3:3 + frames, :c] = -777.0
+    assert (host == -777.0).all(), 'a kernel wrote outside its (frames, channels) block'
+    assert not (inside == -777.0).any()
+    want = load_golden(name)
+    if case.stride == 1 and frames <= len(want):
+        err = max_abs_err(inside[np.isfinite(want[:frames]).all(1)], want[:frames][np.isfinite(want[:frames]).all(1)])
+        assert err <= case.tol, err
+
+
+def test_fused_reductions_stay_inside_their_block(ns, engine):
+    from signals_b200.chain import ext
+    torch = _torch()
+    hertz, phase, amp = cases.bank_params(3, 300, 100)
+    prm = cases.instance_params(5, 500)
+    for graph, c in ((cases.build_bank(ns, ext, hertz, phase, amp, 3), 3), (cases.build_instances(ns, ext, prm), 2)):
+        for frames in (1, 9, 700):
+            big = torch.full((frames + 8, c + 5), -777.0, dtype=torch.float32, device='cuda')
+            compiled = engine.compile(graph, c, RATE)
+            compiled.render_device(5, frames, big[3:3 + frames, :c])
+            compiled.close()
+            host = big.cpu().numpy()
+            assert not (host[3:3 + frames, :c] == -777.0).any()
+            host[3:3 + frames, :c] = -777.0
+            assert (host == -777.0).all()
