@@ -88,6 +88,8 @@ class Case:
     # 'exact-edges': discontinuous waveform; samples must agree except none (bit-faithful fp64 phase)
     stride: int = 1          # golden stores out[::stride] (long renders)
     note: str = ''
+    block: int = 0           # > 0: rendered as consecutive requests of `block` frames (block-rate parameters are
+                             # re-sampled at the first frame of every request, chain/__init__.py:305-306)
 
 
 def voice_params(seed: int, v: int):
@@ -184,6 +186,54 @@ def _fanout(ns):
     return m
 
 
+def _lfo(ns, wave, hertz, phase=None):
+    return osc(ns, wave, hertz, phase)
+
+
+def _lfo_gain(ns):
+    # tremolo: Gain.right driven by a 2.5 Hz sine (two channels, different LFO phases)
+    g = ns.Gain()
+    g.left = osc(ns, 'Sine', [[440.0, 661.5]])
+    g.right = _lfo(ns, 'Sine', [[2.5, 3.25]], [[0.1, 0.6]])
+    return g
+
+
+def _lfo_hertz(ns):
+    # vibrato: hertz = Mix(880, 220, mix = sawtooth LFO) -- the oscillator's frequency is sampled per request
+    m = ns.Mix()
+    m.left = fixed(ns, [[880.0, 660.0]])
+    m.right = fixed(ns, [[220.0, 330.0]])
+    m.mix = _lfo(ns, 'Sawtooth', [[0.7]], [[0.2]])
+    o = ns.Sine()
+    o.hertz = m
+    o.phase = gain(ns, _lfo(ns, 'Triangle', [[1.3, 0.9]]), [[0.25, 0.5]])
+    return o
+
+
+def _lfo_mix_amp(ns):
+    # crossfade driven by a square LFO scaled into [0.25, 0.75], then Amp with a modulated exponent
+    m = ns.Mix()
+    m.left = osc(ns, 'Sine', [[300.0, 450.0]])
+    m.right = osc(ns, 'Triangle', [[200.0, 150.0]])
+    mx = ns.Mix()
+    mx.left = fixed(ns, [[0.75]])
+    mx.right = fixed(ns, [[0.25]])
+    mx.mix = gain(ns, _lfo(ns, 'Square', [[1.0]], [[0.1]]), [[0.5]])      # -> 0.5 +- ... stays a valid crossfade weight
+    m.mix = mx
+    a = ns.Amp()
+    a.left = m
+    a.right = gain(ns, _lfo(ns, 'Sine', [[0.5]], [[0.25]]), [[2.0]])       # exponent = 2 sin(...) at the request's first frame
+    return a
+
+
+def _lfo_chain(ns):
+    # modulated gain in front of a filter: the Gain cannot fold into the chain, the filter still fuses with its tail
+    g = ns.Gain()
+    g.left = osc(ns, 'Sawtooth', [[220.0, 331.0]])
+    g.right = _lfo(ns, 'Sine', [[4.0]], [[0.3]])
+    return gain(ns, lowpass(ns, g, [[900.0, 2500.0]]), [[0.5, 0.25]])
+
+
 CASES: list[Case] = [
     Case('sine_basic', lambda ns: osc(ns, 'Sine', [[440.0, 1000.0, 27.5, 4186.0]], [[0.0, 0.1, 0.5, 0.9]]), 4800, 4),
     Case('sine_pos1', lambda ns: osc(ns, 'Sine', [[440.0, 12000.0]], [[0.0, 0.37]]), 1000, 2, position=1),
@@ -228,6 +278,15 @@ CASES: list[Case] = [
          24000, 2, tol=1e-4, note='odd order: one first-order section'),
     Case('cascade8', _cascade8, 48000, 4, tol=1e-4, note='config C4 shape: 8 chained LowPass nodes'),
     Case('fanout', _fanout, 4800, 4, tol=1e-4),
+    Case('lfo_gain', _lfo_gain, 2400, 2, position=12345, note='Gain.right driven by an oscillator (block-rate port, fx.py:52)'),
+    Case('lfo_hertz', _lfo_hertz, 2400, 2, position=3 * RATE + 7, tol=2e-6,
+         note='Osc.hertz / Osc.phase driven by emitters (osc.py:28-30); phase ~ 100 cycles at this position'),
+    Case('lfo_mix_amp', _lfo_mix_amp, 2400, 2, position=777, note='Mix.mix and Amp.right modulated (fx.py:39, 59)'),
+    Case('lfo_chain', _lfo_chain, 4800, 2, tol=1e-4, note='modulated Gain feeding a LowPass'),
+    Case('lfo_blockwise', _lfo_gain, 4096, 2, position=1000, block=512,
+         note='8 requests of 512 frames: the LFO is re-sampled at the first frame of each'),
+    Case('lfo_hertz_blockwise', _lfo_hertz, 2048, 2, position=9000, block=256, tol=2e-6,
+         note='per-request frequency: the phase jumps between requests exactly as in the reference'),
     Case('lowpass_60s', lambda ns: _c2(ns, 2, 60), 60 * RATE, 2, tol=1e-4, stride=1009,
          note='cascaded-IIR-over-60-s budget; golden keeps every 1009th frame'),
     Case('cascade8_60s', lambda ns: _cascade8(ns, 2, 61), 60 * RATE, 2, tol=1e-4, stride=1009),

@@ -30,11 +30,18 @@ def main(names=None):
     for case in cases.CASES:
         if names and case.name not in names:
             continue
-        out = ref_harness.render(ref, case.build(ns), case.position, case.frames, case.channels, case.rate)
+        graph = case.build(ns)
+        if case.block:
+            parts = [ref_harness.render(ref, graph, case.position + r, min(case.block, case.frames - r), case.channels, case.rate)
+                     for r in range(0, case.frames, case.block)]
+            out = np.concatenate([np.broadcast_to(b, (min(case.block, case.frames - r), case.channels))
+                                  for b, r in zip(parts, range(0, case.frames, case.block))])
+        else:
+            out = ref_harness.render(ref, graph, case.position, case.frames, case.channels, case.rate)
         out = np.broadcast_to(out, (case.frames, case.channels))[::case.stride]
         np.savez_compressed(os.path.join(GOLDEN_DIR, f'{case.name}.npz'), out=np.ascontiguousarray(out))
         meta['cases'][case.name] = dict(position=case.position, frames=case.frames, channels=case.channels,
-                                        rate=case.rate, stride=case.stride, tol=case.tol, note=case.note,
+                                        rate=case.rate, stride=case.stride, tol=case.tol, note=case.note, block=case.block,
                                         absmax=float(np.nanmax(np.abs(out))))
         print(f'{case.name:24s} {out.shape} absmax={meta["cases"][case.name]["absmax"]:.6g}')
     errors = {}

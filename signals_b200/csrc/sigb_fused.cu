@@ -291,6 +291,59 @@ extern "C" int sigb_launch_voices_finish(const float* partial, int nparts, int f
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_param_eval: block-rate parameter graphs (an LFO on hertz / phase / gain / mix / exponent)
+//
+// The reference samples such parameters once per request, at the request's first frame, in float64
+// (forward_at_block_rate, chain/__init__.py:305-306; osc.py:28-30, fx.py:39,52,59).  One thread per
+// channel interprets the (tiny) program for its own channel in float64 -- width-1 rows are recomputed by
+// every thread, so there is no cross-thread dependency -- and publishes each row as float64 (oscillator
+// hertz / phase) and float32 (gain / mix / exponent).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ double osc_wave_f64(int wave, double cyc) {
+    switch (wave) {
+        case SIGB_WAVE_SINE: return sin(__dmul_rn(__dmul_rn(cyc, 2.0), 3.141592653589793));     // np.sin(t * 2 * np.pi), osc.py:43
+        case SIGB_WAVE_SQUARE: return np_sign(__dadd_rn(0.5, -np_mod<0>(cyc)));
+        case SIGB_WAVE_SAWTOOTH: return __dadd_rn(__dmul_rn(2.0, np_mod<0>(__dadd_rn(cyc, -0.5))), -1.0);
+        default: {
+            const double t = __dadd_rn(cyc, -0.25);
+            return __dmul_rn(__dadd_rn(__dmul_rn(4.0, np_mod<1>(t)), -1.0), np_sign(__dadd_rn(np_mod<0>(t), -0.5)));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_param_eval(const ParamInstr* __restrict__ prog, int n_instr, int n_rows, double* drows,
+                                                    float* frows, int row_stride, int64_t position, int rate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= row_stride) return;
+    double v[SIGB_PARAM_ROWS];
+    for (int r = 0; r < n_rows; ++r) v[r] = drows[(size_t)r * row_stride + c];      // constants are preloaded (replicated)
+    const double tn = __ddiv_rn((double)position, (double)rate);
+    for (int i = 0; i < n_instr; ++i) {
+        const ParamInstr in = prog[i];
+        double y;
+        switch (in.op) {
+            case PRM_OSC: y = osc_wave_f64(in.wave, osc_cycles(tn, v[in.a], v[in.b])); break;               // osc.py:32
+            case PRM_MUL: y = __dmul_rn(v[in.a], v[in.b]); break;                                             // fx.py:46, 52
+            case PRM_MIX: y = __dadd_rn(__dmul_rn(v[in.c], v[in.a]), __dmul_rn(__dadd_rn(1.0, -v[in.c]), v[in.b])); break;   // fx.py:40
+            case PRM_AMP: y = copysign(pow(v[in.a], v[in.b]), v[in.a]); break;                                // fx.py:60
+            default: y = v[in.a]; break;
+        }
+        v[in.dst] = y;
+        drows[(size_t)in.dst * row_stride + c] = y;
+        frows[(size_t)in.dst * row_stride + c] = (float)y;
+    }
+}
+}  // namespace
+
+extern "C" int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, double* drows, float* frows, int row_stride,
+                                      int64_t position, int rate, void* stream) {
+    if (n_instr <= 0) return 0;
+    k_param_eval<<<(row_stride + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prog_dev, n_instr, n_rows, drows, frows, row_stride, position, rate);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // probe: write-only streaming fill (the practical HBM ceiling of a store-only kernel such as C2's)
 // ---------------------------------------------------------------------------------------------
 namespace {

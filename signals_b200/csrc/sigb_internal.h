@@ -109,6 +109,19 @@ struct VoiceSeg {
     double* state;                      // [(k)*C + c]
 };
 
+// Block-rate parameter program (modulated parameters): evaluated in float64 for ONE frame per request, at the
+// request's position, before the block is rendered (BoundPort.forward_at_block_rate, chain/__init__.py:305-306).
+enum { PRM_OSC = 1, PRM_MUL = 2, PRM_MIX = 3, PRM_AMP = 4, PRM_COPY = 5 };
+struct ParamInstr {
+    int32_t op;        // PRM_*
+    int32_t wave;      // PRM_OSC: SIGB_WAVE_*
+    int32_t dst;       // row written
+    int32_t a, b, c;   // operand rows (OSC: hertz, phase; MUL: left, right; MIX: left, right, mix; AMP: left, exp)
+    int32_t width;     // channels of dst (operands are 1 or `width` wide)
+    int32_t wa, wb, wc;
+};
+#define SIGB_PARAM_ROWS 96              // rows per parameter program (values live in a per-thread array)
+
 #define SIGB_VOICE_SEGS 24              // segments per k_voices launch
 #define SIGB_VOICE_K 16                 // rows per tile
 #define SIGB_VOICE_THREADS 256
@@ -141,6 +154,8 @@ int sigb_launch_bank(const BankDev* a, void* stream);
 int sigb_voices_ctas(int channels, int M);                         // CTAs (= partials) a segment of `channels` needs
 int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream);
 int sigb_launch_voices_finish(const float* partial, int nparts, int frames, float* out, int64_t ld_out, void* stream);
+int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, double* drows, float* frows, int row_stride,
+                           int64_t position, int rate, void* stream);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

@@ -84,6 +84,7 @@ struct ChainSpec {
     int state_cur = 0;           // which copy of the state arena holds the live state
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     int dst_node = -1;
+    int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
     std::vector<double> gain_d;  // folded gain in float64 (fused reductions derive their weights from it)
     bool has_gain = false;
     double max_abs_hertz = 0.0, max_abs_phase = 0.0;   // SRC_OSC: sizes the phase-word guard band
@@ -94,6 +95,7 @@ struct EwiseSpec {
     int C = 0;
     int a_node = -1, b_node = -1;   // -1 = zeros(1,1)
     Table p;
+    int p_row = -1;                 // modulated parameter: row of the block-rate parameter program instead of `p`
     int dst_node = -1;
     int dst_coff = 0;
 };
@@ -148,6 +150,15 @@ struct sigb_plan {
     std::vector<BankSpec> banks;
     std::vector<VoicesSpec> voices;
     std::vector<Launch> launches;
+    // block-rate parameter program (modulated parameters), evaluated once per request at its position
+    std::vector<ParamInstr> pprog;
+    std::vector<std::vector<double>> prow_const;   // per row: constant values (empty: computed row)
+    std::vector<int> prow_width;                   // natural channel count of the row's node
+    std::vector<int> pnode_row;                    // node -> row (-1: not in the program)
+    int pwidth = 1;                                // row stride = widest consumer
+    ParamInstr* d_pprog = nullptr;
+    double* d_prow_d = nullptr;
+    float* d_prow_f = nullptr;
     std::vector<unsigned char> arena;   // host image of all parameter tables
     unsigned char* d_arena = nullptr;
     int64_t n_state = 0;
@@ -275,6 +286,9 @@ struct Builder {
     int node_C(int i) const { return i == p->root ? p->channels : p->nodes[i].channels; }
 
     int ensure(int i);            // materialise node i's value (emits launches); returns status
+    int param_row(int idx, int* row);          // value of node idx in the block-rate parameter program
+    int param_port(int idx, int C, int* row);  // ... checked against a consumer of C channels
+    bool gain_is_const(int i) const { return p->nodes[i].kind != SIGB_NODE_GAIN || const_of(p, p->nodes[i].in[1]) != nullptr; }
     int build_chain(int i);
     int make_chain(int i, ChainSpec& ch, bool scan_tables);
     bool pure_osc_run(int i, int* nsec, int* wave) const;
@@ -293,13 +307,76 @@ struct Builder {
     }
 };
 
+int Builder::param_row(int idx, int* row) {
+    if (p->pnode_row.empty()) p->pnode_row.assign(p->nodes.size() + 1, -1);
+    const size_t slot = idx < 0 ? p->nodes.size() : (size_t)idx;       // the shared zeros(1,1) of unconnected ports
+    if (p->pnode_row[slot] >= 0) {
+        *row = p->pnode_row[slot];
+        return SIGB_OK;
+    }
+    if ((int)p->prow_const.size() >= SIGB_PARAM_ROWS)
+        return fail(SIGB_EUNSUPPORTED, "block-rate parameter graph larger than " + std::to_string(SIGB_PARAM_ROWS) + " nodes");
+    const std::vector<double>* cv = const_of(p, idx);
+    auto new_row = [&](int width) {
+        p->prow_const.emplace_back();
+        p->prow_width.push_back(width);
+        return (int)p->prow_const.size() - 1;
+    };
+    if (cv) {
+        const int r = new_row((int)cv->size());
+        p->prow_const[r] = *cv;
+        p->pnode_row[slot] = *row = r;
+        return SIGB_OK;
+    }
+    const sigb_node& n = p->nodes[idx];
+    ParamInstr in;
+    std::memset(&in, 0, sizeof(in));
+    int nops = 0;
+    switch (n.kind) {
+        case SIGB_NODE_OSC: in.op = PRM_OSC; in.wave = n.subtype; nops = 2; break;     // hertz, phase
+        case SIGB_NODE_GAIN: case SIGB_NODE_RINGMOD: in.op = PRM_MUL; nops = 2; break;
+        case SIGB_NODE_MIX: in.op = PRM_MIX; nops = 3; break;                           // left, right, mix
+        case SIGB_NODE_AMP: in.op = PRM_AMP; nops = 2; break;
+        default:
+            return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(idx) + ": this node kind cannot drive a block-rate parameter "
+                        "(supported: Fixed, oscillators, Gain, Mix, RingMod, Amp)");
+    }
+    int rows[3] = {0, 0, 0}, width = 1;
+    for (int k = 0; k < nops; ++k) {
+        int st = param_row(n.in[k], &rows[k]);
+        if (st != SIGB_OK) return st;
+        const int w = p->prow_width[rows[k]];
+        if (w != 1 && width != 1 && w != width)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(idx) + ": parameter operands of " + std::to_string(w) + " and " + std::to_string(width) + " channels");
+        width = std::max(width, w);
+    }
+    in.a = rows[0]; in.b = rows[1]; in.c = rows[2];
+    in.dst = new_row(width);
+    in.width = width;
+    p->pprog.push_back(in);
+    p->pnode_row[slot] = *row = in.dst;
+    return SIGB_OK;
+}
+
+int Builder::param_port(int idx, int C, int* row) {
+    int st = param_row(idx, row);
+    if (st != SIGB_OK) return st;
+    const int w = p->prow_width[*row];
+    if (w != 1 && w != C)
+        return fail(SIGB_ESHAPE, "node " + std::to_string(idx) + ": block-rate parameter with " + std::to_string(w) + " channels incompatible with " + std::to_string(C));
+    p->pwidth = std::max(p->pwidth, std::max(C, w));
+    return SIGB_OK;
+}
+
 int Builder::ensure(int i) {
     if (i < 0) return SIGB_OK;
     if (p->vals[i].kind != VK_NONE) return SIGB_OK;
     const sigb_node& n = p->nodes[i];
     switch (n.kind) {
-        case SIGB_NODE_OSC:
         case SIGB_NODE_GAIN:
+            if (!gain_is_const(i)) return build_ewise(i);      // modulated gain: not folded into a chain
+            return build_chain(i);
+        case SIGB_NODE_OSC:
         case SIGB_NODE_FILTER: return build_chain(i);
         case SIGB_NODE_MIX:
         case SIGB_NODE_RINGMOD:
@@ -344,8 +421,16 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
         if (n.kind == SIGB_NODE_OSC) {
             const std::vector<double>* hz = const_of(p, n.in[0]);
             const std::vector<double>* ph = const_of(p, n.in[1]);
-            if (!hz || !ph)
-                return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(cur) + ": oscillator hertz/phase driven by a non-constant emitter");
+            if (!hz || !ph) {
+                // modulated frequency / phase: sampled once per request in float64 by the parameter program
+                // (osc.py:28-30); the chain kernels then take their float64 waveform path
+                int st = param_port(n.in[0], C, &ch.hertz_row);
+                if (st == SIGB_OK) st = param_port(n.in[1], C, &ch.phase_row);
+                if (st != SIGB_OK) return st;
+                ch.src_kind = SRC_OSC;
+                ch.wave = n.subtype;
+                break;
+            }
             std::vector<double> hzv, phv;
             if (!rep(*hz, C, &hzv) || !rep(*ph, C, &phv))
                 return fail(SIGB_ESHAPE, "node " + std::to_string(cur) + ": hertz/phase channels incompatible with " + std::to_string(C));
@@ -392,7 +477,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
             break;
         }
         const sigb_node& u = p->nodes[up];
-        bool fusable = is_chain_kind(u.kind) && p->uses[up] == 1 && p->vals[up].kind == VK_NONE;
+        bool fusable = is_chain_kind(u.kind) && p->uses[up] == 1 && p->vals[up].kind == VK_NONE && gain_is_const(up);
         if (fusable && u.kind == SIGB_NODE_FILTER && nsec + section_count(u.order) > SIGB_MAX_SEC) fusable = false;
         // a filter needs its input at full width (fx.py:105 indexes input_[:, i])
         if (n.kind == SIGB_NODE_FILTER && C > 1 && u.channels != C)
@@ -545,12 +630,12 @@ bool Builder::pure_osc_run(int i, int* nsec, int* wave) const {
         const sigb_node& n = p->nodes[cur];
         if (n.kind == SIGB_NODE_OSC) {
             *wave = n.subtype;
-            return true;
+            return const_of(p, n.in[0]) && const_of(p, n.in[1]);     // modulated oscillators are not fused
         }
         if (n.kind == SIGB_NODE_FILTER) {
             if (n.order < 1) return false;
             *nsec += section_count(n.order);
-        } else if (n.kind != SIGB_NODE_GAIN) {
+        } else if (n.kind != SIGB_NODE_GAIN || !gain_is_const(cur)) {
             return false;
         }
         cur = n.in[0];
@@ -667,19 +752,24 @@ int Builder::build_ewise(int i) {
     e.a_node = n.in[0];
     e.b_node = n.in[1];
     std::vector<double> pv;
+    // block-rate parameter port: a constant row, or (modulated) a row of the parameter program
+    auto param = [&](int port_node, const char* what) -> int {
+        const std::vector<double>* m = const_of(p, port_node);
+        if (!m) return param_port(port_node, C, &e.p_row);
+        if (!rep(*m, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": " + what + " channels incompatible");
+        return SIGB_OK;
+    };
     if (n.kind == SIGB_NODE_MIX) {
         e.op = EW_MIX;
-        const std::vector<double>* m = const_of(p, n.in[2]);
-        if (!m) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": Mix.mix driven by a non-constant emitter");
-        if (!rep(*m, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": mix channels incompatible");
+        int st = param(n.in[2], "mix");
+        if (st != SIGB_OK) return st;
     } else if (n.kind == SIGB_NODE_RINGMOD) {
         e.op = EW_RINGMOD;
     } else {
-        e.op = EW_AMP;
+        e.op = n.kind == SIGB_NODE_GAIN ? EW_GAIN : EW_AMP;
         e.b_node = -1;
-        const std::vector<double>* x = const_of(p, n.in[1]);
-        if (!x) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": Amp.right driven by a non-constant emitter");
-        if (!rep(*x, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": exponent channels incompatible");
+        int st = param(n.in[1], n.kind == SIGB_NODE_GAIN ? "gain" : "exponent");
+        if (st != SIGB_OK) return st;
     }
     for (int opnd : {e.a_node, e.b_node}) {
         if (opnd < 0) continue;
@@ -815,6 +905,21 @@ int upload(sigb_plan* p) {
         CUDA_TRY(cudaMalloc(&p->d_state, 2 * p->n_state * sizeof(double)));
         CUDA_TRY(cudaMemset(p->d_state, 0, 2 * p->n_state * sizeof(double)));
     }
+    if (!p->pprog.empty()) {
+        const size_t nrows = p->prow_const.size(), ps = (size_t)p->pwidth;
+        std::vector<double> img(nrows * ps, 0.0);
+        for (size_t r = 0; r < nrows; ++r) {
+            const std::vector<double>& cv = p->prow_const[r];
+            if (cv.empty()) continue;
+            for (size_t c = 0; c < ps; ++c) img[r * ps + c] = cv[std::min(c, cv.size() - 1)];     // replicated to the row stride
+        }
+        CUDA_TRY(cudaMalloc(&p->d_prow_d, img.size() * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&p->d_prow_f, img.size() * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(p->d_prow_d, img.data(), img.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(p->d_prow_f, 0, img.size() * sizeof(float)));
+        CUDA_TRY(cudaMalloc(&p->d_pprog, p->pprog.size() * sizeof(ParamInstr)));
+        CUDA_TRY(cudaMemcpy(p->d_pprog, p->pprog.data(), p->pprog.size() * sizeof(ParamInstr), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaEventCreate(&p->ev0));
     CUDA_TRY(cudaEventCreate(&p->ev1));
     p->uploaded = true;
@@ -887,8 +992,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.warm_rows = ch.warm_rows;
             a.position = abs_row0;
             std::memcpy(a.sec_kind, ch.sec_kind, sizeof(a.sec_kind));
-            a.hertz = ch.hertz.dev<double>(base);
-            a.phase = ch.phase.dev<double>(base);
+            a.hertz = ch.hertz_row >= 0 ? p->d_prow_d + (size_t)ch.hertz_row * p->pwidth : ch.hertz.dev<double>(base);
+            a.phase = ch.phase_row >= 0 ? p->d_prow_d + (size_t)ch.phase_row * p->pwidth : ch.phase.dev<double>(base);
             a.theta0 = ch.theta0.dev<unsigned long long>(base);
             a.dtheta = ch.dtheta.dev<unsigned long long>(base);
             a.constv = ch.constv.dev<float>(base);
@@ -912,7 +1017,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
             int done = 0;
-            if (ch.src_kind == SRC_OSC) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
+            if (ch.src_kind == SRC_OSC && ch.hertz_row < 0) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
             // kernel choice: cascades of >= 3 sections run section-pipelined (k_cascade_pipe); shallower
             // chains stay on the time-parallel scan kernel, which measured faster for them (C2: 1.07e12 vs
             // 0.82e12 voice-samples/s) unless "cascade_pipe" forces the pipeline from n sections
@@ -970,7 +1075,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             Operand ob = operand_of(p, e.b_node, abs_row0, out, ld_out);
             a.a = oa.ptr; a.lda = oa.ld; a.acs = oa.cs; a.a_rows = oa.rows;
             a.b = ob.ptr; a.ldb = ob.ld; a.bcs = ob.cs; a.b_rows = ob.rows;
-            a.p = e.p.dev<float>(base);
+            a.p = e.p_row >= 0 ? p->d_prow_f + (size_t)e.p_row * p->pwidth : e.p.dev<float>(base);
             int err = sigb_launch_ewise(&a, st);
             if (err) return fail(SIGB_ECUDA, std::string("k_ewise: ") + cudaGetErrorString((cudaError_t)err));
             p->launch_count++;
@@ -1070,6 +1175,15 @@ int64_t slab_rows(sigb_plan* p, int64_t frames) {
     return std::min(frames, rows);
 }
 
+int run_params(sigb_plan* p, int64_t position, cudaStream_t st) {
+    if (p->pprog.empty()) return SIGB_OK;
+    int e = sigb_launch_param_eval(p->d_pprog, (int)p->pprog.size(), (int)p->prow_const.size(), p->d_prow_d, p->d_prow_f, p->pwidth,
+                                   position, p->rate, st);
+    if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
+    p->launch_count++;
+    return SIGB_OK;
+}
+
 // the body of sigb_render: seek handling + slab loop, all on `st`
 int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
     if (!p->have_pos || p->next_pos != position) {
@@ -1086,12 +1200,14 @@ int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int
                 CUDA_TRY(cudaMalloc(&p->scratch, need * sizeof(float)));
                 p->scratch_floats = need;
             }
-            int e = run_slab(p, position - pre, (int)pre, p->scratch, p->channels, st);
+            int e = run_params(p, position - pre, st);         // the context request samples its parameters at ITS position
+            if (e == SIGB_OK) e = run_slab(p, position - pre, (int)pre, p->scratch, p->channels, st);
             if (e != SIGB_OK) return e;
         }
     }
     const int64_t slab = slab_rows(p, frames);
     int e = ensure_bufs(p, slab);
+    if (e == SIGB_OK) e = run_params(p, position, st);       // block-rate parameters: once per request, at its first frame
     if (e != SIGB_OK) return e;
     for (int64_t r = 0; r < frames; r += slab) {
         const int rows = (int)std::min(slab, frames - r);
@@ -1310,6 +1426,9 @@ extern "C" int sigb_plan_destroy(sigb_plan* plan) {
     for (BufInfo& b : plan->bufs)
         if (b.ptr) cudaFree(b.ptr);
     if (plan->d_arena) cudaFree(plan->d_arena);
+    if (plan->d_pprog) cudaFree(plan->d_pprog);
+    if (plan->d_prow_d) cudaFree(plan->d_prow_d);
+    if (plan->d_prow_f) cudaFree(plan->d_prow_f);
     if (plan->d_state) cudaFree(plan->d_state);
     if (plan->scratch) cudaFree(plan->scratch);
     for (int i = 0; i < 2; ++i) {
@@ -1333,6 +1452,7 @@ extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t 
     std::string s = "{\"channels\": " + std::to_string(plan->channels) + ", \"rate\": " + std::to_string(plan->rate) +
                     ", \"context\": " + std::to_string(plan->context) + ", \"buffers\": " + std::to_string(plan->bufs.size()) +
                     ", \"state_doubles\": " + std::to_string(plan->n_state) + ", \"param_bytes\": " + std::to_string(plan->arena.size()) +
+                    ", \"modulated_parameters\": " + std::to_string(plan->pprog.size()) +
                     ", \"launches\": [";
     bool first = true;
     for (const Launch& l : plan->launches) {

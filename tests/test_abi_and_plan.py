@@ -105,10 +105,33 @@ def test_unsupported_nodes_raise_at_compile_time(ns, engine):
         engine.compile(f, 1, 48000, 16)
 
 
-def test_modulated_parameter_is_rejected_for_now(ns, engine):
+def test_modulated_parameters_lower_to_a_parameter_program(ns, engine):
+    """An emitter other than Fixed on a block-rate port (osc.py:28-30, fx.py:39,52,59) becomes a float64
+    parameter program evaluated once per request; a modulated Gain is not folded into its chain."""
+    d = engine.compile(cases.CASES_BY_NAME['lfo_hertz'].build(ns), 2, 48000).describe()
+    assert d['modulated_parameters'] >= 3                      # Mix, Gain, and the three LFO oscillators
+    assert [l['kind'] for l in d['launches']] == ['chain']
+    d = engine.compile(cases.CASES_BY_NAME['lfo_chain'].build(ns), 2, 48000).describe()
+    assert [l['kind'] for l in d['launches']] == ['chain', 'ewise', 'chain'] and d['launches'][1]['op'] == 'gain'
+    assert d['launches'][2]['source'] == 'block' and d['launches'][2]['gain'] is True
+    # a voice bank with a modulated oscillator is not fused with its mix-down
+    ps = ext.PanSum()
+    ps.input = cases.CASES_BY_NAME['lfo_gain'].build(ns)
+    ps.pan = cases.fixed(ns, [[0.2, 0.8]])
+    kinds = [l['kind'] for l in engine.compile(ps, 2, 48000).describe()['launches']]
+    assert 'voices' not in kinds and kinds[-1] == 'reduce'
+
+
+def test_modulated_filter_cutoff_and_pan_are_still_rejected(ns, engine):
     lfo = cases.osc(ns, 'Sine', [[2.0]])
+    f = fx.LowPass()
+    f.input = cases.osc(ns, 'Sine', [[440.0]])
+    f.cutoff = lfo
+    with pytest.raises(chain.UnsupportedGraph):
+        engine.compile(f, 1, 48000, 16)
+    # a filter inside a parameter graph has no one-frame meaning here either
     car = osc.Sine()
-    car.hertz = lfo
+    car.hertz = cases.lowpass(ns, cases.osc(ns, 'Sine', [[3.0]]), [[10.0]])
     with pytest.raises(chain.UnsupportedGraph):
         engine.compile(car, 1, 48000, 16)
 

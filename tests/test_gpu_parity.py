@@ -24,7 +24,11 @@ def render_case(engine, ns, case, **options):
     compiled = engine.compile(case.build(ns), case.channels, case.rate, case.frames)
     for k, v in options.items():
         compiled.set_option(k, v)
-    out = compiled.render_device(case.position, case.frames).cpu().numpy()
+    if case.block:       # consecutive requests: block-rate parameters are re-sampled at each request's first frame
+        out = np.concatenate([compiled.render_device(case.position + r, min(case.block, case.frames - r)).cpu().numpy()
+                              for r in range(0, case.frames, case.block)])
+    else:
+        out = compiled.render_device(case.position, case.frames).cpu().numpy()
     launches = compiled.launch_count
     compiled.close()
     assert launches > 0, 'no CUDA kernel was launched'

@@ -18,7 +18,12 @@ def test_oracle_matches_reference_golden(case, ns):
     if case.frames > 500000 and os.environ.get('SIGB_FAST_TESTS'):
         pytest.skip('long render')
     want = load_golden(case.name)
-    got = np_oracle.GraphOracle(case.rate).render(case.build(ns), case.position, case.frames, case.channels)
+    graph, orc = case.build(ns), np_oracle.GraphOracle(case.rate)
+    if case.block:
+        got = np.concatenate([orc.render(graph, case.position + r, min(case.block, case.frames - r), case.channels)
+                              for r in range(0, case.frames, case.block)])
+    else:
+        got = orc.render(graph, case.position, case.frames, case.channels)
     got = got[::case.stride]
     assert got.shape == want.shape
     assert max_abs_err(got, want) == 0.0
