@@ -222,7 +222,11 @@ def _lfo_mix_amp(ns):
     m.mix = mx
     a = ns.Amp()
     a.left = m
-    a.right = gain(ns, _lfo(ns, 'Sine', [[0.5]], [[0.25]]), [[2.0]])       # exponent = 2 sin(...) at the request's first frame
+    ex = ns.Mix()                       # exponent = Mix(3, 2, mix = square LFO in {+1, -1}) in {3, 1}: integer-valued, so
+    ex.left = fixed(ns, [[3.0]])        # negative inputs stay finite (a fractional exponent is NaN there, fx.py:60)
+    ex.right = fixed(ns, [[2.0]])
+    ex.mix = _lfo(ns, 'Square', [[1.0]], [[0.1]])
+    a.right = ex
     return a
 
 
