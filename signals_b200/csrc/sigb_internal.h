@@ -123,7 +123,6 @@ struct ParamInstr {
 #define SIGB_PARAM_ROWS 96              // rows per parameter program (values live in a per-thread array)
 
 #define SIGB_VOICE_SEGS 24              // segments per k_voices launch
-#define SIGB_VOICE_K 16                 // rows per tile
 #define SIGB_VOICE_THREADS 256
 
 struct VoicesDev {
