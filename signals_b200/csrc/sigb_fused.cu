@@ -353,6 +353,35 @@ __global__ void __launch_bounds__(256) k_probe_fill(float4* __restrict__ out, in
 }
 }  // namespace
 
+namespace {
+// tiled fill: the C2 store pattern -- a warp owns a (rows_per_tile x width_bytes) tile of a (frames, 4096) float
+// block and walks time; `width` floats per tile row (32 = the scan kernel's 128-byte rows)
+__global__ void __launch_bounds__(256) k_probe_fill_tiled(float* __restrict__ out, int frames, int C, int width, int rows_per_tile, float v) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int tiles_x = C / width;
+    const int steps = frames / rows_per_tile;
+    const long long total = (long long)tiles_x * steps;
+    const float4 val = make_float4(v, v, v, v);
+    const int lanes_per_row = width / 4;                 // float4 lanes covering one tile row
+    const int rows_per_instr = 32 / lanes_per_row;
+    // tile-major order cut into equal contiguous pieces per warp (as the scan kernel's persistent pieces)
+    const long long quota = (total + nwarps - 1) / nwarps;
+    for (long long it = (long long)warp * quota; it < min(total, (long long)(warp + 1) * quota); ++it) {
+        const int tx = (int)(it / steps), st = (int)(it % steps);
+        float* base = out + (size_t)st * rows_per_tile * C + (size_t)tx * width;
+        for (int r = lane / lanes_per_row; r < rows_per_tile; r += rows_per_instr)
+            __stcs(reinterpret_cast<float4*>(base + (size_t)r * C) + (lane % lanes_per_row), val);
+    }
+}
+}  // namespace
+
+extern "C" int sigb_probe_fill_tiled(float* out_dev, int32_t frames, int32_t C, int32_t width, int32_t rows_per_tile, int32_t blocks, void* stream) {
+    k_probe_fill_tiled<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, frames, C, width, rows_per_tile, 1.0f);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int sigb_probe_fill(float* out_dev, int64_t n_floats, float value, int32_t blocks, void* stream) {
     k_probe_fill<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(out_dev), n_floats / 4, value);
     return (int)cudaGetLastError();

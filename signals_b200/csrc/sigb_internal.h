@@ -48,6 +48,7 @@ struct ChainDev {
     // scan helpers (time-parallel kernel): transition A^L per section, and the zero-input
     // output response of each state over one sub-chunk
     const double* apow;             // [(s*4+k)*C + c], row-major 2x2
+    const double* apow_h;           // [(s*4+k)*C + c]  A^(L/2) in float64 (channel-pair kernel: carry chained per 8-row sub-chunk)
     const float* ztab;              // [((s*L + k)*2 + j)*C + c]
     const float* m8;                // [(s*4+k)*C + c]  float32 A^(L/2) (packed kernel: stitches the two halves)
     const float* hrec;              // [(s*2+k)*C + c]  k: 0 = tr(A), 1 = -det(A) (zero-input output recurrence)

@@ -724,6 +724,244 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------
+// k_chain_scan3: the channel-pair variant of the packed time-parallel kernel (single section)
+//
+// Measured on B200 (tools/probe_fill.py): a store-only kernel writing 128-byte rows of a (frames, 4096)
+// block tops out at 4.57 TB/s, with 256-byte rows at 6.0 TB/s -- k_chain_scan2's 32-channel tiles sit AT that
+// first ceiling.  Here a tile is 64 adjacent channels: the two lanes of every packed register are channels c
+// and c + 32 of the SAME rows (instead of two 8-row halves of one channel), a sub-chunk is 8 rows, and each
+// worker hands the TMA engine (8 x 64) tiles, i.e. 256-byte rows.  There is nothing to stitch; the scanner
+// chains the float64 carry through the sub-chunks directly, c_{q+1} = A^8 c_q + z_q, and publishes c_q as the
+// true initial state of sub-chunk q.  Workers are software-pipelined as in k_chain_scan2.
+// ------------------------------------------------------------------------------------------
+template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3 = true>      // R3 = rows per sub-chunk: 8 or 16
+__global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
+k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * R3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);                        // [NW][R3][64] output tiles (TMA source)
+    float4* zs = reinterpret_cast<float4*>(stage + NW * R3 * 64);            // [NW][32] end states of channels (c, c+32)
+    float4* si = zs + NW * 32;                                                // [NW][32] true initial states
+    double* tnb = reinterpret_cast<double*>(si + NW * 32);                    // [NW][R3] n / rate (generic oscillators)
+
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const size_t C = (size_t)a.C;
+    const bool bulk = use_tma != 0;
+    const double rate = (double)a.rate;
+
+    const int tiles = (a.C + 63) / 64;
+    const long long total = (long long)tiles * nsteps;
+    const long long quota = (total + gridDim.x - 1) / gridDim.x;
+    long long lin = (long long)blockIdx.x * quota;
+    const long long lin_end = min(total, lin + quota);
+
+    while (lin < lin_end) {
+        const int tile_idx = (int)(lin / nsteps);
+        const int s0 = (int)(lin - (long long)tile_idx * nsteps);
+        const int s1 = (int)min((long long)nsteps, s0 + (lin_end - lin));
+        const int w0 = max(0, s0 - warm_steps);
+        lin += s1 - s0;
+
+        const int cA = tile_idx * 64 + lane, cB = cA + 32;
+        const bool liveA = cA < a.C, liveB = cB < a.C;
+        const int ccA = liveA ? cA : a.C - 1, ccB = liveB ? cB : a.C - 1;
+
+        if (w == NW) {
+            // ---------------- scanner warp: lane = channels (c, c + 32), float64 carry chain ----------------
+            double mA[4], mB[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mA[k] = (R3 == SIGB_SCAN_L ? a.apow : a.apow_h)[(size_t)k * C + ccA];
+                mB[k] = (R3 == SIGB_SCAN_L ? a.apow : a.apow_h)[(size_t)k * C + ccB];
+            }
+            double a1 = w0 == 0 ? a.state[(size_t)0 * C + ccA] : 0.0, a2 = w0 == 0 ? a.state[(size_t)1 * C + ccA] : 0.0;
+            double b1 = w0 == 0 ? a.state[(size_t)0 * C + ccB] : 0.0, b2 = w0 == 0 ? a.state[(size_t)1 * C + ccB] : 0.0;
+            for (int step = w0; step < s1; ++step) {
+                const int grp = (step - w0) % NG;
+                bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                float4 z[WG];
+#pragma unroll
+                for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < WG; ++q) {
+                    si[(grp * WG + q) * 32 + lane] = make_float4((float)a1, (float)a2, (float)b1, (float)b2);
+                    const double na1 = fma(mA[0], a1, fma(mA[1], a2, (double)z[q].x));
+                    const double na2 = fma(mA[2], a1, fma(mA[3], a2, (double)z[q].y));
+                    const double nb1 = fma(mB[0], b1, fma(mB[1], b2, (double)z[q].z));
+                    const double nb2 = fma(mB[2], b1, fma(mB[3], b2, (double)z[q].w));
+                    a1 = na1; a2 = na2; b1 = nb1; b2 = nb2;
+                }
+                bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+            }
+            if (s1 == nsteps) {       // the piece that finishes a tile hands its state to the next launch
+                if (liveA) { a.state_out[(size_t)0 * C + cA] = a1; a.state_out[(size_t)1 * C + cA] = a2; }
+                if (liveB) { a.state_out[(size_t)0 * C + cB] = b1; a.state_out[(size_t)1 * C + cB] = b2; }
+            }
+        } else {
+            // ---------------- worker warps: lane = channels (c, c + 32), warp = 8-row sub-chunk ----------------
+            const int grp = w / WG, q = w % WG;
+            const float2 gain2 = a.gain ? pk(a.gain[ccA], a.gain[ccB]) : pk1(1.0f);
+            int64_t row = ((int64_t)w0 + grp) * STEP + (int64_t)q * R3;
+            const int64_t row_stride = (int64_t)NG * STEP;
+            float* outp = a.out + row * a.ld_out + cA;
+            const int64_t out_stride = row_stride * a.ld_out;
+            float* tile = stage + w * (R3 * 64);
+            const int kind = a.sec_kind[0];
+
+            SecPar ps;       // both lanes of every field: channel c and channel c + 32
+            {
+                const float gA = a.coef[(size_t)0 * C + ccA], gB = a.coef[(size_t)0 * C + ccB];
+                const float dA = a.coef[(size_t)2 * C + ccA], dB = a.coef[(size_t)2 * C + ccB];
+                ps.g = pk(gA, gB);
+                ps.nc = pk(-a.coef[(size_t)1 * C + ccA], -a.coef[(size_t)1 * C + ccB]);
+                ps.d = pk(dA, dB);
+                ps.gd = pk(gA * dA, gB * dB);
+                ps.gd2 = pk(2.0f * (gA * dA), 2.0f * (gB * dB));
+                ps.g2 = pk(2.0f * gA, 2.0f * gB);
+                ps.al = pk(a.hrec[(size_t)0 * C + ccA], a.hrec[(size_t)0 * C + ccB]);
+                ps.be = pk(a.hrec[(size_t)1 * C + ccA], a.hrec[(size_t)1 * C + ccB]);
+            }
+            // zero-input output at samples 0 and 1 per unit state: rows 0, 1 of the response table
+            const float2 zp0 = pk(a.ztab[((size_t)0 * 2 + 0) * C + ccA], a.ztab[((size_t)0 * 2 + 0) * C + ccB]);
+            const float2 zr0 = pk(a.ztab[((size_t)0 * 2 + 1) * C + ccA], a.ztab[((size_t)0 * 2 + 1) * C + ccB]);
+            const float2 zp1 = pk(a.ztab[((size_t)1 * 2 + 0) * C + ccA], a.ztab[((size_t)1 * 2 + 0) * C + ccB]);
+            const float2 zr1 = pk(a.ztab[((size_t)1 * 2 + 1) * C + ccA], a.ztab[((size_t)1 * 2 + 1) * C + ccB]);
+
+            unsigned long long thA = 0, thB = 0, stepA = 0, stepB = 0;
+            int dhiA = 0, dhiB = 0;
+            double hzA = 0.0, hzB = 0.0, phA = 0.0, phB = 0.0;
+            float2 cv = pk1(0.0f);
+            if (SRC == SRC_OSC) {
+                if (FASTSINE) {
+                    const unsigned long long dA = a.dtheta[ccA], dB = a.dtheta[ccB];
+                    thA = a.theta0[ccA] + (unsigned long long)(a.position + row) * dA;
+                    thB = a.theta0[ccB] + (unsigned long long)(a.position + row) * dB;
+                    stepA = dA * (unsigned long long)row_stride;
+                    stepB = dB * (unsigned long long)row_stride;
+                    dhiA = (int)((dA + 0x80000000ull) >> 32);
+                    dhiB = (int)((dB + 0x80000000ull) >> 32);
+                } else {
+                    hzA = a.hertz[ccA]; hzB = a.hertz[ccB];
+                    phA = a.phase[ccA]; phB = a.phase[ccB];
+                }
+            }
+            if (SRC == SRC_CONST) cv = pk(a.constv[ccA], a.constv[ccB]);
+
+            auto gen = [&](float2 (&v)[R3], int64_t grow) {
+                if (SRC == SRC_OSC) {
+                    if (FASTSINE) {
+                        int ha = (int)(thA >> 32), hb = (int)(thB >> 32);
+#pragma unroll
+                        for (int k = 0; k < R3; ++k) {
+                            const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
+                            v[k] = pk(__sinf(r.x), __sinf(r.y));
+                            ha += dhiA;
+                            hb += dhiB;
+                        }
+                        thA += stepA;
+                        thB += stepB;
+                    } else {
+                        if (lane < R3) tnb[w * R3 + lane] = __ddiv_rn((double)(a.position + grow + lane), rate);
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < R3; ++k)
+                            v[k] = pk(osc_wave(a.wave, osc_cycles(tnb[w * R3 + k], hzA, phA)),
+                                      osc_wave(a.wave, osc_cycles(tnb[w * R3 + k], hzB, phB)));
+                        __syncwarp();
+                    }
+                } else if (SRC == SRC_BUF) {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k)
+                        v[k] = pk(liveA ? load_src(a, grow + k, cA) : 0.0f, liveB ? load_src(a, grow + k, cB) : 0.0f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) v[k] = cv;
+                }
+            };
+
+            int step = w0 + grp;
+            float2 vn[PIPE3 ? R3 : 1];
+            float2 s1n = pk1(0.0f), s2n = pk1(0.0f);
+            if (PIPE3 && step < s1) {
+                gen(reinterpret_cast<float2(&)[R3]>(vn), row);
+                svf2_block<R3>(kind, ps, reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
+            }
+            while (step < s1) {
+                float2 v[R3];
+                const int next = step + NG;
+                if (PIPE3) {
+                    zs[w * 32 + lane] = make_float4(s1n.x, s2n.x, s1n.y, s2n.y);
+                    bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+#pragma unroll
+                    for (int k = 0; k < R3; ++k) v[k] = vn[PIPE3 ? k : 0];
+                    if (next < s1) {      // the next step's zero-state render hides the scanner's turn-around
+                        s1n = pk1(0.0f);
+                        s2n = pk1(0.0f);
+                        gen(reinterpret_cast<float2(&)[R3]>(vn), row + row_stride);
+                        svf2_block<R3>(kind, ps, reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
+                    }
+                } else {
+                    s1n = pk1(0.0f);
+                    s2n = pk1(0.0f);
+                    gen(v, row);
+                    svf2_block<R3>(kind, ps, v, s1n, s2n);
+                    zs[w * 32 + lane] = make_float4(s1n.x, s2n.x, s1n.y, s2n.y);
+                    bar_arrive(1 + 2 * grp, (WG + 1) * 32);
+                }
+                bar_sync(2 + 2 * grp, (WG + 1) * 32);
+                const float4 ia = si[w * 32 + lane];
+                {   // zero-input response of the true initial state, advanced by its 2-term recurrence
+                    const float2 i1 = pk(ia.x, ia.z), i2 = pk(ia.y, ia.w);
+                    float2 h0 = __ffma2_rn(zp0, i1, __fmul2_rn(zr0, i2));
+                    float2 h1 = __ffma2_rn(zp1, i1, __fmul2_rn(zr1, i2));
+                    v[0] = __fadd2_rn(v[0], h0);
+                    v[1] = __fadd2_rn(v[1], h1);
+#pragma unroll
+                    for (int k = 2; k < R3; ++k) {
+                        const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
+                        v[k] = __fadd2_rn(v[k], hn);
+                        h0 = h1;
+                        h1 = hn;
+                    }
+                }
+                if (step >= s0) {
+                    if (bulk) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < R3; ++k) {
+                            const float2 o = __fmul2_rn(v[k], gain2);
+                            tile[k * 64 + lane] = o.x;
+                            tile[k * 64 + 32 + lane] = o.y;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_tile(&out_map, tile_idx * 64, (int)row, tile);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < R3; ++k) {
+                            const float2 o = __fmul2_rn(v[k], gain2);
+                            if (liveA) __stcs(outp + (int64_t)k * a.ld_out, o.x);
+                            if (liveB) __stcs(outp + (int64_t)k * a.ld_out + 32, o.y);
+                        }
+                    }
+                }
+                outp += out_stride;
+                row += row_stride;
+                step = next;
+            }
+        }
+        __syncthreads();     // piece boundary: the barrier protocol restarts
+    }
+    if (bulk && w < NW && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // k_ewise / k_reduce
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ew_load(const float* p, int64_t ld, int cs, int64_t rows, int64_t r, int c) {
@@ -958,6 +1196,62 @@ cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     }
 }
 
+template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3>
+cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    constexpr int NW = NG * WG;
+    constexpr int STEP = WG * R3;
+    const int nsteps = a.frames / STEP;
+    *rows_done = nsteps * STEP;
+    if (nsteps == 0) return cudaSuccess;
+    const size_t smem = (size_t)NW * R3 * 64 * sizeof(float) + (size_t)NW * 32 * sizeof(float4) * 2 + (size_t)NW * R3 * sizeof(double);
+    auto kern = k_chain_scan3<SRC, NG, WG, FASTSINE, R3, PIPE3>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    // 2-D tensor map with a 64 x 8 box: 256-byte rows per TMA store
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    int use_tma = 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (g_scan_tma && enc && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && ((a.ld_out * 4) & 15) == 0) {
+        cuuint64_t dims[2] = {(cuuint64_t)a.C, (cuuint64_t)(nsteps * STEP)};
+        cuuint64_t strides[1] = {(cuuint64_t)a.ld_out * 4};
+        cuuint32_t box[2] = {64u, (cuuint32_t)R3};
+        cuuint32_t estr[2] = {1u, 1u};
+        use_tma = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    const int tiles = (a.C + 63) / 64;
+    const int sms = sm_count();
+    int grid_x = tiles, warm_steps = 0;
+    if (g_scan_split && a.warm_rows >= 0) {
+        const int ws = (a.warm_rows + STEP - 1) / STEP;
+        const long long total = (long long)tiles * nsteps;
+        const long long quota = (total + sms - 1) / sms;
+        if (tiles % sms != 0 && quota >= 8ll * ws && quota >= 4) {
+            grid_x = (int)((total + quota - 1) / quota);
+            warm_steps = ws;
+        }
+    }
+    dim3 grid(grid_x), block((NW + 1) * 32);
+    kern<<<grid, block, smem, st>>>(a, nsteps, warm_steps, map, use_tma);
+    return cudaGetLastError();
+}
+
+template <int NG, int WG, int R3, bool PIPE3 = true>
+cudaError_t launch_scan3_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
+    const bool fast = a.src_kind == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
+    switch (a.src_kind) {
+        case SRC_OSC:
+            return fast ? launch_scan3_t<SRC_OSC, NG, WG, true, R3, PIPE3>(a, st, rows_done) : launch_scan3_t<SRC_OSC, NG, WG, false, R3, PIPE3>(a, st, rows_done);
+        case SRC_BUF: return launch_scan3_t<SRC_BUF, NG, WG, false, R3, PIPE3>(a, st, rows_done);
+        default: return launch_scan3_t<SRC_CONST, NG, WG, false, R3, PIPE3>(a, st, rows_done);
+    }
+}
+
 }  // namespace
 
 // scan geometry: (groups, worker warps per group).  Deep cascades keep the block at 512 threads
@@ -971,6 +1265,11 @@ static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
             case 7: *ng = 5; *wg = 6; break;
             case 8: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;     // single section: software-pipelined workers
             case 9: *ng = (nsec == 1 ? 3 : 5); *wg = 8; break;
+            case 13: *ng = 5; *wg = (nsec == 1 ? 5 : 6); break;   // 13-17: channel-pair kernel (64-channel tiles)
+            case 14: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 8 : 6); break;
+            case 15: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;
+            case 16: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;
+            case 17: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 13 : 6); break;
             default: *ng = 4; *wg = 7; break;
         }
         return;
@@ -1009,6 +1308,7 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     *rows_done = 0;
     if (a->frames <= 0 || a->C <= 0 || a->nsec < 1 || a->nsec > 8) return 0;
+    if (variant >= 13 && a->C <= 32) variant = 9;      // one 32-channel tile: the 64-channel kernel would idle half its lanes
     int ng, wg;
     scan_geometry(a->nsec, variant, &ng, &wg);
     if (variant >= 4) {
@@ -1023,6 +1323,11 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     } while (0)
         if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, 1>(*a, st, rows_done);
         if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, 1>(*a, st, rows_done);
+        if (variant == 13 && a->nsec == 1) return (int)launch_scan3_n<5, 5, 16, false>(*a, st, rows_done);
+        if (variant == 14 && a->nsec == 1) return (int)launch_scan3_n<3, 8, 16, false>(*a, st, rows_done);
+        if (variant == 15 && a->nsec == 1) return (int)launch_scan3_n<4, 6, 16, false>(*a, st, rows_done);
+        if (variant == 16 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false>(*a, st, rows_done);
+        if (variant == 17 && a->nsec == 1) return (int)launch_scan3_n<2, 13, 16, false>(*a, st, rows_done);
         if (ng == 7) SCAN2_DISPATCH(7, 4);
         if (ng == 2) SCAN2_DISPATCH(2, 15);
         if (ng == 5) SCAN2_DISPATCH(5, 6);

@@ -78,7 +78,7 @@ struct ChainSpec {
     int nsec = 0;                // padded section count the kernels run
     int nsec_real = 0;
     uint8_t sec_kind[SIGB_MAX_SEC] = {0};
-    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, ztab, m8, hrec;
+    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, apow_h, ztab, m8, hrec;
     int src_node = -1;           // SRC_BUF: node whose value is read
     int64_t state_off = 0;       // doubles into the state arena
     int state_cur = 0;           // which copy of the state arena holds the live state
@@ -167,7 +167,7 @@ struct sigb_plan {
     int zero_const_node = -1;
     Val zero_val;
     // options
-    int64_t opt_scan_variant = 9;
+    int64_t opt_scan_variant = 16;
     int64_t opt_force_seq = 0;
     int64_t opt_scan_max_tiles = 148 * 6;
     int64_t opt_slab_frames = 0;
@@ -512,6 +512,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
         const size_t CS = scan_tables ? (size_t)C : 0;      // scan-only tables are left empty when unused
         std::vector<float> coef((size_t)ch.nsec * 3 * C, 0.0f);
         std::vector<double> apow((size_t)ch.nsec * 4 * CS, 0.0);
+        std::vector<double> apow_h((size_t)ch.nsec * 4 * CS, 0.0);
         std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * CS, 0.0f);
         std::vector<float> m8((size_t)ch.nsec * 4 * CS, 0.0f);
         std::vector<float> hrec((size_t)ch.nsec * 2 * CS, 0.0f);
@@ -522,6 +523,8 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
                 if (!scan_tables) continue;
                 apow[((size_t)s * 4 + 0) * C + c] = 1.0;
                 apow[((size_t)s * 4 + 3) * C + c] = 1.0;
+                apow_h[((size_t)s * 4 + 0) * C + c] = 1.0;
+                apow_h[((size_t)s * 4 + 3) * C + c] = 1.0;
                 m8[((size_t)s * 4 + 0) * C + c] = 1.0f;
                 m8[((size_t)s * 4 + 3) * C + c] = 1.0f;
             }
@@ -559,6 +562,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
                     sigb_section_transition(secs[k], SIGB_SCAN_L / 2, mh);
                     sigb_section_transition(secs[k], 1, m1);
                     for (int j = 0; j < 4; ++j) m8[((size_t)s * 4 + j) * C + c] = (float)mh[j];
+                    for (int j = 0; j < 4; ++j) apow_h[((size_t)s * 4 + j) * C + c] = mh[j];
                     hrec[((size_t)s * 2 + 0) * C + c] = (float)(m1[0] + m1[3]);                     // tr(A)
                     hrec[((size_t)s * 2 + 1) * C + c] = (float)(-(m1[0] * m1[3] - m1[1] * m1[2]));  // -det(A)
                     sec_warm[k] = std::max(sec_warm[k], sigb_section_decay_rows(m1));
@@ -576,6 +580,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
         ch.coef = put_vec(p, coef);
         if (scan_tables) {
             ch.apow = put_vec(p, apow);
+            ch.apow_h = put_vec(p, apow_h);
             ch.ztab = put_vec(p, ztab);
             ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
             if (nsec >= 2 && ch.warm_rows >= 0) {
@@ -1000,6 +1005,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.coef = ch.coef.dev<float>(base);
             a.gain = ch.gain.dev<float>(base);
             a.apow = ch.apow.dev<double>(base);
+            a.apow_h = ch.apow_h.dev<double>(base);
             a.ztab = ch.ztab.dev<float>(base);
             a.m8 = ch.m8.dev<float>(base);
             a.hrec = ch.hrec.dev<float>(base);

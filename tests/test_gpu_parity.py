@@ -55,7 +55,7 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'pipe', 'pipe2'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'scan13', 'scan14', 'scan15', 'scan16', 'scan17', 'pipe', 'pipe2'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
     the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""

@@ -16,5 +16,5 @@ BCMD="python bench.py --steps 3 --warmup 3 --e2e-steps 0 --no-cpu-baseline"
 timeout 300 $BCMD > gpurun_out/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $BCMD > gpurun_out/ncu_l_$TAG.log 2>&1
 timeout 300 $BCMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_chain_scan2 -s 3 -c 1 -f -o gpurun_out/prof_$TAG $BCMD > gpurun_out/ncu_f_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_chain_scan3 -s 3 -c 1 -f -o gpurun_out/prof_$TAG $BCMD > gpurun_out/ncu_f_$TAG.log 2>&1
 ls -la gpurun_out

@@ -26,3 +26,10 @@ print(f'torch fill_: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
 src = torch.empty(n // 2, dtype=torch.float32, device='cuda'); dst = torch.empty_like(src)
 ms = timed(lambda: dst.copy_(src))
 print(f'torch copy_ (read+write bytes): {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+
+L.sigb_probe_fill_tiled.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+for width in (32, 64, 128, 256):
+    for rows in (16, 64):
+        for blocks in (148 * 3, 148 * 6):
+            ms = timed(lambda: L.sigb_probe_fill_tiled(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, rows, blocks, ctypes.c_void_p(st)))
+            print(f'tiled fill: {width * 4:4d}-byte rows x {rows:2d} rows per tile, {blocks:4d} CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
