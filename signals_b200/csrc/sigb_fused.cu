@@ -378,6 +378,7 @@ __global__ void __launch_bounds__(256) k_probe_fill_tiled(float* __restrict__ ou
 }  // namespace
 
 extern "C" int sigb_probe_fill_tiled(float* out_dev, int32_t frames, int32_t C, int32_t width, int32_t rows_per_tile, int32_t blocks, void* stream) {
+    if (width < 4 || width > 128 || (width & (width - 1)) != 0 || C % width != 0 || rows_per_tile < 1) return (int)cudaErrorInvalidValue;
     k_probe_fill_tiled<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, frames, C, width, rows_per_tile, 1.0f);
     return (int)cudaGetLastError();
 }

@@ -28,7 +28,7 @@ ms = timed(lambda: dst.copy_(src))
 print(f'torch copy_ (read+write bytes): {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
 
 L.sigb_probe_fill_tiled.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
-for width in (32, 64, 128, 256):
+for width in (32, 64, 128):        # floats per tile row; a warp's float4 lanes cover at most 128 floats (512 bytes)
     for rows in (16, 64):
         for blocks in (148 * 3, 148 * 6):
             ms = timed(lambda: L.sigb_probe_fill_tiled(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, rows, blocks, ctypes.c_void_p(st)))
