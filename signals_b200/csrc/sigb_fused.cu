@@ -147,6 +147,12 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
         if ((int)blockIdx.x >= a.seg[i].cta0) si = i;
     const VoiceSeg& sg = a.seg[si];
     const int cta = blockIdx.x - sg.cta0;
+    // time segment of this CTA: rows [row_store, row_end) are its share; a later segment starts warm_rows
+    // earlier from zero filter state (the bank's decay horizon) without storing
+    const int row_store = blockIdx.y * a.seg_rows;
+    const int row_end = min(a.frames, row_store + a.seg_rows);
+    const int row_begin = blockIdx.y == 0 ? 0 : max(0, row_store - (sg.nsec ? (a.warm_rows + VK - 1) / VK * VK : 0));
+    const bool first_seg = row_begin == 0;
     const int wave = sg.wave, guard = sg.guard;
     const int fk = sg.nsec == 0 ? -1 : sg.sec_kind;
     const size_t C = (size_t)sg.C;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
         const int cc = live ? c : sg.C - 1;
         chan[m] = live ? c : -1;
         const unsigned long long dth = sg.dtheta[cc];
-        th[m] = sg.theta0[cc] + (unsigned long long)a.position * dth + 0x80000000ull;   // + 1/2 ulp of the top word
+        th[m] = sg.theta0[cc] + (unsigned long long)(a.position + row_begin) * dth + 0x80000000ull;   // + 1/2 ulp of the top word
         dK[m] = dth * (unsigned long long)VK;
         dhi[m] = (int)((dth + 0x80000000ull) >> 32);
         wt[m] = live ? make_float2(sg.wl[cc], sg.wr[cc]) : make_float2(0.0f, 0.0f);
@@ -171,16 +177,16 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             g[m] = sg.coef[0 * C + cc];
             cf[m] = sg.coef[1 * C + cc];
             d[m] = sg.coef[2 * C + cc];
-            s1[m] = (float)sg.state[0 * C + cc];
-            s2[m] = (float)sg.state[1 * C + cc];
+            s1[m] = first_seg ? (float)sg.state[0 * C + cc] : 0.0f;
+            s2[m] = first_seg ? (float)sg.state[1 * C + cc] : 0.0f;
         }
     }
     float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)blockIdx.x * a.frames;
     const double rate = (double)a.rate;
     constexpr int PARTS = VT / VK;          // threads that share one row in the CTA reduction
 
-    for (int n0 = 0; n0 < a.frames; n0 += VK) {
-        const int kmax = min(VK, a.frames - n0);
+    for (int n0 = row_begin; n0 < row_end; n0 += VK) {
+        const int kmax = min(VK, row_end - n0);
         float x[M][VK];
         int w[M];
 #pragma unroll
@@ -234,16 +240,16 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
                 s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
                 s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
             }
-            if (part == 0 && k < kmax) part_out[n0 + k] = s;
+            if (part == 0 && k < kmax && n0 + k >= row_store) part_out[n0 + k] = s;
         }
         __syncthreads();
     }
-    if (fk >= 0) {
+    if (fk >= 0 && row_end == a.frames) {      // the last segment hands the filter state to the next call
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (chan[m] >= 0) {
-                sg.state[0 * C + chan[m]] = (double)s1[m];
-                sg.state[1 * C + chan[m]] = (double)s2[m];
+                sg.state_out[0 * C + chan[m]] = (double)s1[m];
+                sg.state_out[1 * C + chan[m]] = (double)s2[m];
             }
         }
     }
@@ -277,8 +283,9 @@ extern "C" int sigb_voices_ctas(int channels, int M) { return (channels + VT * M
 
 extern "C" int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream) {
     if (a->frames <= 0 || nparts <= 0) return 0;
-    if (a->M == 4) k_voices<4, 8><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
-    else k_voices<1, 16><<<nparts, VT, 0, (cudaStream_t)stream>>>(*a);
+    const dim3 grid(nparts, a->tseg > 0 ? a->tseg : 1);
+    if (a->M == 4) k_voices<4, 8><<<grid, VT, 0, (cudaStream_t)stream>>>(*a);
+    else k_voices<1, 16><<<grid, VT, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 

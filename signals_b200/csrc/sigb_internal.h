@@ -107,7 +107,8 @@ struct VoiceSeg {
     const float* coef;                  // [(k)*C + c], k: g c d
     const float* wl;                    // [C] gain * (1 - pan)
     const float* wr;                    // [C] gain * pan
-    double* state;                      // [(k)*C + c]
+    double* state;                      // [(k)*C + c]  read by the CTAs of the first time segment
+    double* state_out;                  // written by the CTAs of the last time segment (the other copy)
 };
 
 // Block-rate parameter program (modulated parameters): evaluated in float64 for ONE frame per request, at the
@@ -131,6 +132,9 @@ struct VoicesDev {
     int32_t rate;
     int32_t frames;
     int32_t M;                          // channels per thread (1 or 4)
+    int32_t tseg;                       // time segments (blockIdx.y)
+    int32_t seg_rows;                   // rows per segment (multiple of 8)
+    int32_t warm_rows;                  // rows a later segment re-renders from zero state without storing
     int64_t position;
     float* partial;                     // [nparts][frames][2]
     VoiceSeg seg[SIGB_VOICE_SEGS];

@@ -124,6 +124,7 @@ struct VoicesSpec {
     int M = 1;
     int nparts = 0;
     int partial_buf = -1;      // index into Plan::bufs (2 * nparts "channels")
+    int state_cur = 0;         // which copy of the state arena holds the live filter state
     int dst_node = -1;
 };
 
@@ -177,6 +178,7 @@ struct sigb_plan {
     int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
+    int64_t opt_voices_segments = 0;    // time segments of k_voices: 0 auto, 1 never split, n > 1 forced
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
     bool uploaded = false;
@@ -554,7 +556,12 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
                     const int s = s0 + k;
                     ch.sec_kind[s] = (uint8_t)secs[k].kind;
                     for (int j = 0; j < 3; ++j) coef[((size_t)s * 3 + j) * C + c] = cf[j];
-                    if (!scan_tables) continue;
+                    if (!scan_tables) {
+                        double m1[4];
+                        sigb_section_transition(secs[k], 1, m1);
+                        sec_warm[k] = std::max(sec_warm[k], sigb_section_decay_rows(m1));
+                        continue;
+                    }
                     sigb_section_transition(secs[k], SIGB_SCAN_L, m);
                     sigb_section_zero_input(secs[k], SIGB_SCAN_L, tab);
                     for (int j = 0; j < 4; ++j) apow[((size_t)s * 4 + j) * C + c] = m[j];
@@ -578,11 +585,11 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
             for (double wv : sec_warm) warm += wv;   // sections in series: budget the decays one after another
         }
         ch.coef = put_vec(p, coef);
+        ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
         if (scan_tables) {
             ch.apow = put_vec(p, apow);
             ch.apow_h = put_vec(p, apow_h);
             ch.ztab = put_vec(p, ztab);
-            ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
             if (nsec >= 2 && ch.warm_rows >= 0) {
                 // Cascades: the per-section budgets add up far too conservatively.  Simulate, in float64, the
                 // zero-input decay (to 2^-44) of the slowest channels -- largest pole radius, largest sum of
@@ -1103,8 +1110,25 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             if (err) return fail(SIGB_ECUDA, std::string("k_bank: ") + cudaGetErrorString((cudaError_t)err));
             p->launch_count++;
         } else if (l.kind == LK_VOICES) {
-            const VoicesSpec& vs = p->voices[l.idx];
+            VoicesSpec& vs = p->voices[l.idx];
             float* partial = p->bufs[vs.partial_buf].ptr;
+            // time segments: a small bank (few CTAs) is also cut along time; later segments warm their filters
+            // up from zero state over the bank's decay horizon (2^-40), oscillators need no warm-up at all
+            int warm = 0;
+            for (const VoiceSegSpec& sg : vs.segs) {
+                if (sg.ch.nsec_real == 0) continue;
+                warm = sg.ch.warm_rows < 0 ? -1 : (warm < 0 ? -1 : std::max(warm, sg.ch.warm_rows));
+                if (warm < 0) break;
+            }
+            int nseg = 1;
+            if (warm >= 0 && p->opt_voices_segments != 1) {
+                const int slots = 148 * (vs.M == 4 ? 2 : 3);
+                const int want = p->opt_voices_segments > 1 ? (int)p->opt_voices_segments : (2 * slots + vs.nparts - 1) / vs.nparts;
+                const int fit = warm > 0 ? rows / (8 * warm) : rows / 64;
+                nseg = std::max(1, std::min(std::min(want, fit), 64));
+            }
+            const int seg_rows = ((rows + nseg - 1) / nseg + 7) / 8 * 8;
+            nseg = (rows + seg_rows - 1) / seg_rows;
             int part0 = 0;
             for (size_t s0 = 0; s0 < vs.segs.size(); s0 += SIGB_VOICE_SEGS) {
                 VoicesDev a;
@@ -1115,6 +1139,9 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 a.M = vs.M;
                 a.position = abs_row0;
                 a.partial = partial + (int64_t)part0 * rows * 2;
+                a.tseg = nseg;
+                a.seg_rows = seg_rows;
+                a.warm_rows = std::max(warm, 0);
                 int ctas = 0;
                 for (int k = 0; k < a.nseg; ++k) {
                     const VoiceSegSpec& sg = vs.segs[s0 + k];
@@ -1131,9 +1158,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     d.coef = sg.ch.coef.dev<float>(base);
                     d.wl = sg.wl.dev<float>(base);
                     d.wr = sg.wr.dev<float>(base);
-                    d.state = p->d_state ? p->d_state + sg.ch.state_off : nullptr;
-                    // guard band (units of 2^-32 cycles): in-tile drift of the rounded increment, the
-                    // rounding of the top word, and the float64 rounding of the reference's own phase
+                    d.state = p->d_state ? p->d_state + vs.state_cur * p->n_state + sg.ch.state_off : nullptr;
+                    d.state_out = p->d_state ? p->d_state + (vs.state_cur ^ 1) * p->n_state + sg.ch.state_off : nullptr;
                     d.guard = phase_guard(sg.ch.max_abs_hertz, sg.ch.max_abs_phase, abs_row0 + rows, p->rate);
                     ctas += sigb_voices_ctas(sg.ch.C, vs.M);
                 }
@@ -1142,6 +1168,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 p->launch_count++;
                 part0 += ctas;
             }
+            vs.state_cur ^= 1;
             const Val& dv = p->vals[vs.dst_node];
             float* o = dv.buf < 0 ? out : p->bufs[dv.buf].ptr;
             const int64_t ldo = dv.buf < 0 ? ld_out : dv.channels;
@@ -1515,6 +1542,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "cascade_pipe") plan->opt_cascade_pipe = value;
     else if (k == "pipe_segments") plan->opt_pipe_segments = value;
     else if (k == "pipe_spw") plan->opt_pipe_spw = value;
+    else if (k == "voices_segments") plan->opt_voices_segments = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);

@@ -591,3 +591,50 @@ def test_fused_reductions_stay_inside_their_block(ns, engine):
             assert not (host[3:3 + frames, :c] == -777.0).any()
             host[3:3 + frames, :c] = -777.0
             assert (host == -777.0).all()
+
+
+def test_single_section_kernel_ragged_tiles_and_plain_stores(ns, engine):
+    """k_chain_scan3 (64-channel tiles): channel counts that leave the second half of a tile partly or wholly
+    dead, a Buffer source, and an output block whose row pitch defeats the TMA store (plain STG path)."""
+    from signals_b200.chain import ext
+    torch = _torch()
+    rng = np.random.default_rng(46)
+    for ch in (40, 70, 97):
+        frames = 5000
+        x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
+        cut = np.exp(rng.uniform(np.log(150.0), np.log(9000.0), (1, ch)))
+        node = cases.lowpass(ns, ext.Buffer(x), [cut[0]], 'HighPass')
+        want, _ = np_oracle.render_cascade(x.astype(np.float64), cut, RATE, btype='hp')
+        compiled = engine.compile(node, ch, RATE)
+        a = compiled.render_device(0, frames).cpu().numpy()                 # TMA stores when ch % 4 == 0
+        big = torch.full((frames, ch + 1), 5.0, dtype=torch.float32, device='cuda')
+        compiled.reset()
+        compiled.render_device(0, frames, big[:, :ch])                       # pitch ch + 1: never TMA
+        compiled.close()
+        b = big.cpu().numpy()
+        assert (b[:, ch] == 5.0).all()
+        assert max_abs_err(a, want) <= 1e-4 and max_abs_err(b[:, :ch], want) <= 1e-4
+        assert np.array_equal(a, b[:, :ch])
+
+
+def test_instances_time_segments_match_oracle(ns, engine):
+    """k_voices cuts a small bank along time as well (later segments warm their filters up from zero state over
+    the decay horizon, oscillators need none): every segment must match the oracle, agree with the unsegmented
+    render, and hand the true filter state to the next call."""
+    from signals_b200.chain import ext
+    prm = cases.instance_params(57, 600)
+    prm['cutoff'] = np.clip(prm['cutoff'], 500.0, None)          # decay horizon ~1200 rows -> several segments fit
+    frames = 60000
+    compiled = engine.compile(cases.build_instances(ns, ext, prm), 2, RATE)
+    first = compiled.render_device(0, frames).cpu().numpy()
+    second = compiled.render_device(frames, 2000).cpu().numpy()
+    launches_split = compiled.launch_count
+    compiled.set_option('voices_segments', 1)
+    compiled.reset()
+    whole = compiled.render_device(0, frames).cpu().numpy()
+    compiled.close()
+    want = np_oracle.render_instances(prm, 0, frames + 2000, RATE)
+    err = max_abs_err(np.concatenate([first, second]), want)
+    print(f'instances time segments: max-abs {err:.3e} (mix peak {np.abs(want).max():.3f}), {launches_split} launches')
+    assert err <= 1e-6
+    assert max_abs_err(first, whole) <= 2e-7
