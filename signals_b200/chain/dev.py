@@ -143,7 +143,10 @@ class SinkDevice(Device, Receiver, ExplicitChannels):
             # fast path: sigb_render_host writes the device's float32 buffer directly (dev.py:173 + :178 in one call)
             from signals_b200 import engine
             eng = engine.default_engine()
-            eng.plan_for(bound.sig, channels, rate, frames).render_host(loc.position, frames, outdata[:frames, :channels])
+            compiled = eng.plan_for(bound.sig, channels, rate, frames)
+            compiled.render_host(loc.position, frames, outdata[:frames, :channels])
+            if compiled.records.taps:
+                eng.serve_taps(bound.sig, loc)
         else:
             outdata[:, :channels] = self.input.request(loc)
         self.frame_position += frames

@@ -25,6 +25,10 @@ class Vis(PassThroughResult, abc.ABC):
     def flags(cls) -> SignalFlags:
         return super().flags() | SignalFlags.VIS
 
+    def deliver(self, position: int, rate: int, block) -> None:
+        """The reference queues every block it forwards for the GUI thread (vis.py:61-64)."""
+        self.q.put(block)
+
 
 class Wave(Vis):
 

@@ -208,6 +208,24 @@ class Engine:
         out = compiled.render_device(loc.position, frames)
         return out.cpu().numpy().astype(self.result_dtype, copy=False)
 
+    def serve_taps(self, emitter, loc: BlockLoc) -> int:
+        """Deliver to every enabled tap under ``emitter`` (Wave / Spec / FileWriter) the block it would have seen
+        in the reference's recursion: a render of the tap's own input, device -> host, then ``tap.deliver``.
+        Taps are side effects of the host (GUI queue, file), not part of the fused block render, so this is a
+        separate, optional pass; returns the number of taps served."""
+        frames, channels = loc.shape
+        compiled = self.plan_for(emitter, channels, loc.rate, frames)
+        served = 0
+        for tap, creq in compiled.records.taps:
+            src = tap.inputs_by_port.get('input')
+            if src is None or not getattr(tap.get_state(), 'enabled', True):
+                continue
+            tap_loc = BlockLoc(position=loc.position, rate=loc.rate, shape=type(loc.shape)(frames=frames, channels=creq))
+            block = self.render(src, tap_loc)
+            tap.deliver(loc.position, loc.rate, np.broadcast_to(block, (frames, creq)))
+            served += 1
+        return served
+
     def render_device(self, emitter, loc: BlockLoc, out=None):
         frames, channels = loc.shape
         return self.plan_for(emitter, channels, loc.rate, frames).render_device(loc.position, frames, out)

@@ -51,6 +51,7 @@ class GraphRecords:
     rate: int
     buffers: dict        # record index -> Buffer node (bound to device memory by the engine)
     sources: list        # record index -> originating node object (diagnostics)
+    taps: list = dataclasses.field(default_factory=list)   # (tap node, requested channels): pass-through side-effect nodes
 
     def node_array(self):
         arr = (_lib.SigbNode * len(self.nodes))()
@@ -72,6 +73,7 @@ class _Lowering:
         self.buffers: dict = {}
         self.memo: dict = {}
         self.active: set = set()
+        self.taps: list = []
 
     # -- record helpers ---------------------------------------------------------------------
     def emit(self, source, kind: int, channels: int, inputs=(-1, -1, -1), subtype: int = 0, order: int = 0,
@@ -131,6 +133,8 @@ class _Lowering:
         if kind in _TAPS:
             # the tap's audio result IS its input (PassThroughResult.forward, chain/__init__.py:409-417);
             # queueing blocks for the GUI / writing the file is host-side work outside the render
+            if not any(t is node for t, _ in self.taps):
+                self.taps.append((node, creq))
             return self.port(node, 'input', creq, F)
         if kind == 'Fixed':
             value = np.asarray(st.value, dtype=np.float64)
@@ -224,7 +228,7 @@ def lower(emitter, channels: int, rate: int, frames: int = 0) -> GraphRecords:
         raise BadShape(emitter, (frames, ch), (frames, channels))
     data = np.concatenate(lw.tables) if lw.tables else np.zeros(0)
     return GraphRecords(nodes=lw.nodes, data=np.ascontiguousarray(data, dtype=np.float64), root=root,
-                        channels=lw.channels, rate=lw.rate, buffers=lw.buffers, sources=lw.sources)
+                        channels=lw.channels, rate=lw.rate, buffers=lw.buffers, sources=lw.sources, taps=lw.taps)
 
 
 def signature(emitter) -> tuple:

@@ -135,13 +135,16 @@ class Patch:
             raise PatchError(f'sink {sink_at} has no input')
         return sink, emitter
 
-    def render(self, position: int, frames: int, rate: int = 48000, sink_at: typing.Optional[str] = None) -> np.ndarray:
+    def render(self, position: int, frames: int, rate: int = 48000, sink_at: typing.Optional[str] = None,
+               taps: bool = False) -> np.ndarray:
         """What the sink's callback would deliver for ``frames`` frames from ``position``: float32
         ``(frames, sink channels)``, rendered by the CUDA path."""
         from signals_b200 import engine
         sink, emitter = self.root(sink_at)
         loc = BlockLoc(position=position, rate=rate, shape=Shape(frames=frames, channels=sink.get_state().channels))
         block = engine.default_engine().render(emitter, loc)
+        if taps:        # FileWriter / Wave nodes on the way get their blocks too (chain/files.py:99-102, chain/vis.py:61-64)
+            engine.default_engine().serve_taps(emitter, loc)
         return np.broadcast_to(block, tuple(loc.shape)).astype(np.float32)
 
 

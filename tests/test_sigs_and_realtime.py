@@ -176,3 +176,86 @@ def test_script_renders_through_the_sink_device():
     audio = streams[-1].audio()
     assert audio.shape == (4800, 1)
     assert max_abs_err(audio, np_oracle.example_sine_block(0, 4800, 48000.0)) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# file nodes
+# ------------------------------------------------------------------------------------------------
+
+def test_wav_codec_round_trip(tmp_path):
+    from signals_b200 import wavio
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, (1000, 3)).astype(np.float32)
+    path = str(tmp_path / 'a.wav')
+    w = wavio.WavWriter(path, 48000, 3)
+    w.write(0, x[:400])
+    w.write(400, x[400:])
+    w.write(100, x[100:200])                      # positioned rewrite, like SoundFile.seek + write (files.py:54-56)
+    w.close()
+    y, rate = wavio.read(path)
+    assert rate == 48000 and y.dtype == np.float32 and np.array_equal(x, y)
+    # a 16-bit PCM file as other tools write them
+    import struct
+    pcm = (x[:, :1] * 32767).astype('<i2')
+    with open(tmp_path / 'b.wav', 'wb') as f:
+        f.write(b'RIFF' + struct.pack('<I', 36 + pcm.nbytes) + b'WAVEfmt ' + struct.pack('<IHHIIHH', 16, 1, 1, 44100, 88200, 2, 16))
+        f.write(b'data' + struct.pack('<I', pcm.nbytes) + pcm.tobytes())
+    z, rate = wavio.read(str(tmp_path / 'b.wav'))
+    assert rate == 44100 and z.shape == (1000, 1) and np.abs(z - pcm / 32768.0).max() == 0.0
+
+
+def test_file_reader_lowers_to_an_hbm_buffer(tmp_path, engine):
+    from signals_b200 import wavio
+    from signals_b200.chain import files
+    x = np.linspace(-1, 1, 600, dtype=np.float32).reshape(300, 2)
+    w = wavio.WavWriter(str(tmp_path / 'in.wav'), 48000, 2)
+    w.write(0, x)
+    w.close()
+    r = files.FileReader()
+    r.get_state().path = str(tmp_path / 'in.wav')
+    assert r.channels == 2 and r.file_rate == 48000 and np.array_equal(r.samples, x)
+    f = fx.HighPass()
+    f.input = r
+    from oracle import cases
+    f.cutoff = cases.fixed(cases.b200_namespace(), [[500.0, 900.0]])
+    d = engine.compile(f, 2, 48000).describe()
+    assert d['launches'] == [d['launches'][0]] and d['launches'][0]['source'] == 'block' and d['launches'][0]['sections'] == 1
+    assert discovery.load_signal('signals.chain.files.FileReader') is files.FileReader
+
+
+@pytest.mark.gpu
+def test_file_nodes_on_the_gpu_path(tmp_path):
+    """FileReader -> LowPass -> FileWriter -> Wave -> sink, written as a patch: the sink block equals the oracle's
+    filter of the file, the FileWriter's WAV holds exactly the block that passed through it, and the Wave tap
+    queued it -- blockwise, with the filter state carried across the requests."""
+    from signals_b200 import engine, wavio
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (6000, 2)).astype(np.float32)
+    w = wavio.WavWriter(str(tmp_path / 'in.wav'), 48000, 2)
+    w.write(0, x)
+    w.close()
+    patch = sigs.loads(f"""
+        sink 9a default channels=2
+        + 1a signals.chain.files.FileReader path={tmp_path / 'in.wav'}
+        + 1b signals.chain.fixed.Fixed value=[[1200,3000]]
+        + 2a signals.chain.fx.LowPass
+        + 3a signals.chain.files.FileWriter path={tmp_path / 'out.wav'}
+        + 4a signals.chain.vis.Wave
+        > 1a 2a.input
+        > 1b 2a.cutoff
+        > 2a 3a.input
+        > 3a 4a.input
+        > 4a 9a.input
+    """)
+    engine.default_engine().clear()
+    blocks = [patch.render(p, 1500, taps=True) for p in range(0, 6000, 1500)]
+    got = np.concatenate(blocks)
+    want, _ = np_oracle.render_cascade(x.astype(np.float64), np.array([[1200.0, 3000.0]]), RATE)
+    assert max_abs_err(got, want) <= 1e-4
+    patch.nodes['3a'].destroy()                                     # closes the file
+    written, rate = wavio.read(str(tmp_path / 'out.wav'))
+    assert rate == RATE and written.shape == (6000, 2)
+    # the taps re-render their input per request from a fresh plan position sequence: same carried state, same bits
+    assert max_abs_err(written, got) <= 1e-6
+    q = patch.nodes['4a'].q
+    assert q.qsize() == 4 and q.get().shape == (1500, 2)
