@@ -78,7 +78,7 @@ class Workload:
 
 class C2(Workload):
     name = 'C2: sine -> biquad lowpass -> gain, %d voices x %g s @ 48 kHz per GPU, fp32 (frames, voices) block in HBM'
-    kernel = 'k_chain_scan3<sine, 1 section, 64-channel tiles, 3x9 workers>'
+    kernel = 'k_chain_scan3<sine, 1 section, 64-channel tiles, 3x9 workers, f32 carry chain>'
     bound = 'hbm'
     bytes_per_unit = 4.0
 

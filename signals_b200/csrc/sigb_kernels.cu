@@ -734,7 +734,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 // chains the float64 carry through the sub-chunks directly, c_{q+1} = A^8 c_q + z_q, and publishes c_q as the
 // true initial state of sub-chunk q.  Workers are software-pipelined as in k_chain_scan2.
 // ------------------------------------------------------------------------------------------
-template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3 = true>      // R3 = rows per sub-chunk: 8 or 16
+template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3 = true, bool F32CARRY = false>      // R3 = rows per sub-chunk: 8 or 16
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
     constexpr int NW = NG * WG;
@@ -778,6 +778,30 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             }
             double a1 = w0 == 0 ? a.state[(size_t)0 * C + ccA] : 0.0, a2 = w0 == 0 ? a.state[(size_t)1 * C + ccA] : 0.0;
             double b1 = w0 == 0 ? a.state[(size_t)0 * C + ccB] : 0.0, b2 = w0 == 0 ? a.state[(size_t)1 * C + ccB] : 0.0;
+            if (F32CARRY) {
+                // float32 chain, both channels packed: c_{q+1} = A c_q + z_q is contractive and rounds once per 16 rows,
+                // i.e. far less often than the workers' own float32 recurrence (4 FFMA2 per sub-chunk instead of 8 DFMA)
+                const float2 m0 = pk((float)mA[0], (float)mB[0]), m1 = pk((float)mA[1], (float)mB[1]);
+                const float2 m2 = pk((float)mA[2], (float)mB[2]), m3 = pk((float)mA[3], (float)mB[3]);
+                float2 c1 = pk((float)a1, (float)b1), c2 = pk((float)a2, (float)b2);
+                for (int step = w0; step < s1; ++step) {
+                    const int grp = (step - w0) % NG;
+                    bar_sync(1 + 2 * grp, (WG + 1) * 32);
+                    float4 z[WG];
+#pragma unroll
+                    for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
+#pragma unroll
+                    for (int q = 0; q < WG; ++q) {
+                        si[(grp * WG + q) * 32 + lane] = make_float4(c1.x, c2.x, c1.y, c2.y);
+                        const float2 n1 = __ffma2_rn(m0, c1, __ffma2_rn(m1, c2, pk(z[q].x, z[q].z)));
+                        const float2 n2 = __ffma2_rn(m2, c1, __ffma2_rn(m3, c2, pk(z[q].y, z[q].w)));
+                        c1 = n1;
+                        c2 = n2;
+                    }
+                    bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+                }
+                a1 = c1.x; b1 = c1.y; a2 = c2.x; b2 = c2.y;
+            } else {
             for (int step = w0; step < s1; ++step) {
                 const int grp = (step - w0) % NG;
                 bar_sync(1 + 2 * grp, (WG + 1) * 32);
@@ -794,6 +818,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     a1 = na1; a2 = na2; b1 = nb1; b2 = nb2;
                 }
                 bar_arrive(2 + 2 * grp, (WG + 1) * 32);
+            }
             }
             if (s1 == nsteps) {       // the piece that finishes a tile hands its state to the next launch
                 if (liveA) { a.state_out[(size_t)0 * C + cA] = a1; a.state_out[(size_t)1 * C + cA] = a2; }
@@ -1196,7 +1221,7 @@ cudaError_t launch_scan2_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     }
 }
 
-template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3>
+template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3, bool F32CARRY>
 cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * R3;
@@ -1204,7 +1229,7 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     *rows_done = nsteps * STEP;
     if (nsteps == 0) return cudaSuccess;
     const size_t smem = (size_t)NW * R3 * 64 * sizeof(float) + (size_t)NW * 32 * sizeof(float4) * 2 + (size_t)NW * R3 * sizeof(double);
-    auto kern = k_chain_scan3<SRC, NG, WG, FASTSINE, R3, PIPE3>;
+    auto kern = k_chain_scan3<SRC, NG, WG, FASTSINE, R3, PIPE3, F32CARRY>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1241,14 +1266,14 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     return cudaGetLastError();
 }
 
-template <int NG, int WG, int R3, bool PIPE3 = true>
+template <int NG, int WG, int R3, bool PIPE3 = true, bool F32CARRY = false>
 cudaError_t launch_scan3_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const bool fast = a.src_kind == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
     switch (a.src_kind) {
         case SRC_OSC:
-            return fast ? launch_scan3_t<SRC_OSC, NG, WG, true, R3, PIPE3>(a, st, rows_done) : launch_scan3_t<SRC_OSC, NG, WG, false, R3, PIPE3>(a, st, rows_done);
-        case SRC_BUF: return launch_scan3_t<SRC_BUF, NG, WG, false, R3, PIPE3>(a, st, rows_done);
-        default: return launch_scan3_t<SRC_CONST, NG, WG, false, R3, PIPE3>(a, st, rows_done);
+            return fast ? launch_scan3_t<SRC_OSC, NG, WG, true, R3, PIPE3, F32CARRY>(a, st, rows_done) : launch_scan3_t<SRC_OSC, NG, WG, false, R3, PIPE3, F32CARRY>(a, st, rows_done);
+        case SRC_BUF: return launch_scan3_t<SRC_BUF, NG, WG, false, R3, PIPE3, F32CARRY>(a, st, rows_done);
+        default: return launch_scan3_t<SRC_CONST, NG, WG, false, R3, PIPE3, F32CARRY>(a, st, rows_done);
     }
 }
 
@@ -1268,7 +1293,7 @@ static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
             case 13: *ng = 5; *wg = (nsec == 1 ? 5 : 6); break;   // 13-17: channel-pair kernel (64-channel tiles)
             case 14: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 8 : 6); break;
             case 15: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;
-            case 16: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;
+            case 16: case 18: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;     // 18: float32 carry chain
             case 17: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 13 : 6); break;
             default: *ng = 4; *wg = 7; break;
         }
@@ -1328,6 +1353,7 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
         if (variant == 15 && a->nsec == 1) return (int)launch_scan3_n<4, 6, 16, false>(*a, st, rows_done);
         if (variant == 16 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false>(*a, st, rows_done);
         if (variant == 17 && a->nsec == 1) return (int)launch_scan3_n<2, 13, 16, false>(*a, st, rows_done);
+        if (variant == 18 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false, true>(*a, st, rows_done);
         if (ng == 7) SCAN2_DISPATCH(7, 4);
         if (ng == 2) SCAN2_DISPATCH(2, 15);
         if (ng == 5) SCAN2_DISPATCH(5, 6);

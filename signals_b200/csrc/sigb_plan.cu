@@ -168,7 +168,7 @@ struct sigb_plan {
     int zero_const_node = -1;
     Val zero_val;
     // options
-    int64_t opt_scan_variant = 16;
+    int64_t opt_scan_variant = 18;
     int64_t opt_force_seq = 0;
     int64_t opt_scan_max_tiles = 148 * 6;
     int64_t opt_slab_frames = 0;

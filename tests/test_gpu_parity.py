@@ -55,7 +55,7 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'scan13', 'scan14', 'scan15', 'scan16', 'scan17', 'pipe', 'pipe2'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'scan13', 'scan14', 'scan15', 'scan16', 'scan17', 'scan18', 'pipe', 'pipe2'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
     the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""
@@ -638,3 +638,24 @@ def test_instances_time_segments_match_oracle(ns, engine):
     print(f'instances time segments: max-abs {err:.3e} (mix peak {np.abs(want).max():.3f}), {launches_split} launches')
     assert err <= 1e-6
     assert max_abs_err(first, whole) <= 2e-7
+
+
+def test_single_section_kernel_60s_low_cutoffs(ns, engine):
+    """The default single-section kernel chains its sub-chunk carries in float32: 96 voices x 60 s with cutoffs
+    down to 20 Hz (poles at radius 0.998) must stay inside the cascaded-IIR budget, and streaming the minute in
+    ten calls must agree with the single request."""
+    v, frames = 96, 60 * RATE
+    hertz, phase, cutoff, g = cases.voice_params(88, v)
+    cutoff[:32] = np.linspace(20.0, 100.0, 32)
+    graph = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff]), [g])
+    compiled = engine.compile(graph, v, RATE)
+    whole = compiled.render_device(0, frames).cpu().numpy()
+    compiled.reset()
+    parts = np.concatenate([compiled.render_device(k * frames // 10, frames // 10).cpu().numpy() for k in range(10)])
+    compiled.close()
+    pick = np.concatenate([np.arange(0, 32, 4), [40, 70, 95]])
+    want = np_oracle.render_voice_chain(0, frames, RATE, hertz[pick], phase[pick], cutoff[pick], g[pick])
+    err = max_abs_err(whole[:, pick], want)
+    print(f'single-section kernel, 60 s, cutoffs from 20 Hz: max-abs {err:.3e}; streamed vs whole {max_abs_err(parts, whole):.3e}')
+    assert err <= 1e-4
+    assert max_abs_err(parts, whole) <= 2e-5
