@@ -792,9 +792,9 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
 #pragma unroll
                     for (int q = 0; q < WG; ++q) {
-                        si[(grp * WG + q) * 32 + lane] = make_float4(c1.x, c2.x, c1.y, c2.y);
-                        const float2 n1 = __ffma2_rn(m0, c1, __ffma2_rn(m1, c2, pk(z[q].x, z[q].z)));
-                        const float2 n2 = __ffma2_rn(m2, c1, __ffma2_rn(m3, c2, pk(z[q].y, z[q].w)));
+                        si[(grp * WG + q) * 32 + lane] = make_float4(c1.x, c1.y, c2.x, c2.y);
+                        const float2 n1 = __ffma2_rn(m0, c1, __ffma2_rn(m1, c2, pk(z[q].x, z[q].y)));
+                        const float2 n2 = __ffma2_rn(m2, c1, __ffma2_rn(m3, c2, pk(z[q].z, z[q].w)));
                         c1 = n1;
                         c2 = n2;
                     }
@@ -810,10 +810,10 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 for (int q = 0; q < WG; ++q) z[q] = zs[(grp * WG + q) * 32 + lane];
 #pragma unroll
                 for (int q = 0; q < WG; ++q) {
-                    si[(grp * WG + q) * 32 + lane] = make_float4((float)a1, (float)a2, (float)b1, (float)b2);
+                    si[(grp * WG + q) * 32 + lane] = make_float4((float)a1, (float)b1, (float)a2, (float)b2);
                     const double na1 = fma(mA[0], a1, fma(mA[1], a2, (double)z[q].x));
-                    const double na2 = fma(mA[2], a1, fma(mA[3], a2, (double)z[q].y));
-                    const double nb1 = fma(mB[0], b1, fma(mB[1], b2, (double)z[q].z));
+                    const double na2 = fma(mA[2], a1, fma(mA[3], a2, (double)z[q].z));
+                    const double nb1 = fma(mB[0], b1, fma(mB[1], b2, (double)z[q].y));
                     const double nb2 = fma(mB[2], b1, fma(mB[3], b2, (double)z[q].w));
                     a1 = na1; a2 = na2; b1 = nb1; b2 = nb2;
                 }
@@ -917,7 +917,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 float2 v[R3];
                 const int next = step + NG;
                 if (PIPE3) {
-                    zs[w * 32 + lane] = make_float4(s1n.x, s2n.x, s1n.y, s2n.y);
+                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of c, s1 of c+32, s2 of c, s2 of c+32)
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
 #pragma unroll
                     for (int k = 0; k < R3; ++k) v[k] = vn[PIPE3 ? k : 0];
@@ -932,13 +932,13 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     s2n = pk1(0.0f);
                     gen(v, row);
                     svf2_block<R3>(kind, ps, v, s1n, s2n);
-                    zs[w * 32 + lane] = make_float4(s1n.x, s2n.x, s1n.y, s2n.y);
+                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of c, s1 of c+32, s2 of c, s2 of c+32)
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
                 }
                 bar_sync(2 + 2 * grp, (WG + 1) * 32);
                 const float4 ia = si[w * 32 + lane];
                 {   // zero-input response of the true initial state, advanced by its 2-term recurrence
-                    const float2 i1 = pk(ia.x, ia.z), i2 = pk(ia.y, ia.w);
+                    const float2 i1 = pk(ia.x, ia.y), i2 = pk(ia.z, ia.w);
                     float2 h0 = __ffma2_rn(zp0, i1, __fmul2_rn(zr0, i2));
                     float2 h1 = __ffma2_rn(zp1, i1, __fmul2_rn(zr1, i2));
                     v[0] = __fadd2_rn(v[0], h0);
@@ -1348,11 +1348,11 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     } while (0)
         if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, 1>(*a, st, rows_done);
         if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, 1>(*a, st, rows_done);
-        if (variant == 13 && a->nsec == 1) return (int)launch_scan3_n<5, 5, 16, false>(*a, st, rows_done);
-        if (variant == 14 && a->nsec == 1) return (int)launch_scan3_n<3, 8, 16, false>(*a, st, rows_done);
-        if (variant == 15 && a->nsec == 1) return (int)launch_scan3_n<4, 6, 16, false>(*a, st, rows_done);
+        if (variant == 13 && a->nsec == 1) return (int)launch_scan3_n<5, 5, 16, false, true>(*a, st, rows_done);
+        if (variant == 14 && a->nsec == 1) return (int)launch_scan3_n<3, 8, 16, false, true>(*a, st, rows_done);
+        if (variant == 15 && a->nsec == 1) return (int)launch_scan3_n<4, 6, 16, false, true>(*a, st, rows_done);
         if (variant == 16 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false>(*a, st, rows_done);
-        if (variant == 17 && a->nsec == 1) return (int)launch_scan3_n<2, 13, 16, false>(*a, st, rows_done);
+        if (variant == 17 && a->nsec == 1) return (int)launch_scan3_n<2, 13, 16, false, true>(*a, st, rows_done);
         if (variant == 18 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false, true>(*a, st, rows_done);
         if (ng == 7) SCAN2_DISPATCH(7, 4);
         if (ng == 2) SCAN2_DISPATCH(2, 15);
