@@ -373,19 +373,24 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
         int t = 0;
         for (; t < t_lo && t < iters; ++t) iteration(t);
         if (t_lo < t_hi) {
-            auto steady = [&](auto kind_tag) {
+            auto steady = [&](auto kind_tag, auto one_tag) {
                 constexpr int KIND = decltype(kind_tag)::value;
+                constexpr bool ONE = decltype(one_tag)::value;        // one granule per thread (256-thread CTA): no inner loops
                 unsigned my_addr = ring_base + (unsigned)(my_slot - ring) * 4u;
                 for (; t < t_hi; ++t) {
-                    for (int j = 0; j < gpt; ++j)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off + j * row_skip_smem), "l"(g_src + j * row_skip_src) : "memory");
+                    if (ONE) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off), "l"(g_src) : "memory");
+                    } else {
+                        for (int j = 0; j < gpt; ++j)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_addr + g_off + j * row_skip_smem), "l"(g_src + j * row_skip_src) : "memory");
+                    }
                     cp_async_commit();
                     g_src += src_step;
                     issue_addr += CHUNK_FLOATS * 4u;
                     if (issue_addr == ring_end) issue_addr = ring_base;
                     cp_async_wait<PRE>();
                     __syncthreads();
-                    for (int j = 0; j < gpt; ++j) {
+                    for (int j = 0; j < (ONE ? 1 : gpt); ++j) {
                         float4 v;
                         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(drain_addr + g_off + j * row_skip_smem) : "memory");
                         v.x *= gain4.x; v.y *= gain4.y; v.z *= gain4.z; v.w *= gain4.w;
@@ -406,11 +411,20 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
                 c += done;
                 my_slot = ring + (my_addr - ring_base) / 4u;
             };
-            switch (kind) {
-                case 0: steady(std::integral_constant<int, 0>{}); break;
-                case SEC_HP: steady(std::integral_constant<int, SEC_HP>{}); break;
-                case SEC_FIRST_ORDER: steady(std::integral_constant<int, SEC_FIRST_ORDER>{}); break;
-                default: steady(std::integral_constant<int, SEC_FIRST_ORDER | SEC_HP>{}); break;
+            if (gpt == 1) {
+                switch (kind) {
+                    case 0: steady(std::integral_constant<int, 0>{}, std::true_type{}); break;
+                    case SEC_HP: steady(std::integral_constant<int, SEC_HP>{}, std::true_type{}); break;
+                    case SEC_FIRST_ORDER: steady(std::integral_constant<int, SEC_FIRST_ORDER>{}, std::true_type{}); break;
+                    default: steady(std::integral_constant<int, SEC_FIRST_ORDER | SEC_HP>{}, std::true_type{}); break;
+                }
+            } else {
+                switch (kind) {
+                    case 0: steady(std::integral_constant<int, 0>{}, std::false_type{}); break;
+                    case SEC_HP: steady(std::integral_constant<int, SEC_HP>{}, std::false_type{}); break;
+                    case SEC_FIRST_ORDER: steady(std::integral_constant<int, SEC_FIRST_ORDER>{}, std::false_type{}); break;
+                    default: steady(std::integral_constant<int, SEC_FIRST_ORDER | SEC_HP>{}, std::false_type{}); break;
+                }
             }
         }
         for (; t < iters; ++t) iteration(t);
