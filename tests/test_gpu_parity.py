@@ -659,3 +659,31 @@ def test_single_section_kernel_60s_low_cutoffs(ns, engine):
     print(f'single-section kernel, 60 s, cutoffs from 20 Hz: max-abs {err:.3e}; streamed vs whole {max_abs_err(parts, whole):.3e}')
     assert err <= 1e-4
     assert max_abs_err(parts, whole) <= 2e-5
+
+
+def test_wide_pointwise_nodes_vector_path(ns, engine):
+    """Mix / RingMod / Amp / modulated Gain on 64-channel blocks take the 128-bit k_ewise_v4 path (the golden
+    cases are 2-4 channels wide and stay on the scalar kernel); 63 channels fall back to it."""
+    rng = np.random.default_rng(64)
+    for c in (64, 63):
+        hz_a, hz_b = rng.uniform(100, 2000, c), rng.uniform(50, 900, c)
+        m = ns.Mix()
+        m.left = cases.osc(ns, 'Sine', [hz_a], [rng.uniform(0, 1, c)])
+        m.right = cases.osc(ns, 'Sawtooth', [hz_b])
+        m.mix = cases.fixed(ns, [rng.uniform(0, 1, c)])
+        r = ns.RingMod()
+        r.left = m
+        r.right = cases.osc(ns, 'Triangle', [rng.uniform(1, 20, c)], [rng.uniform(0, 1, c)])
+        a = ns.Amp()
+        a.left = r
+        a.right = cases.fixed(ns, [rng.integers(1, 4, c).astype(float)])
+        g = ns.Gain()
+        g.left = a
+        g.right = cases.osc(ns, 'Sine', [rng.uniform(0.5, 3.0, c)], [rng.uniform(0, 1, c)])     # modulated gain
+        compiled = engine.compile(g, c, RATE)
+        kinds = [l['kind'] for l in compiled.describe()['launches']]
+        assert kinds.count('ewise') == 4
+        got = compiled.render_device(777, 3000).cpu().numpy()
+        compiled.close()
+        want = np_oracle.GraphOracle(RATE).render(g, 777, 3000, c)
+        assert max_abs_err(got, want) <= 2e-6, c
