@@ -54,6 +54,16 @@ struct ChainDev {
     const float* hrec;              // [(s*2+k)*C + c]  k: 0 = tr(A), 1 = -det(A) (zero-input output recurrence)
     float* out;
     int64_t ld_out;
+    // epilogue fused into a stateless chain (k_chain_seq): out = op(chain value, other operand), fx.py:35-46.
+    // The other operand is a materialised block (epi_buf) or a second oscillator evaluated in registers.
+    int32_t epi_op;                 // 0 none, EW_MIX, EW_RINGMOD
+    int32_t epi_side;               // 0: the chain is `left`, 1: the chain is `right`
+    const float* epi_p;             // EW_MIX: mix[C]
+    const float* epi_buf; int64_t epi_ld; int32_t epi_cs; int64_t epi_rows;
+    int32_t epi_wave;               // second oscillator: SIGB_WAVE_*, -1 when the other operand is epi_buf
+    const double* epi_hertz;        // [C]
+    const double* epi_phase;        // [C]
+    const float* epi_gain;          // [C] or nullptr
 };
 
 struct EwiseDev {

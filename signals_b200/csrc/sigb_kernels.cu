@@ -87,10 +87,20 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
     if (SRC == SRC_CONST) cv = a.constv[c];
     const double rate = (double)a.rate;
     float* outp = a.out + (int64_t)r0 * a.ld_out + c;
+    // fused Mix / RingMod epilogue (stateless chains only): the other operand never leaves registers when it is
+    // an oscillator, and is read once when it is a materialised block
+    const int epi = a.epi_op;
+    double hz2 = 0.0, ph2 = 0.0;
+    float g2 = 1.0f, mixp = 0.0f;
+    if (epi) {
+        if (a.epi_wave >= 0) { hz2 = a.epi_hertz[c]; ph2 = a.epi_phase[c]; g2 = a.epi_gain ? a.epi_gain[c] : 1.0f; }
+        if (a.epi_p) mixp = a.epi_p[c];
+    }
     for (int r = r0; r < r1; ++r) {
         float x;
+        double tn = 0.0;
+        if (SRC == SRC_OSC || epi) tn = __ddiv_rn((double)(a.position + r), rate);
         if (SRC == SRC_OSC) {
-            double tn = __ddiv_rn((double)(a.position + r), rate);
             x = osc_wave(a.wave, osc_cycles(tn, hz, ph));
         } else if (SRC == SRC_BUF) {
             x = load_src(a, r, c);
@@ -99,7 +109,15 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
         }
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) x = svf_any(a.sec_kind[s], x, g[s], cc[s], d[s], s1[s], s2[s]);
-        __stcs(outp, x * gain);
+        x *= gain;
+        if (epi) {
+            float o;
+            if (a.epi_wave >= 0) o = osc_wave(a.epi_wave, osc_cycles(tn, hz2, ph2)) * g2;
+            else o = (a.epi_rows >= 0 && r >= a.epi_rows) ? 0.0f : __ldg(a.epi_buf + (int64_t)r * a.epi_ld + (int64_t)c * a.epi_cs);
+            const float left = a.epi_side ? o : x, right = a.epi_side ? x : o;
+            x = epi == EW_MIX ? mixp * left + (1.0f - mixp) * right : left * right;      // fx.py:40, 46
+        }
+        __stcs(outp, x);
         outp += a.ld_out;
     }
 #pragma unroll

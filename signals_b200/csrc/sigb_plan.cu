@@ -28,6 +28,7 @@ thread_local std::string g_last_error;
 // defaults applied to plans created afterwards (sigb_set_default_option)
 int64_t g_default_fuse_reduce = 1;
 int64_t g_default_voices_m = 0;
+int64_t g_default_fuse_pointwise = 1;
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -85,6 +86,9 @@ struct ChainSpec {
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     int dst_node = -1;
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
+    // Mix / RingMod fused as an epilogue of a stateless chain (k_chain_seq)
+    int epi_op = 0, epi_side = 0, epi_node = -1, epi_wave = -1, epi_p_row = -1;
+    Table epi_p, epi_hertz, epi_phase, epi_gain;
     std::vector<double> gain_d;  // folded gain in float64 (fused reductions derive their weights from it)
     bool has_gain = false;
     double max_abs_hertz = 0.0, max_abs_phase = 0.0;   // SRC_OSC: sizes the phase-word guard band
@@ -178,6 +182,7 @@ struct sigb_plan {
     int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
+    int64_t opt_fuse_pointwise = 1;     // 0: Mix / RingMod always run on materialised blocks
     int64_t opt_voices_segments = 0;    // time segments of k_voices: 0 auto, 1 never split, n > 1 forced
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
@@ -292,7 +297,9 @@ struct Builder {
     int param_port(int idx, int C, int* row);  // ... checked against a consumer of C channels
     bool gain_is_const(int i) const { return p->nodes[i].kind != SIGB_NODE_GAIN || const_of(p, p->nodes[i].in[1]) != nullptr; }
     int build_chain(int i);
-    int make_chain(int i, ChainSpec& ch, bool scan_tables);
+    int make_chain(int i, ChainSpec& ch, bool scan_tables, int width = 0);
+    bool stateless_osc(int i) const;           // a pure oscillator (+ constant gains) chain nobody else consumes
+    int build_fused_pointwise(int i, bool* done);
     bool pure_osc_run(int i, int* nsec, int* wave) const;
     bool collect_voice_leaves(int idx, std::vector<int>* leaves) const;
     int build_bank(int i);
@@ -300,6 +307,15 @@ struct Builder {
     int build_ewise(int i);
     int build_merge(int i);
     int build_reduce(int i);
+    void mark_consumed(int idx) {       // the run ending at idx lives inside a fused launch: never materialised
+        for (int cur = idx; cur >= 0;) {
+            p->vals[cur].kind = VK_BUF;
+            p->vals[cur].channels = p->nodes[cur].channels;
+            p->vals[cur].buf = -2;
+            if (p->nodes[cur].kind == SIGB_NODE_OSC) break;
+            cur = p->nodes[cur].in[0];
+        }
+    }
     int new_buf(int i) {
         if (i == p->root) return -1;
         BufInfo b;
@@ -408,8 +424,8 @@ int Builder::build_chain(int i) {
 
 // Walks the linear run ending at node i down to its source and fills `ch` with the per-channel tables
 // (no launch is recorded).  scan_tables = false skips the tables only the time-parallel kernels read.
-int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables) {
-    const int C = node_C(i);
+int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
+    const int C = width > 0 ? width : node_C(i);
     ch.C = C;
     ch.dst_node = i;
     std::vector<double> gain(C, 1.0);
@@ -755,7 +771,84 @@ int Builder::build_voices(int i, const std::vector<int>& leaves) {
     return SIGB_OK;
 }
 
+bool Builder::stateless_osc(int i) const {
+    int nsec = 0, wave = 0;
+    return i >= 0 && pure_osc_run(i, &nsec, &wave) && nsec == 0;
+}
+
+// Mix / RingMod with a stateless oscillator chain on one side: that chain's launch evaluates the node as its
+// epilogue (the other side is a second oscillator in registers, or a block read once), so "gain and mix fuse
+// into their producers" instead of costing two materialised operands and a pointwise pass.
+int Builder::build_fused_pointwise(int i, bool* done) {
+    *done = false;
+    const sigb_node& n = p->nodes[i];
+    if (!p->opt_fuse_pointwise || (n.kind != SIGB_NODE_MIX && n.kind != SIGB_NODE_RINGMOD)) return SIGB_OK;
+    const int C = node_C(i);
+    const bool a_st = stateless_osc(n.in[0]), b_st = stateless_osc(n.in[1]);
+    if (!a_st && !b_st) return SIGB_OK;
+    if (n.in[0] == n.in[1]) return SIGB_OK;
+    const int side = b_st ? 1 : 0;                       // which operand becomes the chain
+    const int f = n.in[side], o = n.in[side ^ 1];
+    const bool o_st = side == 1 ? a_st : false;          // both stateless: the other one is the in-register oscillator
+    for (int k : {f, o}) {
+        if (k < 0) continue;
+        const int kc = p->nodes[k].channels;
+        if (kc != 1 && kc != C)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(k) + ": block with " + std::to_string(kc) + " channels incompatible with requested " + std::to_string(C));
+    }
+    ChainSpec ch;
+    int st = make_chain(f, ch, false, C);
+    if (st != SIGB_OK) return st;
+    ch.dst_node = i;
+    ch.epi_op = n.kind == SIGB_NODE_MIX ? EW_MIX : EW_RINGMOD;
+    ch.epi_side = side;
+    if (n.kind == SIGB_NODE_MIX) {
+        const std::vector<double>* m = const_of(p, n.in[2]);
+        if (m) {
+            std::vector<double> pv;
+            if (!rep(*m, C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": mix channels incompatible");
+            ch.epi_p = put_vec(p, std::vector<float>(pv.begin(), pv.end()));
+        } else {
+            st = param_port(n.in[2], C, &ch.epi_p_row);
+            if (st != SIGB_OK) return st;
+        }
+    }
+    if (o_st) {
+        ChainSpec oc;
+        st = make_chain(o, oc, false, C);
+        if (st != SIGB_OK) return st;
+        if (oc.hertz_row >= 0) return fail(SIGB_EUNSUPPORTED, "internal: modulated oscillator in a fused epilogue");
+        ch.epi_wave = oc.wave;
+        ch.epi_hertz = oc.hertz;
+        ch.epi_phase = oc.phase;
+        ch.epi_gain = oc.gain;
+        mark_consumed(o);
+    } else if (o >= 0) {
+        st = ensure(o);
+        if (st != SIGB_OK) return st;
+        ch.epi_node = o;
+    } else {
+        ch.epi_node = -1;                                // unconnected: zeros(1,1)
+    }
+    mark_consumed(f);
+    Val v;
+    v.kind = VK_BUF;
+    v.channels = C;
+    v.buf = new_buf(i);
+    if (v.buf >= 0) p->bufs[v.buf].channels = C;
+    p->vals[i] = v;
+    p->chains.push_back(ch);
+    p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+    *done = true;
+    return SIGB_OK;
+}
+
 int Builder::build_ewise(int i) {
+    {
+        bool done = false;
+        int st = build_fused_pointwise(i, &done);
+        if (st != SIGB_OK || done) return st;
+    }
     const sigb_node& n = p->nodes[i];
     const int C = node_C(i);
     EwiseSpec e;
@@ -1029,6 +1122,25 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             const Val& dv = p->vals[ch.dst_node];
             if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
+            a.epi_op = ch.epi_op;
+            a.epi_wave = -1;
+            if (ch.epi_op) {
+                a.epi_side = ch.epi_side;
+                a.epi_p = ch.epi_p_row >= 0 ? p->d_prow_f + (size_t)ch.epi_p_row * p->pwidth : ch.epi_p.dev<float>(base);
+                if (ch.epi_wave >= 0) {
+                    a.epi_wave = ch.epi_wave;
+                    a.epi_hertz = ch.epi_hertz.dev<double>(base);
+                    a.epi_phase = ch.epi_phase.dev<double>(base);
+                    a.epi_gain = ch.epi_gain.dev<float>(base);
+                } else {
+                    Operand o = operand_of(p, ch.epi_node, abs_row0, out, ld_out);
+                    a.epi_buf = o.ptr; a.epi_ld = o.ld; a.epi_cs = o.cs; a.epi_rows = o.rows;
+                }
+                int e = sigb_launch_chain_seq(&a, st);           // epilogue chains are stateless: the sequential kernel tiles time
+                if (e) return fail(SIGB_ECUDA, std::string("k_chain_seq: ") + cudaGetErrorString((cudaError_t)e));
+                p->launch_count++;
+                continue;
+            }
             int done = 0;
             if (ch.src_kind == SRC_OSC && ch.hertz_row < 0) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
             // kernel choice: cascades of >= 3 sections run section-pipelined (k_cascade_pipe); shallower
@@ -1293,6 +1405,7 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
     std::unique_ptr<sigb_plan> p(new sigb_plan());
     p->opt_fuse_reduce = g_default_fuse_reduce;
     p->opt_voices_m = g_default_voices_m;
+    p->opt_fuse_pointwise = g_default_fuse_pointwise;
     p->channels = channels;
     p->rate = rate;
     p->root = root;
@@ -1496,6 +1609,9 @@ extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t 
             s += "{\"kind\": \"chain\", \"node\": " + std::to_string(c.dst_node) + ", \"channels\": " + std::to_string(c.C) +
                  ", \"source\": \"" + src_names[c.src_kind] + "\"";
             if (c.src_kind == SRC_OSC) s += std::string(", \"wave\": \"") + wave_names[c.wave & 3] + "\"";
+            if (c.epi_op)
+                s += std::string(", \"epilogue\": \"") + (c.epi_op == EW_MIX ? "mix" : "ringmod") + "\", \"other\": \"" +
+                     (c.epi_wave >= 0 ? "osc" : "block") + "\"";
             s += ", \"sections\": " + std::to_string(c.nsec_real) + ", \"sections_padded\": " + std::to_string(c.nsec) +
                  ", \"warm_rows\": " + std::to_string(c.warm_rows) +
                  ", \"gain\": " + (c.gain.off >= 0 ? "true" : "false") + "}";
@@ -1554,6 +1670,7 @@ extern "C" int sigb_set_default_option(const char* key, int64_t value) {
     const std::string k(key);
     if (k == "fuse_reduce") g_default_fuse_reduce = value;
     else if (k == "voices_m") g_default_voices_m = value;
+    else if (k == "fuse_pointwise") g_default_fuse_pointwise = value;
     else return fail(SIGB_EINVAL, "unknown default option " + k);
     return SIGB_OK;
 }

@@ -285,3 +285,22 @@ def test_pansum_shape_errors(ns, engine):
     prm = cases.instance_params(5, 40)
     with pytest.raises(chain.BadShape):
         engine.compile(cases.build_instances(ns, ext, prm), 3, 48000)      # PanSum yields 2 channels
+
+
+def test_mix_of_oscillators_is_one_launch(ns, engine):
+    """`Gain and mix nodes fuse into their producers`: Mix(Sine, Sawtooth) and RingMod(Sine, Triangle) are ONE
+    chain launch each (the second oscillator stays in registers); a shared operand (fan-out) is not fused."""
+    d = engine.compile(cases.CASES_BY_NAME['mix'].build(ns), 3, 48000).describe()
+    (l,) = d['launches']
+    assert l['kind'] == 'chain' and l['epilogue'] == 'mix' and l['other'] == 'osc' and d['buffers'] == 0
+    d = engine.compile(cases.CASES_BY_NAME['ringmod'].build(ns), 2, 48000).describe()
+    (l,) = d['launches']
+    assert l['epilogue'] == 'ringmod' and l['other'] == 'osc'
+    kinds = [x['kind'] for x in engine.compile(cases.CASES_BY_NAME['fanout'].build(ns), 4, 48000).describe()['launches']]
+    assert 'ewise' in kinds
+    _set_default('fuse_pointwise', 0)
+    try:
+        kinds = [x['kind'] for x in engine.compile(cases.CASES_BY_NAME['mix'].build(ns), 3, 48000).describe()['launches']]
+    finally:
+        _set_default('fuse_pointwise', 1)
+    assert kinds == ['chain', 'chain', 'ewise']

@@ -682,8 +682,34 @@ def test_wide_pointwise_nodes_vector_path(ns, engine):
         g.right = cases.osc(ns, 'Sine', [rng.uniform(0.5, 3.0, c)], [rng.uniform(0, 1, c)])     # modulated gain
         compiled = engine.compile(g, c, RATE)
         kinds = [l['kind'] for l in compiled.describe()['launches']]
-        assert kinds.count('ewise') == 4
+        assert kinds == ['chain', 'chain', 'ewise', 'ewise']      # Mix and RingMod ride on oscillator chains as epilogues
         got = compiled.render_device(777, 3000).cpu().numpy()
         compiled.close()
         want = np_oracle.GraphOracle(RATE).render(g, 777, 3000, c)
         assert max_abs_err(got, want) <= 2e-6, c
+
+
+def test_fused_pointwise_equals_materialised_path(ns, engine):
+    """Mix / RingMod fused as the epilogue of a stateless oscillator chain (second operand: an oscillator kept in
+    registers, or a block read once) against the same graphs run through k_ewise on materialised operands."""
+    for name in ('mix', 'ringmod', 'unconnected', 'lfo_mix_amp', 'broadcast'):
+        case = cases.CASES_BY_NAME[name]
+        fused = render_case(engine, ns, case)
+        _set_default('fuse_pointwise', 0)
+        try:
+            plain = render_case(engine, ns, case)
+        finally:
+            _set_default('fuse_pointwise', 1)
+        ok = np.isfinite(plain)
+        assert max_abs_err(fused[ok], plain[ok]) <= 5e-7, name
+    # one side filtered (materialised), the other a bare oscillator
+    m = ns.Mix()
+    m.left = cases.lowpass(ns, cases.osc(ns, 'Sawtooth', [[220.0, 331.0]]), [[900.0, 2500.0]])
+    m.right = cases.osc(ns, 'Sine', [[440.0]])                       # one channel, broadcast over two
+    m.mix = cases.fixed(ns, [[0.3, 0.8]])
+    compiled = engine.compile(m, 2, RATE)
+    d = compiled.describe()['launches']
+    assert [l['kind'] for l in d] == ['chain', 'chain'] and d[1]['epilogue'] == 'mix' and d[1]['other'] == 'block'
+    got = compiled.render_device(0, 4800).cpu().numpy()
+    compiled.close()
+    assert max_abs_err(got, np_oracle.GraphOracle(RATE).render(m, 0, 4800, 2)) <= 1e-4
