@@ -155,7 +155,7 @@ class C3(Workload):
 
 class C4(Workload):
     name = 'C4: 8-biquad low-pass cascade on %d channels x %g s @ 48 kHz per GPU, streamed in %g s slabs with carried state'
-    kernel = 'k_cascade_pipe<SRC_BUF> (8 section warps per 64-channel tile)'
+    kernel = 'k_cascade_reg (two channels per thread, all 8 sections in registers, time segments)'
     bound = 'hbm'
     bytes_per_unit = 8.0
 

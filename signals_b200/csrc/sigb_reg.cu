@@ -1,0 +1,283 @@
+// k_cascade_reg: register-resident filter cascade (sm_100a) for deep cascades on many channels that read a
+// materialised block (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384
+// channels x 60 s).
+//
+// k_cascade_pipe hands every chunk from section to section through shared memory (one LDS.64 + one STS.64
+// per section per two channel-samples) and measured shared-memory-wavefront / issue bound at 0.42 of the HBM
+// roofline.  Here a thread owns TWO adjacent channels (packed f32x2 math) and keeps ALL sections of them in
+// registers: per row one 8-byte load, NSEC x 6 FFMA2, one multiply by the folded gain, one 8-byte store --
+// nothing else.  The instruction-level parallelism comes from the sections: a block of R rows is evaluated in
+// wavefront order (section s of row r next to section s-1 of row r+1), so up to min(R, NSEC) independent
+// recurrences are in flight per thread.  Thread-level parallelism comes from channels (one warp = 64
+// adjacent channels = 256-byte rows) and from TIME SEGMENTS: segment j > 0 starts `warm` rows early from zero
+// state without storing; the host sizes the warm-up so that the cascade's memory of the unknown true state
+// has decayed below 2^-40 (same contract as k_cascade_pipe / k_chain_scan2).  Segment 0 continues the
+// carried state exactly; the segment that finishes the launch hands its state to the next launch.
+//
+// Section arithmetic (pipe_step of sigb_pipe.cu, same state convention):  with e = x - c s1 - s2,
+//   bp = s1 + g d e;   s1' = s1 + 2 g d e;   lp = s2 + g bp;   s2' = s2 + 2 g bp;   hp = d e
+//
+// Reference semantics: CritFilter._filter, /root/reference/src/signals/chain/fx.py:85-121 (per-channel
+// Butterworth sections run from zero state over the whole request).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "sigb200.h"
+#include "sigb_internal.h"
+#include "sigb_device.cuh"
+
+namespace {
+
+using namespace sigb_dev;
+
+constexpr int RC = 64;          // channels per warp (2 per lane)
+constexpr int RWARPS = 4;       // warps per CTA: 256 adjacent channels, 1 KB of every row
+
+struct RegSec {
+    float2 nc, al, a2, g, g2;   // (-c) (g d) (2 g d) (g) (2 g)
+    float2 d;                   // high-pass output scale (dead code for low-pass cascades)
+    float2 s1, s2;
+};
+
+// One sample (two channels) of a zero-delay-feedback state-variable section, the arithmetic of pipe_step in
+// sigb_pipe.cu.  The two updates that share (e, s1) and the two that share (bp, s2) are written back to back:
+// ptxas marks the shared operands .reuse, which matters because this loop is bound by register-file reads
+// (tools/fma_probe.cu: 96 FMA/clk/SM in this form against 85 with three coefficients and no shared operands).
+template <int KIND>
+__device__ __forceinline__ float2 reg_step(float2 x, RegSec& r) {
+    const float2 xs = __fadd2_rn(x, make_float2(-r.s2.x, -r.s2.y));
+    const float2 e = __ffma2_rn(r.nc, r.s1, xs);
+    const float2 bp = __ffma2_rn(r.al, e, r.s1);
+    r.s1 = __ffma2_rn(r.a2, e, r.s1);
+    const float2 lp = __ffma2_rn(r.g, bp, r.s2);
+    r.s2 = __ffma2_rn(r.g2, bp, r.s2);
+    return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
+}
+
+// a value ptxas must keep in its register (it would rather recompute 2g and 2gd inside the loop than hold them)
+__device__ __forceinline__ float keep(float v) {
+    asm volatile("" : "+f"(v));
+    return v;
+}
+
+// R rows through NSEC sections in wavefront order
+template <int NSEC, int KIND, int R>
+__device__ __forceinline__ void reg_block(float2 (&x)[R], RegSec (&sec)[NSEC]) {
+#pragma unroll
+    for (int dgl = 0; dgl < R + NSEC - 1; ++dgl) {
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            const int r = dgl - s;
+            if (r >= 0 && r < R) x[r] = reg_step<KIND>(x[r], sec[s]);
+        }
+    }
+}
+
+// FAST: every lane of every warp owns two live channels, the source covers all rows of the launch, and both
+// blocks take 8-byte accesses (host-checked) -- the block loop is loads, FFMA2 and stores only.
+// resident CTAs per SM the kernel is compiled for: five coefficient and two state register pairs per section
+// (14 registers) -- up to five sections fit 128 registers, deeper cascades get 168 (at 128 ptxas recomputes
+// 2g and 2gd in the loop)
+__host__ __device__ constexpr int reg_min_blocks(int nsec, int rows) { return (nsec <= 5 && rows <= 4) ? 4 : 3; }
+
+template <int NSEC, int KIND, int R, bool FAST>
+__global__ void __launch_bounds__(RWARPS * 32, reg_min_blocks(NSEC, R))
+k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
+    // Work decomposition: the (tile, block-of-R-rows) space, tile-major, is cut into `npieces` equal contiguous
+    // pieces, one per warp, so every warp slot of the machine gets the same number of rows whatever the tile count
+    // (C4: 256 tiles on 148 x 12 slots).  A piece is walked as sub-ranges [b0, b1) of one tile each.
+    const int lane = threadIdx.x & 31;
+    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (piece >= npieces) return;
+    const size_t C = (size_t)a.C;
+    const int bpt = (a.frames + R - 1) / R;                                // blocks per tile (the last one may be ragged)
+    const int64_t total = (int64_t)tiles * bpt;
+    int64_t blk = total * piece / npieces;
+    const int64_t blk_end = total * (piece + 1) / npieces;
+    const int64_t full_rows = min(a.src_rows, (int64_t)a.frames);          // rows beyond read as zero
+    // FAST only: byte offsets of the block's rows as 32-bit values held in registers (host-checked range)
+    uint32_t src_off[R], out_off[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        src_off[k] = (uint32_t)k * ((uint32_t)a.src_ld * 4u);
+        out_off[k] = (uint32_t)k * ((uint32_t)a.ld_out * 4u);
+        if (FAST && k > 0) { asm volatile("" : "+r"(src_off[k])); asm volatile("" : "+r"(out_off[k])); }
+    }
+  while (blk < blk_end) {
+    const int tile = (int)(blk / bpt);
+    const int b0 = (int)(blk - (int64_t)tile * bpt);
+    const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
+    blk += b1 - b0;
+    const int c0 = tile * RC + 2 * lane;
+    const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
+    const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
+    const int row_store = b0 * R;                                          // first row this sub-range stores
+    const int row_end = min(a.frames, b1 * R);
+    const int row_first = max(0, row_store - warm_rows);                   // warm_rows is a multiple of R
+
+    RegSec sec[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
+        const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
+        sec[s].g = make_float2(ga, gb);
+        sec[s].nc = make_float2(-a.coef[(size_t)(s * 3 + 1) * C + ca], -a.coef[(size_t)(s * 3 + 1) * C + cb]);
+        sec[s].d = make_float2(da, db);
+        sec[s].g2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
+        sec[s].al = make_float2(ga * da, gb * db);
+        sec[s].a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
+        if (row_first == 0) {
+            sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + ca], (float)a.state[(size_t)(s * 2 + 0) * C + cb]);
+            sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + ca], (float)a.state[(size_t)(s * 2 + 1) * C + cb]);
+        } else {
+            sec[s].s1 = sec[s].s2 = make_float2(0.0f, 0.0f);
+        }
+    }
+    float2 gain = make_float2(1.0f, 1.0f);
+    if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
+
+    const float* srcp = a.src + (int64_t)row_first * a.src_ld + (int64_t)ca * a.src_cs;
+    const int64_t cs1 = live1 ? (int64_t)a.src_cs : 0;
+    float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
+
+    // rows [row, row + R) of the source; the caller guarantees row + R <= row_end
+    auto load_block = [&](int row, const float* sp, float2 (&x)[R]) {
+        if (FAST) {
+#pragma unroll
+            for (int k = 0; k < R; ++k)      // 32-bit byte offsets (host-checked): one IMAD.WIDE per row address
+                x[k] = __ldcs(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(sp) + src_off[k]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                const bool in = row + k < full_rows;
+                x[k].x = in ? __ldg(sp + (int64_t)k * a.src_ld) : 0.0f;
+                x[k].y = in ? __ldg(sp + (int64_t)k * a.src_ld + cs1) : 0.0f;
+            }
+        }
+    };
+
+    int row = row_first;
+    const int nfull = (row_end - row_first) / R;                           // whole blocks of R rows
+    float2 nxt[R];
+    if (nfull > 0) load_block(row, srcp, nxt);
+    for (int b = 0; b < nfull; ++b) {
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = nxt[k];
+        srcp += (int64_t)R * a.src_ld;
+        if (b + 1 < nfull) load_block(row + R, srcp, nxt);                 // prefetch the next block behind the math
+        reg_block<NSEC, KIND, R>(x, sec);
+        if (row >= row_store) {
+            if (FAST) {
+#pragma unroll
+                for (int k = 0; k < R; ++k)
+                    __stcs(reinterpret_cast<float2*>(reinterpret_cast<char*>(outp) + out_off[k]), __fmul2_rn(x[k], gain));
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
+                    if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
+                }
+            }
+        }
+        outp += (int64_t)R * a.ld_out;
+        row += R;
+    }
+    // ragged tail (< R rows; only the segment that ends the launch has one): the state stops at the last real row
+    for (; row < row_end; ++row) {
+        float2 x;
+        const bool in = row < full_rows;
+        x.x = in ? __ldg(srcp) : 0.0f;
+        x.y = in ? __ldg(srcp + cs1) : 0.0f;
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) x = reg_step<KIND>(x, sec[s]);
+        if (live0) outp[0] = x.x * gain.x;
+        if (live1) outp[1] = x.y * gain.y;
+        srcp += a.src_ld;
+        outp += a.ld_out;
+    }
+    if (row_end == a.frames) {                // the segment that finishes the launch carries the state on
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            if (live0) {
+                a.state_out[(size_t)(s * 2 + 0) * C + c0] = (double)sec[s].s1.x;
+                a.state_out[(size_t)(s * 2 + 1) * C + c0] = (double)sec[s].s2.x;
+            }
+            if (live1) {
+                a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = (double)sec[s].s1.y;
+                a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = (double)sec[s].s2.y;
+            }
+        }
+    }
+  }
+}
+
+template <int NSEC, int KIND, int R, bool FAST>
+int reg_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
+    k_cascade_reg<NSEC, KIND, R, FAST><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+    return (int)cudaGetLastError();
+}
+
+template <int KIND, int R, bool FAST>
+int reg_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces_i, int warm, cudaStream_t st) {
+    switch (a->nsec) {
+        case 3: return reg_launch<3, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        case 4: return reg_launch<4, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        case 5: return reg_launch<5, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        case 6: return reg_launch<6, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        case 7: return reg_launch<7, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        default: return reg_launch<8, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+    }
+}
+
+}  // namespace
+
+// Whether the register-resident kernel can take this chain: a static property of the chain (never of a
+// particular call's pointers): a materialised source and 3..8 second-order sections of one kind.
+extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
+    if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
+    for (int k = 0; k < a->nsec; ++k)
+        if (a->sec_kind[k] != a->sec_kind[0] || (a->sec_kind[k] & SEC_FIRST_ORDER)) return 0;
+    return 1;
+}
+
+// variant 0 (default): blocks of 4 rows; variant 1: blocks of 8 rows.  max_segments bounds the time segments (1: never split).
+extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
+    // 8-byte loads / stores and no ragged edges: unit channel stride, even leading dimensions, 8-byte aligned bases,
+    // whole 64-channel tiles, a source that covers every row
+    const bool fast = a->src_cs == 1 && (reinterpret_cast<uintptr_t>(a->src) & 7) == 0 && (a->src_ld & 1) == 0 &&
+                      (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
+                      a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
+    const bool wide = fast && variant == 1;
+    const int R = wide ? 8 : 4;
+    const int tiles = (a->C + RC - 1) / RC;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int warps_per_sm = reg_min_blocks(a->nsec, R) * RWARPS;
+    // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
+    // below 1/4 of the piece; never fewer than one per tile
+    const int bpt = (a->frames + R - 1) / R;
+    int warm = 0;
+    int64_t npieces = tiles;
+    if (max_segments > 1 && a->warm_rows >= 0) {
+        warm = (a->warm_rows + R - 1) / R * R;
+        const int64_t slots = (int64_t)sms * warps_per_sm;
+        const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / R);
+        npieces = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
+    } else {
+        warm = bpt * R;              // unknown decay: a piece never starts inside a tile (npieces == tiles)
+    }
+    const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
+    const int npieces_i = (int)npieces;
+    const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
+    if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces_i, warm, st)
+                        : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces_i, warm, st);
+    if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces_i, warm, st)
+                        : reg_launch_nsec<0, 4, true>(a, grid, tiles, npieces_i, warm, st);
+    return hp ? reg_launch_nsec<SEC_HP, 4, false>(a, grid, tiles, npieces_i, warm, st)
+              : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces_i, warm, st);
+}

@@ -407,6 +407,38 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
         print(f'cascade pipe {ch} ch x {nsec} sections: max-abs {err:.3e}')
         assert err <= 1e-4
         assert np.array_equal(parts, whole)      # sequential in time: chunking cannot change a single bit
+    # the same with cascades of ONE kind on a materialised block: k_cascade_reg (all sections in registers;
+    # ragged channel counts take its guarded path, multiples of 64 its 8-byte path, both block widths)
+    for ch, nsec, btype, variant in [(200, 8, 'lp', 0), (68, 5, 'hp', 0), (67, 4, 'lp', 0), (4, 3, 'hp', 0), (128, 8, 'lp', 0),
+                                     (128, 8, 'lp', 1), (64, 3, 'hp', 1), (320, 6, 'lp', 0), (64, 7, 'hp', 0)]:
+        frames = 6000
+        x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
+        cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (nsec, ch)))
+        node = ext.Buffer(x)
+        for s in range(nsec):
+            node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if btype == 'hp' else 'LowPass')
+        want = x.astype(np.float64)
+        for s in range(nsec):
+            want, _ = np_oracle.render_cascade(want, cut[s:s + 1], RATE, btype=btype)
+        compiled = engine.compile(node, ch, RATE)
+        compiled.set_option('reg_variant', variant)
+        pieces = compiled.render_device(0, frames).cpu().numpy()       # short warm-ups: cut into pieces along time
+        compiled.set_option('pipe_segments', 1)
+        compiled.reset()
+        whole = compiled.render_device(0, frames).cpu().numpy()
+        compiled.reset()
+        cuts = [0, 1, 17, 1000, 1016, 4803, frames]
+        parts = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+        assert max_abs_err(pieces, whole) <= 1e-6
+        compiled.set_option('cascade_reg', 0)           # the section-pipelined kernel on the same plan and state convention
+        compiled.reset()
+        piped = compiled.render_device(0, frames).cpu().numpy()
+        compiled.close()
+        err = max_abs_err(whole, want)
+        print(f'cascade reg {ch} ch x {nsec} {btype} sections (variant {variant}): max-abs {err:.3e}, vs k_cascade_pipe {max_abs_err(whole, piped):.3e}')
+        assert err <= 1e-4
+        assert max_abs_err(whole, piped) <= 2e-5
+        assert np.array_equal(parts, whole)      # sequential in time: chunking cannot change a single bit
     # odd channel count (one live channel in the last lane) from an oscillator source, into a padded block
     torch = _torch()
     ch = 67
@@ -426,19 +458,22 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert max_abs_err(got[:, :ch], want) <= 1e-4
 
 
-def test_cascade_pipe_time_segments_match_oracle(ns, engine):
-    """k_cascade_pipe cuts long renders into time segments that warm up from zero state (decayed below
-    2^-40); every segment must match the float64 cascade, the segmented render must agree with the
-    unsegmented one, and the state handed to the next call must be the true one."""
+@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_wide', 'reg_ragged'])
+def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
+    """k_cascade_pipe / k_cascade_reg cut long renders into time segments that warm up from zero state
+    (decayed below 2^-40); every segment must match the float64 cascade, the segmented render must agree
+    with the unsegmented one, and the state handed to the next call must be the true one."""
     from signals_b200.chain import ext
     rng = np.random.default_rng(45)
-    ch, nsec, frames = 192, 8, 60000
+    ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), 8, 60000
     x = rng.uniform(-1, 1, (frames + 4000, ch)).astype(np.float32)
     cut = np.exp(rng.uniform(np.log(600.0), np.log(8000.0), (nsec, ch)))
     node = ext.Buffer(x)
     for s in range(nsec):
         node = cases.lowpass(ns, node, [cut[s]])
     compiled = engine.compile(node, ch, RATE)
+    compiled.set_option('cascade_reg', 0 if kernel == 'pipe' else -1)
+    compiled.set_option('reg_variant', 1 if kernel == 'reg_wide' else 0)
     warm = compiled.describe()['launches'][0]['warm_rows']
     assert 0 < warm < frames // 8, warm                       # so that the launch really is segmented
     first = compiled.render_device(0, frames).cpu().numpy()
