@@ -56,6 +56,20 @@ __device__ __forceinline__ float2 reg_step(float2 x, RegSec& r) {
     return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
 }
 
+constexpr int RING_D = 4;       // blocks of R rows per warp in the cp.async ring (RING_D - 1 in flight)
+
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float2 lds_f2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+
 // a value ptxas must keep in its register (it would rather recompute 2g and 2gd inside the loop than hold them)
 __device__ __forceinline__ float keep(float v) {
     asm volatile("" : "+f"(v));
@@ -88,6 +102,8 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
     // Work decomposition: the (tile, block-of-R-rows) space, tile-major, is cut into `npieces` equal contiguous
     // pieces, one per warp, so every warp slot of the machine gets the same number of rows whatever the tile count
     // (C4: 256 tiles on 148 x 12 slots).  A piece is walked as sub-ranges [b0, b1) of one tile each.
+    __shared__ __align__(16) float2 ring[FAST ? RWARPS * RING_D * R * 32 : 1];
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
     const int lane = threadIdx.x & 31;
     const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
     if (piece >= npieces) return;
@@ -142,48 +158,87 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
     const int64_t cs1 = live1 ? (int64_t)a.src_cs : 0;
     float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
 
-    // rows [row, row + R) of the source; the caller guarantees row + R <= row_end
+    // rows [row, row + R) of the source (guarded path); the caller guarantees row + R <= row_end
     auto load_block = [&](int row, const float* sp, float2 (&x)[R]) {
-        if (FAST) {
 #pragma unroll
-            for (int k = 0; k < R; ++k)      // 32-bit byte offsets (host-checked): one IMAD.WIDE per row address
-                x[k] = __ldcs(reinterpret_cast<const float2*>(reinterpret_cast<const char*>(sp) + src_off[k]));
-        } else {
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                const bool in = row + k < full_rows;
-                x[k].x = in ? __ldg(sp + (int64_t)k * a.src_ld) : 0.0f;
-                x[k].y = in ? __ldg(sp + (int64_t)k * a.src_ld + cs1) : 0.0f;
-            }
+        for (int k = 0; k < R; ++k) {
+            const bool in = row + k < full_rows;
+            x[k].x = in ? __ldg(sp + (int64_t)k * a.src_ld) : 0.0f;
+            x[k].y = in ? __ldg(sp + (int64_t)k * a.src_ld + cs1) : 0.0f;
         }
     };
 
     int row = row_first;
     const int nfull = (row_end - row_first) / R;                           // whole blocks of R rows
-    float2 nxt[R];
-    if (nfull > 0) load_block(row, srcp, nxt);
-    for (int b = 0; b < nfull; ++b) {
-        float2 x[R];
+    if (FAST) {
+        // the source runs RING_D - 1 blocks ahead of the math through a warp-private shared-memory ring filled by
+        // cp.async: a lane only ever reads the 8 bytes per row it copied itself, so no barrier is involved, and
+        // the prefetch depth costs no registers (ncu: waiting on the loads was the top stall with one block ahead)
+        const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RING_D * R * 32) + lane) * 8u;
+        const char* ip = reinterpret_cast<const char*>(srcp);
+        const int64_t step_b = (int64_t)R * a.src_ld * 4;
+        int in_blk = 0;
+        unsigned in_addr = my, out_addr = my;                              // slot addresses advance with wrap-around
+        const unsigned my_end = my + RING_D * R * 256u;
 #pragma unroll
-        for (int k = 0; k < R; ++k) x[k] = nxt[k];
-        srcp += (int64_t)R * a.src_ld;
-        if (b + 1 < nfull) load_block(row + R, srcp, nxt);                 // prefetch the next block behind the math
-        reg_block<NSEC, KIND, R>(x, sec);
-        if (row >= row_store) {
-            if (FAST) {
+        for (int j = 0; j < RING_D - 1; ++j) {
+            if (in_blk < nfull) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) cp_async8(in_addr + k * 256u, ip + src_off[k]);
+                ip += step_b;
+                ++in_blk;
+                in_addr += R * 256u;
+                if (in_addr == my_end) in_addr = my;
+            }
+            cp_async_commit();
+        }
+        for (int b = 0; b < nfull; ++b) {
+            if (in_blk < nfull) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) cp_async8(in_addr + k * 256u, ip + src_off[k]);
+                ip += step_b;
+                ++in_blk;
+                in_addr += R * 256u;
+                if (in_addr == my_end) in_addr = my;
+            }
+            cp_async_commit();
+            cp_async_wait<RING_D - 1>();
+            float2 x[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) x[k] = lds_f2(out_addr + k * 256u);
+            out_addr += R * 256u;
+            if (out_addr == my_end) out_addr = my;
+            reg_block<NSEC, KIND, R>(x, sec);
+            if (row >= row_store) {
 #pragma unroll
                 for (int k = 0; k < R; ++k)
                     __stcs(reinterpret_cast<float2*>(reinterpret_cast<char*>(outp) + out_off[k]), __fmul2_rn(x[k], gain));
-            } else {
+            }
+            outp += (int64_t)R * a.ld_out;
+            row += R;
+        }
+        cp_async_wait<0>();
+        srcp += (int64_t)nfull * R * a.src_ld;
+    } else {
+        float2 nxt[R];
+        if (nfull > 0) load_block(row, srcp, nxt);
+        for (int b = 0; b < nfull; ++b) {
+            float2 x[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) x[k] = nxt[k];
+            srcp += (int64_t)R * a.src_ld;
+            if (b + 1 < nfull) load_block(row + R, srcp, nxt);             // prefetch the next block behind the math
+            reg_block<NSEC, KIND, R>(x, sec);
+            if (row >= row_store) {
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
                     if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
                 }
             }
+            outp += (int64_t)R * a.ld_out;
+            row += R;
         }
-        outp += (int64_t)R * a.ld_out;
-        row += R;
     }
     // ragged tail (< R rows; only the segment that ends the launch has one): the state stops at the last real row
     for (; row < row_end; ++row) {
@@ -243,7 +298,8 @@ extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     return 1;
 }
 
-// variant 0 (default): blocks of 4 rows; variant 1: blocks of 8 rows.  max_segments bounds the time segments (1: never split).
+// variant 0 (default): blocks of 8 rows; variant 1: blocks of 4 rows (measured on C4: 4.59e11 vs 4.48e11
+// channel-samples/s).  max_segments bounds the time segments (1: never split).
 extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->frames <= 0) return 0;
@@ -252,7 +308,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const bool fast = a->src_cs == 1 && (reinterpret_cast<uintptr_t>(a->src) & 7) == 0 && (a->src_ld & 1) == 0 &&
                       (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
                       a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
-    const bool wide = fast && variant == 1;
+    const bool wide = fast && variant != 1;
     const int R = wide ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;

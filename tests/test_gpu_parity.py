@@ -458,7 +458,7 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert max_abs_err(got[:, :ch], want) <= 1e-4
 
 
-@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_wide', 'reg_ragged'])
+@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_r4', 'reg_ragged'])
 def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
     """k_cascade_pipe / k_cascade_reg cut long renders into time segments that warm up from zero state
     (decayed below 2^-40); every segment must match the float64 cascade, the segmented render must agree
@@ -473,7 +473,7 @@ def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
         node = cases.lowpass(ns, node, [cut[s]])
     compiled = engine.compile(node, ch, RATE)
     compiled.set_option('cascade_reg', 0 if kernel == 'pipe' else -1)
-    compiled.set_option('reg_variant', 1 if kernel == 'reg_wide' else 0)
+    compiled.set_option('reg_variant', 1 if kernel == 'reg_r4' else 0)
     warm = compiled.describe()['launches'][0]['warm_rows']
     assert 0 < warm < frames // 8, warm                       # so that the launch really is segmented
     first = compiled.render_device(0, frames).cpu().numpy()

@@ -14,7 +14,6 @@ except Exception as e: print('$name parse failed', e)
 PY
 }
 run reg0
-run reg0_10s --slab-seconds 10
 run reg1 --plan-opt reg_variant=1
-BCMD="python bench.py --config c4 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cascade_reg -s 40 -c 1 -f -o gpurun_out/prof_reg_$TAG $BCMD > gpurun_out/ncu_reg_$TAG.log 2>&1; echo "ncu exit $?"
+run reg0_10s --slab-seconds 10
+run reg1_10s --slab-seconds 10 --plan-opt reg_variant=1
