@@ -238,6 +238,48 @@ def _lfo_chain(ns):
     return gain(ns, lowpass(ns, g, [[900.0, 2500.0]]), [[0.5, 0.25]])
 
 
+def _wah(ns, lo, hi, lfo_hertz, lfo_phase):
+    # cutoff = Mix(hi, lo, mix = 0.5 + 0.5 * sine LFO) sweeps [lo, hi]: an emitter on the filter's cutoff port,
+    # sampled once per request (SingleCritFilter._eval, fx.py:124-129)
+    half = ns.Mix()
+    half.left = fixed(ns, [[1.0]])
+    half.right = fixed(ns, [[0.0]])
+    half.mix = gain(ns, _lfo(ns, 'Sine', lfo_hertz, lfo_phase), [[0.5]])      # in [-0.5, 0.5]
+    w = ns.Mix()                         # 0.5 + half -> [0, 1]
+    w.left = fixed(ns, [[1.0]])
+    w.right = half
+    w.mix = fixed(ns, [[0.5]])           # 0.5 * 1 + 0.5 * half, i.e. [0.25, 0.75]
+    m = ns.Mix()
+    m.left = fixed(ns, hi)
+    m.right = fixed(ns, lo)
+    m.mix = w
+    return m
+
+
+def _with_cutoff(ns, input_, cutoff_emitter, cls='LowPass', order=None):
+    f = lowpass(ns, input_, [[1000.0]], cls, order)
+    f.cutoff = cutoff_emitter
+    return f
+
+
+def _lfo_cutoff(ns):
+    src = osc(ns, 'Sawtooth', [[220.0, 331.0]])
+    return gain(ns, _with_cutoff(ns, src, _wah(ns, [[400.0, 900.0]], [[3000.0, 5200.0]], [[0.7, 1.1]], [[0.1, 0.4]])), [[0.5, 0.25]])
+
+
+def _lfo_cutoff_hp3(ns):
+    src = osc(ns, 'Square', [[220.5, 331.0]])
+    return _with_cutoff(ns, src, _wah(ns, [[300.0, 700.0]], [[2500.0, 4000.0]], [[1.3, 0.9]], [[0.2, 0.7]]), 'HighPass', 3)
+
+
+def _lfo_cutoff_cascade(ns):
+    node = osc(ns, 'Sawtooth', [[110.0, 196.0]])
+    for k in range(4):      # four chained LowPass nodes, each with its own sweeping cutoff: one 4-section launch
+        node = _with_cutoff(ns, node, _wah(ns, [[600.0 + 150 * k, 900.0 + 100 * k]], [[4000.0 + 500 * k, 6000.0 - 300 * k]],
+                                          [[0.5 + 0.2 * k, 0.8 + 0.1 * k]], [[0.1 * k, 0.3 + 0.1 * k]]))
+    return node
+
+
 CASES: list[Case] = [
     Case('sine_basic', lambda ns: osc(ns, 'Sine', [[440.0, 1000.0, 27.5, 4186.0]], [[0.0, 0.1, 0.5, 0.9]]), 4800, 4),
     Case('sine_pos1', lambda ns: osc(ns, 'Sine', [[440.0, 12000.0]], [[0.0, 0.37]]), 1000, 2, position=1),
@@ -291,6 +333,12 @@ CASES: list[Case] = [
          note='8 requests of 512 frames: the LFO is re-sampled at the first frame of each'),
     Case('lfo_hertz_blockwise', _lfo_hertz, 2048, 2, position=9000, block=256, tol=2e-6,
          note='per-request frequency: the phase jumps between requests exactly as in the reference'),
+    Case('lfo_cutoff', _lfo_cutoff, 4800, 2, position=12345, tol=1e-4,
+         note='LowPass.cutoff driven by emitters: designed per request at the request position (fx.py:98-102, 124-129); '
+              'position > 0, so the 100-frame context warm-up runs with the same design'),
+    Case('lfo_cutoff_hp3', _lfo_cutoff_hp3, 4800, 2, position=0, tol=1e-4, note='modulated cutoff, odd order, high-pass'),
+    Case('lfo_cutoff_cascade', _lfo_cutoff_cascade, 9600, 2, position=0, tol=1e-4,
+         note='four chained filters, every cutoff modulated'),
     Case('lowpass_60s', lambda ns: _c2(ns, 2, 60), 60 * RATE, 2, tol=1e-4, stride=1009,
          note='cascaded-IIR-over-60-s budget; golden keeps every 1009th frame'),
     Case('cascade8_60s', lambda ns: _cascade8(ns, 2, 61), 60 * RATE, 2, tol=1e-4, stride=1009),

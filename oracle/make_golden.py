@@ -55,9 +55,14 @@ def main(names=None):
         print(f'{name:32s} reference raises {got} (expected {exc})')
         assert got == exc, (name, got, exc)
     meta['error_cases'] = errors
-    if not names:
-        with open(os.path.join(GOLDEN_DIR, 'META.json'), 'w') as f:
-            json.dump(meta, f, indent=1, sort_keys=True)
+    meta_path = os.path.join(GOLDEN_DIR, 'META.json')
+    if names and os.path.exists(meta_path):      # minting a subset: merge into the existing record
+        with open(meta_path) as f:
+            old = json.load(f)
+        old['cases'].update(meta['cases'])
+        meta = old
+    with open(meta_path, 'w') as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
 
 
 if __name__ == '__main__':

@@ -351,6 +351,45 @@ extern "C" int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_design: per-request filter design for MODULATED cutoffs.  The reference samples a filter's cutoff once per
+// request (SingleCritFilter._eval -> forward_at_block_rate, chain/fx.py:124-129) and designs butter(N, Wn) per
+// channel per block (fx.py:98-102); here one thread per channel turns the cutoff row of the parameter program
+// into the {g, c, d} coefficients of the filter's sections -- sigb_butter_sections / sigb_section_coef
+// (sigb_design.cpp) restated in float64 on the device -- straight into the chain's coefficient table.
+// Wn is clipped to [0, 1] as in fx.py:100-101; scipy then rejects Wn outside (0, 1) with a ValueError, which a
+// device-side design cannot raise: such channels are clamped just inside the open interval.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(128) k_design(float* __restrict__ coef, int C, int s0, int order, const double* __restrict__ cutoff, int rate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double pi = 3.14159265358979323846;
+    double wn = cutoff[c] / ((double)rate / 2.0);
+    wn = fmin(fmax(wn, 1e-9), 1.0 - 1e-9);
+    const double g = tan(pi * wn / 2.0);
+    for (int k = 0; k < order / 2; ++k) {
+        const double r2 = 2.0 * sin(pi * (2.0 * k + 1.0) / (2.0 * order));
+        const size_t s = (size_t)(s0 + k) * 3;
+        coef[(s + 0) * C + c] = (float)g;
+        coef[(s + 1) * C + c] = (float)(r2 + g);
+        coef[(s + 2) * C + c] = (float)(1.0 / (1.0 + r2 * g + g * g));
+    }
+    if (order & 1) {
+        const size_t s = (size_t)(s0 + order / 2) * 3;
+        coef[(s + 0) * C + c] = (float)(g / (1.0 + g));
+        coef[(s + 1) * C + c] = 0.0f;
+        coef[(s + 2) * C + c] = 0.0f;
+    }
+}
+}  // namespace
+
+extern "C" int sigb_launch_design(float* coef, int C, int s0, int order, const double* cutoff, int rate, void* stream) {
+    if (C <= 0) return 0;
+    k_design<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(coef, C, s0, order, cutoff, rate);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // probe: write-only streaming fill (the practical HBM ceiling of a store-only kernel such as C2's)
 // ---------------------------------------------------------------------------------------------
 namespace {

@@ -172,6 +172,7 @@ int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream);
 int sigb_launch_voices_finish(const float* partial, int nparts, int frames, float* out, int64_t ld_out, void* stream);
 int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, double* drows, float* frows, int row_stride,
                            int64_t position, int rate, void* stream);
+int sigb_launch_design(float* coef, int C, int s0, int order, const double* cutoff, int rate, void* stream);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

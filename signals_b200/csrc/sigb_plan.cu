@@ -86,6 +86,10 @@ struct ChainSpec {
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     int dst_node = -1;
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
+    // filters whose cutoff is driven by an emitter: their sections are re-designed on the device once per request
+    // (k_design) from row `row` of the parameter program
+    struct ModFilter { int s0, order, row; };
+    std::vector<ModFilter> mods;
     // Mix / RingMod fused as an epilogue of a stateless chain (k_chain_seq)
     int epi_op = 0, epi_side = 0, epi_node = -1, epi_wave = -1, epi_p_row = -1;
     Table epi_p, epi_hertz, epi_phase, epi_gain;
@@ -555,7 +559,29 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
         for (int f : filters) {
             const sigb_node& n = p->nodes[f];
             const std::vector<double>* cut = const_of(p, n.in[1]);
-            if (!cut) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(f) + ": filter cutoff driven by a non-constant emitter");
+            if (!cut) {
+                // modulated cutoff: sampled once per request by the parameter program, sections designed on the device
+                ChainSpec::ModFilter mf;
+                mf.s0 = s0;
+                mf.order = n.order;
+                int st = param_port(n.in[1], C, &mf.row);
+                if (st != SIGB_OK) return st;
+                if (p->prow_width[mf.row] != C)   // crit_1[0, i] is not broadcast (fx.py:99)
+                    return fail(SIGB_EINDEX, "node " + std::to_string(f) + ": cutoff has " + std::to_string(p->prow_width[mf.row]) + " channels, request has " + std::to_string(C));
+                std::vector<SvfSection> secs = sigb_butter_sections(n.subtype == SIGB_FILT_HIGHPASS, n.order, 0.5);
+                const int ns = (int)secs.size();
+                for (int k = 0; k < ns; ++k) {
+                    float cf[3];
+                    sigb_section_coef(secs[k], cf);          // placeholder until the first request designs them
+                    ch.sec_kind[s0 + k] = (uint8_t)secs[k].kind;
+                    for (int c = 0; c < C; ++c)
+                        for (int j = 0; j < 3; ++j) coef[((size_t)(s0 + k) * 3 + j) * C + c] = cf[j];
+                }
+                ch.mods.push_back(mf);
+                s0 += ns;
+                warm = 1e12;                                 // decay horizon unknown: never cut along time
+                continue;
+            }
             if ((int)cut->size() != C)   // crit_1[0, i] is not broadcast (fx.py:99)
                 return fail(SIGB_EINDEX, "node " + std::to_string(f) + ": cutoff has " + std::to_string(cut->size()) + " channels, request has " + std::to_string(C));
             const int ns = section_count(n.order);
@@ -608,7 +634,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
             ch.apow = put_vec(p, apow);
             ch.apow_h = put_vec(p, apow_h);
             ch.ztab = put_vec(p, ztab);
-            if (nsec >= 2 && ch.warm_rows >= 0) {
+            if (nsec >= 2 && ch.warm_rows >= 0 && ch.mods.empty()) {
                 // Cascades: the per-section budgets add up far too conservatively.  Simulate, in float64, the
                 // zero-input decay (to 2^-44) of the slowest channels -- largest pole radius, largest sum of
                 // section time constants -- and keep a 10 % margin over the worst of them.
@@ -663,7 +689,7 @@ bool Builder::pure_osc_run(int i, int* nsec, int* wave) const {
             return const_of(p, n.in[0]) && const_of(p, n.in[1]);     // modulated oscillators are not fused
         }
         if (n.kind == SIGB_NODE_FILTER) {
-            if (n.order < 1) return false;
+            if (n.order < 1 || !const_of(p, n.in[1])) return false;      // modulated cutoffs are not fused
             *nsec += section_count(n.order);
         } else if (n.kind != SIGB_NODE_GAIN || !gain_is_const(cur)) {
             return false;
@@ -1171,7 +1197,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 }
             }
             const int tiles = (ch.C + 31) / 32;
-            const bool scan_ok = !p->opt_force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
+            // (a chain with a modulated cutoff has no scan tables: only the kernels that read {g, c, d} take it)
+            const bool scan_ok = !p->opt_force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles && ch.mods.empty();
             if (scan_ok) {
                 int e = sigb_launch_chain_scan(&a, (int)p->opt_scan_variant, st, &done);
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
@@ -1330,12 +1357,21 @@ int64_t slab_rows(sigb_plan* p, int64_t frames) {
     return std::min(frames, rows);
 }
 
-int run_params(sigb_plan* p, int64_t position, cudaStream_t st) {
+int run_params(sigb_plan* p, int64_t position, cudaStream_t st, bool design = true) {
     if (p->pprog.empty()) return SIGB_OK;
     int e = sigb_launch_param_eval(p->d_pprog, (int)p->pprog.size(), (int)p->prow_const.size(), p->d_prow_d, p->d_prow_f, p->pwidth,
                                    position, p->rate, st);
     if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
     p->launch_count++;
+    if (!design) return SIGB_OK;
+    for (const ChainSpec& ch : p->chains) {
+        for (const ChainSpec::ModFilter& mf : ch.mods) {
+            float* coef = reinterpret_cast<float*>(p->d_arena + ch.coef.off);
+            e = sigb_launch_design(coef, ch.C, mf.s0, mf.order, p->d_prow_d + (size_t)mf.row * p->pwidth, p->rate, st);
+            if (e) return fail(SIGB_ECUDA, std::string("k_design: ") + cudaGetErrorString((cudaError_t)e));
+            p->launch_count++;
+        }
+    }
     return SIGB_OK;
 }
 
@@ -1355,7 +1391,10 @@ int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int
                 CUDA_TRY(cudaMalloc(&p->scratch, need * sizeof(float)));
                 p->scratch_floats = need;
             }
-            int e = run_params(p, position - pre, st);         // the context request samples its parameters at ITS position
+            // the filter samples its cutoff at the REQUEST's position (fx.py:124-129) and runs context + block with
+            // that one design; the context request it sends upstream samples ITS parameters at its own position
+            int e = run_params(p, position, st, true);
+            if (e == SIGB_OK) e = run_params(p, position - pre, st, false);
             if (e == SIGB_OK) e = run_slab(p, position - pre, (int)pre, p->scratch, p->channels, st);
             if (e != SIGB_OK) return e;
         }
@@ -1624,6 +1663,7 @@ extern "C" int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t 
                      (c.epi_wave >= 0 ? "osc" : "block") + "\"";
             s += ", \"sections\": " + std::to_string(c.nsec_real) + ", \"sections_padded\": " + std::to_string(c.nsec) +
                  ", \"warm_rows\": " + std::to_string(c.warm_rows) +
+                 ", \"modulated_cutoffs\": " + std::to_string(c.mods.size()) +
                  ", \"gain\": " + (c.gain.off >= 0 ? "true" : "false") + "}";
         } else if (l.kind == LK_EWISE) {
             const EwiseSpec& e = plan->ewises[l.idx];

@@ -122,14 +122,23 @@ def test_modulated_parameters_lower_to_a_parameter_program(ns, engine):
     assert 'voices' not in kinds and kinds[-1] == 'reduce'
 
 
-def test_modulated_filter_cutoff_and_pan_are_still_rejected(ns, engine):
-    lfo = cases.osc(ns, 'Sine', [[2.0]])
+def test_modulated_filter_cutoff_plans_on_the_device(ns, engine):
+    """A cutoff driven by an emitter is lowered to a parameter-program row plus a per-request device-side design of
+    the filter's sections (k_design); such a chain never takes the time-parallel kernels (their tables come from a
+    host-side design, warm_rows is unknown), and a cutoff narrower than the request still raises the reference's
+    IndexError (fx.py:99)."""
     f = fx.LowPass()
-    f.input = cases.osc(ns, 'Sine', [[440.0]])
-    f.cutoff = lfo
-    with pytest.raises(chain.UnsupportedGraph):
-        engine.compile(f, 1, 48000, 16)
-    # a filter inside a parameter graph has no one-frame meaning here either
+    f.input = cases.osc(ns, 'Sine', [[440.0, 550.0]])
+    f.cutoff = cases.osc(ns, 'Sine', [[2.0, 3.0]])
+    d = engine.compile(f, 2, 48000, 16).describe()
+    (l,) = d['launches']
+    assert l['kind'] == 'chain' and l['modulated_cutoffs'] == 1 and l['warm_rows'] == -1 and d['modulated_parameters'] >= 1
+    narrow = fx.LowPass()
+    narrow.input = cases.osc(ns, 'Sine', [[440.0, 550.0]])
+    narrow.cutoff = cases.osc(ns, 'Sine', [[2.0]])
+    with pytest.raises(IndexError):
+        engine.compile(narrow, 2, 48000, 16)
+    # a filter inside a parameter graph has no one-frame meaning here
     car = osc.Sine()
     car.hertz = cases.lowpass(ns, cases.osc(ns, 'Sine', [[3.0]]), [[10.0]])
     with pytest.raises(chain.UnsupportedGraph):

@@ -748,3 +748,39 @@ def test_fused_pointwise_equals_materialised_path(ns, engine):
     got = compiled.render_device(0, 4800).cpu().numpy()
     compiled.close()
     assert max_abs_err(got, np_oracle.GraphOracle(RATE).render(m, 0, 4800, 2)) <= 1e-4
+
+
+def test_modulated_cutoff_streams_with_carried_state(ns, engine):
+    """Contiguous requests through a filter whose cutoff is driven by an LFO: the sections are re-designed on the
+    device at the first frame of every request (k_design) and the integrator states carry over.  The reference has
+    no streaming equivalent (it restarts every block from zero state); the expectation is the same
+    state-variable section in float64 with the reference's per-request cutoff sampling (fx.py:124-129)."""
+    src = cases.osc(ns, 'Sawtooth', [[220.0, 331.0]])
+    wah = cases._wah(ns, [[400.0, 900.0]], [[3000.0, 5200.0]], [[7.0, 11.0]], [[0.1, 0.4]])
+    node = cases._with_cutoff(ns, src, wah)
+    block, nblocks = 512, 12
+    compiled = engine.compile(node, 2, RATE)
+    got = np.concatenate([compiled.render_device(b * block, block).cpu().numpy() for b in range(nblocks)])
+    compiled.close()
+    orc = np_oracle.GraphOracle(RATE)
+    x = orc.render(src, 0, block * nblocks, 2)
+    want = np.zeros_like(x)
+    r2 = 2.0 * np.sin(np.pi / 4.0)
+    cutoffs = []
+    for c in range(2):
+        s1 = s2 = 0.0
+        for b in range(nblocks):
+            fc = float(np.broadcast_to(orc.render(wah, b * block, 1, 2), (1, 2))[0, c])
+            if c == 0:
+                cutoffs.append(fc)
+            g = np.tan(np.pi * fc / RATE)
+            d = 1.0 / (1.0 + r2 * g + g * g)
+            for n in range(b * block, (b + 1) * block):
+                hp = (x[n, c] - (r2 + g) * s1 - s2) * d
+                bp = g * hp + s1
+                s1 = g * hp + bp
+                lp = g * bp + s2
+                s2 = g * bp + lp
+                want[n, c] = lp
+    assert max(cutoffs) - min(cutoffs) > 1000.0            # the sweep really moves the filter between requests
+    assert max_abs_err(got, want) <= 1e-4
