@@ -117,11 +117,18 @@ int sigb_plan_destroy(sigb_plan* plan);
 
 /* Plan introspection (host only): JSON description of the fused launches; returns bytes needed. */
 int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
-/* Tuning knobs: "scan_min_tiles", "slab_frames", "force_seq", ... ; unknown key -> SIGB_EINVAL */
+/* Tuning knobs (A/B testing; every setting computes the same transfer function); unknown key -> SIGB_EINVAL:
+ *   "force_seq" (1: k_chain_seq only), "scan_variant" (geometry of the time-parallel scan kernel),
+ *   "scan_max_tiles", "slab_frames", "host_slab_bytes", "buffer_budget",
+ *   "cascade_reg" (-1: register-resident cascade kernel whenever it can take the chain, 0: never),
+ *   "reg_variant" (0: 8-row blocks, 1: 4-row blocks), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
+ *   "pipe_spw", "pipe_segments" (upper bound on the time pieces per tile of the cascade kernels; 1: never cut),
+ *   "voices_segments", "voices_m". */
 int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t value);
 /* Defaults for plans created AFTERWARDS (decisions taken while the plan is built):
  * "fuse_reduce" (1: GroupSum / PanSum over oscillator chains run as one fused render+reduce kernel,
- * 0: always on materialised blocks), "voices_m" (0 auto, 1 or 4 voices per thread in the fused kernel). */
+ * 0: always on materialised blocks), "voices_m" (0 auto, 1 or 4 voices per thread in the fused kernel),
+ * "fuse_pointwise" (1: Mix / RingMod ride on a stateless oscillator chain as its epilogue, 0: always k_ewise). */
 int sigb_set_default_option(const char* key, int64_t value);
 /* Kernels launched by this plan since creation (bench.py's gpu_launches claim). */
 int64_t sigb_plan_launch_count(const sigb_plan* plan);

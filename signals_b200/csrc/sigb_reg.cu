@@ -276,14 +276,14 @@ int reg_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, c
 }
 
 template <int KIND, int R, bool FAST>
-int reg_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces_i, int warm, cudaStream_t st) {
+int reg_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     switch (a->nsec) {
-        case 3: return reg_launch<3, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
-        case 4: return reg_launch<4, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
-        case 5: return reg_launch<5, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
-        case 6: return reg_launch<6, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
-        case 7: return reg_launch<7, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
-        default: return reg_launch<8, KIND, R, FAST>(a, grid, tiles, npieces_i, warm, st);
+        case 3: return reg_launch<3, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
+        case 4: return reg_launch<4, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
+        case 5: return reg_launch<5, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
+        case 6: return reg_launch<6, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
+        case 7: return reg_launch<7, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
+        default: return reg_launch<8, KIND, R, FAST>(a, grid, tiles, npieces, warm, st);
     }
 }
 
@@ -299,7 +299,7 @@ extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
 }
 
 // variant 0 (default): blocks of 8 rows; variant 1: blocks of 4 rows (measured on C4: 4.59e11 vs 4.48e11
-// channel-samples/s).  max_segments bounds the time segments (1: never split).
+// channel-samples/s).  max_segments bounds the pieces per tile (1: never cut along time).
 extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->frames <= 0) return 0;
@@ -318,22 +318,22 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
     int warm = 0;
-    int64_t npieces = tiles;
+    int64_t want = tiles;
     if (max_segments > 1 && a->warm_rows >= 0) {
         warm = (a->warm_rows + R - 1) / R * R;
         const int64_t slots = (int64_t)sms * warps_per_sm;
         const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / R);
-        npieces = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
+        want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
     } else {
         warm = bpt * R;              // unknown decay: a piece never starts inside a tile (npieces == tiles)
     }
+    const int npieces = (int)want;
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
-    const int npieces_i = (int)npieces;
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
-    if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces_i, warm, st)
-                        : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces_i, warm, st);
-    if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces_i, warm, st)
-                        : reg_launch_nsec<0, 4, true>(a, grid, tiles, npieces_i, warm, st);
-    return hp ? reg_launch_nsec<SEC_HP, 4, false>(a, grid, tiles, npieces_i, warm, st)
-              : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces_i, warm, st);
+    if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
+                        : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
+    if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)
+                        : reg_launch_nsec<0, 4, true>(a, grid, tiles, npieces, warm, st);
+    return hp ? reg_launch_nsec<SEC_HP, 4, false>(a, grid, tiles, npieces, warm, st)
+              : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces, warm, st);
 }
