@@ -158,6 +158,16 @@ __device__ __forceinline__ float2 step5(float2 x, Sec5& r) {
         const float2 lp = ffma2(r.g, bp, r.s2);
         r.s2 = ffma2(r.g2, bp, r.s2);
         return lp;
+    } else if (FORM == 3) {
+        // three coefficients, state updates as 2 bp - s1 / 2 lp - s2 with an immediate 2.0 (two register reads each)
+        const float2 two = make_float2(2.0f, 2.0f);
+        const float2 xs = __fadd2_rn(x, make_float2(-r.s2.x, -r.s2.y));
+        const float2 e = ffma2(r.nc, r.s1, xs);
+        const float2 bp = ffma2(r.al, e, r.s1);
+        r.s1 = ffma2(bp, two, make_float2(-r.s1.x, -r.s1.y));
+        const float2 lp = ffma2(r.g, bp, r.s2);
+        r.s2 = ffma2(lp, two, make_float2(-r.s2.x, -r.s2.y));
+        return lp;
     } else {
         const float2 t = __fmul2_rn(r.g, x);
         const float2 y = __fadd2_rn(t, r.s1);
@@ -346,6 +356,8 @@ int main() {
     REPORT("cascade 8 sec packed 5-coef, R=4", 96, 48, (k_sec5<8, 4, 1><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed 5-coef, R=2", 96, 48, (k_sec5<8, 2, 1><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed 5-coef, R=8", 96, 48, (k_sec5<8, 8, 1><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec packed 3-coef imm2, R=4", 96, 48, (k_sec5<8, 4, 3><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec packed 3-coef imm2, R=8", 96, 48, (k_sec5<8, 8, 3><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed DF2T, R=4", 80, 40, (k_sec5<8, 4, 2><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed f32, R=8", 96, 48, (k_sec2<8, 8><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec scalar f32, R=4", 96, 96, (k_sec1<8, 4><<<blocks, threads>>>(out, 0.05f)))
