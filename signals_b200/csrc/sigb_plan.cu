@@ -184,6 +184,7 @@ struct sigb_plan {
     int64_t opt_buffer_budget = 6ll << 30;
     int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
     int64_t opt_cascade_reg = -1;       // -1: register-resident cascade kernel whenever it can take the chain; 0: never
+    int64_t opt_osc_reg = 3;            // oscillator-fed chains of >= n sections run register-resident (k_osc_reg); 0: never
     int64_t opt_reg_variant = 0;        // k_cascade_reg: 0 = blocks of 8 rows, 1 = blocks of 4 rows
     int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
@@ -1187,6 +1188,13 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     ch.state_cur ^= 1;           // the kernel wrote the other copy of the state
                     continue;
                 }
+                if (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg && sigb_osc_reg_ok(&t)) {
+                    int e = sigb_launch_osc_reg(&t, (int)p->opt_pipe_segments, st);
+                    if (e) return fail(SIGB_ECUDA, std::string("k_osc_reg: ") + cudaGetErrorString((cudaError_t)e));
+                    p->launch_count++;
+                    ch.state_cur ^= 1;
+                    continue;
+                }
                 if (sigb_cascade_pipe_ok(&t) &&
                     (deep || forced)) {
                     int e = sigb_launch_cascade_pipe(&t, (int)p->opt_pipe_segments, (int)p->opt_pipe_spw, st);
@@ -1710,6 +1718,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "pipe_spw") plan->opt_pipe_spw = value;
     else if (k == "cascade_reg") plan->opt_cascade_reg = value;
     else if (k == "reg_variant") plan->opt_reg_variant = value;
+    else if (k == "osc_reg") plan->opt_osc_reg = value;
     else if (k == "voices_segments") plan->opt_voices_segments = value;
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);

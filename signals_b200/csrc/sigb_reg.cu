@@ -287,6 +287,159 @@ int reg_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int wa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_osc_reg: the same register-resident cascade fed by an OSCILLATOR evaluated in the thread (config C2's shape:
+// osc -> sections -> gain, write-only).  Per 8-row block a lane takes the exact Q0.64 phase of its two channels at
+// the block's first row (theta0 + n dtheta mod 2^64, carried by one 64-bit add per block), steps the top word by
+// the rounded increment inside the block (drift <= 8 * 2^-33 cycles), evaluates the waveform from the phase word
+// (wave_q32) and -- for the discontinuous waveforms -- redoes a column with the reference's float64 arithmetic
+// (osc.py:32) when it passes within the guard band of a jump, exactly as k_cascade_pipe's source warp does.
+// No scan, no barrier, no shared memory: time pieces with decay warm-up supply the parallelism, and the warm-up
+// costs arithmetic only (nothing is read, nothing is stored), of which a write-bound chain has plenty.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OR = 8;           // rows per block
+// resident CTAs per SM: shallow chains are write-bound and want warps (20 per SM), deep ones need the registers
+__host__ __device__ constexpr int osc_min_blocks(int nsec) { return nsec <= 2 ? 5 : nsec <= 6 ? 3 : 2; }
+
+template <int WAVE>
+__device__ __forceinline__ void osc_rows(const ChainDev& a, int c, unsigned long long th, unsigned long long dth, int64_t n0, float (&x)[OR]) {
+    const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
+    const bool near = gen_tile<WAVE, OR>(w, dhi, a.guard, x);
+    if (WAVE != SIGB_WAVE_SINE && near) {
+        const double hz = a.hertz[c], ph = a.phase[c], rate = (double)a.rate;
+#pragma unroll
+        for (int k = 0; k < OR; ++k) x[k] = osc_wave(WAVE, osc_cycles(__ddiv_rn((double)(n0 + k), rate), hz, ph));
+    }
+}
+
+template <int NSEC, int KIND, int WAVE>
+__global__ void __launch_bounds__(RWARPS * 32, osc_min_blocks(NSEC))
+k_osc_reg(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
+    const int lane = threadIdx.x & 31;
+    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (piece >= npieces) return;
+    const size_t C = (size_t)a.C;
+    const int bpt = (a.frames + OR - 1) / OR;
+    const int64_t total = (int64_t)tiles * bpt;
+    int64_t blk = total * piece / npieces;
+    const int64_t blk_end = total * (piece + 1) / npieces;
+    while (blk < blk_end) {
+        const int tile = (int)(blk / bpt);
+        const int b0 = (int)(blk - (int64_t)tile * bpt);
+        const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
+        blk += b1 - b0;
+        const int c0 = tile * RC + 2 * lane;
+        const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
+        const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
+        const int row_store = b0 * OR;
+        const int row_end = min(a.frames, b1 * OR);
+        const int row_first = max(0, row_store - warm_rows);               // warm_rows is a multiple of OR
+
+        RegSec sec[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
+            const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
+            sec[s].g = make_float2(ga, gb);
+            sec[s].nc = make_float2(-a.coef[(size_t)(s * 3 + 1) * C + ca], -a.coef[(size_t)(s * 3 + 1) * C + cb]);
+            sec[s].d = make_float2(da, db);
+            sec[s].g2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
+            sec[s].al = make_float2(ga * da, gb * db);
+            sec[s].a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
+            if (row_first == 0) {
+                sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + ca], (float)a.state[(size_t)(s * 2 + 0) * C + cb]);
+                sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + ca], (float)a.state[(size_t)(s * 2 + 1) * C + cb]);
+            } else {
+                sec[s].s1 = sec[s].s2 = make_float2(0.0f, 0.0f);
+            }
+        }
+        float2 gain = make_float2(1.0f, 1.0f);
+        if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
+        const unsigned long long dtha = a.dtheta[ca], dthb = a.dtheta[cb];
+        int64_t n = a.position + row_first;
+        unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
+        float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
+        const bool vec = fast && live1;
+
+        for (int row = row_first; row < row_end; row += OR) {
+            float xa[OR], xb[OR];
+            osc_rows<WAVE>(a, ca, tha, dtha, n, xa);
+            osc_rows<WAVE>(a, cb, thb, dthb, n, xb);
+            tha += (unsigned long long)OR * dtha;
+            thb += (unsigned long long)OR * dthb;
+            n += OR;
+            float2 x[OR];
+#pragma unroll
+            for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
+            if (row + OR <= row_end) {
+                reg_block<NSEC, KIND, OR>(x, sec);
+                if (row >= row_store) {
+                    if (vec) {
+#pragma unroll
+                        for (int k = 0; k < OR; ++k) __stcs(reinterpret_cast<float2*>(outp + (int64_t)k * a.ld_out), __fmul2_rn(x[k], gain));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < OR; ++k) {
+                            if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
+                            if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
+                        }
+                    }
+                }
+            } else {
+                // ragged last block of the launch: the state stops at the last real row
+                for (int k = 0; k < row_end - row; ++k) {
+                    float2 y = x[0];
+#pragma unroll
+                    for (int j = 1; j < OR; ++j) if (j == k) y = x[j];
+#pragma unroll
+                    for (int s = 0; s < NSEC; ++s) y = reg_step<KIND>(y, sec[s]);
+                    if (live0) outp[(int64_t)k * a.ld_out] = y.x * gain.x;
+                    if (live1) outp[(int64_t)k * a.ld_out + 1] = y.y * gain.y;
+                }
+            }
+            outp += (int64_t)OR * a.ld_out;
+        }
+        if (row_end == a.frames) {
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                if (live0) {
+                    a.state_out[(size_t)(s * 2 + 0) * C + c0] = (double)sec[s].s1.x;
+                    a.state_out[(size_t)(s * 2 + 1) * C + c0] = (double)sec[s].s2.x;
+                }
+                if (live1) {
+                    a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = (double)sec[s].s1.y;
+                    a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = (double)sec[s].s2.y;
+                }
+            }
+        }
+    }
+}
+
+template <int NSEC, int KIND>
+int osc_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, int fast, cudaStream_t st) {
+    switch (a->wave) {
+        case SIGB_WAVE_SINE: k_osc_reg<NSEC, KIND, SIGB_WAVE_SINE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case SIGB_WAVE_SQUARE: k_osc_reg<NSEC, KIND, SIGB_WAVE_SQUARE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case SIGB_WAVE_SAWTOOTH: k_osc_reg<NSEC, KIND, SIGB_WAVE_SAWTOOTH><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        default: k_osc_reg<NSEC, KIND, SIGB_WAVE_TRIANGLE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int KIND>
+int osc_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, int fast, cudaStream_t st) {
+    switch (a->nsec) {
+        case 1: return osc_launch<1, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 2: return osc_launch<2, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 3: return osc_launch<3, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 4: return osc_launch<4, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 5: return osc_launch<5, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 6: return osc_launch<6, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        case 7: return osc_launch<7, KIND>(a, grid, tiles, npieces, warm, fast, st);
+        default: return osc_launch<8, KIND>(a, grid, tiles, npieces, warm, fast, st);
+    }
+}
+
 }  // namespace
 
 // Whether the register-resident kernel can take this chain: a static property of the chain (never of a
@@ -336,4 +489,37 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
                         : reg_launch_nsec<0, 4, true>(a, grid, tiles, npieces, warm, st);
     return hp ? reg_launch_nsec<SEC_HP, 4, false>(a, grid, tiles, npieces, warm, st)
               : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces, warm, st);
+}
+
+// Oscillator-fed chains: 1..8 second-order sections of one kind, unmodulated oscillator (Q0.64 phase tables present).
+extern "C" int sigb_osc_reg_ok(const ChainDev* a) {
+    if (a->src_kind != SRC_OSC || !a->theta0 || !a->dtheta || a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
+    for (int k = 0; k < a->nsec; ++k)
+        if (a->sec_kind[k] != a->sec_kind[0] || (a->sec_kind[k] & SEC_FIRST_ORDER)) return 0;
+    return 1;
+}
+
+extern "C" int sigb_launch_osc_reg(const ChainDev* a, int max_segments, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
+    const int fast = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0;
+    const int tiles = (a->C + RC - 1) / RC;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int warps_per_sm = osc_min_blocks(a->nsec) * RWARPS;
+    const int bpt = (a->frames + OR - 1) / OR;
+    int warm = 0;
+    int64_t want = tiles;
+    if (max_segments > 1 && a->warm_rows >= 0) {
+        warm = (a->warm_rows + OR - 1) / OR * OR;
+        const int64_t slots = (int64_t)sms * warps_per_sm;
+        const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / OR);
+        want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
+    } else {
+        warm = bpt * OR;
+    }
+    const int npieces = (int)want;
+    const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
+    return (a->sec_kind[0] & SEC_HP) ? osc_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, fast, st)
+                                     : osc_launch_nsec<0>(a, grid, tiles, npieces, warm, fast, st);
 }

@@ -55,11 +55,13 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'scan13', 'scan14', 'scan15', 'scan16', 'scan17', 'scan18', 'pipe', 'pipe2'])
+@pytest.mark.parametrize('mode', ['seq', 'scan0', 'scan1', 'scan2', 'scan3', 'scan4', 'scan5', 'scan6', 'scan7', 'scan8', 'scan9', 'scan13', 'scan14', 'scan15', 'scan16', 'scan17', 'scan18', 'pipe', 'pipe2', 'oscreg'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, each geometry of the time-parallel k_chain_scan (deep cascades forced onto it too) and
-    the section-pipelined k_cascade_pipe (forced from 2 sections) agree with the reference."""
-    opts = dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1) if mode == 'pipe' else dict(cascade_pipe=1, pipe_spw=2) if mode == 'pipe2' else dict(scan_variant=int(mode[4:]), cascade_pipe=0)
+    the section-pipelined k_cascade_pipe (forced from 2 sections) and the register-resident k_osc_reg (from one
+    section) agree with the reference."""
+    opts = (dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1, osc_reg=0) if mode == 'pipe' else dict(cascade_pipe=1, pipe_spw=2, osc_reg=0) if mode == 'pipe2'
+            else dict(osc_reg=1) if mode == 'oscreg' else dict(scan_variant=int(mode[4:]), cascade_pipe=0))
     got = render_case(engine, ns, case, **opts)[::case.stride]
     err = max_abs_err(got, load_golden(case.name))
     assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
@@ -784,3 +786,56 @@ def test_modulated_cutoff_streams_with_carried_state(ns, engine):
                 want[n, c] = lp
     assert max(cutoffs) - min(cutoffs) > 1000.0            # the sweep really moves the filter between requests
     assert max_abs_err(got, want) <= 1e-4
+
+
+@pytest.mark.parametrize('wave,nsec,btype,ch', [('Sine', 1, 'lp', 128), ('Sine', 1, 'lp', 130), ('Square', 2, 'hp', 66),
+                                                ('Sawtooth', 8, 'lp', 64), ('Triangle', 4, 'lp', 5)])
+def test_osc_reg_pieces_and_streaming(wave, nsec, btype, ch, ns, engine):
+    """k_osc_reg (oscillator evaluated in the thread, all sections in registers): time pieces with decay warm-up against
+    the float64 reference render, agreement with the uncut render, state carried into a ragged second request, and
+    agreement of a chunked render with the single request."""
+    rng = np.random.default_rng(46)
+    frames, tail = 60000, 3001
+    cut = np.exp(rng.uniform(np.log(700.0), np.log(8000.0), (nsec, ch)))
+    node = cases.osc(ns, wave, [rng.uniform(55.0, 1760.0, ch)], [rng.uniform(0, 1, ch)])
+    for s in range(nsec):
+        node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if btype == 'hp' else 'LowPass')
+    compiled = engine.compile(node, ch, RATE)
+    compiled.set_option('osc_reg', 1)
+    warm = compiled.describe()['launches'][0]['warm_rows']
+    assert 0 < warm < frames // 8, warm                       # so that the launch really is cut along time
+    first = compiled.render_device(0, frames).cpu().numpy()
+    second = compiled.render_device(frames, tail).cpu().numpy()
+    compiled.set_option('pipe_segments', 1)
+    compiled.reset()
+    whole = compiled.render_device(0, frames).cpu().numpy()
+    compiled.reset()
+    cuts = [0, 1, 9, 1000, 1016, 4803, 20000]
+    parts = np.concatenate([compiled.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+    compiled.close()
+    pick = rng.choice(ch, min(ch, 12), replace=False)
+    sub = cases.osc(ns, wave, [np.asarray(node_hertz(node))[pick]], [np.asarray(node_phase(node))[pick]])
+    for s in range(nsec):
+        sub = cases.lowpass(ns, sub, [cut[s][pick]], 'HighPass' if btype == 'hp' else 'LowPass')
+    want = np_oracle.GraphOracle(RATE).render(sub, 0, frames + tail, len(pick))
+    err = max_abs_err(np.concatenate([first, second])[:, pick], want)
+    print(f'osc_reg {wave} x {nsec} {btype} sections, {ch} ch: warm_rows {warm}, max-abs {err:.3e}')
+    assert err <= 1e-4
+    assert max_abs_err(first, whole) <= 1e-6
+    # (not bit-equal: inside a block the phase word advances by the rounded increment, and the blocks of a chunked
+    # render start at other rows)
+    assert max_abs_err(parts, whole[:20000]) <= 2e-6
+
+
+def _osc_of(node):
+    while 'input' in node.inputs_by_port:
+        node = node.inputs_by_port['input']
+    return node
+
+
+def node_hertz(node):
+    return _osc_of(node).inputs_by_port['hertz'].get_state().value[0]
+
+
+def node_phase(node):
+    return _osc_of(node).inputs_by_port['phase'].get_state().value[0]
