@@ -84,13 +84,13 @@ class C2(Workload):
 
     def __init__(self, args, rank, world):
         super().__init__(args, rank, world)
-        from oracle import cases
+        from signals_b200 import workloads as cases
         self.v = args.voices
         self.out_channels = self.v
         self.params = cases.voice_params(2 + rank, self.v)
 
     def build(self, ns):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         hertz, phase, cutoff, g = self.params
         return cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff]), [g])
 
@@ -106,7 +106,7 @@ class C2(Workload):
         return float(self.v) * self.frames
 
     def cpu_sample(self, workers):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         sv = 192 if workers == 1 else max(workers * 16, 64)
         sf = RATE * 10 if workers == 1 else RATE
         hertz, phase, cutoff, g = cases.voice_params(2, sv)
@@ -123,14 +123,14 @@ class C3(Workload):
 
     def __init__(self, args, rank, world):
         super().__init__(args, rank, world)
-        from oracle import cases
+        from signals_b200 import workloads as cases
         self.p = args.voices
         self.groups = max(1, self.p // 1024)
         self.out_channels = self.groups
         self.params = cases.bank_params(3 + rank, self.p, self.p // self.groups)
 
     def build(self, ns):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         from signals_b200.chain import ext
         return cases.build_bank(ns, ext, *self.params, self.groups)
 
@@ -146,7 +146,7 @@ class C3(Workload):
         return float(self.p) * self.frames
 
     def cpu_sample(self, workers):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         sp, sf = 1024 * max(1, min(workers, 8)), RATE // 2
         hertz, phase, amp = cases.bank_params(3, sp, 1024)
         jobs = [('bank', (hertz[i:i + 1024], phase[i:i + 1024], amp[i:i + 1024], sf)) for i in range(0, sp, 1024)]
@@ -170,7 +170,7 @@ class C4(Workload):
 
     def build(self, ns):
         import torch
-        from oracle import cases
+        from signals_b200 import workloads as cases
         from signals_b200.chain import ext
         g = torch.Generator(device='cuda')
         g.manual_seed(self.seed)
@@ -211,12 +211,12 @@ class C5(Workload):
 
     def __init__(self, args, rank, world):
         super().__init__(args, rank, world)
-        from oracle import cases
+        from signals_b200 import workloads as cases
         self.n = args.voices
         self.prm = cases.instance_params(5, self.n, rank, world)
 
     def build(self, ns):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         from signals_b200.chain import ext
         return cases.build_instances(ns, ext, self.prm)
 
@@ -232,7 +232,7 @@ class C5(Workload):
         return float(len(self.prm['hertz'])) * self.frames
 
     def cpu_sample(self, workers):
-        from oracle import cases
+        from signals_b200 import workloads as cases
         sn, sf = 64 * max(1, workers), RATE
         prm = cases.instance_params(5, sn)
         jobs = []
@@ -367,7 +367,7 @@ class ClockSampler(threading.Thread):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from oracle import cases            # parameter distributions only (shared with the tests)
+    from signals_b200 import workloads as cases     # parameter distributions and graph builders (shared with the tests)
     from signals_b200 import _lib, engine, shard
 
     world = int(os.environ.get('WORLD_SIZE', '1'))

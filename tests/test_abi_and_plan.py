@@ -42,6 +42,15 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith('.py'):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+    # tools/ measure the product: they build their graphs from signals_b200.workloads, never from oracle/
+    for f in os.listdir(os.path.join(ROOT, 'tools')):
+        if f.endswith('.py'):
+            assert not pat.search(open(os.path.join(ROOT, 'tools', f)).read()), f
+    # bench.py may execute oracle/ only in its CPU legs (cpu_baseline and --impl reference)
+    bench = open(os.path.join(ROOT, 'bench.py')).read()
+    uses = [m.start() for m in re.finditer(r'^\s*(import|from)\s+oracle\b', bench, re.M)]
+    cpu_leg, gpu_leg = bench.index('# CPU side: the oracle port'), bench.index('def run_b200(')
+    assert uses and all(cpu_leg < u < gpu_leg for u in uses), 'bench.py imports oracle/ outside its CPU legs'
 
 
 @pytest.mark.parametrize('case', cases.CASES, ids=lambda c: c.name)

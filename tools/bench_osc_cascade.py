@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import cases          # noqa: E402  (graph builders only; nothing from the oracle is measured)
+from signals_b200 import workloads as cases   # noqa: E402
 from signals_b200 import engine   # noqa: E402
 
 RATE, CH, FRAMES, NSEC = 48000, 16384, 480000, 8
