@@ -118,6 +118,51 @@ constexpr int VT = SIGB_VOICE_THREADS;
 template <int KIND, int M, int VK>
 __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M], const float (&c)[M], const float (&d)[M],
                                           float (&s1)[M], float (&s2)[M], int kmax) {
+#ifndef SIGB_VOICES_SCALAR
+    if constexpr (M == 4 && !(KIND & SEC_FIRST_ORDER)) {
+        // second-order sections of four voices as two packed f32x2 recurrences (six FFMA2-class instructions per
+        // two voice-samples instead of seven scalar ones per voice-sample); same arithmetic as pipe_step /
+        // reg_step of the cascade kernels: e = x - c s1 - s2, bp = s1 + g d e, s1' = s1 + 2 g d e,
+        // lp = s2 + g bp, s2' = s2 + 2 g bp, hp = d e
+        float2 nc[2], al[2], a2[2], gg[2], g2[2], dd[2], p1[2], p2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m0 = 2 * h, m1 = 2 * h + 1;
+            gg[h] = make_float2(g[m0], g[m1]);
+            g2[h] = make_float2(2.0f * g[m0], 2.0f * g[m1]);
+            al[h] = make_float2(g[m0] * d[m0], g[m1] * d[m1]);
+            a2[h] = make_float2(2.0f * (g[m0] * d[m0]), 2.0f * (g[m1] * d[m1]));
+            nc[h] = make_float2(-c[m0], -c[m1]);
+            dd[h] = make_float2(d[m0], d[m1]);
+            p1[h] = make_float2(s1[m0], s1[m1]);
+            p2[h] = make_float2(s2[m0], s2[m1]);
+        }
+#pragma unroll
+        for (int k = 0; k < VK; ++k) {
+            if (k < kmax) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 xp = make_float2(x[2 * h][k], x[2 * h + 1][k]);
+                    const float2 xs = __fadd2_rn(xp, make_float2(-p2[h].x, -p2[h].y));
+                    const float2 e = __ffma2_rn(nc[h], p1[h], xs);
+                    const float2 bp = __ffma2_rn(al[h], e, p1[h]);
+                    p1[h] = __ffma2_rn(a2[h], e, p1[h]);
+                    const float2 lp = __ffma2_rn(gg[h], bp, p2[h]);
+                    p2[h] = __ffma2_rn(g2[h], bp, p2[h]);
+                    const float2 y = (KIND & SEC_HP) ? __fmul2_rn(e, dd[h]) : lp;
+                    x[2 * h][k] = y.x;
+                    x[2 * h + 1][k] = y.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            s1[2 * h] = p1[h].x; s1[2 * h + 1] = p1[h].y;
+            s2[2 * h] = p2[h].x; s2[2 * h + 1] = p2[h].y;
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < VK; ++k) {
         if (k < kmax) {
