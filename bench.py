@@ -79,6 +79,7 @@ class Workload:
 class C2(Workload):
     name = 'C2: sine -> biquad lowpass -> gain, %d voices x %g s @ 48 kHz per GPU, fp32 (frames, voices) block in HBM'
     kernel = 'k_chain_scan3<sine, 1 section, 64-channel tiles, 3x9 workers, f32 carry chain>'
+    traffic_profile = 'r01_k_chain_scan3_full.txt'
     bound = 'hbm'
     bytes_per_unit = 4.0
 
@@ -155,7 +156,8 @@ class C3(Workload):
 
 class C4(Workload):
     name = 'C4: 8-biquad low-pass cascade on %d channels x %g s @ 48 kHz per GPU, streamed in %g s slabs with carried state'
-    kernel = 'k_cascade_reg (two channels per thread, all 8 sections in registers, time segments)'
+    kernel = 'k_cascade_reg (two channels per thread, all 8 sections in registers, equal time pieces per warp slot)'
+    traffic_profile = 'r01_k_cascade_reg_full.txt'
     bound = 'hbm'
     bytes_per_unit = 8.0
 
@@ -364,6 +366,23 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(name):
+    """dram__bytes_{read,write}.sum of a committed ncu summary under profiles/ (tools/ncu_summary.py format)."""
+    if not name:
+        return None
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+    got = {}
+    try:
+        with open(os.path.join(ROOT, 'profiles', name)) as f:
+            for ln in f:
+                parts = ln.split()
+                if len(parts) == 3 and parts[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and parts[2] in scale:
+                    got[parts[0].split('_')[-1].split('.')[0]] = float(parts[1]) * scale[parts[2]]
+    except OSError:
+        return None
+    return got if len(got) == 2 else None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -494,7 +513,15 @@ def run_b200(args):
             achieved = wl.bytes_per_unit * wl.launch_units() / (launch_ms * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else '6650 GB/s (of fallback)',
-                    'algorithmic_bytes_per_voice_sample': wl.bytes_per_unit}
+                    'algorithmic_bytes_per_voice_sample': wl.bytes_per_unit,
+                    'algorithmic_bytes_per_launch': wl.bytes_per_unit * wl.launch_units()}
+            # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this very
+            # workload (never measured under the profiler here): only quoted when the launch has the captured size
+            traffic = ncu_traffic(getattr(wl, 'traffic_profile', None))
+            if traffic and abs(traffic['write'] / (4.0 * wl.launch_units()) - 1.0) < 0.02:
+                roof['traffic'] = traffic['read'] + traffic['write']
+                roof['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)'
+                roof['traffic_source'] = 'profiles/' + wl.traffic_profile
         else:
             # transcendental-bound kernels: one MUFU.SIN per unit on the 16-lane/clk/SM special-function pipe
             sm_mhz = clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
