@@ -1,18 +1,23 @@
-// k_cascade_reg: register-resident filter cascade (sm_100a) for deep cascades on many channels that read a
-// materialised block (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384
-// channels x 60 s).
+// k_cascade_reg / k_osc_reg: register-resident filter cascades (sm_100a) for deep cascades on many channels
+// (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384 channels x 60 s).
 //
 // k_cascade_pipe hands every chunk from section to section through shared memory (one LDS.64 + one STS.64
-// per section per two channel-samples) and measured shared-memory-wavefront / issue bound at 0.42 of the HBM
-// roofline.  Here a thread owns TWO adjacent channels (packed f32x2 math) and keeps ALL sections of them in
-// registers: per row one 8-byte load, NSEC x 6 FFMA2, one multiply by the folded gain, one 8-byte store --
-// nothing else.  The instruction-level parallelism comes from the sections: a block of R rows is evaluated in
-// wavefront order (section s of row r next to section s-1 of row r+1), so up to min(R, NSEC) independent
-// recurrences are in flight per thread.  Thread-level parallelism comes from channels (one warp = 64
-// adjacent channels = 256-byte rows) and from TIME SEGMENTS: segment j > 0 starts `warm` rows early from zero
-// state without storing; the host sizes the warm-up so that the cascade's memory of the unknown true state
-// has decayed below 2^-40 (same contract as k_cascade_pipe / k_chain_scan2).  Segment 0 continues the
-// carried state exactly; the segment that finishes the launch hands its state to the next launch.
+// per section per two channel-samples) and measured 0.42 of the HBM roofline.  Here a thread owns TWO adjacent
+// channels (packed f32x2 math) and keeps ALL sections of them in registers: per row one 8-byte source read
+// (k_cascade_reg: through a warp-private cp.async ring; k_osc_reg: an oscillator evaluated in the thread),
+// NSEC x (FADD2 + 5 FFMA2), one multiply by the folded gain, one 8-byte streaming store.  Instruction-level
+// parallelism comes from the sections: a block of R rows is evaluated in wavefront order (section s of row r
+// next to section s-1 of row r+1).  Thread-level parallelism comes from channels (one warp = 64 adjacent
+// channels = 256-byte rows) and from TIME: the (tile, block) space is cut into one equal piece per warp slot of
+// the machine; a piece that starts inside a tile begins `warm` rows early from zero state without storing --
+// the host sizes the warm-up so that the cascade's memory of the unknown true state has decayed below 2^-40
+// (same contract as k_cascade_pipe / k_chain_scan2).  A piece that starts at row 0 continues the carried state
+// exactly; the piece that finishes a tile hands its state to the next launch.
+//
+// What bounds it (tools/fma_probe.cu, profiles/r01_fma_probe.txt): every multiply-add of the section reads
+// three different registers, so the loop is limited by register-file operand reads at ~96 FMA/clk/SM, not by
+// the 128-lane FMA datapath; the five-coefficient form below lets ptxas mark the operands shared by
+// consecutive instructions .reuse (85 -> 96 FMA/clk/SM register-only).
 //
 // Section arithmetic (pipe_step of sigb_pipe.cu, same state convention):  with e = x - c s1 - s2,
 //   bp = s1 + g d e;   s1' = s1 + 2 g d e;   lp = s2 + g bp;   s2' = s2 + 2 g bp;   hp = d e
