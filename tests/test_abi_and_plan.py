@@ -147,6 +147,10 @@ def test_modulated_filter_cutoff_plans_on_the_device(ns, engine):
     narrow.cutoff = cases.osc(ns, 'Sine', [[2.0]])
     with pytest.raises(IndexError):
         engine.compile(narrow, 2, 48000, 16)
+    # four chained filters with modulated cutoffs are still ONE launch: four sections, four per-request designs
+    d = engine.compile(cases.CASES_BY_NAME['lfo_cutoff_cascade'].build(ns), 2, 48000).describe()
+    (l,) = d['launches']
+    assert l['sections'] == 4 and l['modulated_cutoffs'] == 4 and l['source'] == 'osc'
     # a filter inside a parameter graph has no one-frame meaning here
     car = osc.Sine()
     car.hertz = cases.lowpass(ns, cases.osc(ns, 'Sine', [[3.0]]), [[10.0]])
