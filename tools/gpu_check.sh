@@ -17,4 +17,8 @@ timeout 300 $BCMD > gpurun_out/plain_$TAG.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $BCMD > gpurun_out/ncu_l_$TAG.log 2>&1
 timeout 300 $BCMD > gpurun_out/plain2_$TAG.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_chain_scan3 -s 3 -c 1 -f -o gpurun_out/prof_$TAG $BCMD > gpurun_out/ncu_f_$TAG.log 2>&1
+# C4: launch list and full capture of the register-resident cascade kernel (one 10 s slab per launch)
+C4CMD="python bench.py --config c4 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline"
+timeout 300 $C4CMD > gpurun_out/plain_c4_$TAG.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_cascade_reg -s 20 -c 1 -f -o gpurun_out/prof_reg_$TAG $C4CMD > gpurun_out/ncu_reg_$TAG.log 2>&1
 ls -la gpurun_out
