@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SIGB_ABI_VERSION 1
+#define SIGB_ABI_VERSION 2
 
 /* status codes; the Python shim maps them onto the reference's exception types
  * (src/signals/chain/__init__.py:21, 87-104). */
@@ -59,8 +59,11 @@ enum {
                                 in[0]=input (C ch) -> `order` groups of C/order adjacent channels */
     SIGB_NODE_PANSUM = 10,   /* extension: in[0]=input (C ch), in[1]=pan (block rate) -> 2 ch:
                                 L = sum((1-pan) y), R = sum(pan y)                                */
-    SIGB_NODE_BUFFER = 11    /* extension: HBM-resident sample source, (rows, channels) floats,
+    SIGB_NODE_BUFFER = 11,   /* extension: HBM-resident sample source, (rows, channels) floats,
                                 row index = absolute frame position; zeros past the end           */
+    SIGB_NODE_TAP = 12       /* pass-through side-effect node (chain/vis.py:61-64 Wave / Spec, chain/files.py:89-102
+                                FileWriter): in[0]=input; value = its input, kept materialised so that the host can
+                                read the block after the render (sigb_plan_read_tap).  Never the root.            */
 };
 
 /* OSC subtype */
@@ -110,7 +113,27 @@ int sigb_render(sigb_plan* plan, int64_t position, int32_t frames,
  * This is the call that replaces `block = self.input.request(loc)` + the copy into `outdata`
  * (src/signals/chain/dev.py:173,178).  Blocks until `out_host` is complete. */
 int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frames,
-                     float* out_host, int64_t ld_out);
+                     float* out_host, int64_t ld_out, void* after_stream);
+/* `after_stream` (cudaStream_t as void*, NULL = legacy default stream): work the caller has queued there -- the
+ * upload of a bound Buffer, a previous sigb_render -- is ordered before the render, which runs on the plan's own
+ * streams.  Block-rate parameters are sampled ONCE, at `position`, however the request is cut into slabs. */
+
+/* The audio callback's block (SinkDevice._callback, src/signals/chain/dev.py:167-179): the latency path.  The
+ * launches of a block of `frames` rows are captured once into a CUDA graph; every later contiguous block of that
+ * length is ONE cudaGraphLaunch (the kernels read the position from a page-locked block header, the root launch
+ * writes page-locked staging directly), one stream synchronisation and one memcpy into `out_host` (any host
+ * memory).  Seeks, plans with Buffer sources or fused bank / voice reductions, and blocks above "rt_max_bytes"
+ * are served by sigb_render_host.  Same results as sigb_render_host for the same calls. */
+int sigb_render_block(sigb_plan* plan, int64_t position, int32_t frames,
+                      float* out_host, int64_t ld_out);
+/* CUDA graphs launched by sigb_render_block since the plan was created. */
+int64_t sigb_plan_graph_launches(const sigb_plan* plan);
+
+/* Taps: the blocks the SIGB_NODE_TAP nodes saw during the most recent request, copied from the buffers the render
+ * left in HBM (no second render).  Taps are numbered in plan order (topological order of their records).
+ * out_host == NULL only reports `channels`.  SIGB_ESTATE when the request was rendered in several slabs. */
+int sigb_plan_tap_count(const sigb_plan* plan);
+int sigb_plan_read_tap(sigb_plan* plan, int32_t tap, float* out_host, int64_t ld_out, int32_t* channels);
 
 int sigb_state_reset(sigb_plan* plan);          /* zero all filter state; next render is a seek  */
 int sigb_plan_destroy(sigb_plan* plan);
@@ -124,7 +147,13 @@ int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
  *   "reg_variant" (0: 8-row blocks, 1: 4-row blocks), "osc_reg" (oscillator-fed chains of >= n sections run
  *   register-resident, 0: never; default 3), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
  *   "pipe_spw", "pipe_segments" (upper bound on the time pieces per tile of the cascade kernels; 1: never cut),
- *   "voices_segments", "voices_m". */
+ *   "voices_segments" (k_voices: 0 equal pieces per resident CTA, 1 one piece per voice group, n pieces per group),
+ *   "voices_pieces" (automatic mode: pieces per resident CTA slot, default 2), "voices_m",
+ *   "rt_graph" (0: sigb_render_block launches its kernels directly instead of through a captured graph),
+ *   "rt_max_bytes" (largest block sigb_render_block serves itself),
+ *   "blockwise_reference" (1: EVERY request restarts the filters from zero state and `context` warm-up frames, as the
+ *   reference itself does block by block, fx.py:82-83, 93-105 -- for A/B against the reference's blockwise output;
+ *   default 0 carries the true state across contiguous requests). */
 int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t value);
 /* Defaults for plans created AFTERWARDS (decisions taken while the plan is built):
  * "fuse_reduce" (1: GroupSum / PanSum over oscillator chains run as one fused render+reduce kernel,

@@ -13,7 +13,7 @@ SIGB_EINVAL, SIGB_ESHAPE, SIGB_EINDEX, SIGB_ECRIT, SIGB_EUNSUPPORTED, SIGB_ECUDA
     -1, -2, -3, -4, -5, -6, -7, -8
 
 (NODE_ZERO, NODE_FIXED, NODE_OSC, NODE_GAIN, NODE_MIX, NODE_RINGMOD, NODE_AMP, NODE_FILTER, NODE_MERGE,
- NODE_GROUPSUM, NODE_PANSUM, NODE_BUFFER) = range(12)
+ NODE_GROUPSUM, NODE_PANSUM, NODE_BUFFER, NODE_TAP) = range(13)
 WAVE_SINE, WAVE_SQUARE, WAVE_SAWTOOTH, WAVE_TRIANGLE = range(4)
 FILT_LOWPASS, FILT_HIGHPASS = range(2)
 
@@ -62,8 +62,16 @@ def lib() -> ctypes.CDLL:
     L.sigb_plan_bind_buffer_window.restype = ctypes.c_int
     L.sigb_render.argtypes = [vp, i64, i32, vp, i64, vp]
     L.sigb_render.restype = ctypes.c_int
-    L.sigb_render_host.argtypes = [vp, i64, i32, vp, i64]
+    L.sigb_render_host.argtypes = [vp, i64, i32, vp, i64, vp]
     L.sigb_render_host.restype = ctypes.c_int
+    L.sigb_render_block.argtypes = [vp, i64, i32, vp, i64]
+    L.sigb_render_block.restype = ctypes.c_int
+    L.sigb_plan_graph_launches.argtypes = [vp]
+    L.sigb_plan_graph_launches.restype = i64
+    L.sigb_plan_tap_count.argtypes = [vp]
+    L.sigb_plan_tap_count.restype = ctypes.c_int
+    L.sigb_plan_read_tap.argtypes = [vp, i32, vp, i64, ctypes.POINTER(i32)]
+    L.sigb_plan_read_tap.restype = ctypes.c_int
     L.sigb_state_reset.argtypes = [vp]
     L.sigb_state_reset.restype = ctypes.c_int
     L.sigb_plan_destroy.argtypes = [vp]

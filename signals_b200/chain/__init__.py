@@ -159,7 +159,29 @@ class RequestRate(enum.Enum):
     UNUSED_FRAME = enum.auto()
 
 
-state = attr.s(auto_attribs=True, frozen=False, kw_only=True)
+# Graph epoch: bumped by every edit the evaluator can observe -- a port (dis)connected, a state attribute assigned, a
+# state object replaced.  The engine keeps a compiled plan for as long as the epoch stands still (one integer compare
+# per audio callback instead of a walk over the graph); the reference has nothing to invalidate because it re-reads
+# every node's state on every block.  In-place writes INTO a Fixed's value array are invisible here; the engine
+# compares those arrays against its snapshot (signals_b200.engine.Engine.plan_for).
+_epoch = 0
+
+
+def graph_epoch() -> int:
+    return _epoch
+
+
+def touch_graph() -> None:
+    global _epoch
+    _epoch += 1
+
+
+def _on_state_setattr(instance, attribute, value):
+    touch_graph()
+    return value
+
+
+state = attr.s(auto_attribs=True, frozen=False, kw_only=True, on_setattr=_on_state_setattr)
 
 
 class Named:
@@ -194,6 +216,7 @@ class Signal(abc.ABC, Named):
         if not isinstance(new_state, self.State):
             raise BadStateSchema(self, new_state)
         self._state = new_state
+        touch_graph()
 
     def destroy(self) -> None:
         pass
@@ -269,12 +292,14 @@ class Receiver(Signal, abc.ABC):
         def expel(self) -> None:
             self.sig._outputs.discard((self.name, self.parent))
             self.sig = None
+            touch_graph()
 
         def assign(self, input_: Emitter) -> None:
             if self.sig is not None:
                 self.expel()
             self.sig = input_
             input_._outputs.add((self.name, self.parent))
+            touch_graph()
 
         def request(self, loc: BlockLoc) -> np.ndarray:
             """The pull: an unconnected port yields ``zeros((1, 1))``; otherwise the emitter's

@@ -140,13 +140,16 @@ class SinkDevice(Device, Receiver, ExplicitChannels):
         loc = BlockLoc(position=self.frame_position, shape=Shape(channels=channels, frames=frames), rate=rate)
         bound = self._ports['input']
         if bound and outdata.dtype == np.float32 and outdata.strides[1] == 4 and getattr(bound.sig.get_state(), 'enabled', True):
-            # fast path: sigb_render_host writes the device's float32 buffer directly (dev.py:173 + :178 in one call)
+            # fast path (dev.py:173 + :178 in one call): the plan is kept while the graph epoch stands still, the block
+            # is ONE captured CUDA graph launch into page-locked staging and one copy into the device's buffer
+            # (sigb_render_block); taps get their blocks from that same launch
             from signals_b200 import engine
             eng = engine.default_engine()
             compiled = eng.plan_for(bound.sig, channels, rate, frames)
-            compiled.render_host(loc.position, frames, outdata[:frames, :channels])
+            block = outdata[:frames, :channels]
+            compiled.render_block(loc.position, frames, block)
             if compiled.records.taps:
-                eng.serve_taps(bound.sig, loc)
+                eng.serve_taps(bound.sig, loc, rendered=block)
         else:
             outdata[:, :channels] = self.input.request(loc)
         self.frame_position += frames

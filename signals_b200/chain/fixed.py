@@ -6,7 +6,7 @@ import attr
 import numpy as np
 
 from signals_b200 import SignalFlags
-from signals_b200.chain import BadStateValue, Emitter, Request, Shape, state
+from signals_b200.chain import BadStateValue, Emitter, Request, Shape, state, _on_state_setattr
 
 
 def _validate_array(instance, attribute, new_value):
@@ -19,7 +19,7 @@ class Fixed(Emitter):
     class State(Emitter.State):
         value: np.ndarray = attr.ib(factory=Emitter.empty_result,
                                     validator=_validate_array,
-                                    on_setattr=attr.setters.validate)
+                                    on_setattr=[attr.setters.validate, _on_state_setattr])
 
     @classmethod
     def flags(cls) -> SignalFlags:

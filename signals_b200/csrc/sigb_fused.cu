@@ -182,21 +182,39 @@ __device__ __forceinline__ unsigned gen_tiles(const int (&w)[M], const int (&dhi
 }
 
 // M voices per thread, VK rows per tile (M = 4: VK = 8 keeps x[M][VK], the accumulators and the voices'
-// phase / filter / weight registers inside 128 registers)
+// phase / filter / weight registers inside 128 registers).
+//
+// Work decomposition: a *group* is the VT * M voices one CTA holds in registers (all of one segment, i.e. one
+// wave x filter kind); the (group, VK-row block) space, group-major, is cut into `npieces` equal contiguous pieces,
+// one per CTA, so a bank of ANY size fills the machine with equally long pieces (C5 on 8 GPUs leaves 131,072
+// instances = 132 groups per GPU for 296 CTA slots).  A piece is walked as sub-ranges [b0, b1) of one group each;
+// a sub-range that starts inside a group begins `warm_rows` earlier from zero filter state without storing (the
+// bank's decay horizon, sized by the host to 2^-40), oscillators need no warm-up at all; the sub-range that reaches
+// the end of the launch hands the filter state to the next call.
 template <int M, int VK>
 __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_constant__ VoicesDev a) {
     __shared__ float2 red[VK * VT];
     const int tid = threadIdx.x;
+    const int bpg = (a.frames + VK - 1) / VK;                  // blocks per group
+    const int64_t total = (int64_t)a.ngroups * bpg;
+    int64_t blk = total * blockIdx.x / a.npieces;
+    const int64_t blk_end = total * (blockIdx.x + 1) / a.npieces;
+    const double rate = (double)a.rate;
+    constexpr int PARTS = VT / VK;          // threads that share one row in the CTA reduction
+
+  while (blk < blk_end) {
+    const int grp = (int)(blk / bpg);
+    const int b0 = (int)(blk - (int64_t)grp * bpg);
+    const int b1 = (int)min((int64_t)bpg, b0 + (blk_end - blk));
+    blk += b1 - b0;
     int si = 0;
     for (int i = 1; i < a.nseg; ++i)
-        if ((int)blockIdx.x >= a.seg[i].cta0) si = i;
+        if (grp >= a.seg[i].cta0) si = i;
     const VoiceSeg& sg = a.seg[si];
-    const int cta = blockIdx.x - sg.cta0;
-    // time segment of this CTA: rows [row_store, row_end) are its share; a later segment starts warm_rows
-    // earlier from zero filter state (the bank's decay horizon) without storing
-    const int row_store = blockIdx.y * a.seg_rows;
-    const int row_end = min(a.frames, row_store + a.seg_rows);
-    const int row_begin = blockIdx.y == 0 ? 0 : max(0, row_store - (sg.nsec ? (a.warm_rows + VK - 1) / VK * VK : 0));
+    const int cta = grp - sg.cta0;
+    const int row_store = b0 * VK;
+    const int row_end = min(a.frames, b1 * VK);
+    const int row_begin = b0 == 0 ? 0 : max(0, row_store - (sg.nsec ? (a.warm_rows + VK - 1) / VK * VK : 0));
     const bool first_seg = row_begin == 0;
     const int wave = sg.wave, guard = sg.guard;
     const int fk = sg.nsec == 0 ? -1 : sg.sec_kind;
@@ -226,9 +244,7 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             s2[m] = first_seg ? (float)sg.state[1 * C + cc] : 0.0f;
         }
     }
-    float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)blockIdx.x * a.frames;
-    const double rate = (double)a.rate;
-    constexpr int PARTS = VT / VK;          // threads that share one row in the CTA reduction
+    float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)grp * a.frames;
 
     for (int n0 = row_begin; n0 < row_end; n0 += VK) {
         const int kmax = min(VK, row_end - n0);
@@ -266,6 +282,7 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP, M, VK>(x, g, cf, d, s1, s2, kmax); break;
             default: break;
         }
+        if (n0 + VK <= row_store) continue;             // warm-up tile: nothing to reduce or store (uniform over the CTA)
         // CTA reduction in a fixed order: VK rows x 256 threads -> VK float2
 #pragma unroll
         for (int k = 0; k < VK; ++k) {
@@ -289,7 +306,7 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
         }
         __syncthreads();
     }
-    if (fk >= 0 && row_end == a.frames) {      // the last segment hands the filter state to the next call
+    if (fk >= 0 && row_end == a.frames) {      // the sub-range that ends the launch hands the filter state to the next call
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (chan[m] >= 0) {
@@ -298,6 +315,7 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             }
         }
     }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_voices_finish(const float* __restrict__ partial, int nparts, int frames,
@@ -326,11 +344,18 @@ extern "C" int sigb_launch_bank(const BankDev* a, void* stream) {
 
 extern "C" int sigb_voices_ctas(int channels, int M) { return (channels + VT * M - 1) / (VT * M); }
 
-extern "C" int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream) {
-    if (a->frames <= 0 || nparts <= 0) return 0;
-    const dim3 grid(nparts, a->tseg > 0 ? a->tseg : 1);
-    if (a->M == 4) k_voices<4, 8><<<grid, VT, 0, (cudaStream_t)stream>>>(*a);
-    else k_voices<1, 16><<<grid, VT, 0, (cudaStream_t)stream>>>(*a);
+extern "C" int sigb_voices_block_rows(int M) { return M == 4 ? 8 : 16; }
+
+extern "C" int sigb_voices_slots(int M) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms * (M == 4 ? 2 : 3);
+}
+
+extern "C" int sigb_launch_voices(const VoicesDev* a, void* stream) {
+    if (a->frames <= 0 || a->ngroups <= 0 || a->npieces <= 0) return 0;
+    if (a->M == 4) k_voices<4, 8><<<a->npieces, VT, 0, (cudaStream_t)stream>>>(*a);
+    else k_voices<1, 16><<<a->npieces, VT, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 
@@ -365,9 +390,10 @@ __device__ __forceinline__ double osc_wave_f64(int wave, double cyc) {
 }
 
 __global__ void __launch_bounds__(128) k_param_eval(const ParamInstr* __restrict__ prog, int n_instr, int n_rows, double* drows,
-                                                    float* frows, int row_stride, int64_t position, int rate) {
+                                                    float* frows, int row_stride, int64_t position, const int64_t* pos_ptr, int rate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= row_stride) return;
+    if (pos_ptr) position = *pos_ptr;                     // realtime graphs: the block header the host rewrites per launch
     double v[SIGB_PARAM_ROWS];
     for (int r = 0; r < n_rows; ++r) v[r] = drows[(size_t)r * row_stride + c];      // constants are preloaded (replicated)
     const double tn = __ddiv_rn((double)position, (double)rate);
@@ -389,9 +415,9 @@ __global__ void __launch_bounds__(128) k_param_eval(const ParamInstr* __restrict
 }  // namespace
 
 extern "C" int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, double* drows, float* frows, int row_stride,
-                                      int64_t position, int rate, void* stream) {
+                                      int64_t position, const int64_t* pos_ptr, int rate, void* stream) {
     if (n_instr <= 0) return 0;
-    k_param_eval<<<(row_stride + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prog_dev, n_instr, n_rows, drows, frows, row_stride, position, rate);
+    k_param_eval<<<(row_stride + 127) / 128, 128, 0, (cudaStream_t)stream>>>(prog_dev, n_instr, n_rows, drows, frows, row_stride, position, pos_ptr, rate);
     return (int)cudaGetLastError();
 }
 
@@ -401,36 +427,100 @@ extern "C" int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, i
 // channel per block (fx.py:98-102); here one thread per channel turns the cutoff row of the parameter program
 // into the {g, c, d} coefficients of the filter's sections -- sigb_butter_sections / sigb_section_coef
 // (sigb_design.cpp) restated in float64 on the device -- straight into the chain's coefficient table.
-// Wn is clipped to [0, 1] as in fx.py:100-101; scipy then rejects Wn outside (0, 1) with a ValueError, which a
-// device-side design cannot raise: such channels are clamped just inside the open interval.
+// Wn is clipped to [0, 1] as in fx.py:100-101; scipy then rejects Wn outside (0, 1) with a ValueError
+// ("Digital filter critical frequencies must be 0 < Wn < 1").  A device-side design cannot raise: it sets
+// *err_flag (page-locked host memory the runtime checks after the render, SIGB_ECRIT) and designs that channel just
+// inside the open interval so that the block itself stays finite.
 // ---------------------------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(128) k_design(float* __restrict__ coef, int C, int s0, int order, const double* __restrict__ cutoff, int rate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const double pi = 3.14159265358979323846;
-    double wn = cutoff[c] / ((double)rate / 2.0);
-    wn = fmin(fmax(wn, 1e-9), 1.0 - 1e-9);
-    const double g = tan(pi * wn / 2.0);
-    for (int k = 0; k < order / 2; ++k) {
-        const double r2 = 2.0 * sin(pi * (2.0 * k + 1.0) / (2.0 * order));
-        const size_t s = (size_t)(s0 + k) * 3;
-        coef[(s + 0) * C + c] = (float)g;
-        coef[(s + 1) * C + c] = (float)(r2 + g);
-        coef[(s + 2) * C + c] = (float)(1.0 / (1.0 + r2 * g + g * g));
+// one sample of a section in float64 (sigb_section_step of sigb_design.cpp)
+__device__ __forceinline__ double design_step(int kind, double g, double r2, double x, double& s1, double& s2) {
+    if (kind & SEC_FIRST_ORDER) {
+        const double G = g / (1.0 + g);
+        const double v = (x - s1) * G;
+        const double lp = v + s1;
+        s1 = lp + v;
+        return (kind & SEC_HP) ? x - lp : lp;
     }
-    if (order & 1) {
-        const size_t s = (size_t)(s0 + order / 2) * 3;
-        coef[(s + 0) * C + c] = (float)(g / (1.0 + g));
-        coef[(s + 1) * C + c] = 0.0f;
-        coef[(s + 2) * C + c] = 0.0f;
+    const double d = 1.0 / (1.0 + r2 * g + g * g);
+    const double hp = (x - (r2 + g) * s1 - s2) * d;
+    const double bp = g * hp + s1;
+    s1 = g * hp + bp;
+    const double lp = g * bp + s2;
+    s2 = g * bp + lp;
+    return (kind & SEC_HP) ? hp : lp;
+}
+
+__global__ void __launch_bounds__(128) k_design(const DesignDev a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = a.C;
+    double warm = 0.0;
+    if (c < C) {
+        const double pi = 3.14159265358979323846;
+        double wn = a.cutoff[c] / ((double)a.rate / 2.0);
+        if (!(wn > 0.0 && wn < 1.0)) {                 // also catches NaN
+            if (a.err_flag) *a.err_flag = 1;
+            wn = wn >= 1.0 ? 1.0 - 1e-9 : 1e-9;
+        }
+        const double g = tan(pi * wn / 2.0);
+        const int nsec = a.order / 2 + (a.order & 1);
+        for (int k = 0; k < nsec; ++k) {
+            const bool first = k == a.order / 2;        // the odd order's first-order section comes last
+            const int kind = (a.highpass ? SEC_HP : 0) | (first ? SEC_FIRST_ORDER : 0);
+            const double r2 = first ? 0.0 : 2.0 * sin(pi * (2.0 * k + 1.0) / (2.0 * a.order));
+            const size_t s = (size_t)(a.s0 + k);
+            if (first) {
+                a.coef[(s * 3 + 0) * C + c] = (float)(g / (1.0 + g));
+                a.coef[(s * 3 + 1) * C + c] = 0.0f;
+                a.coef[(s * 3 + 2) * C + c] = 0.0f;
+            } else {
+                a.coef[(s * 3 + 0) * C + c] = (float)g;
+                a.coef[(s * 3 + 1) * C + c] = (float)(r2 + g);
+                a.coef[(s * 3 + 2) * C + c] = (float)(1.0 / (1.0 + r2 * g + g * g));
+            }
+            if (!a.apow) continue;
+            // the linear-system tables of the time-parallel kernels (make_chain of sigb_plan.cu, on the device):
+            // images of the two unit states over SIGB_SCAN_L rows of zero input
+            double a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0, m1[4] = {1.0, 0.0, 0.0, 1.0};
+            for (int r = 0; r < SIGB_SCAN_L; ++r) {
+                const double ya = design_step(kind, g, r2, 0.0, a1, a2);
+                const double yb = design_step(kind, g, r2, 0.0, b1, b2);
+                a.ztab[((s * SIGB_SCAN_L + r) * 2 + 0) * C + c] = (float)ya;
+                a.ztab[((s * SIGB_SCAN_L + r) * 2 + 1) * C + c] = (float)yb;
+                if (r == 0) { m1[0] = a1; m1[1] = b1; m1[2] = a2; m1[3] = b2; }
+                if (r == SIGB_SCAN_L / 2 - 1) {
+                    const double mh[4] = {a1, b1, a2, b2};
+                    for (int j = 0; j < 4; ++j) {
+                        a.apow_h[(s * 4 + j) * C + c] = mh[j];
+                        a.m8[(s * 4 + j) * C + c] = (float)mh[j];
+                    }
+                }
+            }
+            a.apow[(s * 4 + 0) * C + c] = a1; a.apow[(s * 4 + 1) * C + c] = b1;
+            a.apow[(s * 4 + 2) * C + c] = a2; a.apow[(s * 4 + 3) * C + c] = b2;
+            const double tr = m1[0] + m1[3], det = m1[0] * m1[3] - m1[1] * m1[2];
+            a.hrec[(s * 2 + 0) * C + c] = (float)tr;
+            a.hrec[(s * 2 + 1) * C + c] = (float)(-det);
+            // decay horizon (sigb_section_decay_rows): rows until the zero-input response is below 2^-40, doubled
+            const double disc = tr * tr - 4.0 * det;
+            const double rho = disc < 0.0 ? sqrt(fabs(det)) : fmax(fabs(tr + sqrt(disc)), fabs(tr - sqrt(disc))) / 2.0;
+            warm += !(rho < 1.0) ? 1e9 : (rho < 1e-12 ? 2.0 : 2.0 * (40.0 * 0.6931471805599453 / -log(rho)) + 16.0);
+        }
+    }
+    if (a.warm_out) {
+        // sections in series: a channel's decays are budgeted one after another; the filter's horizon is the
+        // slowest channel's (the host adds the horizons of the chain's filters)
+        int w = (int)fmin(ceil(warm), 1.0e9);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+        if ((threadIdx.x & 31) == 0 && w > 0) atomicMax(a.warm_out, w);
     }
 }
 }  // namespace
 
-extern "C" int sigb_launch_design(float* coef, int C, int s0, int order, const double* cutoff, int rate, void* stream) {
-    if (C <= 0) return 0;
-    k_design<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(coef, C, s0, order, cutoff, rate);
+extern "C" int sigb_launch_design(const DesignDev* a, void* stream) {
+    if (a->C <= 0) return 0;
+    k_design<<<(a->C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
     return (int)cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ struct ChainDev {
     int32_t warm_rows;              // rows after which the filters forget their initial state (< 2^-40); -1: unknown
     int32_t guard;                  // phase-word guard band around waveform discontinuities (pipelined kernel)
     int64_t position;               // absolute index of row 0
+    const int64_t* pos_ptr;         // realtime graphs (k_chain_seq only): when set, row 0 is *pos_ptr -- a block header the
+                                    // host rewrites before every launch of the captured CUDA graph
     uint8_t sec_kind[SIGB_MAX_SEC];
     // SRC_OSC
     const double* hertz;            // [C]
@@ -108,7 +110,7 @@ struct VoiceSeg {
     int32_t wave;                       // SIGB_WAVE_*
     int32_t nsec;                       // 0 or 1
     int32_t sec_kind;                   // SEC_* bits of the section
-    int32_t cta0;                       // first CTA (= partial index) of this segment in the launch
+    int32_t cta0;                       // first voice group (= partial index) of this segment in the launch
     int32_t guard;                      // phase-word guard band around waveform discontinuities
     const unsigned long long* theta0;   // [C] Q0.64 phase / increment (all waves)
     const unsigned long long* dtheta;
@@ -132,6 +134,17 @@ struct ParamInstr {
     int32_t width;     // channels of dst (operands are 1 or `width` wide)
     int32_t wa, wb, wc;
 };
+// Per-request design of ONE filter whose cutoff is modulated (k_design): sections [s0, s0 + ceil(order / 2)) of a chain
+// of C channels.  coef is always written; the scan tables only when apow != nullptr.
+struct DesignDev {
+    int32_t C, s0, order, highpass, rate;
+    const double* cutoff;               // [C] the parameter-program row
+    float* coef;                        // chain tables, laid out as in ChainDev
+    double* apow; double* apow_h; float* ztab; float* m8; float* hrec;
+    int* err_flag;                      // set to 1 when a cutoff leaves (0, rate/2) (scipy's ValueError, fx.py:102)
+    int* warm_out;                      // atomicMax: decay horizon of this filter in rows (slowest channel)
+};
+
 #define SIGB_PARAM_ROWS 96              // rows per parameter program (values live in a per-thread array)
 
 #define SIGB_VOICE_SEGS 24              // segments per k_voices launch
@@ -142,9 +155,9 @@ struct VoicesDev {
     int32_t rate;
     int32_t frames;
     int32_t M;                          // channels per thread (1 or 4)
-    int32_t tseg;                       // time segments (blockIdx.y)
-    int32_t seg_rows;                   // rows per segment (multiple of 8)
-    int32_t warm_rows;                  // rows a later segment re-renders from zero state without storing
+    int32_t ngroups;                    // CTA-sized voice groups (= rows of `partial`) in this launch
+    int32_t npieces;                    // CTAs: equal contiguous pieces of the (group, row block) space, group-major
+    int32_t warm_rows;                  // rows a piece that starts inside a group re-renders from zero state without storing
     int64_t position;
     float* partial;                     // [nparts][frames][2]
     VoiceSeg seg[SIGB_VOICE_SEGS];
@@ -170,11 +183,13 @@ void sigb_set_scan_tma(int on);
 void sigb_set_scan_split(int on);
 int sigb_launch_bank(const BankDev* a, void* stream);
 int sigb_voices_ctas(int channels, int M);                         // CTAs (= partials) a segment of `channels` needs
-int sigb_launch_voices(const VoicesDev* a, int nparts, void* stream);
+int sigb_voices_block_rows(int M);                                 // rows per block of the (group, block) space
+int sigb_voices_slots(int M);                                      // CTAs of k_voices resident on the device at once
+int sigb_launch_voices(const VoicesDev* a, void* stream);
 int sigb_launch_voices_finish(const float* partial, int nparts, int frames, float* out, int64_t ld_out, void* stream);
 int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, double* drows, float* frows, int row_stride,
-                           int64_t position, int rate, void* stream);
-int sigb_launch_design(float* coef, int C, int s0, int order, const double* cutoff, int rate, void* stream);
+                           int64_t position, const int64_t* pos_ptr, int rate, void* stream);
+int sigb_launch_design(const DesignDev* a, void* stream);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus
 }

@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
     if (SRC == SRC_OSC) { hz = a.hertz[c]; ph = a.phase[c]; }
     if (SRC == SRC_CONST) cv = a.constv[c];
     const double rate = (double)a.rate;
+    const int64_t position = a.pos_ptr ? *a.pos_ptr : a.position;     // realtime graphs read the block header
     float* outp = a.out + (int64_t)r0 * a.ld_out + c;
     // fused Mix / RingMod epilogue (stateless chains only): the other operand never leaves registers when it is
     // an oscillator, and is read once when it is a materialised block
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
     for (int r = r0; r < r1; ++r) {
         float x;
         double tn = 0.0;
-        if (SRC == SRC_OSC || epi) tn = __ddiv_rn((double)(a.position + r), rate);
+        if (SRC == SRC_OSC || epi) tn = __ddiv_rn((double)(position + r), rate);
         if (SRC == SRC_OSC) {
             x = osc_wave(a.wave, osc_cycles(tn, hz, ph));
         } else if (SRC == SRC_BUF) {

@@ -84,11 +84,12 @@ struct ChainSpec {
     int64_t state_off = 0;       // doubles into the state arena
     int state_cur = 0;           // which copy of the state arena holds the live state
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
+    double warm_static = 0.0;    // ... the share of the filters with constant cutoffs (modulated ones add theirs per request)
     int dst_node = -1;
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
     // filters whose cutoff is driven by an emitter: their sections are re-designed on the device once per request
     // (k_design) from row `row` of the parameter program
-    struct ModFilter { int s0, order, row; };
+    struct ModFilter { int s0, order, row, highpass, slot; };   // slot: index of this filter's decay horizon in d_warm
     std::vector<ModFilter> mods;
     // Mix / RingMod fused as an epilogue of a stateless chain (k_chain_seq)
     int epi_op = 0, epi_side = 0, epi_node = -1, epi_wave = -1, epi_p_row = -1;
@@ -190,7 +191,8 @@ struct sigb_plan {
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
     int64_t opt_fuse_pointwise = 1;     // 0: Mix / RingMod always run on materialised blocks
-    int64_t opt_voices_segments = 0;    // time segments of k_voices: 0 auto, 1 never split, n > 1 forced
+    int64_t opt_voices_segments = 0;    // k_voices: 0 auto (equal pieces per CTA slot), 1 one piece per voice group, n > 1: n pieces per group
+    int64_t opt_voices_pieces = 2;      // k_voices, automatic mode: pieces per resident CTA slot
     int64_t opt_voices_m = 0;           // 0: auto; 1 or 4: channels per thread in k_voices
     // runtime
     bool uploaded = false;
@@ -206,6 +208,29 @@ struct sigb_plan {
     float* stage[2] = {nullptr, nullptr};
     int64_t stage_floats = 0;
     cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_caller = nullptr;
+    // modulated cutoffs: per-filter decay horizons written by k_design, and the "cutoff outside (0, Nyquist)" flag
+    int n_mods = 0;
+    int* d_warm = nullptr;
+    int* h_warm = nullptr;              // page-locked copy
+    int* h_err = nullptr;               // page-locked, device-mapped: k_design stores 1 here
+    // realtime block path (sigb_render_block): one captured CUDA graph per block length, position read from a
+    // page-locked block header, output written straight into page-locked staging
+    struct RtGraph { int frames; cudaGraph_t graph; cudaGraphExec_t exec; int nodes; uint64_t state_sig; };
+    std::vector<RtGraph> rt_graphs;
+    int64_t* rt_hdr = nullptr;          // page-locked, device-mapped: [0] = position of the block
+    float* rt_stage = nullptr;          // page-locked, device-mapped (frames, channels) block
+    int64_t rt_stage_floats = 0;
+    const int64_t* rt_pos_ptr = nullptr;    // set while run_slab records / runs a realtime block
+    int rt_state = 0;                   // 0 unknown, 1 eligible, -1 not (falls back to sigb_render_host)
+    int64_t opt_rt_graph = 1;           // 0: realtime blocks launch their kernels directly (A/B)
+    int64_t opt_rt_max_bytes = 1 << 20; // larger blocks go through sigb_render_host (DMA copies)
+    int64_t opt_restart = 0;            // 1: every request restarts the filters from zero state + context (the reference's
+                                        // own blockwise behaviour, fx.py:82-83, 93-105), for A/B against it
+    int64_t graph_launches = 0;
+    // taps (Wave / Spec / FileWriter inputs kept materialised for sigb_plan_read_tap)
+    std::vector<int> tap_nodes;
+    int64_t last_position = 0, last_frames = 0, last_slab = 0;
 };
 
 namespace {
@@ -409,6 +434,18 @@ int Builder::ensure(int i) {
         case SIGB_NODE_MERGE: return build_merge(i);
         case SIGB_NODE_GROUPSUM:
         case SIGB_NODE_PANSUM: return build_reduce(i);
+        case SIGB_NODE_TAP: {
+            // a pass-through side-effect node: its value IS its input's (chain/__init__.py:409-417), kept materialised
+            // in a plan buffer so that sigb_plan_read_tap can hand the block to the host after the render
+            if (n.in[0] < 0) {
+                p->vals[i] = p->zero_val;
+            } else {
+                int st = ensure(n.in[0]);
+                if (st != SIGB_OK) return st;
+                p->vals[i] = p->vals[n.in[0]];
+            }
+            return SIGB_OK;
+        }
         default: return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": unexpected kind");
     }
 }
@@ -565,6 +602,8 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                 ChainSpec::ModFilter mf;
                 mf.s0 = s0;
                 mf.order = n.order;
+                mf.highpass = n.subtype == SIGB_FILT_HIGHPASS;
+                mf.slot = p->n_mods++;
                 int st = param_port(n.in[1], C, &mf.row);
                 if (st != SIGB_OK) return st;
                 if (p->prow_width[mf.row] != C)   // crit_1[0, i] is not broadcast (fx.py:99)
@@ -579,8 +618,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                         for (int j = 0; j < 3; ++j) coef[((size_t)(s0 + k) * 3 + j) * C + c] = cf[j];
                 }
                 ch.mods.push_back(mf);
-                s0 += ns;
-                warm = 1e12;                                 // decay horizon unknown: never cut along time
+                s0 += ns;                                    // (its decay horizon is designed per request: k_design)
                 continue;
             }
             if ((int)cut->size() != C)   // crit_1[0, i] is not broadcast (fx.py:99)
@@ -630,7 +668,8 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
             for (double wv : sec_warm) warm += wv;   // sections in series: budget the decays one after another
         }
         ch.coef = put_vec(p, coef);
-        ch.warm_rows = (warm < 1e8) ? (int)std::ceil(warm) : -1;
+        ch.warm_static = warm;
+        ch.warm_rows = (warm < 1e8 && ch.mods.empty()) ? (int)std::ceil(warm) : -1;
         if (scan_tables) {
             ch.apow = put_vec(p, apow);
             ch.apow_h = put_vec(p, apow_h);
@@ -661,6 +700,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                     worst = rows < 0 ? (1 << 30) : std::max(worst, rows);
                 }
                 if (worst < (1 << 30)) ch.warm_rows = std::min(ch.warm_rows, (int)(worst * 1.1) + 64);
+                ch.warm_static = ch.warm_rows;
             }
             ch.m8 = put_vec(p, m8);
             ch.hrec = put_vec(p, hrec);
@@ -770,7 +810,7 @@ int Builder::build_voices(int i, const std::vector<int>& leaves) {
     }
     if (coff != Cin) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": merged voices do not cover the input width");
     vs.M = p->opt_voices_m == 1 || p->opt_voices_m == 4 ? (int)p->opt_voices_m
-                                                         : (total >= 148ll * 2 * SIGB_VOICE_THREADS * 2 ? 4 : 1);
+                                                         : (total >= 8ll * SIGB_VOICE_THREADS * 4 ? 4 : 1);
     for (const VoiceSegSpec& sg : vs.segs) vs.nparts += sigb_voices_ctas(sg.ch.C, vs.M);
     BufInfo pb;
     pb.channels = 2 * vs.nparts;
@@ -1054,8 +1094,17 @@ int upload(sigb_plan* p) {
         CUDA_TRY(cudaMalloc(&p->d_pprog, p->pprog.size() * sizeof(ParamInstr)));
         CUDA_TRY(cudaMemcpy(p->d_pprog, p->pprog.data(), p->pprog.size() * sizeof(ParamInstr), cudaMemcpyHostToDevice));
     }
+    if (p->n_mods > 0) {
+        CUDA_TRY(cudaMalloc(&p->d_warm, p->n_mods * sizeof(int)));
+        CUDA_TRY(cudaHostAlloc(&p->h_warm, p->n_mods * sizeof(int), cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc(&p->h_err, sizeof(int), cudaHostAllocMapped));
+        *p->h_err = 0;
+    }
     CUDA_TRY(cudaEventCreate(&p->ev0));
     CUDA_TRY(cudaEventCreate(&p->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_caller, cudaEventDisableTiming));
+    // the uploads above ran on the legacy default stream; renders may use any (non-blocking) stream
+    CUDA_TRY(cudaDeviceSynchronize());
     p->uploaded = true;
     return SIGB_OK;
 }
@@ -1125,6 +1174,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.frames = rows;
             a.warm_rows = ch.warm_rows;
             a.position = abs_row0;
+            a.pos_ptr = p->rt_pos_ptr;
             std::memcpy(a.sec_kind, ch.sec_kind, sizeof(a.sec_kind));
             a.hertz = ch.hertz_row >= 0 ? p->d_prow_d + (size_t)ch.hertz_row * p->pwidth : ch.hertz.dev<double>(base);
             a.phase = ch.phase_row >= 0 ? p->d_prow_d + (size_t)ch.phase_row * p->pwidth : ch.phase.dev<double>(base);
@@ -1171,11 +1221,12 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 continue;
             }
             int done = 0;
+            const bool force_seq = p->opt_force_seq || p->rt_pos_ptr != nullptr;    // realtime blocks: one sequential launch per chain
             if (ch.src_kind == SRC_OSC && ch.hertz_row < 0) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
             // kernel choice: cascades of >= 3 sections run section-pipelined (k_cascade_pipe); shallower
             // chains stay on the time-parallel scan kernel, which measured faster for them (C2: 1.07e12 vs
             // 0.82e12 voice-samples/s) unless "cascade_pipe" forces the pipeline from n sections
-            if (!p->opt_force_seq && p->opt_cascade_pipe != 0 && ch.nsec_real >= 1 && ch.nsec_real <= 8) {
+            if (!force_seq && p->opt_cascade_pipe != 0 && ch.nsec_real >= 1 && ch.nsec_real <= 8) {
                 ChainDev t = a;
                 t.nsec = ch.nsec_real;           // identity padding sections are not run
                 const bool deep = ch.nsec_real >= 3;
@@ -1205,8 +1256,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 }
             }
             const int tiles = (ch.C + 31) / 32;
-            // (a chain with a modulated cutoff has no scan tables: only the kernels that read {g, c, d} take it)
-            const bool scan_ok = !p->opt_force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles && ch.mods.empty();
+            // (a chain with a modulated cutoff gets its scan tables from k_design, once per request)
+            const bool scan_ok = !force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
             if (scan_ok) {
                 int e = sigb_launch_chain_scan(&a, (int)p->opt_scan_variant, st, &done);
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
@@ -1269,23 +1320,16 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
         } else if (l.kind == LK_VOICES) {
             VoicesSpec& vs = p->voices[l.idx];
             float* partial = p->bufs[vs.partial_buf].ptr;
-            // time segments: a small bank (few CTAs) is also cut along time; later segments warm their filters
-            // up from zero state over the bank's decay horizon (2^-40), oscillators need no warm-up at all
+            // decay horizon of the bank's filters (2^-40): what a piece that starts inside a voice group re-renders
+            // from zero state before its first stored row; oscillators need no warm-up at all
             int warm = 0;
             for (const VoiceSegSpec& sg : vs.segs) {
                 if (sg.ch.nsec_real == 0) continue;
                 warm = sg.ch.warm_rows < 0 ? -1 : (warm < 0 ? -1 : std::max(warm, sg.ch.warm_rows));
                 if (warm < 0) break;
             }
-            int nseg = 1;
-            if (warm >= 0 && p->opt_voices_segments != 1) {
-                const int slots = 148 * (vs.M == 4 ? 2 : 3);
-                const int want = p->opt_voices_segments > 1 ? (int)p->opt_voices_segments : (2 * slots + vs.nparts - 1) / vs.nparts;
-                const int fit = warm > 0 ? rows / (8 * warm) : rows / 64;
-                nseg = std::max(1, std::min(std::min(want, fit), 64));
-            }
-            const int seg_rows = ((rows + nseg - 1) / nseg + 7) / 8 * 8;
-            nseg = (rows + seg_rows - 1) / seg_rows;
+            const int VK = sigb_voices_block_rows(vs.M);
+            const int64_t bpg = (rows + VK - 1) / VK;
             int part0 = 0;
             for (size_t s0 = 0; s0 < vs.segs.size(); s0 += SIGB_VOICE_SEGS) {
                 VoicesDev a;
@@ -1296,10 +1340,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 a.M = vs.M;
                 a.position = abs_row0;
                 a.partial = partial + (int64_t)part0 * rows * 2;
-                a.tseg = nseg;
-                a.seg_rows = seg_rows;
                 a.warm_rows = std::max(warm, 0);
-                int ctas = 0;
+                int groups = 0;
                 for (int k = 0; k < a.nseg; ++k) {
                     const VoiceSegSpec& sg = vs.segs[s0 + k];
                     VoiceSeg& d = a.seg[k];
@@ -1307,7 +1349,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     d.wave = sg.ch.wave;
                     d.nsec = sg.ch.nsec_real;
                     d.sec_kind = sg.ch.sec_kind[0];
-                    d.cta0 = ctas;
+                    d.cta0 = groups;
                     d.theta0 = sg.ch.theta0.dev<unsigned long long>(base);
                     d.dtheta = sg.ch.dtheta.dev<unsigned long long>(base);
                     d.hertz = sg.ch.hertz.dev<double>(base);
@@ -1318,12 +1360,27 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     d.state = p->d_state ? p->d_state + vs.state_cur * p->n_state + sg.ch.state_off : nullptr;
                     d.state_out = p->d_state ? p->d_state + (vs.state_cur ^ 1) * p->n_state + sg.ch.state_off : nullptr;
                     d.guard = phase_guard(sg.ch.max_abs_hertz, sg.ch.max_abs_phase, abs_row0 + rows, p->rate);
-                    ctas += sigb_voices_ctas(sg.ch.C, vs.M);
+                    groups += sigb_voices_ctas(sg.ch.C, vs.M);
                 }
-                int err = sigb_launch_voices(&a, ctas, st);
+                // pieces: equal contiguous shares of the (group, row block) space.  With a known decay horizon the
+                // launch is cut into `voices_pieces` pieces per resident CTA slot (more than one, so that the hardware
+                // scheduler evens out the cost differences between wave / filter kinds), as long as the warm-up of a
+                // piece that starts inside a group stays below 1/8 of the piece; otherwise one piece per group.
+                a.ngroups = groups;
+                int64_t np = groups;
+                if (warm >= 0 && p->opt_voices_segments != 1) {
+                    const int64_t total = (int64_t)groups * bpg;
+                    const int64_t target = p->opt_voices_segments > 1 ? (int64_t)groups * p->opt_voices_segments
+                                                                      : (int64_t)sigb_voices_slots(vs.M) * std::max<int64_t>(1, p->opt_voices_pieces);
+                    const int64_t fit = warm > 0 ? std::max<int64_t>(1, total * VK / (8ll * warm)) : total;
+                    np = std::max<int64_t>(1, std::min(std::min(target, fit), total));
+                    if (fit < groups) np = groups;       // too short to cut inside a group: pieces = whole groups, no warm-up
+                }
+                a.npieces = (int)np;
+                int err = sigb_launch_voices(&a, st);
                 if (err) return fail(SIGB_ECUDA, std::string("k_voices: ") + cudaGetErrorString((cudaError_t)err));
                 p->launch_count++;
-                part0 += ctas;
+                part0 += groups;
             }
             vs.state_cur ^= 1;
             const Val& dv = p->vals[vs.dst_node];
@@ -1365,34 +1422,88 @@ int64_t slab_rows(sigb_plan* p, int64_t frames) {
     return std::min(frames, rows);
 }
 
-int run_params(sigb_plan* p, int64_t position, cudaStream_t st, bool design = true) {
+// Block-rate parameters of one request: the parameter program at `position` (k_param_eval), then -- design = true --
+// the per-request design of every filter whose cutoff is modulated (k_design).  `frames` sizes the decision whether
+// the request is long enough for the time-parallel kernels: only then is the decay horizon read back (one
+// synchronisation of `st`), otherwise those chains run unsegmented.
+int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, bool design = true) {
     if (p->pprog.empty()) return SIGB_OK;
     int e = sigb_launch_param_eval(p->d_pprog, (int)p->pprog.size(), (int)p->prow_const.size(), p->d_prow_d, p->d_prow_f, p->pwidth,
-                                   position, p->rate, st);
+                                   position, p->rt_pos_ptr, p->rate, st);
     if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
     p->launch_count++;
-    if (!design) return SIGB_OK;
-    for (const ChainSpec& ch : p->chains) {
+    if (!design || p->n_mods == 0) return SIGB_OK;
+    const bool want_warm = p->rt_pos_ptr == nullptr && !p->opt_force_seq && frames >= 4096;
+    if (want_warm) CUDA_TRY(cudaMemsetAsync(p->d_warm, 0, p->n_mods * sizeof(int), st));
+    for (ChainSpec& ch : p->chains) {
         for (const ChainSpec::ModFilter& mf : ch.mods) {
-            float* coef = reinterpret_cast<float*>(p->d_arena + ch.coef.off);
-            e = sigb_launch_design(coef, ch.C, mf.s0, mf.order, p->d_prow_d + (size_t)mf.row * p->pwidth, p->rate, st);
+            DesignDev d;
+            std::memset(&d, 0, sizeof(d));
+            d.C = ch.C; d.s0 = mf.s0; d.order = mf.order; d.highpass = mf.highpass; d.rate = p->rate;
+            d.cutoff = p->d_prow_d + (size_t)mf.row * p->pwidth;
+            d.coef = reinterpret_cast<float*>(p->d_arena + ch.coef.off);
+            if (ch.apow.off >= 0) {
+                d.apow = reinterpret_cast<double*>(p->d_arena + ch.apow.off);
+                d.apow_h = reinterpret_cast<double*>(p->d_arena + ch.apow_h.off);
+                d.ztab = reinterpret_cast<float*>(p->d_arena + ch.ztab.off);
+                d.m8 = reinterpret_cast<float*>(p->d_arena + ch.m8.off);
+                d.hrec = reinterpret_cast<float*>(p->d_arena + ch.hrec.off);
+            }
+            d.err_flag = p->h_err;
+            d.warm_out = want_warm ? p->d_warm + mf.slot : nullptr;
+            e = sigb_launch_design(&d, st);
             if (e) return fail(SIGB_ECUDA, std::string("k_design: ") + cudaGetErrorString((cudaError_t)e));
             p->launch_count++;
+        }
+        if (!ch.mods.empty()) ch.warm_rows = -1;
+    }
+    if (want_warm) {
+        CUDA_TRY(cudaMemcpyAsync(p->h_warm, p->d_warm, p->n_mods * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (ChainSpec& ch : p->chains) {
+            if (ch.mods.empty()) continue;
+            double w = ch.warm_static;
+            for (const ChainSpec::ModFilter& mf : ch.mods) w += p->h_warm[mf.slot];
+            ch.warm_rows = w < 1e8 ? (int)std::ceil(w) : -1;
         }
     }
     return SIGB_OK;
 }
 
-// the body of sigb_render: seek handling + slab loop, all on `st`
-int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
-    if (!p->have_pos || p->next_pos != position) {
+// scipy's ValueError for a modulated cutoff outside (0, Nyquist) (fx.py:102), raised by the first call that finds the
+// flag k_design left in page-locked memory
+int check_design_error(sigb_plan* p) {
+    if (p->h_err && *reinterpret_cast<volatile int*>(p->h_err)) {
+        *p->h_err = 0;
+        p->have_pos = false;
+        return fail(SIGB_ECRIT, "Digital filter critical frequencies must be 0 < Wn < 1 (modulated cutoff)");
+    }
+    return SIGB_OK;
+}
+
+// device-slab loop of one request (no seek handling, no parameters)
+int run_rows(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
+    const int64_t slab = slab_rows(p, frames);
+    int e = ensure_bufs(p, slab);
+    if (e != SIGB_OK) return e;
+    for (int64_t r = 0; r < frames; r += slab) {
+        const int rows = (int)std::min(slab, frames - r);
+        e = run_slab(p, position + r, rows, out + r * ld_out, ld_out, st);
+        if (e != SIGB_OK) return e;
+    }
+    p->last_slab = slab;
+    return SIGB_OK;
+}
+
+// start of a request: seek handling + the block-rate parameters, sampled ONCE at the request's first frame
+// (forward_at_block_rate, chain/__init__.py:305-306) however the request is later cut into slabs
+int begin_request(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st) {
+    if (!p->have_pos || p->next_pos != position || p->opt_restart) {
         // seek: zero state, then warm the filters up on `context` frames (fx.py:93-105)
         if (p->d_state) CUDA_TRY(cudaMemsetAsync(p->d_state, 0, 2 * p->n_state * sizeof(double), st));
         int64_t pre = std::min<int64_t>(p->context, position);
         if (pre > 0 && p->n_state > 0) {
-            int st_ = ensure_bufs(p, slab_rows(p, std::max(pre, frames)));
-            if (st_ != SIGB_OK) return st_;
-            const int64_t need = pre * p->channels;
+            const int64_t need = std::min<int64_t>(pre, slab_rows(p, pre)) * p->channels;
             if (p->scratch_floats < need) {
                 if (p->scratch) cudaFree(p->scratch);
                 p->scratch = nullptr;
@@ -1401,24 +1512,80 @@ int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int
             }
             // the filter samples its cutoff at the REQUEST's position (fx.py:124-129) and runs context + block with
             // that one design; the context request it sends upstream samples ITS parameters at its own position
-            int e = run_params(p, position, st, true);
-            if (e == SIGB_OK) e = run_params(p, position - pre, st, false);
-            if (e == SIGB_OK) e = run_slab(p, position - pre, (int)pre, p->scratch, p->channels, st);
+            int e = run_params(p, position, frames, st, true);
+            if (e == SIGB_OK) e = run_params(p, position - pre, frames, st, false);
             if (e != SIGB_OK) return e;
+            // warm-up in pieces no longer than a device slab (the intermediate buffers hold one slab)
+            const int64_t slab = slab_rows(p, pre);
+            e = ensure_bufs(p, slab);
+            if (e != SIGB_OK) return e;
+            for (int64_t r = 0; r < pre; r += slab) {
+                e = run_slab(p, position - pre + r, (int)std::min(slab, pre - r), p->scratch, p->channels, st);
+                if (e != SIGB_OK) return e;
+            }
         }
     }
-    const int64_t slab = slab_rows(p, frames);
-    int e = ensure_bufs(p, slab);
-    if (e == SIGB_OK) e = run_params(p, position, st);       // block-rate parameters: once per request, at its first frame
-    if (e != SIGB_OK) return e;
-    for (int64_t r = 0; r < frames; r += slab) {
-        const int rows = (int)std::min(slab, frames - r);
-        e = run_slab(p, position + r, rows, out + r * ld_out, ld_out, st);
-        if (e != SIGB_OK) return e;
-    }
+    return run_params(p, position, frames, st);
+}
+
+void end_request(sigb_plan* p, int64_t position, int64_t frames) {
     p->have_pos = true;
     p->next_pos = position + frames;
+    p->last_position = position;
+    p->last_frames = frames;
+}
+
+// the body of sigb_render: seek handling + parameters + slab loop, all on `st`
+int render_range(sigb_plan* p, int64_t position, int64_t frames, float* out, int64_t ld_out, cudaStream_t st) {
+    int e = begin_request(p, position, frames, st);
+    if (e == SIGB_OK) e = run_rows(p, position, frames, out, ld_out, st);
+    if (e != SIGB_OK) return e;
+    end_request(p, position, frames);
     return SIGB_OK;
+}
+
+int ensure_host_streams(sigb_plan* plan) {
+    if (plan->s_render) return SIGB_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_render, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_rendered[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_copied[i], cudaEventDisableTiming));
+    }
+    return SIGB_OK;
+}
+
+void rt_drop_graphs(sigb_plan* p) {
+    for (sigb_plan::RtGraph& g : p->rt_graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    p->rt_graphs.clear();
+}
+
+// Whether the realtime block path can take this plan: every launch must be position-independent once the position
+// comes from the block header (k_chain_seq, k_ewise, k_reduce, k_param_eval, k_design), i.e. no fused bank / voices
+// kernels and no Buffer source (its window pointer depends on the position).
+// which copy of the double-buffered filter state every launch currently reads: a captured graph holds these pointers
+uint64_t rt_state_sig(const sigb_plan* p) {
+    uint64_t h = 1469598103934665603ull;
+    for (const ChainSpec& ch : p->chains) h = (h ^ (uint64_t)(ch.state_cur + 1)) * 1099511628211ull;
+    for (const VoicesSpec& v : p->voices) h = (h ^ (uint64_t)(v.state_cur + 1)) * 1099511628211ull;
+    return h;
+}
+
+bool rt_eligible(sigb_plan* p) {
+    if (p->rt_state == 0) {
+        bool ok = true;
+        for (const Launch& l : p->launches)
+            if (l.kind == LK_BANK || l.kind == LK_VOICES) ok = false;
+        for (const Val& v : p->vals)
+            if (v.kind == VK_EXT) ok = false;
+        for (const ChainSpec& ch : p->chains)
+            if (ch.nsec > SIGB_MAX_SEC) ok = false;
+        p->rt_state = ok ? 1 : -1;
+    }
+    return p->rt_state > 0;
 }
 
 }  // namespace
@@ -1477,7 +1644,7 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
     p->zero_val.cv.assign(1, 0.0);
     for (int i = 0; i < n_nodes; ++i) {
         const sigb_node& n = p->nodes[i];
-        if (n.kind < SIGB_NODE_ZERO || n.kind > SIGB_NODE_BUFFER) return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": unknown kind");
+        if (n.kind < SIGB_NODE_ZERO || n.kind > SIGB_NODE_TAP) return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": unknown kind");
         if (n.channels < 1) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": channels < 1");
         for (int k = 0; k < 3; ++k)
             if (n.in[k] >= i || n.in[k] < -1) return fail(SIGB_EINVAL, "node " + std::to_string(i) + ": inputs must precede the node (topological order)");
@@ -1495,11 +1662,13 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
         } else if (n.kind == SIGB_NODE_BUFFER) {
             v.kind = VK_EXT;
             v.channels = n.channels;
+        } else if (n.kind == SIGB_NODE_TAP) {
+            p->tap_nodes.push_back(i);            // taps are numbered in record order
         }
         // frame-rate edges (block-rate parameter ports are constants and never materialise)
         int nsig = 0;
         switch (n.kind) {
-            case SIGB_NODE_GAIN: case SIGB_NODE_AMP: case SIGB_NODE_FILTER:
+            case SIGB_NODE_GAIN: case SIGB_NODE_AMP: case SIGB_NODE_FILTER: case SIGB_NODE_TAP:
             case SIGB_NODE_GROUPSUM: case SIGB_NODE_PANSUM: nsig = 1; break;
             case SIGB_NODE_MIX: case SIGB_NODE_RINGMOD: case SIGB_NODE_MERGE: nsig = 2; break;
             default: break;
@@ -1515,6 +1684,7 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
     p->context = p->node_ctx[root];
     p->uses[root]++;
     const sigb_node& rn = p->nodes[root];
+    if (rn.kind == SIGB_NODE_TAP) return fail(SIGB_EINVAL, "a tap cannot be the root (the root block is the caller's `out`)");
     if (rn.channels != 1 && rn.channels != channels)
         return fail(SIGB_ESHAPE, "root block with " + std::to_string(rn.channels) + " channels incompatible with requested " + std::to_string(channels));
     Builder b{p.get()};
@@ -1534,6 +1704,7 @@ extern "C" int sigb_plan_create(const sigb_node* nodes, int32_t n_nodes, int32_t
     *out_plan = p.release();
     return SIGB_OK;
 }
+
 
 extern "C" int sigb_plan_bind_buffer(sigb_plan* plan, int32_t node, const float* dev_ptr, int64_t rows) {
     if (!plan || node < 0 || node >= (int)plan->nodes.size() || plan->nodes[node].kind != SIGB_NODE_BUFFER)
@@ -1555,6 +1726,7 @@ extern "C" int sigb_render(sigb_plan* plan, int64_t position, int32_t frames, fl
     if (!plan || !out || frames < 0 || position < 0 || ld_out < plan->channels)
         return fail(SIGB_EINVAL, "sigb_render: bad arguments");
     int e = upload(plan);
+    if (e == SIGB_OK) e = check_design_error(plan);
     if (e != SIGB_OK) return e;
     if (frames == 0) return SIGB_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1566,20 +1738,18 @@ extern "C" int sigb_render(sigb_plan* plan, int64_t position, int32_t frames, fl
     return SIGB_OK;
 }
 
-extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out) {
+extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out, void* after_stream) {
     if (!plan || !out_host || frames < 0 || position < 0 || ld_out < plan->channels)
         return fail(SIGB_EINVAL, "sigb_render_host: bad arguments");
     int e = upload(plan);
+    if (e == SIGB_OK) e = check_design_error(plan);
     if (e != SIGB_OK) return e;
     if (frames == 0) return SIGB_OK;
-    if (!plan->s_render) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_render, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&plan->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_rendered[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&plan->ev_copied[i], cudaEventDisableTiming));
-        }
-    }
+    e = ensure_host_streams(plan);
+    if (e != SIGB_OK) return e;
+    // work the caller queued on `after_stream` (the upload of a bound Buffer, ...) is ordered before the render
+    CUDA_TRY(cudaEventRecord(plan->ev_caller, (cudaStream_t)after_stream));
+    CUDA_TRY(cudaStreamWaitEvent(plan->s_render, plan->ev_caller, 0));
     const int C = plan->channels;
     int64_t rows = std::max<int64_t>(1, plan->opt_host_slab_bytes / (4ll * C));
     const int64_t step = 7 * SIGB_SCAN_L * 4;
@@ -1593,12 +1763,16 @@ extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frame
         }
         plan->stage_floats = rows * C;
     }
+    // ONE request: seek handling and the block-rate parameters happen once, at the request's first frame; the host
+    // slabs below only cut the rows
+    e = begin_request(plan, position, frames, plan->s_render);
+    if (e != SIGB_OK) return e;
     int slot = 0;
     int64_t n_slabs = 0;
     for (int64_t r = 0; r < frames; r += rows, slot ^= 1, ++n_slabs) {
         const int64_t nr = std::min(rows, frames - r);
         if (n_slabs >= 2) CUDA_TRY(cudaStreamWaitEvent(plan->s_render, plan->ev_copied[slot], 0));
-        e = render_range(plan, position + r, nr, plan->stage[slot], C, plan->s_render);
+        e = run_rows(plan, position + r, nr, plan->stage[slot], C, plan->s_render);
         if (e != SIGB_OK) return e;
         CUDA_TRY(cudaEventRecord(plan->ev_rendered[slot], plan->s_render));
         CUDA_TRY(cudaStreamWaitEvent(plan->s_copy, plan->ev_rendered[slot], 0));
@@ -1612,8 +1786,119 @@ extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frame
         }
         CUDA_TRY(cudaEventRecord(plan->ev_copied[slot], plan->s_copy));
     }
+    end_request(plan, position, frames);
+    if (n_slabs > 1) plan->last_slab = 0;          // intermediate buffers hold the last host slab only
     CUDA_TRY(cudaStreamSynchronize(plan->s_copy));
     CUDA_TRY(cudaStreamSynchronize(plan->s_render));
+    return check_design_error(plan);
+}
+
+// The audio callback's block (SinkDevice._callback, chain/dev.py:167-179): small, latency-bound.  The plan's kernels
+// for a block of `frames` rows are captured ONCE into a CUDA graph; every later block of that length is one
+// cudaGraphLaunch -- the kernels read the block position from a page-locked header and the root launch stores
+// straight into page-locked staging (no copy node) -- one stream synchronisation and one host memcpy into `out_host`.
+// Seeks, plans the graph cannot express (see rt_eligible) and blocks above "rt_max_bytes" take sigb_render_host.
+extern "C" int sigb_render_block(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out) {
+    if (!plan || !out_host || frames < 0 || position < 0 || ld_out < plan->channels)
+        return fail(SIGB_EINVAL, "sigb_render_block: bad arguments");
+    int e = upload(plan);
+    if (e == SIGB_OK) e = check_design_error(plan);
+    if (e != SIGB_OK) return e;
+    if (frames == 0) return SIGB_OK;
+    const int C = plan->channels;
+    const int64_t bytes = (int64_t)frames * C * 4;
+    const bool seek = !plan->have_pos || plan->next_pos != position || plan->opt_restart;
+    if (seek || !rt_eligible(plan) || bytes > plan->opt_rt_max_bytes || slab_rows(plan, frames) < frames)
+        return sigb_render_host(plan, position, frames, out_host, ld_out, nullptr);
+    e = ensure_host_streams(plan);
+    if (e != SIGB_OK) return e;
+    if (!plan->rt_hdr) CUDA_TRY(cudaHostAlloc(&plan->rt_hdr, 64, cudaHostAllocMapped));
+    if (plan->rt_stage_floats < (int64_t)frames * C) {
+        rt_drop_graphs(plan);                              // captured launches point into the old staging
+        if (plan->rt_stage) cudaFreeHost(plan->rt_stage);
+        plan->rt_stage = nullptr;
+        const int64_t want = std::max<int64_t>((int64_t)frames * C, 4096);
+        CUDA_TRY(cudaHostAlloc(&plan->rt_stage, want * sizeof(float), cudaHostAllocMapped));
+        plan->rt_stage_floats = want;
+    }
+    cudaStream_t st = plan->s_render;
+    plan->rt_hdr[0] = position;
+    e = ensure_bufs(plan, frames);
+    if (e != SIGB_OK) return e;
+    auto record = [&]() -> int {                           // the block's launches, position taken from the header
+        plan->rt_pos_ptr = plan->rt_hdr;
+        int r = run_params(plan, position, frames, st);
+        if (r == SIGB_OK) r = run_slab(plan, position, frames, plan->rt_stage, C, st);
+        plan->rt_pos_ptr = nullptr;
+        return r;
+    };
+    if (plan->opt_rt_graph) {
+        sigb_plan::RtGraph* g = nullptr;
+        const uint64_t sig = rt_state_sig(plan);
+        for (sigb_plan::RtGraph& c : plan->rt_graphs)
+            if (c.frames == frames) g = &c;
+        if (g && g->state_sig != sig) {                    // a render on another path moved the live state copy
+            rt_drop_graphs(plan);
+            g = nullptr;
+        }
+        if (!g) {
+            sigb_plan::RtGraph ng{frames, nullptr, nullptr, 0, sig};
+            const int64_t launches0 = plan->launch_count;
+            CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            e = record();
+            cudaError_t ce = cudaStreamEndCapture(st, &ng.graph);
+            plan->launch_count = launches0;                // recorded, not launched
+            if (e != SIGB_OK) { if (ng.graph) cudaGraphDestroy(ng.graph); return e; }
+            if (ce != cudaSuccess) return fail(SIGB_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            CUDA_TRY(cudaGraphInstantiate(&ng.exec, ng.graph, 0));
+            size_t nodes = 0;
+            cudaGraphGetNodes(ng.graph, nullptr, &nodes);
+            ng.nodes = (int)nodes;
+            if (plan->rt_graphs.size() >= 8) rt_drop_graphs(plan);
+            plan->rt_graphs.push_back(ng);
+            g = &plan->rt_graphs.back();
+        }
+        CUDA_TRY(cudaGraphLaunch(g->exec, st));
+        plan->launch_count += g->nodes;
+        plan->graph_launches++;
+    } else {
+        e = record();
+        if (e != SIGB_OK) return e;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (ld_out == C) {
+        std::memcpy(out_host, plan->rt_stage, (size_t)bytes);
+    } else {
+        for (int r = 0; r < frames; ++r) std::memcpy(out_host + (int64_t)r * ld_out, plan->rt_stage + (int64_t)r * C, (size_t)C * 4);
+    }
+    plan->last_slab = frames;
+    end_request(plan, position, frames);
+    return check_design_error(plan);
+}
+
+// Blocks of the most recent request as seen by tap `tap` (a Wave / Spec / FileWriter of the graph; its value is the
+// input it passes through, chain/__init__.py:409-417): copied from the buffer the render left in HBM -- no second
+// render.  SIGB_ESTATE when the request was cut into several slabs (the buffer then holds the last one only).
+extern "C" int sigb_plan_tap_count(const sigb_plan* plan) { return plan ? (int)plan->tap_nodes.size() : 0; }
+
+extern "C" int sigb_plan_read_tap(sigb_plan* plan, int32_t tap, float* out_host, int64_t ld_out, int32_t* channels) {
+    if (!plan || tap < 0 || tap >= (int)plan->tap_nodes.size()) return fail(SIGB_EINVAL, "sigb_plan_read_tap: no such tap");
+    const Val& v = plan->vals[plan->tap_nodes[tap]];
+    if (channels) *channels = v.channels;
+    if (!out_host) return SIGB_OK;
+    if (ld_out < v.channels) return fail(SIGB_EINVAL, "sigb_plan_read_tap: ld_out < channels");
+    const int64_t frames = plan->last_frames;
+    if (frames <= 0 || plan->last_slab < frames) return fail(SIGB_ESTATE, "sigb_plan_read_tap: the last request was rendered in several slabs");
+    cudaStream_t st = plan->s_render ? plan->s_render : nullptr;
+    if (v.kind == VK_CONST) {
+        for (int64_t r = 0; r < frames; ++r)
+            for (int c = 0; c < v.channels; ++c) out_host[r * ld_out + c] = (float)v.cv[c];
+        return SIGB_OK;
+    }
+    if (v.kind != VK_BUF || v.buf < 0 || !plan->bufs[v.buf].ptr) return fail(SIGB_ESTATE, "sigb_plan_read_tap: tap value not materialised");
+    CUDA_TRY(cudaMemcpy2DAsync(out_host, ld_out * sizeof(float), plan->bufs[v.buf].ptr, (size_t)v.channels * sizeof(float),
+                               (size_t)v.channels * sizeof(float), frames, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SIGB_OK;
 }
 
@@ -1639,6 +1924,13 @@ extern "C" int sigb_plan_destroy(sigb_plan* plan) {
         if (plan->ev_rendered[i]) cudaEventDestroy(plan->ev_rendered[i]);
         if (plan->ev_copied[i]) cudaEventDestroy(plan->ev_copied[i]);
     }
+    rt_drop_graphs(plan);
+    if (plan->rt_hdr) cudaFreeHost(plan->rt_hdr);
+    if (plan->rt_stage) cudaFreeHost(plan->rt_stage);
+    if (plan->d_warm) cudaFree(plan->d_warm);
+    if (plan->h_warm) cudaFreeHost(plan->h_warm);
+    if (plan->h_err) cudaFreeHost(plan->h_err);
+    if (plan->ev_caller) cudaEventDestroy(plan->ev_caller);
     if (plan->ev0) cudaEventDestroy(plan->ev0);
     if (plan->ev1) cudaEventDestroy(plan->ev1);
     if (plan->s_render) cudaStreamDestroy(plan->s_render);
@@ -1720,11 +2012,18 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "reg_variant") plan->opt_reg_variant = value;
     else if (k == "osc_reg") plan->opt_osc_reg = value;
     else if (k == "voices_segments") plan->opt_voices_segments = value;
+    else if (k == "voices_pieces") plan->opt_voices_pieces = value;
+    else if (k == "rt_graph") plan->opt_rt_graph = value;
+    else if (k == "rt_max_bytes") plan->opt_rt_max_bytes = value;
+    else if (k == "blockwise_reference") { plan->opt_restart = value; plan->have_pos = false; }
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else return fail(SIGB_EINVAL, "unknown option " + k);
+    rt_drop_graphs(plan);            // captured launches embody the old choice
     return SIGB_OK;
 }
+
+extern "C" int64_t sigb_plan_graph_launches(const sigb_plan* plan) { return plan ? plan->graph_launches : 0; }
 
 extern "C" int sigb_set_default_option(const char* key, int64_t value) {
     if (!key) return fail(SIGB_EINVAL, "null");

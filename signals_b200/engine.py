@@ -14,6 +14,7 @@ import typing
 import numpy as np
 
 from signals_b200 import _lib, plan as plan_mod
+from signals_b200 import chain as chain_mod
 from signals_b200.chain import (BadShape, BlockLoc, ChainLayerError, FilterDesignError, FilterIndexError,
                                 UnsupportedGraph)
 
@@ -104,6 +105,22 @@ class CompiledPlan:
     def reset(self):
         self._lib.sigb_state_reset(self.handle)
 
+    @property
+    def graph_launches(self) -> int:
+        """CUDA graphs launched by ``render_block`` so far."""
+        return int(self._lib.sigb_plan_graph_launches(self.handle))
+
+    def read_tap(self, index: int, frames: int) -> typing.Optional[np.ndarray]:
+        """The block tap ``index`` saw during the most recent request, copied from the buffer the render left in HBM;
+        ``None`` when the library cannot serve it (request rendered in several slabs, tap on a Buffer source)."""
+        ch = ctypes.c_int32()
+        st = self._lib.sigb_plan_read_tap(self.handle, int(index), None, 0, ctypes.byref(ch))
+        if st != _lib.SIGB_OK:
+            return None
+        out = np.empty((frames, ch.value), dtype=np.float32)
+        st = self._lib.sigb_plan_read_tap(self.handle, int(index), ctypes.c_void_p(out.ctypes.data), ch.value, None)
+        return out if st == _lib.SIGB_OK else None
+
     # -- rendering --------------------------------------------------------------------------
     def _bind_buffers(self):
         if self._bound:
@@ -169,9 +186,25 @@ class CompiledPlan:
             ptr, ld = out.data_ptr(), out.stride(0)
         dev = self.device if self.device is not None else torch.cuda.current_device()
         with torch.cuda.device(dev):
-            st = self._lib.sigb_render_host(self.handle, int(position), int(frames), ctypes.c_void_p(ptr), int(ld))
+            # work queued on torch's current stream (the upload of a bound Buffer ...) is ordered before the render
+            after = torch.cuda.current_stream(dev).cuda_stream
+            st = self._lib.sigb_render_host(self.handle, int(position), int(frames), ctypes.c_void_p(ptr), int(ld),
+                                            ctypes.c_void_p(after))
         if st != _lib.SIGB_OK:
             _raise(st, 'sigb_render_host')
+        return out
+
+    def render_block(self, position: int, frames: int, out: np.ndarray):
+        """The audio callback's block (``SinkDevice._callback``, /root/reference/src/signals/chain/dev.py:167-179):
+        one captured CUDA graph launch per contiguous block of a given length, delivered into ``out`` (host float32,
+        unit channel stride) -- ``sigb_render_block``."""
+        if not self._bound:
+            self._bind_buffers()
+        assert out.dtype == np.float32 and out.strides[1] == 4
+        st = self._lib.sigb_render_block(self.handle, int(position), int(frames), ctypes.c_void_p(out.ctypes.data),
+                                         out.strides[0] // 4)
+        if st != _lib.SIGB_OK:
+            _raise(st, 'sigb_render_block')
         return out
 
 
@@ -187,14 +220,27 @@ class Engine:
         return CompiledPlan(plan_mod.lower(emitter, channels, rate, frames), device=self.device)
 
     def plan_for(self, emitter, channels: int, rate: int, frames: int = 0) -> CompiledPlan:
+        """The cached plan of ``emitter``, recompiled when the graph under it was edited.
+
+        A dirty flag, not a walk: every edit of a ``signals_b200.chain`` graph bumps ``chain.graph_epoch()``
+        (port (dis)connected, state attribute assigned, state replaced), so the per-block check is one integer
+        compare plus ``np.array_equal`` on the plan's ``Fixed`` arrays (in-place writes into them do not pass through
+        a setter).  Graphs holding foreign node objects (the reference's own classes) have no hooks and are
+        fingerprinted by ``plan.signature`` as before."""
         key = (id(emitter), int(channels), int(rate))
-        sig = plan_mod.signature(emitter)
         hit = self._plans.get(key)
-        if hit is not None and hit[0] == sig:
-            return hit[1]
         if hit is not None:
-            hit[1].close()
+            sig, compiled, _ = hit
+            if compiled.records.tracked:
+                if sig == chain_mod.graph_epoch() and all(st.value is arr and np.array_equal(arr, snap)
+                                                          for st, arr, snap in compiled.records.fixed_values):
+                    return compiled
+            elif sig == plan_mod.signature(emitter):
+                return compiled
+            compiled.close()
+        epoch = chain_mod.graph_epoch()
         compiled = self.compile(emitter, channels, rate, frames)
+        sig = epoch if compiled.records.tracked else plan_mod.signature(emitter)
         self._plans[key] = (sig, compiled, emitter)
         return compiled
 
@@ -208,20 +254,27 @@ class Engine:
         out = compiled.render_device(loc.position, frames)
         return out.cpu().numpy().astype(self.result_dtype, copy=False)
 
-    def serve_taps(self, emitter, loc: BlockLoc) -> int:
+    def serve_taps(self, emitter, loc: BlockLoc, rendered: typing.Optional[np.ndarray] = None) -> int:
         """Deliver to every enabled tap under ``emitter`` (Wave / Spec / FileWriter) the block it would have seen
-        in the reference's recursion: a render of the tap's own input, device -> host, then ``tap.deliver``.
-        Taps are side effects of the host (GUI queue, file), not part of the fused block render, so this is a
-        separate, optional pass; returns the number of taps served."""
+        in the reference's recursion.  ``rendered`` = the host block the request at ``loc`` has just produced: taps at
+        the root get that block, interior taps get theirs from the buffer the same launch left in HBM
+        (``sigb_plan_read_tap``) -- no second render.  Without ``rendered`` (or when the library cannot serve a
+        tap) the tap's own input is rendered.  Returns the number of taps served."""
         frames, channels = loc.shape
         compiled = self.plan_for(emitter, channels, loc.rate, frames)
         served = 0
-        for tap, creq in compiled.records.taps:
+        for tap, creq, index in compiled.records.taps:
             src = tap.inputs_by_port.get('input')
             if src is None or not getattr(tap.get_state(), 'enabled', True):
                 continue
-            tap_loc = BlockLoc(position=loc.position, rate=loc.rate, shape=type(loc.shape)(frames=frames, channels=creq))
-            block = self.render(src, tap_loc)
+            block = None
+            if index is None:
+                block = rendered                      # a tap at the root sees the rendered block itself
+            elif rendered is not None:
+                block = compiled.read_tap(index, frames)   # kept aside in HBM by the same launch
+            if block is None:                         # no block at hand: a render of the tap's own input
+                tap_loc = BlockLoc(position=loc.position, rate=loc.rate, shape=type(loc.shape)(frames=frames, channels=creq))
+                block = self.render(src, tap_loc)
             tap.deliver(loc.position, loc.rate, np.broadcast_to(block, (frames, creq)))
             served += 1
         return served

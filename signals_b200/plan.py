@@ -24,6 +24,7 @@ import typing
 import numpy as np
 
 from signals_b200 import _lib
+from signals_b200 import chain as _chain
 from signals_b200.chain import BadShape, ChainLayerError, FilterIndexError, UnsupportedGraph
 
 _OSC = {'Sine': _lib.WAVE_SINE, 'Square': _lib.WAVE_SQUARE, 'Sawtooth': _lib.WAVE_SAWTOOTH,
@@ -51,7 +52,11 @@ class GraphRecords:
     rate: int
     buffers: dict        # record index -> Buffer node (bound to device memory by the engine)
     sources: list        # record index -> originating node object (diagnostics)
-    taps: list = dataclasses.field(default_factory=list)   # (tap node, requested channels): pass-through side-effect nodes
+    # pass-through side-effect nodes: (tap node, requested channels, tap index in the plan | None when the tap sits at
+    # the root, where the block it sees IS the rendered output)
+    taps: list = dataclasses.field(default_factory=list)
+    tracked: bool = True  # every node is a signals_b200.chain node (graph edits bump signals_b200.chain.graph_epoch)
+    fixed_values: list = dataclasses.field(default_factory=list)   # (Fixed state object, array, snapshot copy)
 
     def node_array(self):
         arr = (_lib.SigbNode * len(self.nodes))()
@@ -74,6 +79,9 @@ class _Lowering:
         self.memo: dict = {}
         self.active: set = set()
         self.taps: list = []
+        self.n_tap_records = 0
+        self.tracked = True
+        self.fixed_values: list = []
 
     # -- record helpers ---------------------------------------------------------------------
     def emit(self, source, kind: int, channels: int, inputs=(-1, -1, -1), subtype: int = 0, order: int = 0,
@@ -106,21 +114,23 @@ class _Lowering:
         return wide.pop() if wide else 1
 
     # -- the walk ---------------------------------------------------------------------------
-    def visit(self, node, creq: int) -> tuple[int, int]:
+    def visit(self, node, creq: int, at_root: bool = False) -> tuple[int, int]:
         key = (id(node), creq)
         if key in self.memo:
             return self.memo[key]
         if id(node) in self.active:
             raise ChainLayerError('Cycle detected')
         self.active.add(id(node))
+        if not isinstance(node, _chain.Signal):
+            self.tracked = False          # e.g. the reference's own node objects: no edit hooks, the engine re-walks
         try:
-            result = self._lower(node, creq)
+            result = self._lower(node, creq, at_root)
         finally:
             self.active.discard(id(node))
         self.memo[key] = result
         return result
 
-    def _lower(self, node, creq: int) -> tuple[int, int]:
+    def _lower(self, node, creq: int, at_root: bool = False) -> tuple[int, int]:
         kind = node_kind(node)
         st = node.get_state()
         if not getattr(st, 'enabled', True):
@@ -133,15 +143,28 @@ class _Lowering:
         if kind in _TAPS:
             # the tap's audio result IS its input (PassThroughResult.forward, chain/__init__.py:409-417);
             # queueing blocks for the GUI / writing the file is host-side work outside the render
-            if not any(t is node for t, _ in self.taps):
-                self.taps.append((node, creq))
-            return self.port(node, 'input', creq, F)
+            src = node.inputs_by_port.get('input')
+            if at_root or src is None:
+                # at the root the tap sees the rendered block itself; nothing to keep aside
+                if not any(t[0] is node for t in self.taps):
+                    self.taps.append((node, creq, None))
+                if src is None:
+                    return -1, 1
+                idx, ch = self.visit(src, creq, at_root=True)
+                if ch not in (1, creq):
+                    raise BadShape(src, (F, ch), (F, creq))
+                return idx, ch
+            idx, ch = self.port(node, 'input', creq, F)
+            self.taps.append((node, creq, self.n_tap_records))
+            self.n_tap_records += 1
+            return self.emit(node, _lib.NODE_TAP, ch, (idx,)), ch
         if kind == 'Fixed':
             value = np.asarray(st.value, dtype=np.float64)
             rows, ch = value.shape
             if rows != 1:
                 raise UnsupportedGraph(f'Fixed with {rows} rows: frame-rate tables are served by signals_b200.chain.ext.Buffer')
             off = self.n_data
+            self.fixed_values.append((st, st.value, np.array(st.value, copy=True)))
             self.tables.append(np.ascontiguousarray(value[0]))
             self.n_data += ch
             return self.emit(node, _lib.NODE_FIXED, ch, rows=1, data_off=off), ch
@@ -223,12 +246,13 @@ class _Lowering:
 def lower(emitter, channels: int, rate: int, frames: int = 0) -> GraphRecords:
     """Lower the sub-graph under ``emitter`` for a ``(frames, channels)`` request at ``rate`` Hz."""
     lw = _Lowering(int(channels), int(rate), int(frames))
-    root, ch = lw.visit(emitter, lw.channels)
+    root, ch = lw.visit(emitter, lw.channels, at_root=True)
     if ch not in (1, lw.channels):
         raise BadShape(emitter, (frames, ch), (frames, channels))
     data = np.concatenate(lw.tables) if lw.tables else np.zeros(0)
     return GraphRecords(nodes=lw.nodes, data=np.ascontiguousarray(data, dtype=np.float64), root=root,
-                        channels=lw.channels, rate=lw.rate, buffers=lw.buffers, sources=lw.sources, taps=lw.taps)
+                        channels=lw.channels, rate=lw.rate, buffers=lw.buffers, sources=lw.sources, taps=lw.taps,
+                        tracked=lw.tracked, fixed_values=lw.fixed_values)
 
 
 def signature(emitter) -> tuple:

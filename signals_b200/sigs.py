@@ -144,7 +144,7 @@ class Patch:
         loc = BlockLoc(position=position, rate=rate, shape=Shape(frames=frames, channels=sink.get_state().channels))
         block = engine.default_engine().render(emitter, loc)
         if taps:        # FileWriter / Wave nodes on the way get their blocks too (chain/files.py:99-102, chain/vis.py:61-64)
-            engine.default_engine().serve_taps(emitter, loc)
+            engine.default_engine().serve_taps(emitter, loc, rendered=np.broadcast_to(block, tuple(loc.shape)))
         return np.broadcast_to(block, tuple(loc.shape)).astype(np.float32)
 
 

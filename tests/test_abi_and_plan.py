@@ -22,7 +22,7 @@ def test_header_symbols_are_exported():
     lib = _lib.lib()
     missing = [name for name in sorted(declared) if not hasattr(lib, name)]
     assert not missing, missing
-    assert lib.sigb_abi_version() == 1
+    assert lib.sigb_abi_version() == 2
 
 
 def test_no_fallback_without_gpu(ns, engine):
