@@ -43,6 +43,7 @@ class Case:
     note: str = ''
     block: int = 0           # > 0: rendered as consecutive requests of `block` frames (block-rate parameters are
                              # re-sampled at the first frame of every request, chain/__init__.py:305-306)
+    options: dict = dataclasses.field(default_factory=dict)     # sigb_plan_set_option settings the GPU render needs
 
 
 def _c2(ns, v=8, seed=2, wave='Sine', cls='LowPass'):
@@ -90,6 +91,13 @@ def _cascade8(ns, v=4, seed=4):
     for _ in range(8):
         x = lowpass(ns, x, [np.exp(rng.uniform(np.log(200.0), np.log(8000.0), v))])
     return x
+
+
+def _cascade2(ns):
+    node = osc(ns, 'Sawtooth', [[220.0, 331.0]])
+    for cut in ([[900.0, 2500.0]], [[1200.0, 3000.0]]):
+        node = lowpass(ns, node, cut)
+    return node
 
 
 def _broadcast(ns):
@@ -261,6 +269,16 @@ CASES: list[Case] = [
     Case('lowpass_test_sigs', _lowpass_test_sigs, 48000, 2, tol=1e-4, note='src/signals/lowpass_test.sigs'),
     Case('lowpass_blockwise', lambda ns: _c2(ns, 4, 7), 512, 4, position=4800, tol=1e-4,
          note='position>0: zero-state restart + 100-frame context warm-up (chain/fx.py:93-105)'),
+    Case('lowpass_blockwise_stream', lambda ns: _c2(ns, 4, 7), 3072, 4, position=4800, block=512, tol=1e-4,
+         options={'blockwise_reference': 1},
+         note='six consecutive 512-frame requests as the reference itself renders them: every request restarts the filter from '
+              'zero state 100 frames early (fx.py:82-83, 93-105).  The plan reproduces that with blockwise_reference=1; its '
+              'default carries the true state instead (SURVEY 8c: the single-request render is the oracle)'),
+    Case('cascade2_seek', _cascade2, 512, 2, position=4800, tol=2e-4,
+         note='two chained LowPass nodes, request at position > 0: the reference warms the downstream filter on an upstream '
+              'context block that was itself restarted 200 frames early, and the main block on one restarted 100 frames early '
+              '(nested restarts); the plan warms the whole chain once from position - 200 with carried state.  Both are '
+              'approximations of the stream from position 0; they differ by the upstream transient (8.3e-5 here)'),
     Case('lowpass_order4', lambda ns: lowpass(ns, osc(ns, 'Square', [[220.5, 331.0]]), [[900.0, 2500.0]], order=4),
          24000, 2, tol=1e-4, note='CritFilter.order class knob, chain/fx.py:66'),
     Case('highpass_order3', lambda ns: lowpass(ns, osc(ns, 'Sawtooth', [[220.5, 331.0]]), [[900.0, 2500.0]], 'HighPass', 3),
@@ -300,4 +318,10 @@ ERROR_CASES = [
      lambda ns: lowpass(ns, osc(ns, 'Sine', [[100.0]]), [[0.0]]), 256, 1, 'ValueError'),
     ('mono_input_multichannel_filter',
      lambda ns: lowpass(ns, osc(ns, 'Sine', [[100.0]]), [[500.0, 600.0]]), 256, 2, 'IndexError'),
+]
+
+# graphs that compile but whose RENDER the reference rejects (the parameter only exists at run time)
+RUNTIME_ERROR_CASES = [
+    ('modulated_cutoff_below_zero',      # an LFO drives the cutoff to -1000 Hz at position 0: butter() rejects Wn = 0 (after the clip)
+     lambda ns: _with_cutoff(ns, osc(ns, 'Sine', [[440.0]]), gain(ns, _lfo(ns, 'Sine', [[0.25]], [[0.75]]), [[1000.0]])), 256, 1, 'ValueError'),
 ]

@@ -45,7 +45,7 @@ def main(names=None):
                                         absmax=float(np.nanmax(np.abs(out))))
         print(f'{case.name:24s} {out.shape} absmax={meta["cases"][case.name]["absmax"]:.6g}')
     errors = {}
-    for name, build, frames, channels, exc in cases.ERROR_CASES:
+    for name, build, frames, channels, exc in cases.ERROR_CASES + cases.RUNTIME_ERROR_CASES:
         try:
             ref_harness.render(ref, build(ns), 0, frames, channels)
             got = None
@@ -60,6 +60,7 @@ def main(names=None):
         with open(meta_path) as f:
             old = json.load(f)
         old['cases'].update(meta['cases'])
+        old['error_cases'] = meta['error_cases']
         meta = old
     with open(meta_path, 'w') as f:
         json.dump(meta, f, indent=1, sort_keys=True)

@@ -2,9 +2,10 @@
 //
 //   k_chain_seq   one thread per channel walking time sequentially (state in registers);
 //                 stateless chains (no filter sections) are tiled over time as well.
-//   k_chain_scan  the time-parallel kernel: a CTA owns a tile of 32 channels and walks time in
+//   k_chain_scan2 / k_chain_scan3
+//                 the time-parallel kernels: a CTA owns a tile of 32 / 64 channels and walks time in
 //                 steps; each worker warp renders one sub-chunk of a step from zero filter state,
-//                 a scanner warp chains the sub-chunk end states with the fp64 2x2 transition
+//                 a scanner warp chains the sub-chunk end states with the 2x2 transition
 //                 A^L of each state-variable section, and the workers add the zero-input
 //                 response of the true initial state before storing.
 //   k_ewise       binary / pointwise nodes on materialised blocks (Mix, RingMod, Amp, Gain, copy).
@@ -129,196 +130,20 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
 }
 
 // ------------------------------------------------------------------------------------------
-// k_chain_scan
+// named barriers of the time-parallel kernels: NG groups of WG worker warps + 1 scanner warp.  Group g renders steps
+// g, g+NG, g+2NG, ...; a step is WG sub-chunks of L rows.  Barrier 1+2g: "end states of group g published",
+// 2+2g: "initial states for group g published".
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// NG groups of WG worker warps + 1 scanner warp.  Group g renders steps g, g+NG, g+2NG, ...;
-// a step is WG sub-chunks of L rows.  Named barrier 1+2g: "end states of group g published",
-// 2+2g: "initial states for group g published".
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
-__global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
-k_chain_scan(const ChainDev a, int nsteps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
-    constexpr int NW = NG * WG;
-    constexpr int STEP = WG * L;                    // rows per step
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);            // [NW][L][32] output staging tiles (TMA source)
-    float2* zs = reinterpret_cast<float2*>(stage + NW * L * 32);  // [NW][32] sub-chunk end states
-    float2* si = zs + NW * 32;                                     // [NW][32] true initial states
-    float2* tab = si + NW * 32;                                    // [NSEC][L][32] zero-input responses
-    double* tnb = reinterpret_cast<double*>(tab + NSEC * L * 32);  // [NW][L] n/rate (generic osc)
-
-    const int lane = threadIdx.x & 31;
-    const int w = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
-    const bool live = c < a.C;
-    const int cc = live ? c : a.C - 1;
-    const size_t C = (size_t)a.C;
-
-    for (int i = threadIdx.x; i < NSEC * L * 32; i += blockDim.x) {
-        int l = i & 31, k = (i >> 5) % L, s = (i >> 5) / L;
-        int ch = min(blockIdx.x * 32 + l, a.C - 1);
-        tab[i] = make_float2(a.ztab[((size_t)(s * L + k) * 2 + 0) * C + ch],
-                             a.ztab[((size_t)(s * L + k) * 2 + 1) * C + ch]);
-    }
-    __syncthreads();
-
-    if (w == NW) {
-        // ---------------- scanner warp: lane = channel, fp64 carries ----------------
-        double m[NSEC][4], c1[NSEC], c2[NSEC];
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) m[s][k] = a.apow[(size_t)(s * 4 + k) * C + cc];
-            c1[s] = a.state[(size_t)(s * 2 + 0) * C + cc];
-            c2[s] = a.state[(size_t)(s * 2 + 1) * C + cc];
-        }
-        for (int step = 0; step < nsteps; ++step) {
-            const int grp = step % NG;
-#pragma unroll
-            for (int s = 0; s < NSEC; ++s) {
-                bar_sync(1 + 2 * grp, (WG + 1) * 32);
-                constexpr int ZB = 8;                       // end states fetched ZB at a time
-                for (int q0 = 0; q0 < WG; q0 += ZB) {
-                    float2 z[ZB];
-#pragma unroll
-                    for (int j = 0; j < ZB; ++j)
-                        if (q0 + j < WG) z[j] = zs[(grp * WG + q0 + j) * 32 + lane];
-#pragma unroll
-                    for (int j = 0; j < ZB; ++j) {
-                        if (q0 + j < WG) {
-                            si[(grp * WG + q0 + j) * 32 + lane] = make_float2((float)c1[s], (float)c2[s]);
-                            double n1 = fma(m[s][0], c1[s], fma(m[s][1], c2[s], (double)z[j].x));
-                            double n2 = fma(m[s][2], c1[s], fma(m[s][3], c2[s], (double)z[j].y));
-                            c1[s] = n1;
-                            c2[s] = n2;
-                        }
-                    }
-                }
-                bar_arrive(2 + 2 * grp, (WG + 1) * 32);
-            }
-        }
-        if (live) {
-#pragma unroll
-            for (int s = 0; s < NSEC; ++s) {
-                a.state[(size_t)(s * 2 + 0) * C + c] = c1[s];
-                a.state[(size_t)(s * 2 + 1) * C + c] = c2[s];
-            }
-        }
-        return;
-    }
-
-    // ---------------- worker warps: lane = channel, warp = sub-chunk ----------------
-    const int grp = w / WG, q = w % WG;
-    float g[NSEC], cf[NSEC], d[NSEC];
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        g[s] = a.coef[(size_t)(s * 3 + 0) * C + cc];
-        cf[s] = a.coef[(size_t)(s * 3 + 1) * C + cc];
-        d[s] = a.coef[(size_t)(s * 3 + 2) * C + cc];
-    }
-    const float gain = a.gain ? a.gain[cc] : 1.0f;
-    // first row of this warp's first sub-chunk; advances by NG*STEP rows per iteration
-    int64_t row = (int64_t)grp * STEP + (int64_t)q * L;
-    const int64_t row_stride = (int64_t)NG * STEP;
-    float* outp = a.out + row * a.ld_out + c;
-    const int64_t out_stride = row_stride * a.ld_out;
-    const bool bulk = use_tma != 0;
-    unsigned long long th = 0, th_step = 0;
-    int dhi = 0;
-    double hz = 0.0, ph = 0.0;
-    float cv = 0.0f;
-    if (SRC == SRC_OSC) {
-        if (FASTSINE) {
-            // exact Q0.64 phase at the first row of every sub-chunk; inside a sub-chunk the top word
-            // advances by the rounded top word of the increment (<= L * 2^-33 cycles of drift)
-            const unsigned long long dth = a.dtheta[cc];
-            th = a.theta0[cc] + (unsigned long long)(a.position + row) * dth;
-            th_step = dth * (unsigned long long)row_stride;
-            dhi = (int)((dth + 0x80000000ull) >> 32);
-        } else {
-            hz = a.hertz[cc];
-            ph = a.phase[cc];
-        }
-    }
-    if (SRC == SRC_CONST) cv = a.constv[cc];
-    const double rate = (double)a.rate;
-
-    for (int step = grp; step < nsteps; step += NG) {
-        float v[L];
-        if (SRC == SRC_OSC) {
-            if (FASTSINE) {
-                int hi = (int)(th >> 32);
-#pragma unroll
-                for (int k = 0; k < L; ++k) {
-                    v[k] = sine_q32(hi);
-                    hi += dhi;
-                }
-                th += th_step;
-            } else {
-                if (lane < L) tnb[w * L + lane] = __ddiv_rn((double)(a.position + row + lane), rate);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < L; ++k) v[k] = osc_wave(a.wave, osc_cycles(tnb[w * L + k], hz, ph));
-                __syncwarp();
-            }
-        } else if (SRC == SRC_BUF) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) v[k] = live ? load_src(a, row + k, c) : 0.0f;
-        } else {
-#pragma unroll
-            for (int k = 0; k < L; ++k) v[k] = cv;
-        }
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-            float s1 = 0.0f, s2 = 0.0f;
-            if (ALLLP) {
-#pragma unroll
-                for (int k = 0; k < L; ++k) v[k] = svf_lp2(v[k], g[s], cf[s], d[s], s1, s2);
-            } else {
-                const int kind = a.sec_kind[s];
-#pragma unroll
-                for (int k = 0; k < L; ++k) v[k] = svf_any(kind, v[k], g[s], cf[s], d[s], s1, s2);
-            }
-            zs[w * 32 + lane] = make_float2(s1, s2);
-            bar_arrive(1 + 2 * grp, (WG + 1) * 32);
-            bar_sync(2 + 2 * grp, (WG + 1) * 32);
-            const float2 i0 = si[w * 32 + lane];
-#pragma unroll
-            for (int k = 0; k < L; ++k) {
-                const float2 t = tab[(s * L + k) * 32 + lane];
-                v[k] = fmaf(t.x, i0.x, fmaf(t.y, i0.y, v[k]));
-            }
-        }
-        if (bulk) {
-            // stage the (L x 32) tile in shared memory (one STS per sample, immediate offsets), then
-            // one elected lane hands the whole tile to the TMA engine
-            float* tile = stage + w * (L * 32);
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < L; ++k) tile[k * 32 + lane] = v[k] * gain;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_tile(&out_map, blockIdx.x * 32, (int)row, tile);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else if (live) {
-#pragma unroll
-            for (int k = 0; k < L; ++k) __stcs(outp + (int64_t)k * a.ld_out, v[k] * gain);
-        }
-        outp += out_stride;
-        row += row_stride;
-    }
-    if (bulk && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 // ------------------------------------------------------------------------------------------
 // k_chain_scan2: the packed (f32x2) time-parallel kernel
 //
-// Same decomposition as k_chain_scan, but every worker thread renders its 16-row sub-chunk as TWO
+// Decomposition: a CTA owns a tile of 32 channels and walks time in steps; each worker warp renders one sub-chunk of a
+// step from zero filter state, a scanner warp chains the sub-chunk end states with the fp64 2x2 transition A^L of each
+// state-variable section, and the workers add the zero-input response of the true initial state before storing.
+// Every worker thread renders its 16-row sub-chunk as TWO
 // independent 8-row halves from zero state, carried in the two lanes of packed float2 registers, so
 // the state-variable section, the zero-input correction and the gain run as FFMA2/FMUL2/FADD2 (one
 // issue slot per two samples).  The halves are stitched inside the thread with the fp32 transition
@@ -1176,52 +1001,6 @@ bool make_out_map(const ChainDev& a, int rows, CUtensorMap* map) {
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, bool ALLLP>
-cudaError_t launch_scan_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
-    constexpr int NW = NG * WG;
-    constexpr int STEP = WG * L;
-    const int nsteps = a.frames / STEP;
-    *rows_done = nsteps * STEP;
-    if (nsteps == 0) return cudaSuccess;
-    size_t smem = (size_t)NW * 32 * sizeof(float2) * 2 + (size_t)NSEC * L * 32 * sizeof(float2) +
-                  (size_t)NW * L * sizeof(double) + 128 + (size_t)NW * L * 32 * sizeof(float);
-    auto kern = k_chain_scan<SRC, NSEC, NG, WG, FASTSINE, ALLLP>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    CUtensorMap map;
-    memset(&map, 0, sizeof(map));
-    const int use_tma = g_scan_tma && make_out_map(a, nsteps * STEP, &map) ? 1 : 0;
-    dim3 grid((a.C + 31) / 32), block((NW + 1) * 32);
-    kern<<<grid, block, smem, st>>>(a, nsteps, map, use_tma);
-    return cudaGetLastError();
-}
-
-template <int SRC, int NSEC, int NG, int WG>
-cudaError_t launch_scan_src(const ChainDev& a, cudaStream_t st, int* rows_done) {
-    bool alllp = true;
-    for (int s = 0; s < a.nsec; ++s) alllp = alllp && a.sec_kind[s] == 0;
-    const bool fast = SRC == SRC_OSC && a.wave == SIGB_WAVE_SINE && a.theta0 != nullptr;
-    if (SRC == SRC_OSC && fast) {
-        return alllp ? launch_scan_t<SRC_OSC, NSEC, NG, WG, true, true>(a, st, rows_done)
-                     : launch_scan_t<SRC_OSC, NSEC, NG, WG, true, false>(a, st, rows_done);
-    }
-    return alllp ? launch_scan_t<SRC, NSEC, NG, WG, false, true>(a, st, rows_done)
-                 : launch_scan_t<SRC, NSEC, NG, WG, false, false>(a, st, rows_done);
-}
-
-template <int NSEC, int NG, int WG>
-cudaError_t launch_scan_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
-    switch (a.src_kind) {
-        case SRC_OSC: return launch_scan_src<SRC_OSC, NSEC, NG, WG>(a, st, rows_done);
-        case SRC_BUF: return launch_scan_src<SRC_BUF, NSEC, NG, WG>(a, st, rows_done);
-        default: return launch_scan_src<SRC_CONST, NSEC, NG, WG>(a, st, rows_done);
-    }
-}
-
 template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, int PIPE = 0>
 cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     constexpr int NW = NG * WG;
@@ -1331,38 +1110,29 @@ cudaError_t launch_scan3_n(const ChainDev& a, cudaStream_t st, int* rows_done) {
 
 }  // namespace
 
+// Scan variants (A/B; every one computes the same transfer function):
+//   9   k_chain_scan2  32-channel tiles, packed two half sub-chunks per thread (the kernel for 2 sections, for deep
+//                      cascades forced onto the scan, and for chains of at most 32 channels)
+//   16  k_chain_scan3  64-channel tiles, float64 carry chain in the scanner      (single section)
+//   18  k_chain_scan3  64-channel tiles, packed float32 carry chain (default)    (single section)
+// Other values fall to the nearest of these (geometries measured in round 1 and dropped: DESIGN section 9).
+static int scan_normalise(int nsec, int C, int variant) {
+    if (nsec != 1 || C <= 32) return 9;          // one 32-channel tile: the 64-channel kernel would idle half its lanes
+    return variant == 16 ? 16 : variant >= 13 ? 18 : 9;
+}
+
 // scan geometry: (groups, worker warps per group).  Deep cascades keep the block at 512 threads
 // so the scanner's fp64 transition matrices stay in registers.
 static void scan_geometry(int nsec, int variant, int* ng, int* wg) {
-    if (variant >= 4) {               // packed kernel k_chain_scan2
-        if (nsec > 2) { *ng = 4; *wg = 7; return; }
-        switch (variant) {
-            case 5: *ng = 7; *wg = 4; break;
-            case 6: *ng = 2; *wg = 15; break;
-            case 7: *ng = 5; *wg = 6; break;
-            case 8: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;     // single section: software-pipelined workers
-            case 9: *ng = (nsec == 1 ? 3 : 5); *wg = 8; break;
-            case 13: *ng = 5; *wg = (nsec == 1 ? 5 : 6); break;   // 13-17: channel-pair kernel (64-channel tiles)
-            case 14: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 8 : 6); break;
-            case 15: *ng = (nsec == 1 ? 4 : 5); *wg = 6; break;
-            case 16: case 18: *ng = (nsec == 1 ? 3 : 5); *wg = (nsec == 1 ? 9 : 6); break;     // 18: float32 carry chain
-            case 17: *ng = (nsec == 1 ? 2 : 5); *wg = (nsec == 1 ? 13 : 6); break;
-            default: *ng = 4; *wg = 7; break;
-        }
-        return;
-    }
-    if (nsec > 2) { *ng = 2; *wg = 7; return; }
-    switch (variant) {
-        case 1: *ng = 2; *wg = 15; break;
-        case 2: *ng = 4; *wg = 7; break;
-        case 3: *ng = 2; *wg = 7; break;
-        default: *ng = 1; *wg = 31; break;
-    }
+    if (nsec > 2) { *ng = 4; *wg = 7; return; }
+    if (nsec == 2) { *ng = 5; *wg = 6; return; }
+    if (variant >= 13) { *ng = 3; *wg = 9; return; }
+    *ng = 3; *wg = 8;
 }
 
 extern "C" int sigb_scan_rows_per_step(int nsec, int variant) {
     int ng, wg;
-    scan_geometry(nsec, variant, &ng, &wg);
+    scan_geometry(nsec, scan_normalise(nsec, 64, variant), &ng, &wg);
     return wg * L;
 }
 
@@ -1385,47 +1155,13 @@ extern "C" int sigb_launch_chain_scan(const ChainDev* a, int variant, void* stre
     cudaStream_t st = (cudaStream_t)stream;
     *rows_done = 0;
     if (a->frames <= 0 || a->C <= 0 || a->nsec < 1 || a->nsec > 8) return 0;
-    if (variant >= 13 && a->C <= 32) variant = 9;      // one 32-channel tile: the 64-channel kernel would idle half its lanes
-    int ng, wg;
-    scan_geometry(a->nsec, variant, &ng, &wg);
-    if (variant >= 4) {
-        if (a->nsec > 2) {
-            if (a->nsec <= 4) return (int)launch_scan2_n<4, 4, 7>(*a, st, rows_done);
-            return (int)launch_scan2_n<8, 4, 7>(*a, st, rows_done);
-        }
-#define SCAN2_DISPATCH(NG, WG)                                                        \
-    do {                                                                              \
-        if (a->nsec == 1) return (int)launch_scan2_n<1, NG, WG>(*a, st, rows_done);   \
-        return (int)launch_scan2_n<2, NG, WG>(*a, st, rows_done);                     \
-    } while (0)
-        if (variant == 8 && a->nsec == 1) return (int)launch_scan2_n<1, 4, 6, 1>(*a, st, rows_done);
-        if (variant == 9 && a->nsec == 1) return (int)launch_scan2_n<1, 3, 8, 1>(*a, st, rows_done);
-        if (variant == 13 && a->nsec == 1) return (int)launch_scan3_n<5, 5, 16, false, true>(*a, st, rows_done);
-        if (variant == 14 && a->nsec == 1) return (int)launch_scan3_n<3, 8, 16, false, true>(*a, st, rows_done);
-        if (variant == 15 && a->nsec == 1) return (int)launch_scan3_n<4, 6, 16, false, true>(*a, st, rows_done);
-        if (variant == 16 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false>(*a, st, rows_done);
-        if (variant == 17 && a->nsec == 1) return (int)launch_scan3_n<2, 13, 16, false, true>(*a, st, rows_done);
-        if (variant == 18 && a->nsec == 1) return (int)launch_scan3_n<3, 9, 16, false, true>(*a, st, rows_done);
-        if (ng == 7) SCAN2_DISPATCH(7, 4);
-        if (ng == 2) SCAN2_DISPATCH(2, 15);
-        if (ng == 5) SCAN2_DISPATCH(5, 6);
-        SCAN2_DISPATCH(4, 7);
-#undef SCAN2_DISPATCH
-    }
-    if (a->nsec > 2) {
-        if (a->nsec <= 4) return (int)launch_scan_n<4, 2, 7>(*a, st, rows_done);
-        return (int)launch_scan_n<8, 2, 7>(*a, st, rows_done);
-    }
-#define SCAN_DISPATCH(NG, WG)                                                        \
-    do {                                                                             \
-        if (a->nsec == 1) return (int)launch_scan_n<1, NG, WG>(*a, st, rows_done);   \
-        return (int)launch_scan_n<2, NG, WG>(*a, st, rows_done);                     \
-    } while (0)
-    if (ng == 2 && wg == 15) SCAN_DISPATCH(2, 15);
-    if (ng == 4) SCAN_DISPATCH(4, 7);
-    if (ng == 2) SCAN_DISPATCH(2, 7);
-    SCAN_DISPATCH(1, 31);
-#undef SCAN_DISPATCH
+    variant = scan_normalise(a->nsec, a->C, variant);
+    if (a->nsec > 4) return (int)launch_scan2_n<8, 4, 7>(*a, st, rows_done);
+    if (a->nsec > 2) return (int)launch_scan2_n<4, 4, 7>(*a, st, rows_done);
+    if (a->nsec == 2) return (int)launch_scan2_n<2, 5, 6>(*a, st, rows_done);
+    if (variant == 16) return (int)launch_scan3_n<3, 9, 16, false>(*a, st, rows_done);
+    if (variant == 18) return (int)launch_scan3_n<3, 9, 16, false, true>(*a, st, rows_done);
+    return (int)launch_scan2_n<1, 3, 8, 1>(*a, st, rows_done);       // single section: software-pipelined workers
 }
 
 extern "C" int sigb_launch_ewise(const EwiseDev* a, void* stream) {

@@ -1263,10 +1263,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
                 if (done > 0) {
                     p->launch_count++;
-                    if (p->opt_scan_variant >= 4) {   // the packed kernel wrote the other copy
-                        ch.state_cur ^= 1;
-                        std::swap(a.state, a.state_out);
-                    }
+                    ch.state_cur ^= 1;                // the time-parallel kernels write the other copy of the state
+                    std::swap(a.state, a.state_out);
                 }
             }
             if (done < rows) {

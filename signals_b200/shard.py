@@ -44,6 +44,29 @@ def reduce_mix(partial, dst: typing.Optional[int] = 0, group=None):
     return partial
 
 
+def render_reduced(compiled, position: int, frames: int, out, dst: typing.Optional[int] = 0, group=None,
+                   tail_fraction: float = 0.125):
+    """This rank's fused render of ``(frames, 2)`` into ``out`` + the single reduce of the mix, with the collective
+    hidden behind the render: the first ``1 - tail_fraction`` of the block is reduced (asynchronously, on the
+    communicator's stream) while the tail is still being rendered, so only the tail's reduce is exposed.  Without a
+    process group (one GPU) it is just the render."""
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return compiled.render_device(position, frames, out)
+    head = frames - max(8, int(frames * tail_fraction)) // 8 * 8
+    if head <= 0 or head >= frames:
+        compiled.render_device(position, frames, out)
+        return reduce_mix(out, dst=dst, group=group)
+    compiled.render_device(position, head, out[:head])
+    op = dist.ReduceOp.SUM
+    work = (dist.all_reduce(out[:head], op=op, group=group, async_op=True) if dst is None
+            else dist.reduce(out[:head], dst=dst, op=op, group=group, async_op=True))
+    compiled.render_device(position + head, frames - head, out[head:frames])
+    work.wait()
+    reduce_mix(out[head:frames], dst=dst, group=group)
+    return out
+
+
 class ShardedMix:
     """A voice bank split over the ranks of a process group.
 
@@ -66,8 +89,10 @@ class ShardedMix:
     def render(self, position: int, frames: int, out=None, dst: typing.Optional[int] = 0):
         """Returns the CUDA ``(frames, channels)`` mix (complete on ``dst``, or on every rank when
         ``dst`` is None; other ranks hold their own partial)."""
-        out = self.compiled.render_device(position, frames, out)
-        return reduce_mix(out, dst=dst, group=self.group)
+        if out is None:
+            import torch
+            out = torch.empty((frames, self.channels), dtype=torch.float32, device=self.engine.device or 'cuda')
+        return render_reduced(self.compiled, position, frames, out, dst=dst, group=self.group)
 
     def close(self):
         self.compiled.close()

@@ -1,0 +1,271 @@
+"""GPU: the round-2 paths, all through the C ABI -- the realtime block path (sigb_render_block: captured CUDA graph,
+pinned header / staging), taps read back from the same launch, block-rate parameters sampled once per request by
+sigb_render_host, modulated cutoffs on the time-parallel kernels (k_design writes their tables), the device-side
+"cutoff outside (0, Nyquist)" error, seek warm-up in slab-sized pieces, and the equal-piece decomposition of k_voices."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, max_abs_err
+from oracle import cases, np_oracle
+
+pytestmark = pytest.mark.gpu
+
+RATE = 48000
+
+
+def _blocks(compiled, frames, block, how):
+    out = np.empty((frames, compiled.channels), dtype=np.float32)
+    for r in range(0, frames, block):
+        n = min(block, frames - r)
+        if how == 'block':
+            compiled.render_block(r, n, out[r:r + n])
+        else:
+            compiled.render_host(r, n, out[r:r + n])
+    return out
+
+
+@pytest.mark.parametrize('name', ['lowpass_c2_8v', 'cascade8', 'mix', 'lfo_chain', 'lfo_cutoff_cascade', 'fanout', 'highpass_order3'])
+@pytest.mark.parametrize('graph', [1, 0])
+def test_render_block_equals_render_host(name, graph, ns, engine):
+    """The audio-callback path: 384-frame blocks through sigb_render_block (one captured CUDA graph launch per
+    block, or the same launches issued directly) carry the filter state and re-sample the block-rate parameters at every
+    block exactly as sigb_render_host does for the same sequence of requests."""
+    case = cases.CASES_BY_NAME[name]
+    frames, block = 384 * 9 + 100, 384
+    a = engine.compile(case.build(ns), case.channels, RATE)
+    a.set_option('force_seq', 1)          # the block path runs one sequential launch per chain: compare like with like
+    want = _blocks(a, frames, block, 'host')
+    a.close()
+    b = engine.compile(case.build(ns), case.channels, RATE)
+    b.set_option('rt_graph', graph)
+    got = _blocks(b, frames, block, 'block')
+    g = b.graph_launches
+    b.close()
+    assert np.array_equal(got, want), f'{name}: max-abs {max_abs_err(got, want):.3e}'
+    # first block = seek (served by render_host), then one graph launch per full block and per ragged last block
+    assert g == (frames // block if graph else 0)
+
+
+def test_render_block_seek_and_recapture(ns, engine):
+    """A seek falls back to the host path (zero state + context warm-up) and the blocks after it replay the graph; a
+    device render in between moves the live copy of the double-buffered state and the graph is re-captured."""
+    case = cases.CASES_BY_NAME['lowpass_c2_8v']
+    c = engine.compile(case.build(ns), case.channels, RATE)
+    ref = engine.compile(case.build(ns), case.channels, RATE)
+    out = np.empty((512, case.channels), np.float32)
+    want = np.empty_like(out)
+    for pos in (0, 512, 1024, 40000, 40512):
+        c.render_block(pos, 512, out)
+        ref.render_host(pos, 512, want)
+        assert max_abs_err(out, want) <= 2e-6, pos
+    dev = c.render_device(41024, 4096).cpu().numpy()            # time-parallel kernel: flips the state copy
+    wdev = ref.render_device(41024, 4096).cpu().numpy()
+    assert max_abs_err(dev, wdev) <= 2e-6
+    for pos in (45120, 45632):
+        c.render_block(pos, 512, out)
+        ref.render_host(pos, 512, want)
+        assert max_abs_err(out, want) <= 2e-6, pos
+    c.close()
+    ref.close()
+
+
+def test_sink_device_uses_the_graph_path_and_the_dirty_flag(ns):
+    """SinkDevice.render_block: the plan is kept while the graph epoch stands still (no walk), every contiguous
+    callback is one CUDA graph launch, an edited parameter recompiles, and an in-place write into a Fixed's array is
+    noticed too."""
+    from signals_b200 import engine as engine_mod
+    from signals_b200.chain import dev
+    info = dev.DeviceInfo(name='t', index=0, hostapi=0, max_input_channels=0, max_output_channels=2, default_low_input_latency=0.0,
+                          default_low_output_latency=0.0, default_high_input_latency=0.0, default_high_output_latency=0.0,
+                          default_samplerate=float(RATE))
+    eng = engine_mod.default_engine()
+    eng.clear()
+    sink = dev.SinkDevice(info)
+    hz = cases.fixed(ns, [[500.0]])
+    osc = ns.Sine()
+    osc.hertz = hz
+    sink.input = cases.gain(ns, osc, [[0.2]])
+    out = np.zeros((512, 1), np.float32)
+    blocks = []
+    for _ in range(6):
+        sink.render_block(out, 512, RATE)
+        blocks.append(out.copy())
+    compiled = eng.plan_for(sink._ports['input'].sig, 1, RATE, 512)
+    assert compiled.graph_launches == 5
+    want = np_oracle.example_sine_block(0, 6 * 512, RATE)
+    assert max_abs_err(np.concatenate(blocks), want) <= 1e-6
+    hz.get_state().value = np.array([[250.0]])                       # setter -> epoch -> recompile
+    sink.render_block(out, 512, RATE)
+    assert eng.plan_for(sink._ports['input'].sig, 1, RATE, 512) is not compiled
+    assert max_abs_err(out, np_oracle.example_sine_block(6 * 512, 512, RATE, frequency=250.0)) <= 1e-6
+    hz.get_state().value[0, 0] = 125.0                               # in-place write: caught by the snapshot compare
+    sink.render_block(out, 512, RATE)
+    assert max_abs_err(out, np_oracle.example_sine_block(7 * 512, 512, RATE, frequency=125.0)) <= 1e-6
+    eng.clear()
+
+
+def test_interior_taps_are_served_by_the_same_launch(ns):
+    """Wave taps inside the graph: their blocks come from the buffers the one render left in HBM (sigb_plan_read_tap),
+    not from a second render; a tap at the root gets the rendered block itself."""
+    from signals_b200 import engine as engine_mod
+    from signals_b200.chain import vis
+    eng = engine_mod.Engine()
+    src = cases.osc(ns, 'Sawtooth', [[220.0, 330.0]])
+    t1 = vis.Wave()
+    t1.input = src
+    lp = cases.lowpass(ns, t1, [[900.0, 1500.0]])
+    t2 = vis.Wave()
+    t2.input = cases.gain(ns, lp, [[0.5, 0.25]])
+    from signals_b200.chain import BlockLoc, Shape
+    compiled = eng.plan_for(t2, 2, RATE, 1000)
+    kinds = [(l['kind'], l.get('sections')) for l in compiled.describe()['launches']]
+    assert kinds == [('chain', 0), ('chain', 1)]                       # the interior tap keeps the oscillator block aside
+    launches = []
+    for pos in (0, 1000):
+        loc = BlockLoc(position=pos, rate=RATE, shape=Shape(frames=1000, channels=2))
+        block = eng.render(t2, loc)
+        n0 = compiled.launch_count
+        assert eng.serve_taps(t2, loc, rendered=block) == 2
+        launches.append(compiled.launch_count - n0)
+    assert launches == [0, 0]                                          # no kernel ran for the taps
+    orc = np_oracle.GraphOracle(RATE)
+    got_src = np.concatenate([t1.q.get(), t1.q.get()])
+    got_out = np.concatenate([t2.q.get(), t2.q.get()])
+    assert max_abs_err(got_src, orc.render(src, 0, 2000, 2)) <= 1e-6
+    assert max_abs_err(got_out, orc.render(t2.inputs_by_port['input'], 0, 2000, 2)) <= 1e-4
+    eng.clear()
+
+
+@pytest.mark.parametrize('name', ['lfo_hertz', 'lfo_gain', 'lfo_cutoff', 'lfo_mix_amp'])
+def test_render_host_samples_block_rate_parameters_once_per_request(name, ns, engine):
+    """One request = one sampling of the modulated parameters, at its first frame (forward_at_block_rate,
+    chain/__init__.py:305-306), however sigb_render_host cuts the request into staging slabs."""
+    case = cases.CASES_BY_NAME[name]
+    a = engine.compile(case.build(ns), case.channels, RATE)
+    want = a.render_device(case.position, case.frames).cpu().numpy()
+    a.close()
+    b = engine.compile(case.build(ns), case.channels, RATE)
+    b.set_option('host_slab_bytes', 4 * case.channels * 500)        # ~500-row host slabs
+    got = b.render_host(case.position, case.frames)
+    b.close()
+    assert max_abs_err(got, want) <= 1e-6, name
+    assert max_abs_err(got[::case.stride], load_golden(name)) <= case.tol
+
+
+@pytest.mark.parametrize('name', ['lfo_cutoff', 'lfo_cutoff_hp3', 'lfo_cutoff_cascade'])
+def test_modulated_cutoffs_run_on_the_time_parallel_kernels(name, ns, engine):
+    """k_design writes the scan tables and the decay horizon of the request's design, so a chain with an LFO on its
+    cutoff takes the same time-parallel kernels as a constant one: same launches as the unmodulated chain, same result as
+    the sequential kernel, and the reference's golden."""
+    case = cases.CASES_BY_NAME[name]
+    frames = max(case.frames, 48000)
+    seq = engine.compile(case.build(ns), case.channels, RATE)
+    seq.set_option('force_seq', 1)
+    want = seq.render_device(case.position, frames).cpu().numpy()
+    seq.close()
+    par = engine.compile(case.build(ns), case.channels, RATE)
+    got = par.render_device(case.position, frames).cpu().numpy()
+    n_par = par.launch_count
+    par.close()
+    assert max_abs_err(got, want) <= 2e-5, name
+    assert max_abs_err(got[:case.frames:case.stride], load_golden(name)) <= case.tol
+    # param eval + one design per modulated filter (x2: seek samples the context position too) + the chain kernels
+    assert n_par >= 3
+
+
+def test_modulated_cutoff_time_pieces_match_the_float64_section(ns, engine):
+    """A long request with a modulated cutoff on 256 channels: the scan kernel cuts tiles along time with the decay
+    horizon k_design reported; compare with the float64 state-variable section at the sampled cutoff."""
+    ch, frames = 256, 96000
+    rng = np.random.default_rng(11)
+    hz = rng.uniform(60.0, 2000.0, ch)
+    src = cases.osc(ns, 'Sine', [hz])
+    lo, hi = rng.uniform(300.0, 600.0, ch), rng.uniform(2000.0, 6000.0, ch)
+    wah = cases._wah(ns, [lo], [hi], [rng.uniform(0.5, 3.0, ch)], [rng.uniform(0.0, 1.0, ch)])
+    node = cases._with_cutoff(ns, src, wah)
+    c = engine.compile(node, ch, RATE)
+    pos = 4800
+    got = c.render_device(pos, frames).cpu().numpy()
+    c.close()
+    want = np_oracle.GraphOracle(RATE).render(node, pos, frames, ch)
+    # the oracle restarts 100 frames before the request from zero state, as the plan does on a seek
+    assert max_abs_err(got, want) <= 1e-4
+
+
+def test_modulated_cutoff_outside_nyquist_raises_like_scipy(ns, engine):
+    """A cutoff driven to <= 0 Hz: scipy.signal.butter raises ValueError in the reference (fx.py:102); the device-side
+    design flags it and the call that finds the flag raises the same error class."""
+    from signals_b200.chain import FilterDesignError
+    src = cases.osc(ns, 'Sine', [[440.0]])
+    lfo = cases.osc(ns, 'Sine', [[0.25]], [[0.75]])                 # -1 at position 0
+    node = cases._with_cutoff(ns, src, cases.gain(ns, lfo, [[1000.0]]))
+    c = engine.compile(node, 1, RATE)
+    out = np.empty((256, 1), np.float32)
+    with pytest.raises(FilterDesignError):
+        c.render_host(0, 256, out)
+    with pytest.raises(ValueError):
+        np_oracle.GraphOracle(RATE).render(node, 0, 256, 1)
+    c.close()
+
+
+def test_seek_warmup_runs_in_slab_sized_pieces(ns, engine):
+    """A device slab shorter than the seek's context (64 rows against 800 frames of context for 8 chained filters): the
+    warm-up runs slab by slab inside buffers of one slab (canary rows behind the output stay untouched)."""
+    import torch
+    case = cases.CASES_BY_NAME['cascade8']
+    src = cases.gain(ns, case.build(ns), [[1.0] * case.channels])
+    mix = ns.Mix()                      # forces materialised intermediates (plan buffers)
+    mix.left = src
+    mix.right = cases.osc(ns, 'Sine', [[100.0] * case.channels])
+    mix.mix = cases.fixed(ns, [[0.5] * case.channels])
+    lp = cases.lowpass(ns, mix, [[2000.0] * case.channels])
+    a = engine.compile(lp, case.channels, RATE)
+    want = a.render_device(5000, 700).cpu().numpy()
+    a.close()
+    b = engine.compile(lp, case.channels, RATE)
+    b.set_option('slab_frames', 64)
+    out = torch.full((700 + 64, case.channels), 7.0, device='cuda')
+    b.render_device(5000, 700, out)
+    got = out.cpu().numpy()
+    b.close()
+    assert np.all(got[700:] == 7.0)
+    assert max_abs_err(got[:700], want) <= 2e-6
+
+
+@pytest.mark.parametrize('n,frames,pieces', [(9000, 24000, 0), (9000, 24000, 7), (2500, 30000, 0), (40, 5000, 0)])
+def test_voice_bank_pieces_match_oracle(n, frames, pieces, ns, engine):
+    """k_voices cuts the (voice group, row block) space into equal pieces per CTA slot: any bank size, pieces that
+    start inside a group (decay warm-up), pieces that span several groups, and the state handed to the next call."""
+    from signals_b200.chain import ext
+    prm = cases.instance_params(77, n)
+    prm['cutoff'] = np.clip(prm['cutoff'], 600.0, None)              # decay horizon ~1000 rows: cuts inside groups fit
+    compiled = engine.compile(cases.build_instances(ns, ext, prm), 2, RATE)
+    if pieces:
+        compiled.set_option('voices_pieces', pieces)
+    first = compiled.render_device(0, frames).cpu().numpy()
+    second = compiled.render_device(frames, 1000).cpu().numpy()
+    compiled.set_option('voices_segments', 1)                        # one piece per group: no cuts along time
+    compiled.reset()
+    whole = compiled.render_device(0, frames).cpu().numpy()
+    compiled.close()
+    want = np_oracle.render_instances(prm, 0, frames + 1000, RATE)
+    err = max_abs_err(np.concatenate([first, second]), want)
+    assert err <= 1e-6, err
+    assert max_abs_err(first, whole) <= 2e-7
+
+
+def test_blockwise_reference_option_is_what_separates_the_two_stream_semantics(ns, engine):
+    """Golden lowpass_blockwise_stream = the reference driven block by block (every request restarts the filter 100
+    frames early).  blockwise_reference=1 reproduces it (checked by the golden test); the default carries the true state,
+    which is the single-request render (the oracle) and differs from the blockwise reference by a few 1e-4."""
+    case = cases.CASES_BY_NAME['lowpass_blockwise_stream']
+    c = engine.compile(case.build(ns), case.channels, RATE)
+    c.render_device(0, case.position)                                   # stream from 0 up to the first block
+    carried = np.concatenate([c.render_device(case.position + r, case.block).cpu().numpy() for r in range(0, case.frames, case.block)])
+    c.close()
+    hertz, phase, cutoff, g = cases.voice_params(7, 4)
+    single = np_oracle.render_voice_chain(0, case.position + case.frames, RATE, hertz, phase, cutoff, g)[case.position:]
+    assert max_abs_err(carried, single) <= 1e-5
+    d = max_abs_err(carried, load_golden(case.name))
+    print(f'carried state vs the reference\'s blockwise render: {d:.3e}')
+    assert 1e-5 < d < 5e-3

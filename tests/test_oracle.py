@@ -34,10 +34,10 @@ def test_golden_meta_lists_every_case():
         meta = json.load(f)
     assert set(meta['cases']) == {c.name for c in cases.CASES}
     assert meta['reference_pins'] == {'numpy': '1.23.0', 'scipy': '1.10.1'}
-    assert set(meta['error_cases']) == {e[0] for e in cases.ERROR_CASES}
+    assert set(meta['error_cases']) == {e[0] for e in cases.ERROR_CASES + cases.RUNTIME_ERROR_CASES}
 
 
-@pytest.mark.parametrize('name,build,frames,channels,exc', cases.ERROR_CASES, ids=lambda v: v if isinstance(v, str) else '')
+@pytest.mark.parametrize('name,build,frames,channels,exc', cases.ERROR_CASES + cases.RUNTIME_ERROR_CASES, ids=lambda v: v if isinstance(v, str) else '')
 def test_oracle_error_cases(name, build, frames, channels, exc, ns):
     with pytest.raises(Exception) as info:
         np_oracle.GraphOracle().render(build(ns), 0, frames, channels)
