@@ -741,8 +741,8 @@ def measure(ctx, wl, steps, warmup, e2e_steps, cpu_baseline):
 # ------------------------------------------------------------------------------------------------
 def c1_graphs(ns):
     """(name, build() -> emitter) of the two realtime graphs: scripts/example_sine.py as a graph, and the reference's
-    lowpass_test.sigs fixture (Triangle 440 -> Gain 0.2 -> LowPass 600 -> FileWriter -> Wave; taps disabled so that
-    the number is the render, not the WAV file or the GUI queue)."""
+    lowpass_test.sigs fixture's audio path (Triangle 440 -> Gain 0.2 -> LowPass 600; the sink is attached to the LowPass,
+    above the FileWriter / Wave taps, so that the number is the render, not the WAV file or the GUI queue)."""
     from signals_b200 import sigs
     from signals_b200 import workloads as cases
 
@@ -751,12 +751,10 @@ def c1_graphs(ns):
 
     def lowpass_patch():
         patch = sigs.load(os.path.join(ROOT, 'tests', 'golden', 'lowpass_test.sigs'))
-        for node in patch.nodes.values():
-            if type(node).__name__ in ('FileWriter', 'Wave', 'Spec'):
-                node.get_state().enabled = False
-        return patch.root()[1]
+        (lp,) = [n for n in patch.nodes.values() if type(n).__name__ == 'LowPass']
+        return lp
 
-    return [('Sine<-Fixed -> Gain (scripts/example_sine.py as a graph)', sine_gain), ('lowpass_test.sigs', lowpass_patch)]
+    return [('Sine<-Fixed -> Gain (scripts/example_sine.py as a graph)', sine_gain), ('lowpass_test.sigs (audio path)', lowpass_patch)]
 
 
 def measure_c1(ctx, callbacks=1500, cpu=True):

@@ -148,7 +148,7 @@ int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
  *   register-resident, 0: never; default 3), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
  *   "pipe_spw", "pipe_segments" (upper bound on the time pieces per tile of the cascade kernels; 1: never cut),
  *   "voices_segments" (k_voices: 0 equal pieces per resident CTA, 1 one piece per voice group, n pieces per group),
- *   "voices_pieces" (automatic mode: pieces per resident CTA slot, default 2), "voices_m",
+ *   "voices_pieces" (automatic mode: pieces per resident CTA slot, default 16), "voices_m",
  *   "rt_graph" (0: sigb_render_block launches its kernels directly instead of through a captured graph),
  *   "rt_max_bytes" (largest block sigb_render_block serves itself),
  *   "blockwise_reference" (1: EVERY request restarts the filters from zero state and `context` warm-up frames, as the

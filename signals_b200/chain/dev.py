@@ -139,7 +139,7 @@ class SinkDevice(Device, Receiver, ExplicitChannels):
         channels = self._state.channels
         loc = BlockLoc(position=self.frame_position, shape=Shape(channels=channels, frames=frames), rate=rate)
         bound = self._ports['input']
-        if bound and outdata.dtype == np.float32 and outdata.strides[1] == 4 and getattr(bound.sig.get_state(), 'enabled', True):
+        if bound and outdata.dtype == np.float32 and outdata.strides[1] == 4:
             # fast path (dev.py:173 + :178 in one call): the plan is kept while the graph epoch stands still, the block
             # is ONE captured CUDA graph launch into page-locked staging and one copy into the device's buffer
             # (sigb_render_block); taps get their blocks from that same launch

@@ -130,6 +130,68 @@ __global__ void __launch_bounds__(128) k_chain_seq(const ChainDev a, int rows_pe
 }
 
 // ------------------------------------------------------------------------------------------
+// k_chain_rt: the latency kernel -- one WARP per channel.
+//
+// k_chain_seq walks a channel's rows in one thread: source (float64 phase, division, waveform) and filter recurrence
+// alternate in a single dependency chain, ~400 cycles per row for an oscillator source (measured: a 512-frame
+// block of Triangle -> Gain -> LowPass took 110 us).  For the audio callback's blocks (SinkDevice._callback,
+// chain/dev.py:167-179: a few channels x 128..1024 rows) the machine is empty, so a warp per channel splits the two:
+// the 32 lanes evaluate the source of 32 consecutive rows in parallel, then every lane runs the SAME sequential
+// recurrence over those 32 samples (broadcast by shuffle; redundant lanes cost nothing under SIMT) and lane k keeps
+// row k.  What remains on the critical path is the recurrence itself, ~20 cycles per row.
+// Same arithmetic in the same order as k_chain_seq: the two kernels agree bit for bit.
+// ------------------------------------------------------------------------------------------
+template <int SRC, int NSEC>
+__global__ void __launch_bounds__(128) k_chain_rt(const ChainDev a) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= a.C) return;
+    float g[NSEC], cc[NSEC], d[NSEC], s1[NSEC], s2[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        g[s] = a.coef[(size_t)(s * 3 + 0) * a.C + c];
+        cc[s] = a.coef[(size_t)(s * 3 + 1) * a.C + c];
+        d[s] = a.coef[(size_t)(s * 3 + 2) * a.C + c];
+        s1[s] = (float)a.state[(size_t)(s * 2 + 0) * a.C + c];
+        s2[s] = (float)a.state[(size_t)(s * 2 + 1) * a.C + c];
+    }
+    const float gain = a.gain ? a.gain[c] : 1.0f;
+    double hz = 0.0, ph = 0.0;
+    float cv = 0.0f;
+    if (SRC == SRC_OSC) { hz = a.hertz[c]; ph = a.phase[c]; }
+    if (SRC == SRC_CONST) cv = a.constv[c];
+    const double rate = (double)a.rate;
+    const int64_t position = a.pos_ptr ? *a.pos_ptr : a.position;     // realtime graphs read the block header
+    for (int r0 = 0; r0 < a.frames; r0 += 32) {
+        const int r = r0 + lane;
+        float x = 0.0f;
+        if (r < a.frames) {
+            if (SRC == SRC_OSC) x = osc_wave(a.wave, osc_cycles(__ddiv_rn((double)(position + r), rate), hz, ph));
+            else if (SRC == SRC_BUF) x = load_src(a, r, c);
+            else x = cv;
+        }
+        const int n = min(32, a.frames - r0);
+        float mine = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            if (k < n) {                                   // uniform over the warp
+                float v = __shfl_sync(0xffffffffu, x, k);
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s) v = svf_any(a.sec_kind[s], v, g[s], cc[s], d[s], s1[s], s2[s]);
+                if (lane == k) mine = v;
+            }
+        }
+        if (r < a.frames) a.out[(int64_t)r * a.ld_out + c] = mine * gain;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            a.state[(size_t)(s * 2 + 0) * a.C + c] = (double)s1[s];
+            a.state[(size_t)(s * 2 + 1) * a.C + c] = (double)s2[s];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // named barriers of the time-parallel kernels: NG groups of WG worker warps + 1 scanner warp.  Group g renders steps
 // g, g+NG, g+2NG, ...; a step is WG sub-chunks of L rows.  Barrier 1+2g: "end states of group g published",
 // 2+2g: "initial states for group g published".
@@ -959,6 +1021,18 @@ cudaError_t launch_seq_src(const ChainDev& a, cudaStream_t st) {
         segs = min(segs, 65535);
         rows_per_seg = (a.frames + segs - 1) / segs;
         grid.y = (a.frames + rows_per_seg - 1) / rows_per_seg;
+    }
+    // few channels: a warp per channel keeps the source off the recurrence's critical path (k_chain_rt)
+    if (nsec >= 1 && a.epi_op == 0 && (int64_t)a.C * 32 <= (int64_t)sm_count() * 2048) {
+        dim3 rgrid((a.C * 32 + 127) / 128);
+#define RT_CASE(N) k_chain_rt<SRC, N><<<rgrid, block, 0, st>>>(a)
+        if (nsec == 1) RT_CASE(1);
+        else if (nsec == 2) RT_CASE(2);
+        else if (nsec <= 4) RT_CASE(4);
+        else if (nsec <= 8) RT_CASE(8);
+        else RT_CASE(16);
+#undef RT_CASE
+        return cudaGetLastError();
     }
 #define SEQ_CASE(N) k_chain_seq<SRC, N><<<grid, block, 0, st>>>(a, rows_per_seg)
     if (nsec == 0) SEQ_CASE(0);

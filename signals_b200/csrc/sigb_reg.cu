@@ -28,6 +28,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "sigb200.h"
 #include "sigb_internal.h"
@@ -274,6 +275,237 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_cascade_stream: the register-resident cascade as a CONTINUOUS software pipeline over rows.
+//
+// k_cascade_reg evaluates blocks of R rows in wavefront order: R + NSEC - 1 diagonals per block, the first and
+// last NSEC - 1 of them partly filled (average 4.3 independent section steps per diagonal for 8 sections x 8 rows),
+// and the pipeline drains and refills at every block.  Here section s works on row t - s at tick t for the whole
+// sub-range: every tick is NSEC INDEPENDENT section steps (one per section, on NSEC different rows), one new row in
+// and one finished row out; the pipeline fills once at the start of a sub-range and drains once at its end.
+// p[s] holds the row waiting for section s (the output of section s - 1 from the previous tick).
+//
+// IMM2: three-coefficient form of the section -- the state updates as 2 bp - s1 / 2 lp - s2 (one shared register
+// pair holding 2.0 instead of two more coefficient pairs per section): 10 registers per section instead of 14, so
+// 8 sections fit 128 registers and 16 warps per SM instead of 12.
+// ---------------------------------------------------------------------------------------------------------
+struct StreamSec {
+    float2 nc, al, g;           // (-c) (g d) (g)
+    float2 a2, g2;              // (2 g d) (2 g): only read by the five-coefficient form
+    float2 d;                   // high-pass output scale
+    float2 s1, s2;
+};
+
+template <int KIND, bool IMM2>
+__device__ __forceinline__ float2 stream_step(float2 x, StreamSec& r, const float2 two) {
+    const float2 xs = __fadd2_rn(x, make_float2(-r.s2.x, -r.s2.y));
+    const float2 e = __ffma2_rn(r.nc, r.s1, xs);
+    const float2 bp = __ffma2_rn(r.al, e, r.s1);
+    if (IMM2) r.s1 = __ffma2_rn(two, bp, make_float2(-r.s1.x, -r.s1.y));
+    else r.s1 = __ffma2_rn(r.a2, e, r.s1);
+    const float2 lp = __ffma2_rn(r.g, bp, r.s2);
+    if (IMM2) r.s2 = __ffma2_rn(two, lp, make_float2(-r.s2.x, -r.s2.y));
+    else r.s2 = __ffma2_rn(r.g2, bp, r.s2);
+    return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
+}
+
+// one tick with sections [LO, HI] active (HI down to LO, so that p[s + 1] is read before section s overwrites it);
+// u enters section LO when LO == 0; the return value is the output of the last section when HI == NSEC - 1
+template <int NSEC, int KIND, bool IMM2, int LO, int HI>
+__device__ __forceinline__ float2 stream_tick(float2 u, float2 (&p)[NSEC], StreamSec (&sec)[NSEC], const float2 two) {
+    float2 out = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int s = HI; s >= LO; --s) {
+        const float2 y = stream_step<KIND, IMM2>(s == 0 ? u : p[s], sec[s], two);
+        if (s == NSEC - 1) out = y;
+        else p[s + 1] = y;
+    }
+    return out;
+}
+
+// resident CTAs per SM: 14 registers per section with five coefficients, 10 with three (+2 for a high-pass's output scale)
+__host__ __device__ constexpr int stream_min_blocks(int nsec, bool imm2, bool hp) {
+    return imm2 ? (nsec <= 4 ? 5 : (hp && nsec >= 7) ? 3 : 4) : (nsec <= 5 ? 4 : 3);
+}
+
+// FAST layout only (host-checked: whole 64-channel tiles, 8-byte aligned even leading dimensions, source covers every
+// row, 3 <= NSEC <= 8); rows come in blocks of 8 through the same warp-private cp.async ring as k_cascade_reg, but
+// every tick reads its input row from the ring and stores its finished row at once, so no block of rows is held in
+// registers (the registers go to the sections: 16 warps per SM with the three-coefficient form).
+template <int NSEC, int KIND, bool IMM2>
+__global__ void __launch_bounds__(RWARPS * 32, stream_min_blocks(NSEC, IMM2, (KIND & SEC_HP) != 0))
+k_cascade_stream(const ChainDev a, int tiles, int npieces, int warm_rows) {
+    constexpr int R = 8;
+    static_assert(NSEC >= 2 && NSEC <= 8, "pipeline depth");
+    __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
+    const int lane = threadIdx.x & 31;
+    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (piece >= npieces) return;
+    const size_t C = (size_t)a.C;
+    const int bpt = (a.frames + R - 1) / R;
+    const int64_t total = (int64_t)tiles * bpt;
+    int64_t blk = total * piece / npieces;
+    const int64_t blk_end = total * (piece + 1) / npieces;
+    const int64_t ld_in = (int64_t)a.src_ld * 4, ld_o = (int64_t)a.ld_out * 4;       // row strides in bytes
+    float2 two = make_float2(2.0f, 2.0f);
+    asm volatile("" : "+f"(two.x), "+f"(two.y));          // one register pair, not an immediate per use
+  while (blk < blk_end) {
+    const int tile = (int)(blk / bpt);
+    const int b0 = (int)(blk - (int64_t)tile * bpt);
+    const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
+    blk += b1 - b0;
+    const int c0 = tile * RC + 2 * lane;
+    const int row_store = b0 * R;
+    const int row_end = min(a.frames, b1 * R);
+    const int row_first = max(0, row_store - warm_rows);                   // warm_rows is a multiple of R
+    const int nfull = (row_end - row_first) / R;                           // whole blocks of R rows
+
+    StreamSec sec[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
+        const float2 c = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 1) * C + c0);
+        const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
+        sec[s].g = g;
+        sec[s].nc = make_float2(-c.x, -c.y);
+        sec[s].d = d;
+        sec[s].al = make_float2(g.x * d.x, g.y * d.y);
+        sec[s].g2 = make_float2(keep(2.0f * g.x), keep(2.0f * g.y));
+        sec[s].a2 = make_float2(keep(2.0f * (g.x * d.x)), keep(2.0f * (g.y * d.y)));
+        if (row_first == 0) {
+            sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + c0], (float)a.state[(size_t)(s * 2 + 0) * C + c0 + 1]);
+            sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + c0], (float)a.state[(size_t)(s * 2 + 1) * C + c0 + 1]);
+        } else {
+            sec[s].s1 = sec[s].s2 = make_float2(0.0f, 0.0f);
+        }
+    }
+    float2 gain = make_float2(1.0f, 1.0f);
+    if (a.gain) gain = make_float2(a.gain[c0], a.gain[c0 + 1]);
+
+    const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
+    // outputs lag the inputs by NSEC - 1 rows: the row finished at the tick that reads row t is row t - (NSEC - 1)
+    char* op = reinterpret_cast<char*>(a.out + ((int64_t)row_first - (NSEC - 1)) * a.ld_out + c0);
+    const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RING_D * R * 32) + lane) * 8u;
+    const unsigned my_end = my + RING_D * R * 256u;
+    unsigned in_addr = my, out_addr = my;
+    int in_blk = 0;
+    auto prefetch = [&]() {
+        if (in_blk < nfull) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                cp_async8(in_addr + k * 256u, ip);
+                ip += ld_in;
+            }
+            ++in_blk;
+            in_addr += R * 256u;
+            if (in_addr == my_end) in_addr = my;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < RING_D - 1; ++j) prefetch();
+
+    float2 p[NSEC];
+    int row = row_first;                                                   // first input row of the current block
+    // one block of R ticks; FIRST: the pipeline fills (tick k < NSEC - 1 runs sections 0 .. k only); STORE: 0 none
+    // (warm-up), 1 every finished row, 2 the rows finished from tick NSEC - 1 on (the block that straddles row_store,
+    // and the first block of a sub-range that starts at row 0)
+    auto run_block = [&](auto first_tag, auto store_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
+        constexpr int STORE = decltype(store_tag)::value;
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const float2 u = lds_f2(out_addr + k * 256u);
+            float2 y;
+            if (FIRST && k < NSEC - 1) {
+                // fill: sections 0 .. k
+#pragma unroll
+                for (int s = NSEC - 2; s >= 0; --s)
+                    if (s <= k) p[s + 1] = stream_step<KIND, IMM2>(s == 0 ? u : p[s], sec[s], two);
+                y = u;
+            } else {
+                y = stream_tick<NSEC, KIND, IMM2, 0, NSEC - 1>(u, p, sec, two);
+            }
+            if (STORE == 1 || (STORE == 2 && k >= NSEC - 1)) __stcs(reinterpret_cast<float2*>(op), __fmul2_rn(y, gain));
+            op += ld_o;
+        }
+        out_addr += R * 256u;
+        if (out_addr == my_end) out_addr = my;
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    for (int b = 0; b < nfull; ++b) {
+        prefetch();
+        cp_async_wait<RING_D - 1>();
+        if (b == 0) {
+            if (row >= row_store) run_block(T{}, std::integral_constant<int, 2>{});
+            else run_block(T{}, std::integral_constant<int, 0>{});
+        } else if (row > row_store) {
+            run_block(F{}, std::integral_constant<int, 1>{});
+        } else if (row == row_store) {
+            run_block(F{}, std::integral_constant<int, 2>{});
+        } else {
+            run_block(F{}, std::integral_constant<int, 0>{});
+        }
+        row += R;
+    }
+    cp_async_wait<0>();
+    if (nfull > 0) {
+        // drain: NSEC - 1 more ticks without input finish the last NSEC - 1 rows; section s stops after row `row - 1`
+#pragma unroll
+        for (int j = 1; j < NSEC; ++j) {
+            float2 y = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int s = NSEC - 1; s >= 1; --s) {
+                if (s >= j) {
+                    const float2 v = stream_step<KIND, IMM2>(p[s], sec[s], two);
+                    if (s == NSEC - 1) y = v;
+                    else p[s + 1] = v;
+                }
+            }
+            if (row > row_store) __stcs(reinterpret_cast<float2*>(op), __fmul2_rn(y, gain));
+            op += ld_o;
+        }
+    }
+    // ragged tail (< R rows; only the sub-range that ends the launch has one)
+    {
+        const float* srcp = a.src + (int64_t)row * a.src_ld + c0;
+        float* outp = a.out + (int64_t)row * a.ld_out + c0;
+        for (; row < row_end; ++row) {
+            float2 x = *reinterpret_cast<const float2*>(srcp);
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) x = stream_step<KIND, IMM2>(x, sec[s], two);
+            *reinterpret_cast<float2*>(outp) = __fmul2_rn(x, gain);
+            srcp += a.src_ld;
+            outp += a.ld_out;
+        }
+    }
+    if (row_end == a.frames) {
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            a.state_out[(size_t)(s * 2 + 0) * C + c0] = (double)sec[s].s1.x;
+            a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = (double)sec[s].s1.y;
+            a.state_out[(size_t)(s * 2 + 1) * C + c0] = (double)sec[s].s2.x;
+            a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = (double)sec[s].s2.y;
+        }
+    }
+  }
+}
+
+template <int KIND, bool IMM2>
+int stream_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
+    switch (a->nsec) {
+        case 3: k_cascade_stream<3, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 4: k_cascade_stream<4, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 5: k_cascade_stream<5, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 6: k_cascade_stream<6, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_stream<7, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        default: k_cascade_stream<8, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+    }
+    return (int)cudaGetLastError();
+}
+
 template <int NSEC, int KIND, int R, bool FAST>
 int reg_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     k_cascade_reg<NSEC, KIND, R, FAST><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
@@ -467,11 +699,12 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
                       (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
                       a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
     const bool wide = fast && variant != 1;
+    const bool streaming = fast && (variant == 2 || variant == 3);         // continuous software pipeline over rows
     const int R = wide ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = reg_min_blocks(a->nsec, R) * RWARPS;
+    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, variant == 3, (a->sec_kind[0] & SEC_HP) != 0) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -488,6 +721,10 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const int npieces = (int)want;
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
+    if (streaming && variant == 3) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
+                                          : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
+    if (streaming) return hp ? stream_launch_nsec<SEC_HP, false>(a, grid, tiles, npieces, warm, st)
+                          : stream_launch_nsec<0, false>(a, grid, tiles, npieces, warm, st);
     if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
                         : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
     if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)
