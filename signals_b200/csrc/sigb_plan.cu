@@ -2025,6 +2025,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "blockwise_reference") { plan->opt_restart = value; plan->have_pos = false; }
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
+    else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);
     rt_drop_graphs(plan);            // captured launches embody the old choice
     return SIGB_OK;

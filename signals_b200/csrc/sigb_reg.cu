@@ -38,6 +38,8 @@ namespace {
 
 using namespace sigb_dev;
 
+int g_reg_pieces = 1;           // pieces per warp slot of the machine (A/B: more pieces even out the tail, each costs a warm-up)
+
 constexpr int RC = 64;          // channels per warp (2 per lane)
 constexpr int RWARPS = 4;       // warps per CTA: 256 adjacent channels, 1 KB of every row
 
@@ -277,6 +279,10 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 
 // ---------------------------------------------------------------------------------------------------------
 // k_cascade_stream: the register-resident cascade as a CONTINUOUS software pipeline over rows.
+//
+// MEASURED (C4, one B200 under its power cap, profiles/r02_c4_variants.txt): no faster than k_cascade_reg -- 4.50-4.63e11
+// against 4.56e11 channel-samples/s -- so neither the pipeline refill per block nor the 12 resident warps are what
+// holds the cascade at ~77 FP32 lane-ops/clk/SM; kept as `reg_variant` 3 for A/B.
 //
 // k_cascade_reg evaluates blocks of R rows in wavefront order: R + NSEC - 1 diagonals per block, the first and
 // last NSEC - 1 of them partly filled (average 4.3 independent section steps per diagonal for 8 sections x 8 rows),
@@ -681,6 +687,8 @@ int osc_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int wa
 
 // Whether the register-resident kernel can take this chain: a static property of the chain (never of a
 // particular call's pointers): a materialised source and 3..8 second-order sections of one kind.
+extern "C" void sigb_set_reg_pieces(int n) { g_reg_pieces = n; }
+
 extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
     for (int k = 0; k < a->nsec; ++k)
@@ -699,12 +707,12 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
                       (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
                       a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
     const bool wide = fast && variant != 1;
-    const bool streaming = fast && (variant == 2 || variant == 3);         // continuous software pipeline over rows
+    const bool streaming = fast && variant == 3;                           // continuous software pipeline over rows (A/B)
     const int R = wide ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, variant == 3, (a->sec_kind[0] & SEC_HP) != 0) : reg_min_blocks(a->nsec, R)) * RWARPS;
+    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -712,7 +720,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     int64_t want = tiles;
     if (max_segments > 1 && a->warm_rows >= 0) {
         warm = (a->warm_rows + R - 1) / R * R;
-        const int64_t slots = (int64_t)sms * warps_per_sm;
+        const int64_t slots = (int64_t)sms * warps_per_sm * std::max(1, g_reg_pieces);
         const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / R);
         want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
     } else {
@@ -721,10 +729,8 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const int npieces = (int)want;
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
-    if (streaming && variant == 3) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
-                                          : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
-    if (streaming) return hp ? stream_launch_nsec<SEC_HP, false>(a, grid, tiles, npieces, warm, st)
-                          : stream_launch_nsec<0, false>(a, grid, tiles, npieces, warm, st);
+    if (streaming) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
+                          : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
     if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
                         : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
     if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)

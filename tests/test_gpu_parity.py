@@ -460,14 +460,14 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert max_abs_err(got[:, :ch], want) <= 1e-4
 
 
-@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_r4', 'reg_ragged', 'stream5', 'stream3', 'stream3_hp', 'stream3_4sec', 'stream5_ragged_rows'])
+@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_r4', 'reg_ragged', 'stream3', 'stream3_hp', 'stream3_4sec', 'stream3_ragged_rows'])
 def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
     """k_cascade_pipe / k_cascade_reg cut long renders into time segments that warm up from zero state
     (decayed below 2^-40); every segment must match the float64 cascade, the segmented render must agree
     with the unsegmented one, and the state handed to the next call must be the true one."""
     from signals_b200.chain import ext
     rng = np.random.default_rng(45)
-    ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), (4 if kernel == 'stream3_4sec' else 8), (60003 if kernel == 'stream5_ragged_rows' else 60000)
+    ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), (4 if kernel == 'stream3_4sec' else 8), (60003 if kernel == 'stream3_ragged_rows' else 60000)
     cls, btype = ('HighPass', 'hp') if kernel == 'stream3_hp' else ('LowPass', 'lp')
     x = rng.uniform(-1, 1, (frames + 4000, ch)).astype(np.float32)
     cut = np.exp(rng.uniform(np.log(600.0), np.log(8000.0), (nsec, ch)))
@@ -476,8 +476,8 @@ def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
         node = cases.lowpass(ns, node, [cut[s]], cls)
     compiled = engine.compile(node, ch, RATE)
     compiled.set_option('cascade_reg', 0 if kernel == 'pipe' else -1)
-    # 2 / 3: k_cascade_stream (continuous software pipeline over rows) with five / three coefficients per section
-    compiled.set_option('reg_variant', 1 if kernel == 'reg_r4' else 2 if kernel.startswith('stream5') else 3 if kernel.startswith('stream3') else 0)
+    # 3: k_cascade_stream (continuous software pipeline over rows, three coefficients per section)
+    compiled.set_option('reg_variant', 1 if kernel == 'reg_r4' else 3 if kernel.startswith('stream3') else 0)
     warm = compiled.describe()['launches'][0]['warm_rows']
     assert 0 < warm < frames // 8, warm                       # so that the launch really is segmented
     first = compiled.render_device(0, frames).cpu().numpy()
