@@ -236,7 +236,7 @@ CASES: list[Case] = [
     Case('sine_pos1', lambda ns: osc(ns, 'Sine', [[440.0, 12000.0]], [[0.0, 0.37]]), 1000, 2, position=1),
     Case('sine_pos47999', lambda ns: osc(ns, 'Sine', [[440.0, 12000.0]], [[0.0, 0.37]]), 1000, 2, position=47999),
     Case('sine_pos2e31', lambda ns: osc(ns, 'Sine', [[440.0, 439.99]], [[0.0, 0.37]]), 1000, 2, position=2 ** 31 + 5,
-         tol=2e-6, note='reference fp64 phase itself carries ~3e-8 cycles of rounding at n=2^31'),
+         note='reference fp64 phase itself carries ~3e-8 cycles of rounding at n=2^31 (achieved 4.0e-7)'),
     Case('sine_60s_tail', lambda ns: osc(ns, 'Sine', [[4186.0, 27.5, 999.999]], [[0.0, 0.5, 0.123]]), 4800, 3,
          position=60 * RATE - 4800),
     Case('vis_test_sigs', lambda ns: osc(ns, 'Sine', [[220]]), 4800, 1,
@@ -286,13 +286,13 @@ CASES: list[Case] = [
     Case('cascade8', _cascade8, 48000, 4, tol=1e-4, note='config C4 shape: 8 chained LowPass nodes'),
     Case('fanout', _fanout, 4800, 4, tol=1e-4),
     Case('lfo_gain', _lfo_gain, 2400, 2, position=12345, note='Gain.right driven by an oscillator (block-rate port, fx.py:52)'),
-    Case('lfo_hertz', _lfo_hertz, 2400, 2, position=3 * RATE + 7, tol=2e-6,
+    Case('lfo_hertz', _lfo_hertz, 2400, 2, position=3 * RATE + 7,
          note='Osc.hertz / Osc.phase driven by emitters (osc.py:28-30); phase ~ 100 cycles at this position'),
     Case('lfo_mix_amp', _lfo_mix_amp, 2400, 2, position=777, note='Mix.mix and Amp.right modulated (fx.py:39, 59)'),
     Case('lfo_chain', _lfo_chain, 4800, 2, tol=1e-4, note='modulated Gain feeding a LowPass'),
     Case('lfo_blockwise', _lfo_gain, 4096, 2, position=1000, block=512,
          note='8 requests of 512 frames: the LFO is re-sampled at the first frame of each'),
-    Case('lfo_hertz_blockwise', _lfo_hertz, 2048, 2, position=9000, block=256, tol=2e-6,
+    Case('lfo_hertz_blockwise', _lfo_hertz, 2048, 2, position=9000, block=256,
          note='per-request frequency: the phase jumps between requests exactly as in the reference'),
     Case('lfo_cutoff', _lfo_cutoff, 4800, 2, position=12345, tol=1e-4,
          note='LowPass.cutoff driven by emitters: designed per request at the request position (fx.py:98-102, 124-129); '

@@ -36,8 +36,19 @@ constexpr int BANK_J = BANK_TN / 32;
 constexpr int BANK_GB = 8;         // groups per work item (one 32-byte sector of an output row)
 constexpr int BANK_PCHUNK = 1024;  // partials staged in shared memory at a time
 
-__global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n_items, int gblocks) {
-    __shared__ int4 par[BANK_PCHUNK];                         // {B - 128 D, D, amplitude bits, 0}
+// Two pipes instead of one.  A lane owns rows lane, lane + 32, ..., lane + 224 of the tile.  Evaluating every sample
+// with MUFU.SIN makes the kernel MUFU-bound (16 results / clk / SM; round 1: 4.0e12 partial-samples/s at 0.86 of that
+// pipe while the FMA pipe idled at 28 %).  Here only rows lane + 32 and lane + 160 (j = 1 and 5) are evaluated
+// transcendentally -- sine AND cosine -- and their neighbours j = 0, 2, 3 / 4, 6, 7 come from the angle-addition
+// rotation by the partial's 32-row phase advance D32, whose (cos, sin) the host tabulates in float64 -> float32
+// once per plan:   sin(t +- D32) = sin t cos D32 +- cos t sin D32,  cos(t + D32) = cos t cos D32 - sin t sin D32.
+// The two groups ride in the two lanes of packed f32x2 registers, so the eight samples cost 4 MUFU + ~10 FFMA2-class
+// instructions: the MUFU load halves and the kernel becomes FMA-pipe / issue bound.  At most two rotation steps
+// separate a sample from a transcendental evaluation (error: tests/test_gpu_parity.py::test_bank_*).
+template <int UNROLL>           // partials per loop iteration: 1 -> 64 registers, 4 CTAs per SM; 2 -> 80 registers, 3 CTAs per SM
+__global__ void __launch_bounds__(BANK_THREADS, UNROLL == 1 ? 4 : 3) k_bank(const BankDev a, int n_items, int gblocks) {
+    __shared__ int4 par[BANK_PCHUNK];                         // {phase word at tile row 0, per-row increment, amplitude bits, 0}
+    __shared__ float4 rot[BANK_PCHUNK];                       // {cos D32, sin D32, -sin D32, 0}
     __shared__ float red[BANK_WARPS][BANK_TN];
     __shared__ float outtile[BANK_TN][BANK_GB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -54,7 +65,7 @@ __global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n
 
         for (int gi = 0; gi < g_count; ++gi) {
             const int g = g_first + gi;
-            float2 acc[BANK_J / 2];
+            float2 acc[BANK_J / 2];                           // acc[j] = rows (lane + 32 j, lane + 32 (j + 4))
 #pragma unroll
             for (int j = 0; j < BANK_J / 2; ++j) acc[j] = make_float2(0.0f, 0.0f);
 
@@ -69,27 +80,37 @@ __global__ void __launch_bounds__(BANK_THREADS, 4) k_bank(const BankDev a, int n
                     const int D = (int)((dth + 0x80000000ull) >> 32);
                     const float amp = a.gain ? a.gain[p] : 1.0f;
                     par[q] = make_int4(B - (BANK_TN / 2) * D, D, __float_as_int(amp), 0);
+                    const float2 cs = a.rot32[p];
+                    rot[q] = make_float4(cs.x, cs.y, -cs.y, 0.0f);
                 }
                 __syncthreads();
+#pragma unroll UNROLL
                 for (int q = warp; q < cnt; q += BANK_WARPS) {
-                    const int4 e = par[q];                    // broadcast read
-                    int w = e.x + lane * e.y;
+                    const int4 e = par[q];                    // broadcast reads
+                    const float4 cs = rot[q];
                     const int step = e.y << 5;
+                    const int wA = e.x + lane * e.y + step;   // row lane + 32   (j = 1)
+                    const int wB = wA + 4 * step;             // row lane + 160  (j = 5)
                     const float amp = __int_as_float(e.z);
                     const float2 amp2 = make_float2(amp, amp);
-#pragma unroll
-                    for (int j = 0; j < BANK_J / 2; ++j) {
-                        const float2 r = __fmul2_rn(make_float2((float)w, (float)(w + step)), make_float2(kTwoPiQ32, kTwoPiQ32));
-                        w += 2 * step;
-                        acc[j] = __ffma2_rn(amp2, make_float2(__sinf(r.x), __sinf(r.y)), acc[j]);
-                    }
+                    const float2 CC = make_float2(cs.x, cs.x), SS = make_float2(cs.y, cs.y), NS = make_float2(cs.z, cs.z);
+                    const float2 r = __fmul2_rn(make_float2((float)wA, (float)wB), make_float2(kTwoPiQ32, kTwoPiQ32));
+                    const float2 S1 = __fmul2_rn(make_float2(__sinf(r.x), __sinf(r.y)), amp2);
+                    const float2 C1 = __fmul2_rn(make_float2(__cosf(r.x), __cosf(r.y)), amp2);
+                    // j = 0 / 4: one step back;  j = 2 / 6 and 3 / 7: one and two steps forward
+                    acc[0] = __ffma2_rn(C1, NS, __ffma2_rn(S1, CC, acc[0]));
+                    acc[1] = __fadd2_rn(acc[1], S1);
+                    const float2 S2 = __ffma2_rn(C1, SS, __fmul2_rn(S1, CC));
+                    const float2 C2 = __ffma2_rn(S1, NS, __fmul2_rn(C1, CC));
+                    acc[2] = __fadd2_rn(acc[2], S2);
+                    acc[3] = __ffma2_rn(C2, SS, __ffma2_rn(S2, CC, acc[3]));
                 }
             }
             // cross-warp sum in a fixed order
 #pragma unroll
             for (int j = 0; j < BANK_J / 2; ++j) {
-                red[warp][lane + 32 * (2 * j)] = acc[j].x;
-                red[warp][lane + 32 * (2 * j + 1)] = acc[j].y;
+                red[warp][lane + 32 * j] = acc[j].x;
+                red[warp][lane + 32 * (j + 4)] = acc[j].y;
             }
             __syncthreads();
             {
@@ -330,6 +351,9 @@ __global__ void __launch_bounds__(256) k_voices_finish(const float* __restrict__
 
 }  // namespace
 
+static int g_bank_unroll = 2;      // measured on C3: 5.45e12 (1) / 5.99e12 (2) partial-samples/s
+extern "C" void sigb_set_bank_unroll(int n) { g_bank_unroll = n; }
+
 extern "C" int sigb_launch_bank(const BankDev* a, void* stream) {
     if (a->frames <= 0 || a->P <= 0 || a->groups <= 0) return 0;
     const int tiles = (a->frames + BANK_TN - 1) / BANK_TN;
@@ -337,8 +361,13 @@ extern "C" int sigb_launch_bank(const BankDev* a, void* stream) {
     const long long items = (long long)tiles * gblocks;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = (int)(items < (long long)sms * 4 ? items : (long long)sms * 4);
-    k_bank<<<grid, BANK_THREADS, 0, (cudaStream_t)stream>>>(*a, (int)items, gblocks);
+    if (g_bank_unroll == 2) {
+        const int grid = (int)(items < (long long)sms * 3 ? items : (long long)sms * 3);
+        k_bank<2><<<grid, BANK_THREADS, 0, (cudaStream_t)stream>>>(*a, (int)items, gblocks);
+    } else {
+        const int grid = (int)(items < (long long)sms * 4 ? items : (long long)sms * 4);
+        k_bank<1><<<grid, BANK_THREADS, 0, (cudaStream_t)stream>>>(*a, (int)items, gblocks);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -481,12 +510,17 @@ __global__ void __launch_bounds__(128) k_design(const DesignDev a) {
             if (!a.apow) continue;
             // the linear-system tables of the time-parallel kernels (make_chain of sigb_plan.cu, on the device):
             // images of the two unit states over SIGB_SCAN_L rows of zero input
-            double a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0, m1[4] = {1.0, 0.0, 0.0, 1.0};
+            double a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0, m1[4] = {1.0, 0.0, 0.0, 1.0}, ya0 = 0.0, yb0 = 0.0;
             for (int r = 0; r < SIGB_SCAN_L; ++r) {
                 const double ya = design_step(kind, g, r2, 0.0, a1, a2);
                 const double yb = design_step(kind, g, r2, 0.0, b1, b2);
                 a.ztab[((s * SIGB_SCAN_L + r) * 2 + 0) * C + c] = (float)ya;
                 a.ztab[((s * SIGB_SCAN_L + r) * 2 + 1) * C + c] = (float)yb;
+                if (r == 0) { ya0 = ya; yb0 = yb; }
+                if (r == 1) {       // first differences of the zero-input output (delta form of its recurrence)
+                    a.hrec[(s * 4 + 2) * C + c] = (float)(ya - ya0);
+                    a.hrec[(s * 4 + 3) * C + c] = (float)(yb - yb0);
+                }
                 if (r == 0) { m1[0] = a1; m1[1] = b1; m1[2] = a2; m1[3] = b2; }
                 if (r == SIGB_SCAN_L / 2 - 1) {
                     const double mh[4] = {a1, b1, a2, b2};
@@ -499,8 +533,8 @@ __global__ void __launch_bounds__(128) k_design(const DesignDev a) {
             a.apow[(s * 4 + 0) * C + c] = a1; a.apow[(s * 4 + 1) * C + c] = b1;
             a.apow[(s * 4 + 2) * C + c] = a2; a.apow[(s * 4 + 3) * C + c] = b2;
             const double tr = m1[0] + m1[3], det = m1[0] * m1[3] - m1[1] * m1[2];
-            a.hrec[(s * 2 + 0) * C + c] = (float)tr;
-            a.hrec[(s * 2 + 1) * C + c] = (float)(-det);
+            a.hrec[(s * 4 + 0) * C + c] = (float)det;
+            a.hrec[(s * 4 + 1) * C + c] = (float)(tr - 1.0 - det);
             // decay horizon (sigb_section_decay_rows): rows until the zero-input response is below 2^-40, doubled
             const double disc = tr * tr - 4.0 * det;
             const double rho = disc < 0.0 ? sqrt(fabs(det)) : fmax(fabs(tr + sqrt(disc)), fabs(tr - sqrt(disc))) / 2.0;

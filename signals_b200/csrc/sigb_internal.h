@@ -1,6 +1,7 @@
 // Internal structures shared by the host planner and the kernels of libsigb200.so.
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #define SIGB_MAX_SEC 16       // sections per fused chain launch (longer cascades are split)
 #ifndef SIGB_SCAN_L
@@ -53,7 +54,8 @@ struct ChainDev {
     const double* apow_h;           // [(s*4+k)*C + c]  A^(L/2) in float64 (channel-pair kernel: carry chained per 8-row sub-chunk)
     const float* ztab;              // [((s*L + k)*2 + j)*C + c]
     const float* m8;                // [(s*4+k)*C + c]  float32 A^(L/2) (packed kernel: stitches the two halves)
-    const float* hrec;              // [(s*2+k)*C + c]  k: 0 = tr(A), 1 = -det(A) (zero-input output recurrence)
+    const float* hrec;              // [(s*4+k)*C + c]  zero-input output recurrence in delta form: k: 0 = det(A), 1 = tr(A) - 1 - det(A),
+                                    //                  2, 3 = first difference of the zero-input output per unit state
     float* out;
     int64_t ld_out;
     // epilogue fused into a stateless chain (k_chain_seq): out = op(chain value, other operand), fx.py:35-46.
@@ -99,6 +101,7 @@ struct BankDev {
     const unsigned long long* theta0;   // [P]
     const unsigned long long* dtheta;   // [P]
     const float* gain;                  // [P] or nullptr (unit amplitude)
+    const float2* rot32;                // [P] (cos, sin) of the phase advance over 32 rows, 2 pi frac(32 hertz / rate)
     float* out;
     int64_t ld_out;
 };
@@ -183,6 +186,7 @@ int sigb_scan_rows_per_step(int nsec, int variant);
 void sigb_set_scan_tma(int on);
 void sigb_set_scan_split(int on);
 int sigb_launch_bank(const BankDev* a, void* stream);
+void sigb_set_bank_unroll(int n);
 int sigb_voices_ctas(int channels, int M);                         // CTAs (= partials) a segment of `channels` needs
 int sigb_voices_block_rows(int M);                                 // rows per block of the (group, block) space
 int sigb_voices_slots(int M);                                      // CTAs of k_voices resident on the device at once

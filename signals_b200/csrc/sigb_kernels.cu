@@ -219,9 +219,9 @@ __device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }
 struct SecPar {            // per-thread parameters of one section (packed where the math is packed)
     float2 g, nc, d;       // (g,g) (-c,-c) (d,d); first-order: g = (G,G)
     float2 gd, gd2, g2;    // (g d) (2 g d) (2 g): six-instruction low-pass form
-    float2 al, be;         // zero-input recurrence coefficients
+    float2 al, be;         // zero-input recurrence in delta form: al = det(A), be = tr(A) - 1 - det(A)
     float m8[4];           // A^8, row-major
-    float p0, r0, p1, r1;  // zero-input output at samples 0 and 1 of a half, per unit state
+    float p0, r0, p1, r1;  // zero-input output at sample 0 (p0, r0) and its first difference (p1, r1), per unit state
 };
 
 // With e = x - c s1 - s2:  hp = d e;  bp = s1 + g d e;  s1' = s1 + 2 g d e;  lp = s2 + g bp;  s2' = s2 + 2 g bp
@@ -315,10 +315,10 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                                                     a.coef[(size_t)(s * 3 + 2) * C + ch], 0.0f);
             par[(s * 4 + 1) * 32 + l] = make_float4(a.m8[(size_t)(s * 4 + 0) * C + ch], a.m8[(size_t)(s * 4 + 1) * C + ch],
                                                     a.m8[(size_t)(s * 4 + 2) * C + ch], a.m8[(size_t)(s * 4 + 3) * C + ch]);
-            par[(s * 4 + 2) * 32 + l] = make_float4(a.hrec[(size_t)(s * 2 + 0) * C + ch], a.hrec[(size_t)(s * 2 + 1) * C + ch], 0.0f, 0.0f);
-            // zero-input output at samples 0 and 1: rows 0,1 of the response table
+            par[(s * 4 + 2) * 32 + l] = make_float4(a.hrec[(size_t)(s * 4 + 0) * C + ch], a.hrec[(size_t)(s * 4 + 1) * C + ch], 0.0f, 0.0f);
+            // zero-input output at sample 0 (row 0 of the response table) and its first difference (float64 on the host)
             par[(s * 4 + 3) * 32 + l] = make_float4(a.ztab[((size_t)(s * L + 0) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 0) * 2 + 1) * C + ch],
-                                                    a.ztab[((size_t)(s * L + 1) * 2 + 0) * C + ch], a.ztab[((size_t)(s * L + 1) * 2 + 1) * C + ch]);
+                                                    a.hrec[(size_t)(s * 4 + 2) * C + ch], a.hrec[(size_t)(s * 4 + 3) * C + ch]);
         }
         __syncthreads();
 
@@ -527,16 +527,17 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             auto correct = [&](const SecPar& ps, float2 (&v)[H], float2 ia, float za1, float za2) {
                 const float ib1 = fmaf(ps.m8[0], ia.x, fmaf(ps.m8[1], ia.y, za1));
                 const float ib2 = fmaf(ps.m8[2], ia.x, fmaf(ps.m8[3], ia.y, za2));
-                float2 h0 = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
-                float2 h1 = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
-                v[0] = __fadd2_rn(v[0], h0);
-                v[1] = __fadd2_rn(v[1], h1);
+                // h[k] = tr h[k-1] - det h[k-2] in DELTA form: dh[k] = det dh[k-1] + (tr - 1 - det) h[k-1], h[k] = h[k-1] + dh[k].
+                // With tr ~ 2 and det ~ 1 at low cutoffs the direct form amplifies float32 rounding like k^2 (6.6e-6 on a
+                // 300 Hz section over 16 rows); the delta form only adds one rounding of h per row.
+                float2 h = pk(fmaf(ps.p0, ia.x, ps.r0 * ia.y), fmaf(ps.p0, ib1, ps.r0 * ib2));
+                float2 dh = pk(fmaf(ps.p1, ia.x, ps.r1 * ia.y), fmaf(ps.p1, ib1, ps.r1 * ib2));
+                v[0] = __fadd2_rn(v[0], h);
 #pragma unroll
-                for (int k = 2; k < H; ++k) {       // advanced by its 2-term recurrence
-                    const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
-                    v[k] = __fadd2_rn(v[k], hn);
-                    h0 = h1;
-                    h1 = hn;
+                for (int k = 1; k < H; ++k) {
+                    if (k > 1) dh = __ffma2_rn(ps.al, dh, __fmul2_rn(ps.be, h));
+                    h = __fadd2_rn(h, dh);
+                    v[k] = __fadd2_rn(v[k], h);
                 }
             };
             auto store = [&](float2 (&v)[H], int64_t srow, float* soutp) {
@@ -751,14 +752,14 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 ps.gd = pk(gA * dA, gB * dB);
                 ps.gd2 = pk(2.0f * (gA * dA), 2.0f * (gB * dB));
                 ps.g2 = pk(2.0f * gA, 2.0f * gB);
-                ps.al = pk(a.hrec[(size_t)0 * C + ccA], a.hrec[(size_t)0 * C + ccB]);
-                ps.be = pk(a.hrec[(size_t)1 * C + ccA], a.hrec[(size_t)1 * C + ccB]);
+                ps.al = pk(a.hrec[(size_t)0 * C + ccA], a.hrec[(size_t)0 * C + ccB]);       // det(A)
+                ps.be = pk(a.hrec[(size_t)1 * C + ccA], a.hrec[(size_t)1 * C + ccB]);       // tr(A) - 1 - det(A)
             }
-            // zero-input output at samples 0 and 1 per unit state: rows 0, 1 of the response table
+            // zero-input output at sample 0 per unit state (row 0 of the response table) and its first difference
             const float2 zp0 = pk(a.ztab[((size_t)0 * 2 + 0) * C + ccA], a.ztab[((size_t)0 * 2 + 0) * C + ccB]);
             const float2 zr0 = pk(a.ztab[((size_t)0 * 2 + 1) * C + ccA], a.ztab[((size_t)0 * 2 + 1) * C + ccB]);
-            const float2 zp1 = pk(a.ztab[((size_t)1 * 2 + 0) * C + ccA], a.ztab[((size_t)1 * 2 + 0) * C + ccB]);
-            const float2 zr1 = pk(a.ztab[((size_t)1 * 2 + 1) * C + ccA], a.ztab[((size_t)1 * 2 + 1) * C + ccB]);
+            const float2 zp1 = pk(a.hrec[(size_t)2 * C + ccA], a.hrec[(size_t)2 * C + ccB]);
+            const float2 zr1 = pk(a.hrec[(size_t)3 * C + ccA], a.hrec[(size_t)3 * C + ccB]);
 
             unsigned long long thA = 0, thB = 0, stepA = 0, stepB = 0;
             int dhiA = 0, dhiB = 0;
@@ -843,18 +844,17 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 }
                 bar_sync(2 + 2 * grp, (WG + 1) * 32);
                 const float4 ia = si[w * 32 + lane];
-                {   // zero-input response of the true initial state, advanced by its 2-term recurrence
+                {   // zero-input response of the true initial state, advanced by its 2-term recurrence in delta form
+                    // (dh[k] = det dh[k-1] + (tr - 1 - det) h[k-1], h[k] = h[k-1] + dh[k]: see k_chain_scan2's `correct`)
                     const float2 i1 = pk(ia.x, ia.y), i2 = pk(ia.z, ia.w);
-                    float2 h0 = __ffma2_rn(zp0, i1, __fmul2_rn(zr0, i2));
-                    float2 h1 = __ffma2_rn(zp1, i1, __fmul2_rn(zr1, i2));
-                    v[0] = __fadd2_rn(v[0], h0);
-                    v[1] = __fadd2_rn(v[1], h1);
+                    float2 h = __ffma2_rn(zp0, i1, __fmul2_rn(zr0, i2));
+                    float2 dh = __ffma2_rn(zp1, i1, __fmul2_rn(zr1, i2));
+                    v[0] = __fadd2_rn(v[0], h);
 #pragma unroll
-                    for (int k = 2; k < R3; ++k) {
-                        const float2 hn = __ffma2_rn(ps.al, h1, __fmul2_rn(ps.be, h0));
-                        v[k] = __fadd2_rn(v[k], hn);
-                        h0 = h1;
-                        h1 = hn;
+                    for (int k = 1; k < R3; ++k) {
+                        if (k > 1) dh = __ffma2_rn(ps.al, dh, __fmul2_rn(ps.be, h));
+                        h = __fadd2_rn(h, dh);
+                        v[k] = __fadd2_rn(v[k], h);
                     }
                 }
                 if (step >= s0) {

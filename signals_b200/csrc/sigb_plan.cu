@@ -81,6 +81,7 @@ struct ChainSpec {
     uint8_t sec_kind[SIGB_MAX_SEC] = {0};
     Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, apow_h, ztab, m8, hrec;
     int src_node = -1;           // SRC_BUF: node whose value is read
+    int src_osc_node = -1;       // SRC_OSC: the oscillator node
     int64_t state_off = 0;       // doubles into the state arena
     int state_cur = 0;           // which copy of the state arena holds the live state
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
@@ -119,6 +120,7 @@ struct ReduceSpec {
 // oscillator bank fused with its GroupSum (k_bank)
 struct BankSpec {
     ChainSpec ch;
+    Table rot32;                 // (cos, sin) of each partial's phase advance over 32 rows (k_bank's rotation)
     int groups = 0;
     int dst_node = -1;
 };
@@ -498,6 +500,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
             if (!rep(*hz, C, &hzv) || !rep(*ph, C, &phv))
                 return fail(SIGB_ESHAPE, "node " + std::to_string(cur) + ": hertz/phase channels incompatible with " + std::to_string(C));
             ch.src_kind = SRC_OSC;
+            ch.src_osc_node = cur;
             ch.wave = n.subtype;
             ch.hertz = put_vec(p, hzv);
             ch.phase = put_vec(p, phv);
@@ -578,7 +581,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
         std::vector<double> apow_h((size_t)ch.nsec * 4 * CS, 0.0);
         std::vector<float> ztab((size_t)ch.nsec * SIGB_SCAN_L * 2 * CS, 0.0f);
         std::vector<float> m8((size_t)ch.nsec * 4 * CS, 0.0f);
-        std::vector<float> hrec((size_t)ch.nsec * 2 * CS, 0.0f);
+        std::vector<float> hrec((size_t)ch.nsec * 4 * CS, 0.0f);
         for (int s = 0; s < ch.nsec; ++s) {   // identity padding: high-pass with g = 0 passes x through
             ch.sec_kind[s] = SEC_HP;
             for (int c = 0; c < C; ++c) {
@@ -590,6 +593,7 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                 apow_h[((size_t)s * 4 + 3) * C + c] = 1.0;
                 m8[((size_t)s * 4 + 0) * C + c] = 1.0f;
                 m8[((size_t)s * 4 + 3) * C + c] = 1.0f;
+                hrec[((size_t)s * 4 + 0) * C + c] = 1.0f;      // identity: det = 1, tr - 1 - det = 0, differences 0
             }
         }
         int s0 = 0;
@@ -654,8 +658,16 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                     sigb_section_transition(secs[k], 1, m1);
                     for (int j = 0; j < 4; ++j) m8[((size_t)s * 4 + j) * C + c] = (float)mh[j];
                     for (int j = 0; j < 4; ++j) apow_h[((size_t)s * 4 + j) * C + c] = mh[j];
-                    hrec[((size_t)s * 2 + 0) * C + c] = (float)(m1[0] + m1[3]);                     // tr(A)
-                    hrec[((size_t)s * 2 + 1) * C + c] = (float)(-(m1[0] * m1[3] - m1[1] * m1[2]));  // -det(A)
+                    {   // zero-input output recurrence h[k] = tr h[k-1] - det h[k-2] in delta form (see k_chain_scan2)
+                        const double tr = m1[0] + m1[3], det = m1[0] * m1[3] - m1[1] * m1[2];
+                        double a1 = 1.0, a2 = 0.0, b1 = 0.0, b2 = 1.0;      // outputs at samples 0 and 1 per unit state, float64
+                        const double ya0 = sigb_section_step(secs[k], 0.0, a1, a2), yb0 = sigb_section_step(secs[k], 0.0, b1, b2);
+                        const double ya1 = sigb_section_step(secs[k], 0.0, a1, a2), yb1 = sigb_section_step(secs[k], 0.0, b1, b2);
+                        hrec[((size_t)s * 4 + 0) * C + c] = (float)det;
+                        hrec[((size_t)s * 4 + 1) * C + c] = (float)(tr - 1.0 - det);
+                        hrec[((size_t)s * 4 + 2) * C + c] = (float)(ya1 - ya0);
+                        hrec[((size_t)s * 4 + 3) * C + c] = (float)(yb1 - yb0);
+                    }
                     sec_warm[k] = std::max(sec_warm[k], sigb_section_decay_rows(m1));
                     const double rho = sigb_section_radius(m1);
                     rho_max[c] = std::max(rho_max[c], rho);
@@ -758,6 +770,17 @@ int Builder::build_bank(int i) {
     if (st != SIGB_OK) return st;
     b.groups = n.order;
     b.dst_node = i;
+    {   // 32-row phase advance per partial: frac(32 hertz / rate) exactly (Q0.64), then cos / sin in float64
+        const std::vector<double>& hz = *const_of(p, p->nodes[b.ch.src_osc_node].in[0]);
+        std::vector<float> rot((size_t)b.ch.C * 2);
+        for (int c = 0; c < b.ch.C; ++c) {
+            const unsigned long long d32 = ratio_q64(hz[hz.size() == 1 ? 0 : c], p->rate) << 5;
+            const double ang = 6.283185307179586476925 * std::ldexp((double)(long long)d32, -64);
+            rot[2 * c + 0] = (float)std::cos(ang);
+            rot[2 * c + 1] = (float)std::sin(ang);
+        }
+        b.rot32 = put_vec(p, rot);
+    }
     if (b.groups < 1 || b.ch.C % b.groups != 0)
         return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": " + std::to_string(b.ch.C) + " channels do not split into " + std::to_string(b.groups) + " groups");
     if (i == p->root && b.groups != p->channels)
@@ -1310,6 +1333,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.theta0 = b.ch.theta0.dev<unsigned long long>(base);
             a.dtheta = b.ch.dtheta.dev<unsigned long long>(base);
             a.gain = b.ch.gain.dev<float>(base);
+            a.rot32 = b.rot32.dev<float2>(base);
             const Val& dv = p->vals[b.dst_node];
             if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
@@ -2026,6 +2050,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
+    else if (k == "bank_unroll") sigb_set_bank_unroll((int)value); // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);
     rt_drop_graphs(plan);            // captured launches embody the old choice
     return SIGB_OK;

@@ -287,6 +287,8 @@ def test_bank_fused_vs_oracle(partials, groups, frames, position, ns, engine):
     want = np_oracle.render_bank(position, frames, RATE, hertz, phase, amp, groups)
     err = max_abs_err(got, want)
     print(f'bank {partials}->{groups}: max-abs {err:.3e}')
+    # at position 2^31 the REFERENCE's own float64 phase (n / rate * hertz ~ 5.4e8 cycles at 12 kHz) is rounded to 1.2e-7
+    # cycles = 7.5e-7 rad per partial, while the Q0.64 phase here is exact: the 2e-6 there is the reference's rounding
     assert err <= (2e-6 if position > 2 ** 31 else 1e-6)
 
 
@@ -725,7 +727,10 @@ def test_wide_pointwise_nodes_vector_path(ns, engine):
         got = compiled.render_device(777, 3000).cpu().numpy()
         compiled.close()
         want = np_oracle.GraphOracle(RATE).render(g, 777, 3000, c)
-        assert max_abs_err(got, want) <= 2e-6, c
+        err = max_abs_err(got, want)
+        print(f'Mix -> RingMod -> Amp -> Gain on {c} channels: max-abs {err:.3e}')
+        # Amp raises to the power 1..3: |d(x^3)| = 3 x^2 |dx| triples the oscillators' 3.4e-7, hence 2e-6 and not 1e-6
+        assert err <= 2e-6, c
 
 
 def test_fused_pointwise_equals_materialised_path(ns, engine):

@@ -270,3 +270,64 @@ def test_blockwise_reference_option_is_what_separates_the_two_stream_semantics(n
     d = max_abs_err(carried, load_golden(case.name))
     print(f'carried state vs the reference\'s blockwise render: {d:.3e}')
     assert 1e-5 < d < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE full sizes against float64 oracle renders of the WHOLE blocks (fixtures: oracle/make_fullsize.py).  A cell of
+# the grids sums 1,000 rows x 64 channels: it moves by tens to hundreds when a single 64-channel x 16-row tile of the
+# block is wrong and by < 0.1 under the per-sample budgets, so every tile of the block is covered, not a sample of voices.
+# ------------------------------------------------------------------------------------------------
+def _load(name, key):
+    import os
+    from conftest import GOLDEN_DIR
+    with np.load(os.path.join(GOLDEN_DIR, name)) as z:
+        return z[key]
+
+
+def _grid(block, rows=1000, ch=64):
+    f, c = block.shape
+    return block.double().reshape(f // rows, rows, c // ch, ch).sum(dim=(1, 3)).cpu().numpy()
+
+
+def test_full_size_c2_every_tile_against_the_oracle(ns, engine):
+    v, frames = 4096, 10 * RATE
+    hertz, phase, cutoff, g = cases.voice_params(2, v)
+    graph = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff]), [g])
+    compiled = engine.compile(graph, v, RATE)
+    got = _grid(compiled.render_device(0, frames))
+    compiled.close()
+    want = _load('full_c2_grid.npz', 'grid')
+    dev = np.abs(got - want)
+    print(f'C2 full block, {want.size} cells of 1000 x 64: max cell deviation {dev.max():.3e} (cells up to {np.abs(want).max():.1f})')
+    assert dev.max() <= 0.05
+
+
+def test_full_size_c4_every_tile_against_the_oracle(ns, engine):
+    import torch
+    from oracle.make_fullsize import c4_noise
+    from signals_b200.chain import ext
+    ch, frames = 16384, RATE
+    rng = np.random.default_rng(4)
+    cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (8, ch)))
+    node = ext.Buffer(torch.from_numpy(c4_noise(frames, ch)).cuda())
+    for s in range(8):
+        node = cases.lowpass(ns, node, [cut[s]])
+    compiled = engine.compile(node, ch, RATE, frames)
+    got = _grid(compiled.render_device(0, frames))
+    compiled.close()
+    want = _load('full_c4_grid.npz', 'grid')
+    dev = np.abs(got - want)
+    print(f'C4 full width, first second, {want.size} cells of 1000 x 64: max cell deviation {dev.max():.3e} (cells up to {np.abs(want).max():.1f})')
+    assert dev.max() <= 0.05
+
+
+def test_full_size_c5_mix_against_the_oracle(ns, engine):
+    from signals_b200.chain import ext
+    n, frames = 1 << 20, 4800
+    compiled = engine.compile(cases.build_instances(ns, ext, cases.instance_params(5, n)), 2, RATE)
+    got = compiled.render_device(0, frames).cpu().numpy()
+    compiled.close()
+    want = _load('full_c5_mix.npz', 'mix')
+    err = max_abs_err(got, want)
+    print(f'C5, all 1,048,576 instances, first {frames} frames of the mix: max-abs {err:.3e} (peak {np.abs(want).max():.3f})')
+    assert err <= 1e-6
