@@ -249,8 +249,7 @@ class C5(Workload):
 
     def describe(self):
         return {'workload': self.name % (self.n, self.seconds), 'instances_total': self.n, 'frames': self.frames, 'rate': RATE,
-                'sharding': 'instance i on rank i %% %d; one reduce (NCCL) of the (frames, 2) mix per step, the last 1/8 of the block '
-                            'rendered while the first 7/8 are being reduced' % self.world,
+                'sharding': 'instance i on rank i %% %d; one reduce (NCCL) of the (frames, 2) mix per step' % self.world,
                 'l2': 'compute-bound; parameter tables %.0f MB per GPU stream from L2/HBM once per step' % (self.n / self.world * 52 / 1e6)}
 
     def units_per_step(self):
@@ -660,6 +659,15 @@ def measure(ctx, wl, steps, warmup, e2e_steps, cpu_baseline):
                 copy_wait.append(dt - (t1 - t0))
         if wl.slab_frames:
             h2d += int(host_in.numel() * 4 * ((frames + eslab - 1) // eslab))
+        # what the platform gives a plain pinned device->host copy of one such block while all N ranks copy at once:
+        # the ceiling of the host-buffer leg (at N = 8 the ranks share the host's PCIe uplinks)
+        probe = []
+        for _ in range(2):
+            ctx.barrier()
+            t0 = time.perf_counter()
+            host_out.copy_(out[:eslab], non_blocking=True)
+            torch.cuda.synchronize()
+            probe.append(host_out.numel() * 4 / (time.perf_counter() - t0) / 1e9)
         te = ctx.max_over_ranks(sum(e2e_times))
         d2h = int(4 * wl.out_channels * frames)
         e2e = {'value': wl.units_per_step() * len(e2e_times) / te, 'unit': 'voice-samples/s', 'h2d_bytes_per_step': h2d,
@@ -667,6 +675,7 @@ def measure(ctx, wl, steps, warmup, e2e_steps, cpu_baseline):
                'what': 'Engine.compile(graph) + CompiledPlan.render_host(pinned fp32 block), every step',
                'step_s_min': float(np.min(e2e_times)), 'step_s_max': float(np.max(e2e_times)),
                'render_host_gbs_this_rank': (d2h + h2d) / float(np.mean(copy_wait)) / 1e9,
+               'plain_d2h_memcpy_gbs_this_rank_all_ranks_copying': float(max(probe)),
                'compile_s_mean': float(np.mean(e2e_times) - np.mean(copy_wait)),
                'pinned_numa_node': ctx.locality.get('numa_node'), 'cpus_bound': ctx.locality.get('cpus_bound'),
                'gpu_launches_per_step': int(e2e_launches)}

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sigb200.h"
@@ -270,6 +271,24 @@ bool rep(const std::vector<double>& v, int C, std::vector<double>* out) {
 
 int section_count(int order) { return order / 2 + (order & 1); }
 
+// Per-channel table building for large banks (C5: a million instances) on all host cores: fn(begin, end, worker) over
+// disjoint channel ranges.  Small banks run inline.
+template <class Fn>
+void parallel_channels(int n, Fn fn, int* n_workers = nullptr) {
+    const int hw = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    const int workers = n < 32768 ? 1 : std::min(hw, n / 8192);
+    if (n_workers) *n_workers = workers;
+    if (workers <= 1) {
+        fn(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int w = 0; w < workers; ++w)
+        th.emplace_back([=]() { fn((int)((int64_t)n * w / workers), (int)((int64_t)n * (w + 1) / workers), w); });
+    for (std::thread& t : th) t.join();
+}
+constexpr int kMaxWorkers = 32;
+
 // guard band (units of 2^-32 cycles) around waveform discontinuities for the phase-word fast paths:
 // in-tile drift of the rounded increment, the rounding of the top word, and the float64 rounding of
 // the reference's own phase (3 roundings of relative size 2^-53 on `cycles` cycles)
@@ -510,10 +529,13 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
             }
             {   // Q0.64 phase / increment: sine fast path of the chain kernels, every wave in k_voices
                 std::vector<unsigned long long> t0(C), dt(C);
-                for (int c = 0; c < C; ++c) {
-                    t0[c] = frac_q64(phv[c]);
-                    dt[c] = ratio_q64(hzv[c], p->rate);
-                }
+                const int rate = p->rate;
+                parallel_channels(C, [&](int c0, int c1, int) {
+                    for (int c = c0; c < c1; ++c) {
+                        t0[c] = frac_q64(phv[c]);
+                        dt[c] = ratio_q64(hzv[c], rate);
+                    }
+                });
                 ch.theta0 = put_vec(p, t0);
                 ch.dtheta = put_vec(p, dt);
             }
@@ -629,20 +651,30 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
             if ((int)cut->size() != C)   // crit_1[0, i] is not broadcast (fx.py:99)
                 return fail(SIGB_EINDEX, "node " + std::to_string(f) + ": cutoff has " + std::to_string(cut->size()) + " channels, request has " + std::to_string(C));
             const int ns = section_count(n.order);
-            float tab[SIGB_SCAN_L * 2];
             std::vector<double> sec_warm(ns, 0.0);
-            for (int c = 0; c < C; ++c) {
-                double wn = (*cut)[c] / (p->rate / 2.0);
+            std::vector<double> warm_w((size_t)kMaxWorkers * ns, 0.0);       // per-worker maxima (merged below)
+            std::vector<uint8_t> kinds(ns, 0);
+            int bad[kMaxWorkers] = {0};
+            const int rate = p->rate;
+            const bool hp_filter = n.subtype == SIGB_FILT_HIGHPASS;
+            const int order = n.order;
+            parallel_channels(C, [&](int cbeg, int cend, int worker) {
+              float tab[SIGB_SCAN_L * 2];
+              double* sec_warm = warm_w.data() + (size_t)worker * ns;        // shadows the merged vector
+              for (int c = cbeg; c < cend; ++c) {
+                double wn = (*cut)[c] / (rate / 2.0);
                 wn = std::min(std::max(wn, 0.0), 1.0);   // fx.py:100-101
-                if (!(wn > 0.0 && wn < 1.0))              // scipy.signal.butter: "0 < Wn < 1"
-                    return fail(SIGB_ECRIT, "node " + std::to_string(f) + ": Digital filter critical frequencies must be 0 < Wn < 1");
-                std::vector<SvfSection> secs = sigb_butter_sections(n.subtype == SIGB_FILT_HIGHPASS, n.order, wn);
+                if (!(wn > 0.0 && wn < 1.0)) {            // scipy.signal.butter: "0 < Wn < 1"
+                    bad[worker] = 1;
+                    return;
+                }
+                std::vector<SvfSection> secs = sigb_butter_sections(hp_filter, order, wn);
                 for (int k = 0; k < ns; ++k) {
                     float cf[3];
                     double m[4];
                     sigb_section_coef(secs[k], cf);
                     const int s = s0 + k;
-                    ch.sec_kind[s] = (uint8_t)secs[k].kind;
+                    if (c == cbeg) kinds[k] = (uint8_t)secs[k].kind;         // uniform over the channels
                     for (int j = 0; j < 3; ++j) coef[((size_t)s * 3 + j) * C + c] = cf[j];
                     if (!scan_tables) {
                         double m1[4];
@@ -676,7 +708,14 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                         for (int j = 0; j < 2; ++j)
                             ztab[(((size_t)s * SIGB_SCAN_L + r) * 2 + j) * C + c] = tab[r * 2 + j];
                 }
+              }
+            });
+            for (int w = 0; w < kMaxWorkers; ++w) {
+                if (bad[w])
+                    return fail(SIGB_ECRIT, "node " + std::to_string(f) + ": Digital filter critical frequencies must be 0 < Wn < 1");
+                for (int k = 0; k < ns; ++k) sec_warm[k] = std::max(sec_warm[k], warm_w[(size_t)w * ns + k]);
             }
+            for (int k = 0; k < ns; ++k) ch.sec_kind[s0 + k] = kinds[k];
             s0 += ns;
             for (double wv : sec_warm) warm += wv;   // sections in series: budget the decays one after another
         }

@@ -45,15 +45,18 @@ def reduce_mix(partial, dst: typing.Optional[int] = 0, group=None):
 
 
 def render_reduced(compiled, position: int, frames: int, out, dst: typing.Optional[int] = 0, group=None,
-                   tail_fraction: float = 0.125):
-    """This rank's fused render of ``(frames, 2)`` into ``out`` + the single reduce of the mix, with the collective
-    hidden behind the render: the first ``1 - tail_fraction`` of the block is reduced (asynchronously, on the
-    communicator's stream) while the tail is still being rendered, so only the tail's reduce is exposed.  Without a
-    process group (one GPU) it is just the render."""
+                   tail_fraction: float = 0.0):
+    """This rank's fused render of ``(frames, 2)`` into ``out`` + the single reduce of the mix.
+
+    ``tail_fraction`` > 0 hides the collective behind the render: the first ``1 - tail_fraction`` of the block is
+    reduced asynchronously while the tail is still being rendered.  Measured on 8 B200s (C5, 131,072 instances per
+    GPU): the reduce of the 3.84 MB mix takes 0.036 ms against a 42 ms render, while cutting the render in two costs
+    ~8 ms (two launches, more piece warm-ups, a short tail block that cannot fill the machine) -- so the default is one
+    render and one reduce."""
     dist = _dist()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return compiled.render_device(position, frames, out)
-    head = frames - max(8, int(frames * tail_fraction)) // 8 * 8
+    head = frames - max(8, int(frames * tail_fraction)) // 8 * 8 if tail_fraction > 0 else frames
     if head <= 0 or head >= frames:
         compiled.render_device(position, frames, out)
         return reduce_mix(out, dst=dst, group=group)
