@@ -12,6 +12,7 @@ The default run also measures the other BASELINE configs and appends them to the
             the N-rank mix is compared with rank 0's own render of the whole bank (`parity_n_vs_1`).
   extra.c3  (N=1) additive bank, 65,536 sine partials -> 64 channels (fused oscillator + mix reduction)
   extra.c4  (N=1) 8-biquad cascade, 16,384 channels x 60 s streamed in 10 s slabs with carried state
+  extra.c2m (N=1) C2 with every cutoff driven by an LFO emitter: same time-parallel kernel, no cliff (`vs_unmodulated_c2`)
   extra.c1  (N=1) the audio callback: p50/p99 latency per block at 128/384/512/1024 frames for
             Sine<-Fixed -> Gain (scripts/example_sine.py as a graph) and for lowpass_test.sigs, through
             SinkDevice.render_block, with the reference's blockwise CPU render timed beside it.
@@ -41,8 +42,8 @@ if ROOT not in sys.path:
 RATE = 48000
 METRIC = 'voice-samples/sec'
 # (voices, seconds, steps, e2e steps) when a config is the headline / when it rides along in `extra`
-DEFAULTS = {'c2': (4096, 10.0, 20, 10), 'c3': (65536, 10.0, 5, 3), 'c4': (16384, 60.0, 2, 1), 'c5': (1 << 20, 10.0, 3, 2)}
-EXTRA_STEPS = {'c3': 5, 'c4': 2, 'c5': 3}
+DEFAULTS = {'c2': (4096, 10.0, 20, 10), 'c2m': (4096, 10.0, 10, 0), 'c3': (65536, 10.0, 5, 3), 'c4': (16384, 60.0, 2, 1), 'c5': (1 << 20, 10.0, 3, 2)}
+EXTRA_STEPS = {'c3': 5, 'c4': 2, 'c5': 3, 'c2m': 10}
 FMA_PROBE_CEILING = 96.0        # FMA lane-ops / clk / SM the section arithmetic reaches register-only (profiles/r01_fma_probe.txt)
 
 
@@ -52,14 +53,14 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'])
+    ap.add_argument('--config', default='c2', choices=['c1', 'c2', 'c2m', 'c3', 'c4', 'c5'])
     ap.add_argument('--voices', type=int, default=None, help='voices / partials / channels / instances (config default if omitted)')
     ap.add_argument('--seconds', type=float, default=None)
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--slab-seconds', type=float, default=10.0, help='c4: seconds of audio per streamed slab')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='headline config only')
-    ap.add_argument('--extra', default='c5,c3,c4,c1', help='configs appended to the default (c2) line')
+    ap.add_argument('--extra', default='c5,c3,c4,c2m,c1', help='configs appended to the default (c2) line')
     ap.add_argument('--scan-variant', type=int, default=None)
     ap.add_argument('--plan-opt', action='append', default=[], help='key=value passed to sigb_plan_set_option (A/B testing)')
     ap.add_argument('--default-opt', action='append', default=[], help='key=value passed to sigb_set_default_option')
@@ -139,6 +140,23 @@ class C2(Workload):
         hertz, phase, cutoff, g = cases.voice_params(2, sv)
         jobs = [('blockwise', (hertz[i:i + per], phase[i:i + per], cutoff[i:i + per], g[i:i + per], sf, 512)) for i in range(0, sv, per)]
         return jobs, sv * sf, '%d of %d voices x %g s in 512-frame requests (per-block butter() per channel + 100-frame context)' % (sv, self.v, sf / RATE)
+
+
+class C2M(C2):
+    """C2 with every voice's cutoff driven by its own LFO (an emitter on LowPass.cutoff, fx.py:124-129): the filter is
+    designed on the device once per request (k_design) and must stay on the same time-parallel kernel -- A/B against C2."""
+    name = 'C2 with a modulated cutoff per voice (Mix / Sine LFO emitters on LowPass.cutoff), %d voices x %g s @ 48 kHz per GPU'
+    kernel = 'k_param_eval + k_design (scan tables and decay horizon of the request) + k_chain_scan3'
+    traffic_profile = None
+
+    def build(self, ns):
+        from signals_b200 import workloads as cases
+        hertz, phase, cutoff, g = self.params
+        rng = np.random.default_rng(1000 + self.rank)
+        lfo_hz, lfo_ph = rng.uniform(0.1, 4.0, self.v), rng.uniform(0.0, 1.0, self.v)
+        f = cases.lowpass(ns, cases.osc(ns, 'Sine', [hertz], [phase]), [cutoff])
+        f.cutoff = cases.sweep(ns, [cutoff / 1.5], [cutoff * 1.5], [lfo_hz], [lfo_ph])
+        return cases.gain(ns, f, [g])
 
 
 class C3(Workload):
@@ -268,7 +286,7 @@ class C5(Workload):
         return jobs, sn * sf, '%d of %d instances x %g s' % (sn, self.n, sf / RATE)
 
 
-WORKLOADS = {'c2': C2, 'c3': C3, 'c4': C4, 'c5': C5}
+WORKLOADS = {'c2': C2, 'c2m': C2M, 'c3': C3, 'c4': C4, 'c5': C5}
 
 
 def make_workload(name, args, rank, world, headline):
@@ -834,7 +852,7 @@ def run_b200(args):
         for name in wanted:
             if name == 'c5':                                   # every N: strong scaling with the NCCL reduce
                 r = measure(ctx, make_workload('c5', args, rank, world, False), EXTRA_STEPS['c5'], 3, 0, cpu_baseline=False)
-            elif name in ('c3', 'c4') and world == 1:
+            elif name in ('c3', 'c4', 'c2m') and world == 1:
                 r = measure(ctx, make_workload(name, args, rank, world, False), EXTRA_STEPS[name], 3, 0, cpu_baseline=False)
             elif name == 'c1' and world == 1:
                 r = measure_c1(ctx, cpu=not args.no_cpu_baseline)
@@ -846,6 +864,8 @@ def run_b200(args):
                      if k in r}
                 r['unit'] = 'voice-samples/s'
                 r['n_gpus'] = world
+                if name == 'c2m':
+                    r['vs_unmodulated_c2'] = r['value'] / head['value']
             extra[name] = r
     if rank == 0:
         line = {'metric': METRIC, 'value': head['value'], 'unit': 'voice-samples/s', 'n_gpus': world, 'steps': head['steps'],

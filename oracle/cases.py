@@ -16,7 +16,7 @@ import typing
 import numpy as np
 
 from signals_b200.workloads import (RATE, FILTERS, WAVES, b200_namespace, bank_params, build_bank, build_instances, fixed, gain,   # noqa: F401
-                                    instance_params, lowpass, osc, voice_params)
+                                    instance_params, lowpass, osc, sweep, voice_params)
 
 
 def ref_namespace(ref) -> types.SimpleNamespace:
@@ -190,21 +190,9 @@ def _lfo_chain(ns):
 
 
 def _wah(ns, lo, hi, lfo_hertz, lfo_phase):
-    # cutoff = Mix(hi, lo, mix = 0.5 + 0.5 * sine LFO) sweeps [lo, hi]: an emitter on the filter's cutoff port,
+    # cutoff = Mix(hi, lo, mix = 0.5 + 0.25 * sine LFO) sweeps inside [lo, hi]: an emitter on the filter's cutoff port,
     # sampled once per request (SingleCritFilter._eval, fx.py:124-129)
-    half = ns.Mix()
-    half.left = fixed(ns, [[1.0]])
-    half.right = fixed(ns, [[0.0]])
-    half.mix = gain(ns, _lfo(ns, 'Sine', lfo_hertz, lfo_phase), [[0.5]])      # in [-0.5, 0.5]
-    w = ns.Mix()                         # 0.5 + half -> [0, 1]
-    w.left = fixed(ns, [[1.0]])
-    w.right = half
-    w.mix = fixed(ns, [[0.5]])           # 0.5 * 1 + 0.5 * half, i.e. [0.25, 0.75]
-    m = ns.Mix()
-    m.left = fixed(ns, hi)
-    m.right = fixed(ns, lo)
-    m.mix = w
-    return m
+    return sweep(ns, lo, hi, lfo_hertz, lfo_phase)
 
 
 def _with_cutoff(ns, input_, cutoff_emitter, cls='LowPass', order=None):

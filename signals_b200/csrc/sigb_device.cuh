@@ -146,15 +146,41 @@ __device__ __forceinline__ bool wave_near_edge(int w, int guard) {
 }
 
 // K consecutive samples from phase word w advancing by dhi; returns true when any of them needs the
-// float64 path
+// float64 path (lies within `guard` of a point where wave_q32 may disagree with the reference, see wave_near_edge).
+// The edge test rides on what the waveform computes anyway, one instruction per sample:
+//   Sawtooth / Triangle: the jump / the trough sits where the (shifted) phase word wraps, |v| -> 2^31, and v = (float)w
+//     is already there: |v| >= 2^31 - (guard + 128).  The float is within 64 of the integer up there, so the test can
+//     only fire early (a wider band, never a missed edge).
+//   Square: both jumps (frac 0 and 1/2) are the wrap of the DOUBLED word: (2 w + 2 guard) < 4 guard as unsigned,
+//     exactly wave_near_edge's test, as one shift-add and one compare.
 template <int WAVE, int K>
 __device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[K]) {
     bool near = false;
+    if (WAVE == SIGB_WAVE_SINE) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        x[k] = wave_q32<WAVE>(w);
-        near |= wave_near_edge<WAVE>(w, guard);
-        w += dhi;
+        for (int k = 0; k < K; ++k) {
+            x[k] = wave_q32<SIGB_WAVE_SINE>(w);
+            w += dhi;
+        }
+    } else if (WAVE == SIGB_WAVE_SQUARE) {
+        const unsigned g2 = 2u * (unsigned)guard, g4 = 4u * (unsigned)guard;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            x[k] = wave_q32<SIGB_WAVE_SQUARE>(w);
+            near |= ((unsigned)w << 1) + g2 < g4;
+            w += dhi;
+        }
+    } else {
+        const float thr = 2147483648.0f - (float)(guard + 128);
+        if (WAVE == SIGB_WAVE_TRIANGLE) w -= 0x40000000;      // the trough (frac 3/4) becomes the wrap point
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float v = (float)w;
+            x[k] = WAVE == SIGB_WAVE_SAWTOOTH ? v * 4.656612873077393e-10f                  // 2 frac (- 2 past 1/2)
+                                              : fmaf(-fabsf(v), 9.313225746154785e-10f, 1.0f);   // 1 - 4 |frac - 1/4|
+            near |= fabsf(v) >= thr;
+            w += dhi;
+        }
     }
     return near;
 }

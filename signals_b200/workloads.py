@@ -62,6 +62,25 @@ def lowpass(ns, input_, cutoff, cls: str = 'LowPass', order: int | None = None):
     return f
 
 
+def sweep(ns, lo, hi, lfo_hertz, lfo_phase):
+    """A block-rate parameter sweeping [lo, hi] (arrays broadcast per channel): Mix(hi, lo, mix = 0.5 + 0.25 * sine LFO),
+    an emitter for a filter's cutoff port, sampled once per request (SingleCritFilter._eval, chain/fx.py:124-129)."""
+    lfo = osc(ns, 'Sine', lfo_hertz, lfo_phase)
+    half = ns.Mix()
+    half.left = fixed(ns, [[1.0]])
+    half.right = fixed(ns, [[0.0]])
+    half.mix = gain(ns, lfo, [[0.5]])      # in [-0.5, 0.5]
+    w = ns.Mix()                           # 0.5 * 1 + 0.5 * half, i.e. [0.25, 0.75]
+    w.left = fixed(ns, [[1.0]])
+    w.right = half
+    w.mix = fixed(ns, [[0.5]])
+    m = ns.Mix()
+    m.left = fixed(ns, hi)
+    m.right = fixed(ns, lo)
+    m.mix = w
+    return m
+
+
 def voice_params(seed: int, v: int):
     """SURVEY 8d / BASELINE config C2 parameter distributions."""
     rng = np.random.default_rng(seed)
