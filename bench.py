@@ -95,7 +95,7 @@ class Workload:
 class C2(Workload):
     name = 'C2: sine -> biquad lowpass -> gain, %d voices x %g s @ 48 kHz per GPU, fp32 (frames, voices) block in HBM'
     kernel = 'k_chain_scan3<sine, 1 section, 64-channel tiles, 3x9 workers, f32 carry chain>'
-    traffic_profile = 'r01_k_chain_scan3_full.txt'
+    traffic_profile = 'r02_k_chain_scan3_full.txt'
     bound = 'hbm'
     bytes_per_unit = 4.0
 
@@ -161,7 +161,7 @@ class C2M(C2):
 
 class C3(Workload):
     name = 'C3: additive bank, %d sine partials -> %d channels (fused oscillator + mix reduction), %g s @ 48 kHz per GPU'
-    kernel = 'k_bank'
+    kernel = 'k_bank (two transcendental points per eight samples + angle-addition rotations on the FMA pipe)'
     bound = 'sfu'
     bytes_per_unit = 4.0 / 1024
 
@@ -248,7 +248,7 @@ class C4(Workload):
 
 class C5(Workload):
     name = 'C5: %d randomised osc/filter/gain/pan instances -> stereo mix, %g s @ 48 kHz, sharded by voice (instance i on rank i %% N)'
-    kernel = 'k_voices (+ k_voices_finish)'
+    kernel = 'k_voices (equal pieces of the (voice group, row block) space per CTA slot) + k_voices_finish'
     bound = 'sfu'
     bytes_per_unit = 0.0
     scaling = 'strong'

@@ -103,8 +103,12 @@ int sigb_plan_bind_buffer_window(sigb_plan* plan, int32_t node, const float* dev
 
 /* Render frames [position, position+frames) into `out` (device, row-major, leading dimension
  * `ld_out` floats >= channels).  Filter state is carried when `position` continues the previous
- * call; otherwise state is zeroed and the filters are warmed up on `context` frames before
- * `position` exactly as CritFilter._filter does for every block (fx.py:93-105). */
+ * call; otherwise (a seek) state is zeroed and the whole graph is warmed up once from
+ * `position` - (sum of the `context` frames along the deepest filter chain).  For ONE filter on a path that
+ * is what CritFilter._filter does for every block (fx.py:93-105; golden `lowpass_blockwise`, 8e-8).  For
+ * chained filters the reference nests its restarts (the upstream filter's context block is itself restarted
+ * 100 frames earlier); both are approximations of the stream from position 0 and differ from each other by
+ * the upstream transient (golden `cascade2_seek`: 8.3e-5 at 900..3000 Hz cutoffs, more at lower ones). */
 int sigb_render(sigb_plan* plan, int64_t position, int32_t frames,
                 float* out, int64_t ld_out, void* stream);
 
