@@ -562,16 +562,24 @@ extern "C" int sigb_launch_design(const DesignDev* a, void* stream) {
 // probe: write-only streaming fill (the practical HBM ceiling of a store-only kernel such as C2's)
 // ---------------------------------------------------------------------------------------------
 namespace {
-__global__ void __launch_bounds__(256) k_probe_fill(float4* __restrict__ out, int64_t n4, float v) {
+// store flavour of the probes: 0 = st.global.cs (streaming), 1 = plain st.global (write-back), 2 = st.global.cg, 3 = st.global.wt
+int g_probe_store = 0;
+__device__ __forceinline__ void probe_store(float4* p, float4 v, int how) {
+    if (how == 1) *p = v;
+    else if (how == 2) __stcg(p, v);
+    else if (how == 3) __stwt(p, v);
+    else __stcs(p, v);
+}
+__global__ void __launch_bounds__(256) k_probe_fill(float4* __restrict__ out, int64_t n4, float v, int how) {
     const float4 val = make_float4(v, v, v, v);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) __stcs(out + i, val);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) probe_store(out + i, val, how);
 }
 }  // namespace
 
 namespace {
 // tiled fill: the C2 store pattern -- a warp owns a (rows_per_tile x width_bytes) tile of a (frames, 4096) float
 // block and walks time; `width` floats per tile row (32 = the scan kernel's 128-byte rows)
-__global__ void __launch_bounds__(256) k_probe_fill_tiled(float* __restrict__ out, int frames, int C, int width, int rows_per_tile, float v) {
+__global__ void __launch_bounds__(256) k_probe_fill_tiled(float* __restrict__ out, int frames, int C, int width, int rows_per_tile, float v, int how) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -587,18 +595,50 @@ __global__ void __launch_bounds__(256) k_probe_fill_tiled(float* __restrict__ ou
         const int tx = (int)(it / steps), st = (int)(it % steps);
         float* base = out + (size_t)st * rows_per_tile * C + (size_t)tx * width;
         for (int r = lane / lanes_per_row; r < rows_per_tile; r += rows_per_instr)
+            probe_store(reinterpret_cast<float4*>(base + (size_t)r * C) + (lane % lanes_per_row), val, how);
+    }
+}
+}  // namespace
+
+// mode 1: CTA b owns column stripe b % tiles_x over time piece b / tiles_x and its 8 warps interleave the piece's steps,
+// so CTAs b, b + 1, ... write ADJACENT stripes of the same rows at about the same time (what a cluster of CTAs on adjacent
+// tiles of the scan kernel would do); mode 2: the same with the stripes permuted (adjacent CTAs far apart in columns).
+namespace {
+__global__ void __launch_bounds__(256) k_probe_fill_lockstep(float* __restrict__ out, int frames, int C, int width, int rows_per_tile, int mode, float v) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tiles_x = C / width;
+    const int steps = frames / rows_per_tile;
+    const int pieces_t = gridDim.x / tiles_x;
+    if (pieces_t == 0 || (int)blockIdx.x >= pieces_t * tiles_x) return;
+    int tx = blockIdx.x % tiles_x;
+    if (mode == 2) tx = (int)(((long long)tx * 37) % tiles_x);
+    const int pt = blockIdx.x / tiles_x;
+    const int s0 = (int)((long long)steps * pt / pieces_t), s1 = (int)((long long)steps * (pt + 1) / pieces_t);
+    const float4 val = make_float4(v, v, v, v);
+    const int lanes_per_row = width / 4, rows_per_instr = 32 / lanes_per_row;
+    for (int st = s0 + w; st < s1; st += 8) {
+        float* base = out + (size_t)st * rows_per_tile * C + (size_t)tx * width;
+        for (int r = lane / lanes_per_row; r < rows_per_tile; r += rows_per_instr)
             __stcs(reinterpret_cast<float4*>(base + (size_t)r * C) + (lane % lanes_per_row), val);
     }
 }
 }  // namespace
 
+extern "C" void sigb_probe_set_store(int how) { g_probe_store = how; }
+
 extern "C" int sigb_probe_fill_tiled(float* out_dev, int32_t frames, int32_t C, int32_t width, int32_t rows_per_tile, int32_t blocks, void* stream) {
     if (width < 4 || width > 128 || (width & (width - 1)) != 0 || C % width != 0 || rows_per_tile < 1) return (int)cudaErrorInvalidValue;
-    k_probe_fill_tiled<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, frames, C, width, rows_per_tile, 1.0f);
+    k_probe_fill_tiled<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, frames, C, width, rows_per_tile, 1.0f, g_probe_store);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int sigb_probe_fill_lockstep(float* out_dev, int32_t frames, int32_t C, int32_t width, int32_t rows_per_tile, int32_t blocks, int32_t mode, void* stream) {
+    if (width < 4 || width > 128 || (width & (width - 1)) != 0 || C % width != 0 || rows_per_tile < 1) return (int)cudaErrorInvalidValue;
+    k_probe_fill_lockstep<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, frames, C, width, rows_per_tile, mode, 1.0f);
     return (int)cudaGetLastError();
 }
 
 extern "C" int sigb_probe_fill(float* out_dev, int64_t n_floats, float value, int32_t blocks, void* stream) {
-    k_probe_fill<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(out_dev), n_floats / 4, value);
+    k_probe_fill<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(out_dev), n_floats / 4, value, g_probe_store);
     return (int)cudaGetLastError();
 }

@@ -178,6 +178,80 @@ __device__ __forceinline__ float2 step5(float2 x, Sec5& r) {
     }
 }
 
+// FORM 4 / 5: the two lanes of a packed register hold two TIME PIECES of ONE channel, so every coefficient is a scalar
+// that FFMA2 takes in its broadcast (.F32) form -- half the operand bytes of a coefficient pair.  4: five coefficients,
+// 5: three coefficients + 2.0.
+struct Sec5s { float nc, al, a2, g, g2; float2 s1, s2; };
+template <int FORM>
+__device__ __forceinline__ float2 step5s(float2 x, Sec5s& r) {
+    const float2 xs = __fadd2_rn(x, make_float2(-r.s2.x, -r.s2.y));
+    const float2 e = ffma2(make_float2(r.nc, r.nc), r.s1, xs);
+    const float2 bp = ffma2(make_float2(r.al, r.al), e, r.s1);
+    if (FORM == 4) r.s1 = ffma2(make_float2(r.a2, r.a2), e, r.s1);
+    else r.s1 = ffma2(bp, make_float2(2.0f, 2.0f), make_float2(-r.s1.x, -r.s1.y));
+    const float2 lp = ffma2(make_float2(r.g, r.g), bp, r.s2);
+    if (FORM == 4) r.s2 = ffma2(make_float2(r.g2, r.g2), bp, r.s2);
+    else r.s2 = ffma2(lp, make_float2(2.0f, 2.0f), make_float2(-r.s2.x, -r.s2.y));
+    return lp;
+}
+
+template <int NS, int R, int FORM>
+__global__ void k_sec5s(float* out, float g) {
+    Sec5s s[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const float gg = g * (1.0f + 0.01f * i + 1e-4f * threadIdx.x);
+        s[i].g = gg; s[i].g2 = 2 * gg; s[i].nc = -(1.4f + gg); s[i].al = gg * 0.9f; s[i].a2 = gg * 1.8f;
+        s[i].s1 = s[i].s2 = make_float2(0.f, 0.f);
+    }
+    float2 acc = make_float2(0.f, 0.f);
+    for (int it = 0; it < ITERS / R; ++it) {
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = make_float2(__int_as_float(0x3f800000 | ((it * R + k) * 2654435 & 0x7fffff)) - 1.5f, 0.25f);
+#pragma unroll
+        for (int d = 0; d < R + NS - 1; ++d)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { const int r = d - i; if (r >= 0 && r < R) x[r] = step5s<FORM>(x[r], s[i]); }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { acc.x += x[k].x; acc.y += x[k].y; }
+    }
+    if (acc.x + acc.y == 123.456f) out[0] = acc.x;
+}
+
+// raw FFMA2 chains whose multiplier is a scalar taken in broadcast form
+template <int NCH>
+__global__ void k_ffma2s(float* out, float a, float b) {
+    float2 x[NCH];
+    float aa[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { x[i] = make_float2(threadIdx.x * 1e-3f + i, i); aa[i] = a + (threadIdx.x + i) * 1e-9f; }
+    float2 bb = make_float2(b, b + 1e-3f);
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) x[i] = ffma2(make_float2(aa[i], aa[i]), x[i], bb);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) s += x[i].x + x[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+// ... and the same with a distinct packed multiplier per chain (three distinct 64-bit operands per instruction)
+template <int NCH>
+__global__ void k_ffma2d(float* out, float a, float b) {
+    float2 x[NCH], aa[NCH], bb[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { x[i] = make_float2(threadIdx.x * 1e-3f + i, i); aa[i] = make_float2(a + (threadIdx.x + i) * 1e-9f, a - i * 1e-9f); bb[i] = make_float2(b + i * 1e-6f, b); }
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) x[i] = ffma2(aa[i], x[i], bb[i]);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) s += x[i].x + x[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+
 template <int NS, int R, int FORM>
 __global__ void k_sec5(float* out, float g) {
     Sec5 s[NS];
@@ -358,6 +432,11 @@ int main() {
     REPORT("cascade 8 sec packed 5-coef, R=8", 96, 48, (k_sec5<8, 8, 1><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed 3-coef imm2, R=4", 96, 48, (k_sec5<8, 4, 3><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed 3-coef imm2, R=8", 96, 48, (k_sec5<8, 8, 3><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("FFMA2 x8, scalar-broadcast multiplier", 16, 8, (k_ffma2s<8><<<blocks, threads>>>(out, 0.999f, 0.001f)))
+    REPORT("FFMA2 x8, 3 distinct packed operands", 16, 8, (k_ffma2d<8><<<blocks, threads>>>(out, 0.999f, 0.001f)))
+    REPORT("cascade 8 sec, time-pair lanes, 5 scalar coef, R=8", 96, 48, (k_sec5s<8, 8, 4><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec, time-pair lanes, 5 scalar coef, R=4", 96, 48, (k_sec5s<8, 4, 4><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec, time-pair lanes, 3 scalar coef, R=8", 96, 48, (k_sec5s<8, 8, 5><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed DF2T, R=4", 80, 40, (k_sec5<8, 4, 2><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed f32, R=8", 96, 48, (k_sec2<8, 8><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec scalar f32, R=4", 96, 96, (k_sec1<8, 4><<<blocks, threads>>>(out, 0.05f)))

@@ -1,6 +1,6 @@
 #!/bin/bash
 # N ranks on N GPUs: the default bench line (C2 weak + extra.c5 strong with the NCCL reduce and the N-vs-1 parity)
-N=${1:-8}; TAG=${2:-r02h}
+N=${1:-8}; TAG=${2:-multi}
 mkdir -p gpurun_out
 ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N > gpurun_out/bench${N}_$TAG.json 2> gpurun_out/bench${N}_$TAG.err ) 2>&1 | tail -3
 echo "bench exit $?"; tail -3 gpurun_out/bench${N}_$TAG.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 record: default bench (headline C2 + extra), launch list of the same command, full capture of the dominant kernel.
-TAG=${1:-r02k}
+TAG=${1:-record}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks_$TAG.csv &
 SMI=$!

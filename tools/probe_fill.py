@@ -33,3 +33,23 @@ for width in (32, 64, 128):        # floats per tile row; a warp's float4 lanes 
         for blocks in (148 * 3, 148 * 6):
             ms = timed(lambda: L.sigb_probe_fill_tiled(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, rows, blocks, ctypes.c_void_p(st)))
             print(f'tiled fill: {width * 4:4d}-byte rows x {rows:2d} rows per tile, {blocks:4d} CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+
+# adjacent column stripes written in lockstep by neighbouring CTAs (mode 1) against the same schedule with the stripes permuted (mode 2)
+L.sigb_probe_fill_lockstep.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
+for width in (32, 64):
+    tiles = 4096 // width
+    for mult in (1, 2, 4):
+        blocks = max(1, (148 * mult) // tiles) * tiles
+        for mode in (1, 2):
+            ms = timed(lambda: L.sigb_probe_fill_lockstep(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, 16, blocks, mode, ctypes.c_void_p(st)))
+            print(f'lockstep fill mode {mode}: {width * 4:4d}-byte rows x 16 rows per tile, {blocks:4d} CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+
+# store flavour: streaming (.cs, what the kernels use), plain write-back, .cg, .wt
+for how, name in ((0, 'st.global.cs'), (1, 'st.global (write-back)'), (2, 'st.global.cg'), (3, 'st.global.wt')):
+    L.sigb_probe_set_store(how)
+    ms = timed(lambda: L.sigb_probe_fill(ctypes.c_void_p(out.data_ptr()), n, 1.0, 148 * 32, ctypes.c_void_p(st)))
+    print(f'{name:24s} contiguous fill, 4736 CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+    for width in (32, 64):
+        ms = timed(lambda: L.sigb_probe_fill_tiled(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, 16, 148 * 3, ctypes.c_void_p(st)))
+        print(f'{name:24s} tiled fill {width * 4:4d}-byte rows x 16, 444 CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
+L.sigb_probe_set_store(0)
