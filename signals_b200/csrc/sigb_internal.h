@@ -35,6 +35,7 @@ struct ChainDev {
     const double* phase;            // [C]
     const unsigned long long* theta0;   // [C] frac(phase)    in Q0.64 (sine fast path)
     const unsigned long long* dtheta;   // [C] frac(hertz/rate) in Q0.64
+    const float2* rot1;                 // [C] (cos, sin) of the one-row phase advance 2 pi frac(hertz / rate) (k_chain_scan3's rotation)
     // SRC_BUF: src[row*src_ld + c*src_cs]; rows >= src_rows read as zero
     const float* src;
     int64_t src_ld;
@@ -185,6 +186,7 @@ int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);
 void sigb_set_scan_tma(int on);
 void sigb_set_scan_split(int on);
+void sigb_set_scan_rot(int on);
 int sigb_launch_bank(const BankDev* a, void* stream);
 void sigb_set_bank_unroll(int n);
 int sigb_voices_ctas(int channels, int M);                         // CTAs (= partials) a segment of `channels` needs

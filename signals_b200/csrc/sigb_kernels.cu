@@ -34,6 +34,7 @@ using namespace sigb_dev;
 constexpr int L = SIGB_SCAN_L;
 int g_scan_tma = 1;   // staged TMA tensor stores in k_chain_scan (0: direct STG)
 int g_scan_split = 1; // k_chain_scan2: split tiles along time across SMs (decay warm-up)
+int g_scan_rot = 1;   // k_chain_scan3: sine rows from two-pipe rotations (one sin/cos pair per four rows) instead of one MUFU.SIN per row
 
 int sm_count() {
     static int n = [] {
@@ -643,7 +644,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 // ------------------------------------------------------------------------------------------
 template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3 = true, bool F32CARRY = false>      // R3 = rows per sub-chunk: 8 or 16
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
-k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
+k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma, int rot) {
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * R3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -764,7 +765,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             unsigned long long thA = 0, thB = 0, stepA = 0, stepB = 0;
             int dhiA = 0, dhiB = 0;
             double hzA = 0.0, hzB = 0.0, phA = 0.0, phB = 0.0;
-            float2 cv = pk1(0.0f);
+            float2 cv = pk1(0.0f), rotC = pk1(1.0f), rotS = pk1(0.0f);
             if (SRC == SRC_OSC) {
                 if (FASTSINE) {
                     const unsigned long long dA = a.dtheta[ccA], dB = a.dtheta[ccB];
@@ -774,6 +775,11 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     stepB = dB * (unsigned long long)row_stride;
                     dhiA = (int)((dA + 0x80000000ull) >> 32);
                     dhiB = (int)((dB + 0x80000000ull) >> 32);
+                    if (rot) {
+                        const float2 ra = a.rot1[ccA], rb = a.rot1[ccB];
+                        rotC = pk(ra.x, rb.x);
+                        rotS = pk(ra.y, rb.y);
+                    }
                 } else {
                     hzA = a.hertz[ccA]; hzB = a.hertz[ccB];
                     phA = a.phase[ccA]; phB = a.phase[ccB];
@@ -785,12 +791,34 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 if (SRC == SRC_OSC) {
                     if (FASTSINE) {
                         int ha = (int)(thA >> 32), hb = (int)(thB >> 32);
+                        if (rot) {
+                            // k_bank's two-pipe evaluation: rows 1, 5, 9, 13 of the sub-chunk get a sine AND a
+                            // cosine from the SFU, their neighbours (one row back, two rows forward) the angle-addition
+                            // rotation by the channel's one-row phase advance (cos, sin tabulated in float64 on the host):
+                            // 16 instructions per 4 rows x 2 channels instead of 36
+                            const float2 NS = pk(-rotS.x, -rotS.y);
 #pragma unroll
-                        for (int k = 0; k < R3; ++k) {
-                            const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
-                            v[k] = pk(__sinf(r.x), __sinf(r.y));
-                            ha += dhiA;
-                            hb += dhiB;
+                            for (int q4 = 0; q4 + 3 < R3; q4 += 4) {
+                                const float2 r = __fmul2_rn(pk((float)(ha + dhiA), (float)(hb + dhiB)), pk1(1.4629180792671596e-9f));
+                                const float2 S1 = pk(__sinf(r.x), __sinf(r.y)), C1 = pk(__cosf(r.x), __cosf(r.y));
+                                const float2 t = __fmul2_rn(S1, rotC);
+                                v[q4 + 0] = __ffma2_rn(C1, NS, t);
+                                v[q4 + 1] = S1;
+                                const float2 S2 = __ffma2_rn(C1, rotS, t);
+                                const float2 C2 = __ffma2_rn(S1, NS, __fmul2_rn(C1, rotC));
+                                v[q4 + 2] = S2;
+                                v[q4 + 3] = __ffma2_rn(C2, rotS, __fmul2_rn(S2, rotC));
+                                ha += 4 * dhiA;
+                                hb += 4 * dhiB;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < R3; ++k) {
+                                const float2 r = __fmul2_rn(pk((float)ha, (float)hb), pk1(1.4629180792671596e-9f));
+                                v[k] = pk(__sinf(r.x), __sinf(r.y));
+                                ha += dhiA;
+                                hb += dhiB;
+                            }
                         }
                         thA += stepA;
                         thB += stepB;
@@ -1167,7 +1195,7 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
         }
     }
     dim3 grid(grid_x), block((NW + 1) * 32);
-    kern<<<grid, block, smem, st>>>(a, nsteps, warm_steps, map, use_tma);
+    kern<<<grid, block, smem, st>>>(a, nsteps, warm_steps, map, use_tma, (FASTSINE && g_scan_rot && a.rot1 != nullptr) ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -1212,6 +1240,7 @@ extern "C" int sigb_scan_rows_per_step(int nsec, int variant) {
 
 extern "C" void sigb_set_scan_tma(int on) { g_scan_tma = on; }
 extern "C" void sigb_set_scan_split(int on) { g_scan_split = on; }
+extern "C" void sigb_set_scan_rot(int on) { g_scan_rot = on; }
 
 extern "C" int sigb_launch_chain_seq(const ChainDev* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -80,7 +80,7 @@ struct ChainSpec {
     int nsec = 0;                // padded section count the kernels run
     int nsec_real = 0;
     uint8_t sec_kind[SIGB_MAX_SEC] = {0};
-    Table hertz, phase, theta0, dtheta, constv, coef, gain, apow, apow_h, ztab, m8, hrec;
+    Table hertz, phase, theta0, dtheta, rot1, constv, coef, gain, apow, apow_h, ztab, m8, hrec;
     int src_node = -1;           // SRC_BUF: node whose value is read
     int src_osc_node = -1;       // SRC_OSC: the oscillator node
     int64_t state_off = 0;       // doubles into the state arena
@@ -538,6 +538,16 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                 });
                 ch.theta0 = put_vec(p, t0);
                 ch.dtheta = put_vec(p, dt);
+                if (scan_tables && n.subtype == SIGB_WAVE_SINE) {
+                    // (cos, sin) of the one-row phase advance, from the exact Q0.64 increment in float64
+                    std::vector<float> rot((size_t)C * 2);
+                    for (int c = 0; c < C; ++c) {
+                        const double ang = 6.283185307179586476925 * std::ldexp((double)(long long)dt[c], -64);
+                        rot[2 * c + 0] = (float)std::cos(ang);
+                        rot[2 * c + 1] = (float)std::sin(ang);
+                    }
+                    ch.rot1 = put_vec(p, rot);
+                }
             }
             break;
         }
@@ -1243,6 +1253,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.phase = ch.phase_row >= 0 ? p->d_prow_d + (size_t)ch.phase_row * p->pwidth : ch.phase.dev<double>(base);
             a.theta0 = ch.theta0.dev<unsigned long long>(base);
             a.dtheta = ch.dtheta.dev<unsigned long long>(base);
+            a.rot1 = ch.rot1.dev<float2>(base);
             a.constv = ch.constv.dev<float>(base);
             a.coef = ch.coef.dev<float>(base);
             a.gain = ch.gain.dev<float>(base);
@@ -2094,6 +2105,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "blockwise_reference") { plan->opt_restart = value; plan->have_pos = false; }
     else if (k == "scan_tma") sigb_set_scan_tma((int)value);   // process-wide switch (A/B testing)
     else if (k == "scan_split") sigb_set_scan_split((int)value);
+    else if (k == "scan_rot") sigb_set_scan_rot((int)value);       // process-wide switch (A/B testing)
     else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
     else if (k == "bank_unroll") sigb_set_bank_unroll((int)value); // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);

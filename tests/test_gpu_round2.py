@@ -331,3 +331,55 @@ def test_full_size_c5_mix_against_the_oracle(ns, engine):
     err = max_abs_err(got, want)
     print(f'C5, all 1,048,576 instances, first {frames} frames of the mix: max-abs {err:.3e} (peak {np.abs(want).max():.3f})')
     assert err <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# edges: empty requests, very wide blocks, ragged tiles on every path
+# ------------------------------------------------------------------------------------------------
+def test_empty_requests_are_no_ops_on_every_entry_point(ns, engine):
+    """A request of zero frames (BlockLoc with shape (0, C)) renders nothing, launches nothing and does not disturb the
+    stream position: the next block continues the carried state."""
+    import torch
+    case = cases.CASES_BY_NAME['lowpass_c2_8v']
+    c = engine.compile(case.build(ns), case.channels, RATE)
+    ref = engine.compile(case.build(ns), case.channels, RATE)
+    first = c.render_device(0, 300).cpu().numpy()
+    n0 = c.launch_count
+    c.render_device(300, 0, torch.empty((0, case.channels), device='cuda'))
+    c.render_host(300, 0, np.empty((0, case.channels), np.float32))
+    c.render_block(300, 0, np.empty((0, case.channels), np.float32))
+    assert c.launch_count == n0
+    second = c.render_device(300, 300).cpu().numpy()
+    want = ref.render_device(0, 600).cpu().numpy()
+    assert max_abs_err(np.concatenate([first, second]), want) <= 1e-6
+    c.close()
+    ref.close()
+
+
+def test_very_wide_blocks(ns, engine):
+    """A million-channel oscillator block and a 100,003-channel filtered block (ragged last tiles of every kernel): spot
+    checks against the oracle plus finiteness of the whole block."""
+    import torch
+    rng = np.random.default_rng(123)
+    c = 1_000_003
+    hz, ph = rng.uniform(20.0, 12000.0, c), rng.uniform(0.0, 1.0, c)
+    comp = engine.compile(cases.osc(ns, 'Sine', [hz], [ph]), c, RATE)
+    out = comp.render_device(1000, 48)
+    comp.close()
+    assert bool(torch.isfinite(out).all())
+    pick = np.concatenate([[0, 1, c - 2, c - 1], rng.choice(c, 60, replace=False)])
+    got = out[:, torch.from_numpy(pick).cuda()].cpu().numpy()
+    want = np_oracle.sine(np_oracle.osc_cycles(1000, 48, RATE, hz[pick].reshape(1, -1), ph[pick].reshape(1, -1)))
+    assert max_abs_err(got, want) <= 1e-6
+    del out
+    c = 100_003
+    hz, ph, cut, g = cases.voice_params(9, c)
+    graph = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, 'Sawtooth', [hz], [ph]), [cut]), [g])
+    comp = engine.compile(graph, c, RATE)
+    out = comp.render_device(0, 1500)                 # 10 scan steps + a 60-row tail
+    comp.close()
+    assert bool(torch.isfinite(out).all())
+    pick = np.concatenate([[0, 63, 64, c - 4, c - 1], rng.choice(c, 40, replace=False)])
+    got = out[:, torch.from_numpy(pick).cuda()].cpu().numpy()
+    want = np_oracle.render_voice_chain(0, 1500, RATE, hz[pick], ph[pick], cut[pick], g[pick], wave='Sawtooth')
+    assert max_abs_err(got, want) <= 1e-4
