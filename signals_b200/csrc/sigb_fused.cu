@@ -609,7 +609,21 @@ __global__ void __launch_bounds__(256) k_probe_fill_lockstep(float* __restrict__
     const int tiles_x = C / width;
     const int steps = frames / rows_per_tile;
     const int pieces_t = gridDim.x / tiles_x;
-    if (pieces_t == 0 || (int)blockIdx.x >= pieces_t * tiles_x) return;
+    if (mode != 3 && (pieces_t == 0 || (int)blockIdx.x >= pieces_t * tiles_x)) return;
+    if (mode == 3) {
+        // time-major: all warps of the launch sweep the same narrow band of rows together (item = step * tiles_x + stripe),
+        // so the launch touches a few 2 MB pages at a time instead of one page per warp
+        const int nw = gridDim.x * 8, gw = blockIdx.x * 8 + w;
+        const float4 val3 = make_float4(v, v, v, v);
+        const int lpr = width / 4, rpi = 32 / lpr;
+        for (long long it = gw; it < (long long)tiles_x * steps; it += nw) {
+            const int st = (int)(it / tiles_x), txx = (int)(it % tiles_x);
+            float* base = out + (size_t)st * rows_per_tile * C + (size_t)txx * width;
+            for (int r = lane / lpr; r < rows_per_tile; r += rpi)
+                __stcs(reinterpret_cast<float4*>(base + (size_t)r * C) + (lane % lpr), val3);
+        }
+        return;
+    }
     int tx = blockIdx.x % tiles_x;
     if (mode == 2) tx = (int)(((long long)tx * 37) % tiles_x);
     const int pt = blockIdx.x / tiles_x;

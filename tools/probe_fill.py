@@ -53,3 +53,9 @@ for how, name in ((0, 'st.global.cs'), (1, 'st.global (write-back)'), (2, 'st.gl
         ms = timed(lambda: L.sigb_probe_fill_tiled(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, 16, 148 * 3, ctypes.c_void_p(st)))
         print(f'{name:24s} tiled fill {width * 4:4d}-byte rows x 16, 444 CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
 L.sigb_probe_set_store(0)
+
+# time-major sweep (mode 3): every warp of the launch writes inside the same narrow band of rows (few 2 MB pages live at a time)
+for width in (32, 64):
+    for blocks in (148 * 3, 148 * 6):
+        ms = timed(lambda: L.sigb_probe_fill_lockstep(ctypes.c_void_p(out.data_ptr()), 480000, 4096, width, 16, blocks, 3, ctypes.c_void_p(st)))
+        print(f'time-major tiled fill: {width * 4:4d}-byte rows x 16 rows per tile, {blocks:4d} CTAs: {ms:.3f} ms  {n * 4 / ms / 1e6:.0f} GB/s')
