@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument('--slab-seconds', type=float, default=10.0, help='c4: seconds of audio per streamed slab')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='headline config only')
-    ap.add_argument('--extra', default='c5,c3,c4,c2m,c1', help='configs appended to the default (c2) line')
+    ap.add_argument('--extra', default='c2m,c5,c3,c4,c1', help='configs appended to the default (c2) line')
     ap.add_argument('--scan-variant', type=int, default=None)
     ap.add_argument('--plan-opt', action='append', default=[], help='key=value passed to sigb_plan_set_option (A/B testing)')
     ap.add_argument('--default-opt', action='append', default=[], help='key=value passed to sigb_set_default_option')

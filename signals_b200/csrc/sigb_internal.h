@@ -25,6 +25,9 @@ struct ChainDev {
     int32_t rate;
     int32_t frames;                 // rows this launch covers
     int32_t warm_rows;              // rows after which the filters forget their initial state (< 2^-40); -1: unknown
+    int32_t warm_est;               // modulated cutoffs: the host's estimate of the horizon (previous request), -1: none
+    int32_t n_warm_dev;             // ... and the per-filter horizons k_design wrote for THIS request (scan kernels read them)
+    const int* warm_dev;
     int32_t guard;                  // phase-word guard band around waveform discontinuities (pipelined kernel)
     int64_t position;               // absolute index of row 0
     const int64_t* pos_ptr;         // realtime graphs (k_chain_seq only): when set, row 0 is *pos_ptr -- a block header the

@@ -192,6 +192,16 @@ __global__ void __launch_bounds__(128) k_chain_rt(const ChainDev a) {
     }
 }
 
+// Decay horizon of a chain with modulated cutoffs, in steps: k_design left each modulated filter's horizon (rows, slowest
+// channel) in device memory a moment ago on this stream, so the launch needs no host round trip; the host only had an
+// estimate (the previous request's value) to decide whether to cut tiles along time at all.
+__device__ __forceinline__ int device_warm_steps(const ChainDev& a, int step_rows) {
+    long long w = a.warm_rows > 0 ? a.warm_rows : 0;                 // the filters with constant cutoffs
+    for (int i = 0; i < a.n_warm_dev; ++i) w += a.warm_dev[i];
+    w = min(w, (long long)1 << 30);
+    return (int)((w + step_rows - 1) / step_rows);
+}
+
 // ------------------------------------------------------------------------------------------
 // named barriers of the time-parallel kernels: NG groups of WG worker warps + 1 scanner warp.  Group g renders steps
 // g, g+NG, g+2NG, ...; a step is WG sub-chunks of L rows.  Barrier 1+2g: "end states of group g published",
@@ -267,6 +277,7 @@ __device__ __forceinline__ void svf2_block(int kind, const SecPar& c, float2 (&v
 template <int SRC, int NSEC, int NG, int WG, bool FASTSINE, int PIPE = 0>
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma) {
+    if (a.warm_dev && warm_steps > 0) warm_steps = device_warm_steps(a, WG * L);
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * L;
     constexpr int H = L / 2;
@@ -645,6 +656,7 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 template <int SRC, int NG, int WG, bool FASTSINE, int R3, bool PIPE3 = true, bool F32CARRY = false>      // R3 = rows per sub-chunk: 8 or 16
 __global__ void __launch_bounds__((NG * WG + 1) * 32, 1)
 k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constant__ CUtensorMap out_map, int use_tma, int rot) {
+    if (a.warm_dev && warm_steps > 0) warm_steps = device_warm_steps(a, WG * R3);
     constexpr int NW = NG * WG;
     constexpr int STEP = WG * R3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1128,8 +1140,9 @@ cudaError_t launch_scan2_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const int tiles = (a.C + 31) / 32;
     const int sms = sm_count();
     int grid_x = tiles, warm_steps = 0;
-    if (g_scan_split && a.warm_rows >= 0) {
-        const int ws = (a.warm_rows + STEP - 1) / STEP;
+    const int warm_host = a.warm_dev ? a.warm_est : a.warm_rows;      // modulated cutoffs: last request's horizon as estimate
+    if (g_scan_split && warm_host >= 0) {
+        const int ws = std::max(1, (warm_host + STEP - 1) / STEP);
         const long long total = (long long)tiles * nsteps;
         const long long quota = (total + sms - 1) / sms;
         if (tiles % sms != 0 && quota >= 8ll * ws && quota >= 4) {
@@ -1185,8 +1198,9 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const int tiles = (a.C + 63) / 64;
     const int sms = sm_count();
     int grid_x = tiles, warm_steps = 0;
-    if (g_scan_split && a.warm_rows >= 0) {
-        const int ws = (a.warm_rows + STEP - 1) / STEP;
+    const int warm_host = a.warm_dev ? a.warm_est : a.warm_rows;      // modulated cutoffs: last request's horizon as estimate
+    if (g_scan_split && warm_host >= 0) {
+        const int ws = std::max(1, (warm_host + STEP - 1) / STEP);
         const long long total = (long long)tiles * nsteps;
         const long long quota = (total + sms - 1) / sms;
         if (tiles % sms != 0 && quota >= 8ll * ws && quota >= 4) {

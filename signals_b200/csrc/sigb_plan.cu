@@ -215,6 +215,7 @@ struct sigb_plan {
     cudaEvent_t ev_caller = nullptr;
     // modulated cutoffs: per-filter decay horizons written by k_design, and the "cutoff outside (0, Nyquist)" flag
     int n_mods = 0;
+    bool warm_on_device = false;        // this request's k_design launches wrote the horizons to d_warm
     int* d_warm = nullptr;
     int* h_warm = nullptr;              // page-locked copy
     int* h_err = nullptr;               // page-locked, device-mapped: k_design stores 1 here
@@ -1170,6 +1171,7 @@ int upload(sigb_plan* p) {
     if (p->n_mods > 0) {
         CUDA_TRY(cudaMalloc(&p->d_warm, p->n_mods * sizeof(int)));
         CUDA_TRY(cudaHostAlloc(&p->h_warm, p->n_mods * sizeof(int), cudaHostAllocDefault));
+        std::memset(p->h_warm, 0, p->n_mods * sizeof(int));
         CUDA_TRY(cudaHostAlloc(&p->h_err, sizeof(int), cudaHostAllocMapped));
         *p->h_err = 0;
     }
@@ -1246,6 +1248,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.rate = p->rate;
             a.frames = rows;
             a.warm_rows = ch.warm_rows;
+            a.warm_est = -1;
             a.position = abs_row0;
             a.pos_ptr = p->rt_pos_ptr;
             std::memcpy(a.sec_kind, ch.sec_kind, sizeof(a.sec_kind));
@@ -1333,6 +1336,17 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             // (a chain with a modulated cutoff gets its scan tables from k_design, once per request)
             const bool scan_ok = !force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
             if (scan_ok) {
+                if (!ch.mods.empty() && p->warm_on_device && ch.warm_static < 1e8) {
+                    // the scan kernels read the request's decay horizon on the device (k_design wrote it on this stream);
+                    // the host's estimate -- what earlier requests copied back, possibly stale -- only decides whether
+                    // to cut tiles along time
+                    a.warm_rows = (int)std::ceil(ch.warm_static);
+                    a.warm_dev = p->d_warm + ch.mods.front().slot;
+                    a.n_warm_dev = (int)ch.mods.size();
+                    double est = ch.warm_static;
+                    for (const ChainSpec::ModFilter& mf : ch.mods) est += p->h_warm[mf.slot];
+                    a.warm_est = (int)std::min(est, 1e9);
+                }
                 int e = sigb_launch_chain_scan(&a, (int)p->opt_scan_variant, st, &done);
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_scan: ") + cudaGetErrorString((cudaError_t)e));
                 if (done > 0) {
@@ -1513,7 +1527,9 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
     p->launch_count++;
     if (!design || p->n_mods == 0) return SIGB_OK;
     const bool want_warm = p->rt_pos_ptr == nullptr && !p->opt_force_seq && frames >= 4096;
+    p->warm_on_device = want_warm;
     if (want_warm) CUDA_TRY(cudaMemsetAsync(p->d_warm, 0, p->n_mods * sizeof(int), st));
+    bool need_host = false;         // deep cascades run the register / pipelined kernels, whose launch geometry needs the value
     for (ChainSpec& ch : p->chains) {
         for (const ChainSpec::ModFilter& mf : ch.mods) {
             DesignDev d;
@@ -1534,16 +1550,22 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
             if (e) return fail(SIGB_ECUDA, std::string("k_design: ") + cudaGetErrorString((cudaError_t)e));
             p->launch_count++;
         }
-        if (!ch.mods.empty()) ch.warm_rows = -1;
+        if (!ch.mods.empty()) {
+            ch.warm_rows = -1;
+            if (ch.nsec_real >= 3 || p->opt_cascade_pipe > 0 || (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg)) need_host = true;
+        }
     }
     if (want_warm) {
+        // the copy also refreshes the host's estimate for the NEXT request's scan launches; only deep cascades wait for it
         CUDA_TRY(cudaMemcpyAsync(p->h_warm, p->d_warm, p->n_mods * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        for (ChainSpec& ch : p->chains) {
-            if (ch.mods.empty()) continue;
-            double w = ch.warm_static;
-            for (const ChainSpec::ModFilter& mf : ch.mods) w += p->h_warm[mf.slot];
-            ch.warm_rows = w < 1e8 ? (int)std::ceil(w) : -1;
+        if (need_host) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (ChainSpec& ch : p->chains) {
+                if (ch.mods.empty()) continue;
+                double w = ch.warm_static;
+                for (const ChainSpec::ModFilter& mf : ch.mods) w += p->h_warm[mf.slot];
+                ch.warm_rows = w < 1e8 ? (int)std::ceil(w) : -1;
+            }
         }
     }
     return SIGB_OK;
@@ -1802,12 +1824,12 @@ extern "C" int sigb_plan_bind_buffer_window(sigb_plan* plan, int32_t node, const
 }
 
 extern "C" int sigb_render(sigb_plan* plan, int64_t position, int32_t frames, float* out, int64_t ld_out, void* stream) {
-    if (!plan || !out || frames < 0 || position < 0 || ld_out < plan->channels)
+    if (!plan || (!out && frames != 0) || frames < 0 || position < 0 || ld_out < plan->channels)
         return fail(SIGB_EINVAL, "sigb_render: bad arguments");
+    if (frames == 0) return SIGB_OK;          // an empty block (shape (0, C)): nothing to render, the stream position stands
     int e = upload(plan);
     if (e == SIGB_OK) e = check_design_error(plan);
     if (e != SIGB_OK) return e;
-    if (frames == 0) return SIGB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(cudaEventRecord(plan->ev0, st));
     e = render_range(plan, position, frames, out, ld_out, st);
@@ -1818,12 +1840,12 @@ extern "C" int sigb_render(sigb_plan* plan, int64_t position, int32_t frames, fl
 }
 
 extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out, void* after_stream) {
-    if (!plan || !out_host || frames < 0 || position < 0 || ld_out < plan->channels)
+    if (!plan || (!out_host && frames != 0) || frames < 0 || position < 0 || ld_out < plan->channels)
         return fail(SIGB_EINVAL, "sigb_render_host: bad arguments");
+    if (frames == 0) return SIGB_OK;
     int e = upload(plan);
     if (e == SIGB_OK) e = check_design_error(plan);
     if (e != SIGB_OK) return e;
-    if (frames == 0) return SIGB_OK;
     e = ensure_host_streams(plan);
     if (e != SIGB_OK) return e;
     // work the caller queued on `after_stream` (the upload of a bound Buffer, ...) is ordered before the render
@@ -1878,12 +1900,12 @@ extern "C" int sigb_render_host(sigb_plan* plan, int64_t position, int32_t frame
 // straight into page-locked staging (no copy node) -- one stream synchronisation and one host memcpy into `out_host`.
 // Seeks, plans the graph cannot express (see rt_eligible) and blocks above "rt_max_bytes" take sigb_render_host.
 extern "C" int sigb_render_block(sigb_plan* plan, int64_t position, int32_t frames, float* out_host, int64_t ld_out) {
-    if (!plan || !out_host || frames < 0 || position < 0 || ld_out < plan->channels)
+    if (!plan || (!out_host && frames != 0) || frames < 0 || position < 0 || ld_out < plan->channels)
         return fail(SIGB_EINVAL, "sigb_render_block: bad arguments");
+    if (frames == 0) return SIGB_OK;
     int e = upload(plan);
     if (e == SIGB_OK) e = check_design_error(plan);
     if (e != SIGB_OK) return e;
-    if (frames == 0) return SIGB_OK;
     const int C = plan->channels;
     const int64_t bytes = (int64_t)frames * C * 4;
     const bool seek = !plan->have_pos || plan->next_pos != position || plan->opt_restart;

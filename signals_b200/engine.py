@@ -178,6 +178,8 @@ class CompiledPlan:
         self._bind_buffers()
         if out is None:
             out = np.empty((frames, self.channels), dtype=np.float32)
+        if frames == 0:
+            return out                                # an empty block: nothing to render, the stream position stands
         if isinstance(out, np.ndarray):
             assert out.dtype == np.float32 and out.strides[1] == 4
             ptr, ld = out.ctypes.data, out.strides[0] // 4
@@ -200,6 +202,8 @@ class CompiledPlan:
         unit channel stride) -- ``sigb_render_block``."""
         if not self._bound:
             self._bind_buffers()
+        if frames == 0:
+            return out
         assert out.dtype == np.float32 and out.strides[1] == 4
         st = self._lib.sigb_render_block(self.handle, int(position), int(frames), ctypes.c_void_p(out.ctypes.data),
                                          out.strides[0] // 4)
