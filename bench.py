@@ -43,7 +43,8 @@ RATE = 48000
 METRIC = 'voice-samples/sec'
 # (voices, seconds, steps, e2e steps) when a config is the headline / when it rides along in `extra`
 DEFAULTS = {'c2': (4096, 10.0, 20, 10), 'c2m': (4096, 10.0, 10, 0), 'c3': (65536, 10.0, 5, 3), 'c4': (16384, 60.0, 2, 1), 'c5': (1 << 20, 10.0, 3, 2)}
-EXTRA_STEPS = {'c3': 5, 'c4': 2, 'c5': 3, 'c2m': 10}
+EXTRA_STEPS = {'c3': 5, 'c4': 2, 'c5': 3, 'c2m': 20}
+EXTRA_WARMUP = {'c2m': 10}      # millisecond steps right after a CPU-only phase: let the clocks come back up first
 FMA_PROBE_CEILING = 96.0        # FMA lane-ops / clk / SM the section arithmetic reaches register-only (profiles/r01_fma_probe.txt)
 
 
@@ -853,7 +854,7 @@ def run_b200(args):
             if name == 'c5':                                   # every N: strong scaling with the NCCL reduce
                 r = measure(ctx, make_workload('c5', args, rank, world, False), EXTRA_STEPS['c5'], 3, 0, cpu_baseline=False)
             elif name in ('c3', 'c4', 'c2m') and world == 1:
-                r = measure(ctx, make_workload(name, args, rank, world, False), EXTRA_STEPS[name], 3, 0, cpu_baseline=False)
+                r = measure(ctx, make_workload(name, args, rank, world, False), EXTRA_STEPS[name], EXTRA_WARMUP.get(name, 3), 0, cpu_baseline=False)
             elif name == 'c1' and world == 1:
                 r = measure_c1(ctx, cpu=not args.no_cpu_baseline)
             else:

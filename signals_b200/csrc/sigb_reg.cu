@@ -64,6 +64,38 @@ __device__ __forceinline__ float2 reg_step(float2 x, RegSec& r) {
     return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
 }
 
+// a value ptxas must keep in its register (it would rather recompute 2g and 2gd inside the loop than hold them)
+__device__ __forceinline__ float keep(float v) {
+    asm volatile("" : "+f"(v));
+    return v;
+}
+
+// Coefficients of section s for channels (ca, cb) from the plan's {g, c, d} table.  A FIRST-ORDER section (odd Butterworth
+// orders; table entry {G, 0, 0}, G = g / (1 + g): v = G (x - s1), lp = s1 + v, s1' = s1 + 2 v, hp = x - lp) runs on the very
+// same six instructions with coefficients chosen here, once: c = 1, g d = G, and for a low-pass g = 1, 2g = 0 (so that
+// lp = s2 + 1 bp = bp and s2 stays 0), for a high-pass d = 1 - G (hp = (1 - G) e) and 2g = 0.  The state convention is the
+// other kernels' (s1 as in svf_any, s2 = 0), so streams can still pass between kernels.
+__device__ __forceinline__ void load_section(const ChainDev& a, int s, int ca, int cb, RegSec& r) {
+    const size_t C = (size_t)a.C;
+    const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
+    if (a.sec_kind[s] & SEC_FIRST_ORDER) {
+        r.nc = make_float2(-1.0f, -1.0f);
+        r.al = make_float2(ga, gb);
+        r.a2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
+        r.g = make_float2(1.0f, 1.0f);
+        r.g2 = make_float2(keep(0.0f), keep(0.0f));
+        r.d = make_float2(1.0f - ga, 1.0f - gb);
+        return;
+    }
+    const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
+    r.g = make_float2(ga, gb);
+    r.nc = make_float2(-a.coef[(size_t)(s * 3 + 1) * C + ca], -a.coef[(size_t)(s * 3 + 1) * C + cb]);
+    r.d = make_float2(da, db);
+    r.g2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
+    r.al = make_float2(ga * da, gb * db);
+    r.a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
+}
+
 constexpr int RING_D = 4;       // blocks of R rows per warp in the cp.async ring (RING_D - 1 in flight)
 
 __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gsrc) {
@@ -78,11 +110,6 @@ __device__ __forceinline__ float2 lds_f2(unsigned addr) {
     return v;
 }
 
-// a value ptxas must keep in its register (it would rather recompute 2g and 2gd inside the loop than hold them)
-__device__ __forceinline__ float keep(float v) {
-    asm volatile("" : "+f"(v));
-    return v;
-}
 
 // R rows through NSEC sections in wavefront order
 template <int NSEC, int KIND, int R>
@@ -144,14 +171,7 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
     RegSec sec[NSEC];
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
-        const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
-        const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
-        sec[s].g = make_float2(ga, gb);
-        sec[s].nc = make_float2(-a.coef[(size_t)(s * 3 + 1) * C + ca], -a.coef[(size_t)(s * 3 + 1) * C + cb]);
-        sec[s].d = make_float2(da, db);
-        sec[s].g2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
-        sec[s].al = make_float2(ga * da, gb * db);
-        sec[s].a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
+        load_section(a, s, ca, cb, sec[s]);
         if (row_first == 0) {
             sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + ca], (float)a.state[(size_t)(s * 2 + 0) * C + cb]);
             sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + ca], (float)a.state[(size_t)(s * 2 + 1) * C + cb]);
@@ -581,14 +601,7 @@ k_osc_reg(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
         RegSec sec[NSEC];
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) {
-            const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
-            const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
-            sec[s].g = make_float2(ga, gb);
-            sec[s].nc = make_float2(-a.coef[(size_t)(s * 3 + 1) * C + ca], -a.coef[(size_t)(s * 3 + 1) * C + cb]);
-            sec[s].d = make_float2(da, db);
-            sec[s].g2 = make_float2(keep(2.0f * ga), keep(2.0f * gb));
-            sec[s].al = make_float2(ga * da, gb * db);
-            sec[s].a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
+            load_section(a, s, ca, cb, sec[s]);
             if (row_first == 0) {
                 sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + ca], (float)a.state[(size_t)(s * 2 + 0) * C + cb]);
                 sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + ca], (float)a.state[(size_t)(s * 2 + 1) * C + cb]);
@@ -692,7 +705,7 @@ extern "C" void sigb_set_reg_pieces(int n) { g_reg_pieces = n; }
 extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
     for (int k = 0; k < a->nsec; ++k)
-        if (a->sec_kind[k] != a->sec_kind[0] || (a->sec_kind[k] & SEC_FIRST_ORDER)) return 0;
+        if ((a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP)) return 0;      // first-order sections are welcome (load_section)
     return 1;
 }
 
@@ -707,7 +720,10 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
                       (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
                       a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
     const bool wide = fast && variant != 1;
-    const bool streaming = fast && variant == 3;                           // continuous software pipeline over rows (A/B)
+    bool any_first = false;
+    for (int k = 0; k < a->nsec; ++k) any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
+    // continuous software pipeline over rows (A/B); its 2 lp - s2 update would not keep a first-order section's s2 at 0
+    const bool streaming = fast && variant == 3 && !any_first;
     const int R = wide ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
@@ -743,7 +759,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
 extern "C" int sigb_osc_reg_ok(const ChainDev* a) {
     if (a->src_kind != SRC_OSC || !a->theta0 || !a->dtheta || a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
     for (int k = 0; k < a->nsec; ++k)
-        if (a->sec_kind[k] != a->sec_kind[0] || (a->sec_kind[k] & SEC_FIRST_ORDER)) return 0;
+        if ((a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP)) return 0;
     return 1;
 }
 

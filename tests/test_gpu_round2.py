@@ -383,3 +383,60 @@ def test_very_wide_blocks(ns, engine):
     got = out[:, torch.from_numpy(pick).cuda()].cpu().numpy()
     want = np_oracle.render_voice_chain(0, 1500, RATE, hz[pick], ph[pick], cut[pick], g[pick], wave='Sawtooth')
     assert max_abs_err(got, want) <= 1e-4
+
+
+@pytest.mark.parametrize('cls,btype,order,nodes', [('LowPass', 'lp', 3, 3), ('HighPass', 'hp', 5, 1), ('LowPass', 'lp', 5, 2)])
+def test_odd_order_cascades_on_the_register_kernel(cls, btype, order, nodes, ns, engine):
+    """Odd Butterworth orders end in a first-order section.  k_cascade_reg / k_osc_reg run it on the second-order
+    section's six instructions with coefficients chosen at load time (c = 1, g d = G, 2g = 0; low-pass g = 1, high-pass
+    d = 1 - G), so such cascades no longer fall back to the section-pipelined kernel: same result as that kernel and as the
+    float64 cascade, state carried into a second request, time pieces included."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(71)
+    ch, frames = 192, 40000
+    x = rng.uniform(-1, 1, (frames + 3000, ch)).astype(np.float32)
+    cut = np.exp(rng.uniform(np.log(700.0), np.log(8000.0), (nodes, ch)))
+
+    def graph():
+        node = ext.Buffer(x)
+        for s in range(nodes):
+            node = cases.lowpass(ns, node, [cut[s]], cls, order)
+        return node
+
+    got = {}
+    for kernel in ('reg', 'pipe'):
+        c = engine.compile(graph(), ch, RATE)
+        c.set_option('cascade_reg', -1 if kernel == 'reg' else 0)
+        (launch,) = c.describe()['launches']
+        assert launch['sections'] == nodes * ((order + 1) // 2)
+        first = c.render_device(0, frames).cpu().numpy()
+        second = c.render_device(frames, 3000).cpu().numpy()
+        c.close()
+        got[kernel] = np.concatenate([first, second])
+    pick = rng.choice(ch, 16, replace=False)
+    want, _ = np_oracle.render_cascade(x[:, pick].astype(np.float64), cut[:, pick], RATE, btype, order)
+    err = max_abs_err(got['reg'][:, pick], want)
+    print(f'{nodes} x {cls} order {order} on the register kernel: max-abs {err:.3e}; vs the pipelined kernel {max_abs_err(got["reg"], got["pipe"]):.3e}')
+    assert err <= 1e-4
+    assert max_abs_err(got['reg'], got['pipe']) <= 2e-6
+
+
+def test_odd_order_oscillator_chain_on_the_register_kernel(ns, engine):
+    """Oscillator -> three order-3 high-pass nodes (6 sections, every second one first-order) through k_osc_reg."""
+    ch, frames = 130, 30000
+    hz, ph, cut, g = cases.voice_params(73, ch)
+    node = cases.osc(ns, 'Sawtooth', [hz], [ph])
+    for k in range(3):
+        node = cases.lowpass(ns, node, [np.clip(cut * (1.0 + 0.3 * k), 300.0, 9000.0)], 'HighPass', 3)
+    c = engine.compile(node, ch, RATE)
+    got = c.render_device(0, frames).cpu().numpy()
+    c.close()
+    pick = np.random.default_rng(1).choice(ch, 12, replace=False)
+    orc = np_oracle.GraphOracle(RATE)
+    sub = cases.osc(ns, 'Sawtooth', [hz[pick]], [ph[pick]])
+    for k in range(3):
+        sub = cases.lowpass(ns, sub, [np.clip(cut[pick] * (1.0 + 0.3 * k), 300.0, 9000.0)], 'HighPass', 3)
+    want = orc.render(sub, 0, frames, len(pick))
+    err = max_abs_err(got[:, pick], want)
+    print(f'osc -> 3 x HighPass order 3: max-abs {err:.3e}')
+    assert err <= 1e-4
