@@ -647,9 +647,9 @@ k_chain_scan2(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 //
 // Measured on B200 (tools/probe_fill.py): a store-only kernel writing 128-byte rows of a (frames, 4096)
 // block tops out at 4.57 TB/s, with 256-byte rows at 6.0 TB/s -- k_chain_scan2's 32-channel tiles sit AT that
-// first ceiling.  Here a tile is 64 adjacent channels: the two lanes of every packed register are channels c
-// and c + 32 of the SAME rows (instead of two 8-row halves of one channel), a sub-chunk is 8 rows, and each
-// worker hands the TMA engine (8 x 64) tiles, i.e. 256-byte rows.  There is nothing to stitch; the scanner
+// first ceiling.  Here a tile is 64 adjacent channels: the two lanes of every packed register are the adjacent
+// channels 2 l and 2 l + 1 of the SAME rows (instead of two 8-row halves of one channel), a sub-chunk is R3 rows, and
+// each worker hands the TMA engine (R3 x 64) tiles, i.e. 256-byte rows (one STS.64 per lane per row).  There is nothing to stitch; the scanner
 // chains the float64 carry through the sub-chunks directly, c_{q+1} = A^8 c_q + z_q, and publishes c_q as the
 // true initial state of sub-chunk q.  Workers are software-pipelined as in k_chain_scan2.
 // ------------------------------------------------------------------------------------------
@@ -661,9 +661,14 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
     constexpr int STEP = WG * R3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);                        // [NW][R3][64] output tiles (TMA source)
-    float4* zs = reinterpret_cast<float4*>(stage + NW * R3 * 64);            // [NW][32] end states of channels (c, c+32)
+    float4* zs = reinterpret_cast<float4*>(stage + NW * R3 * 64);            // [NW][32] end states of the lane's two channels
     float4* si = zs + NW * 32;                                                // [NW][32] true initial states
     double* tnb = reinterpret_cast<double*>(si + NW * 32);                    // [NW][R3] n / rate (generic oscillators)
+    // per-lane constants each worker phase needs only briefly (correction: zero-input tables and recurrence; store: gain;
+    // source: rotation) live in shared memory, one copy per CTA (every worker of the CTA has the same channels), and are
+    // re-read per step: the kernel sits on its register limit (72 at 896 threads) and spilled inside the loop
+    float2* cst = reinterpret_cast<float2*>(tnb + NW * R3);                   // [CST_N][32]
+    constexpr int CST_ZP0 = 0, CST_ZR0 = 1, CST_ZP1 = 2, CST_ZR1 = 3, CST_AL = 4, CST_BE = 5, CST_GAIN = 6, CST_ROTC = 7, CST_ROTS = 8;
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -684,12 +689,34 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
         const int w0 = max(0, s0 - warm_steps);
         lin += s1 - s0;
 
-        const int cA = tile_idx * 64 + lane, cB = cA + 32;
+        const int cA = tile_idx * 64 + 2 * lane, cB = cA + 1;       // a lane's packed registers hold two ADJACENT channels
         const bool liveA = cA < a.C, liveB = cB < a.C;
         const int ccA = liveA ? cA : a.C - 1, ccB = liveB ? cB : a.C - 1;
 
+        if (w == 0) {
+            cst[CST_ZP0 * 32 + lane] = pk(a.ztab[((size_t)0 * 2 + 0) * C + ccA], a.ztab[((size_t)0 * 2 + 0) * C + ccB]);
+            cst[CST_ZR0 * 32 + lane] = pk(a.ztab[((size_t)0 * 2 + 1) * C + ccA], a.ztab[((size_t)0 * 2 + 1) * C + ccB]);
+            cst[CST_ZP1 * 32 + lane] = pk(a.hrec[(size_t)2 * C + ccA], a.hrec[(size_t)2 * C + ccB]);
+            cst[CST_ZR1 * 32 + lane] = pk(a.hrec[(size_t)3 * C + ccA], a.hrec[(size_t)3 * C + ccB]);
+            cst[CST_AL * 32 + lane] = pk(a.hrec[(size_t)0 * C + ccA], a.hrec[(size_t)0 * C + ccB]);       // det(A)
+            cst[CST_BE * 32 + lane] = pk(a.hrec[(size_t)1 * C + ccA], a.hrec[(size_t)1 * C + ccB]);       // tr(A) - 1 - det(A)
+            cst[CST_GAIN * 32 + lane] = a.gain ? pk(a.gain[ccA], a.gain[ccB]) : pk1(1.0f);
+            if (FASTSINE && rot) {
+                const float2 ra = a.rot1[ccA], rb = a.rot1[ccB];
+                cst[CST_ROTC * 32 + lane] = pk(ra.x, rb.x);
+                cst[CST_ROTS * 32 + lane] = pk(ra.y, rb.y);
+            }
+        }
+        __syncthreads();
+        const unsigned cst_addr = smem_u32(cst + lane);
+        auto cst_ld = [&](int which) {                       // volatile: not to be hoisted back into registers
+            float2 v2;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v2.x), "=f"(v2.y) : "r"(cst_addr + which * 256u));
+            return v2;
+        };
+
         if (w == NW) {
-            // ---------------- scanner warp: lane = channels (c, c + 32), float64 carry chain ----------------
+            // ---------------- scanner warp: lane = channels (2 l, 2 l + 1) of the tile, float64 carry chain ----------------
             double mA[4], mB[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -745,9 +772,8 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 if (liveB) { a.state_out[(size_t)0 * C + cB] = b1; a.state_out[(size_t)1 * C + cB] = b2; }
             }
         } else {
-            // ---------------- worker warps: lane = channels (c, c + 32), warp = 8-row sub-chunk ----------------
+            // ---------------- worker warps: lane = channels (2 l, 2 l + 1) of the tile, warp = 8-row sub-chunk ----------------
             const int grp = w / WG, q = w % WG;
-            const float2 gain2 = a.gain ? pk(a.gain[ccA], a.gain[ccB]) : pk1(1.0f);
             int64_t row = ((int64_t)w0 + grp) * STEP + (int64_t)q * R3;
             const int64_t row_stride = (int64_t)NG * STEP;
             float* outp = a.out + row * a.ld_out + cA;
@@ -755,7 +781,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             float* tile = stage + w * (R3 * 64);
             const int kind = a.sec_kind[0];
 
-            SecPar ps;       // both lanes of every field: channel c and channel c + 32
+            SecPar ps;       // both lanes of every field: the lane's two adjacent channels
             {
                 const float gA = a.coef[(size_t)0 * C + ccA], gB = a.coef[(size_t)0 * C + ccB];
                 const float dA = a.coef[(size_t)2 * C + ccA], dB = a.coef[(size_t)2 * C + ccB];
@@ -765,19 +791,12 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 ps.gd = pk(gA * dA, gB * dB);
                 ps.gd2 = pk(2.0f * (gA * dA), 2.0f * (gB * dB));
                 ps.g2 = pk(2.0f * gA, 2.0f * gB);
-                ps.al = pk(a.hrec[(size_t)0 * C + ccA], a.hrec[(size_t)0 * C + ccB]);       // det(A)
-                ps.be = pk(a.hrec[(size_t)1 * C + ccA], a.hrec[(size_t)1 * C + ccB]);       // tr(A) - 1 - det(A)
             }
-            // zero-input output at sample 0 per unit state (row 0 of the response table) and its first difference
-            const float2 zp0 = pk(a.ztab[((size_t)0 * 2 + 0) * C + ccA], a.ztab[((size_t)0 * 2 + 0) * C + ccB]);
-            const float2 zr0 = pk(a.ztab[((size_t)0 * 2 + 1) * C + ccA], a.ztab[((size_t)0 * 2 + 1) * C + ccB]);
-            const float2 zp1 = pk(a.hrec[(size_t)2 * C + ccA], a.hrec[(size_t)2 * C + ccB]);
-            const float2 zr1 = pk(a.hrec[(size_t)3 * C + ccA], a.hrec[(size_t)3 * C + ccB]);
 
             unsigned long long thA = 0, thB = 0, stepA = 0, stepB = 0;
             int dhiA = 0, dhiB = 0;
             double hzA = 0.0, hzB = 0.0, phA = 0.0, phB = 0.0;
-            float2 cv = pk1(0.0f), rotC = pk1(1.0f), rotS = pk1(0.0f);
+            float2 cv = pk1(0.0f);
             if (SRC == SRC_OSC) {
                 if (FASTSINE) {
                     const unsigned long long dA = a.dtheta[ccA], dB = a.dtheta[ccB];
@@ -787,11 +806,6 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     stepB = dB * (unsigned long long)row_stride;
                     dhiA = (int)((dA + 0x80000000ull) >> 32);
                     dhiB = (int)((dB + 0x80000000ull) >> 32);
-                    if (rot) {
-                        const float2 ra = a.rot1[ccA], rb = a.rot1[ccB];
-                        rotC = pk(ra.x, rb.x);
-                        rotS = pk(ra.y, rb.y);
-                    }
                 } else {
                     hzA = a.hertz[ccA]; hzB = a.hertz[ccB];
                     phA = a.phase[ccA]; phB = a.phase[ccB];
@@ -808,6 +822,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                             // cosine from the SFU, their neighbours (one row back, two rows forward) the angle-addition
                             // rotation by the channel's one-row phase advance (cos, sin tabulated in float64 on the host):
                             // 16 instructions per 4 rows x 2 channels instead of 36
+                            const float2 rotC = cst_ld(CST_ROTC), rotS = cst_ld(CST_ROTS);
                             const float2 NS = pk(-rotS.x, -rotS.y);
 #pragma unroll
                             for (int q4 = 0; q4 + 3 < R3; q4 += 4) {
@@ -864,7 +879,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 float2 v[R3];
                 const int next = step + NG;
                 if (PIPE3) {
-                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of c, s1 of c+32, s2 of c, s2 of c+32)
+                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of both channels, s2 of both channels)
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
 #pragma unroll
                     for (int k = 0; k < R3; ++k) v[k] = vn[PIPE3 ? k : 0];
@@ -879,7 +894,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                     s2n = pk1(0.0f);
                     gen(v, row);
                     svf2_block<R3>(kind, ps, v, s1n, s2n);
-                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of c, s1 of c+32, s2 of c, s2 of c+32)
+                    zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of both channels, s2 of both channels)
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
                 }
                 bar_sync(2 + 2 * grp, (WG + 1) * 32);
@@ -887,25 +902,26 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 {   // zero-input response of the true initial state, advanced by its 2-term recurrence in delta form
                     // (dh[k] = det dh[k-1] + (tr - 1 - det) h[k-1], h[k] = h[k-1] + dh[k]: see k_chain_scan2's `correct`)
                     const float2 i1 = pk(ia.x, ia.y), i2 = pk(ia.z, ia.w);
-                    float2 h = __ffma2_rn(zp0, i1, __fmul2_rn(zr0, i2));
-                    float2 dh = __ffma2_rn(zp1, i1, __fmul2_rn(zr1, i2));
+                    float2 h = __ffma2_rn(cst_ld(CST_ZP0), i1, __fmul2_rn(cst_ld(CST_ZR0), i2));
+                    float2 dh = __ffma2_rn(cst_ld(CST_ZP1), i1, __fmul2_rn(cst_ld(CST_ZR1), i2));
+                    const float2 al = cst_ld(CST_AL), be = cst_ld(CST_BE);
                     v[0] = __fadd2_rn(v[0], h);
 #pragma unroll
                     for (int k = 1; k < R3; ++k) {
-                        if (k > 1) dh = __ffma2_rn(ps.al, dh, __fmul2_rn(ps.be, h));
+                        if (k > 1) dh = __ffma2_rn(al, dh, __fmul2_rn(be, h));
                         h = __fadd2_rn(h, dh);
                         v[k] = __fadd2_rn(v[k], h);
                     }
                 }
                 if (step >= s0) {
+                    const float2 gain2 = cst_ld(CST_GAIN);
                     if (bulk) {
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                         __syncwarp();
 #pragma unroll
                         for (int k = 0; k < R3; ++k) {
                             const float2 o = __fmul2_rn(v[k], gain2);
-                            tile[k * 64 + lane] = o.x;
-                            tile[k * 64 + 32 + lane] = o.y;
+                            reinterpret_cast<float2*>(tile)[k * 32 + lane] = o;        // one STS.64 per row
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
@@ -918,7 +934,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                         for (int k = 0; k < R3; ++k) {
                             const float2 o = __fmul2_rn(v[k], gain2);
                             if (liveA) __stcs(outp + (int64_t)k * a.ld_out, o.x);
-                            if (liveB) __stcs(outp + (int64_t)k * a.ld_out + 32, o.y);
+                            if (liveB) __stcs(outp + (int64_t)k * a.ld_out + 1, o.y);
                         }
                     }
                 }
@@ -1174,7 +1190,8 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     const int nsteps = a.frames / STEP;
     *rows_done = nsteps * STEP;
     if (nsteps == 0) return cudaSuccess;
-    const size_t smem = (size_t)NW * R3 * 64 * sizeof(float) + (size_t)NW * 32 * sizeof(float4) * 2 + (size_t)NW * R3 * sizeof(double);
+    const size_t smem = (size_t)NW * R3 * 64 * sizeof(float) + (size_t)NW * 32 * sizeof(float4) * 2 + (size_t)NW * R3 * sizeof(double) +
+                        (size_t)9 * 32 * sizeof(float2);
     auto kern = k_chain_scan3<SRC, NG, WG, FASTSINE, R3, PIPE3, F32CARRY>;
     static bool attr_done = false;
     if (!attr_done) {
