@@ -668,7 +668,8 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
     // source: rotation) live in shared memory, one copy per CTA (every worker of the CTA has the same channels), and are
     // re-read per step: the kernel sits on its register limit (72 at 896 threads) and spilled inside the loop
     float2* cst = reinterpret_cast<float2*>(tnb + NW * R3);                   // [CST_N][32]
-    constexpr int CST_ZP0 = 0, CST_ZR0 = 1, CST_ZP1 = 2, CST_ZR1 = 3, CST_AL = 4, CST_BE = 5, CST_GAIN = 6, CST_ROTC = 7, CST_ROTS = 8;
+    constexpr int CST_ZP0 = 0, CST_ZR0 = 1, CST_ZP1 = 2, CST_ZR1 = 3, CST_AL = 4, CST_BE = 5, CST_GAIN = 6, CST_ROTC = 7, CST_ROTS = 8,
+                  CST_G = 9, CST_NC = 10, CST_D = 11, CST_GD = 12, CST_GD2 = 13, CST_G2 = 14;       // the section itself
 
     const int lane = threadIdx.x & 31;
     const int w = threadIdx.x >> 5;
@@ -706,6 +707,14 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                 cst[CST_ROTC * 32 + lane] = pk(ra.x, rb.x);
                 cst[CST_ROTS * 32 + lane] = pk(ra.y, rb.y);
             }
+            const float gA = a.coef[(size_t)0 * C + ccA], gB = a.coef[(size_t)0 * C + ccB];
+            const float dA = a.coef[(size_t)2 * C + ccA], dB = a.coef[(size_t)2 * C + ccB];
+            cst[CST_G * 32 + lane] = pk(gA, gB);
+            cst[CST_NC * 32 + lane] = pk(-a.coef[(size_t)1 * C + ccA], -a.coef[(size_t)1 * C + ccB]);
+            cst[CST_D * 32 + lane] = pk(dA, dB);
+            cst[CST_GD * 32 + lane] = pk(gA * dA, gB * dB);
+            cst[CST_GD2 * 32 + lane] = pk(2.0f * (gA * dA), 2.0f * (gB * dB));
+            cst[CST_G2 * 32 + lane] = pk(2.0f * gA, 2.0f * gB);
         }
         __syncthreads();
         const unsigned cst_addr = smem_u32(cst + lane);
@@ -781,17 +790,14 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             float* tile = stage + w * (R3 * 64);
             const int kind = a.sec_kind[0];
 
-            SecPar ps;       // both lanes of every field: the lane's two adjacent channels
-            {
-                const float gA = a.coef[(size_t)0 * C + ccA], gB = a.coef[(size_t)0 * C + ccB];
-                const float dA = a.coef[(size_t)2 * C + ccA], dB = a.coef[(size_t)2 * C + ccB];
-                ps.g = pk(gA, gB);
-                ps.nc = pk(-a.coef[(size_t)1 * C + ccA], -a.coef[(size_t)1 * C + ccB]);
-                ps.d = pk(dA, dB);
-                ps.gd = pk(gA * dA, gB * dB);
-                ps.gd2 = pk(2.0f * (gA * dA), 2.0f * (gB * dB));
-                ps.g2 = pk(2.0f * gA, 2.0f * gB);
-            }
+            // the section's coefficients (both lanes of every field: the lane's two adjacent channels) are read from
+            // shared memory where the section runs, so that they occupy registers only there
+            auto section = [&](float2 (&vv)[R3], float2& t1, float2& t2) {
+                SecPar ps;
+                ps.g = cst_ld(CST_G); ps.nc = cst_ld(CST_NC); ps.gd = cst_ld(CST_GD); ps.gd2 = cst_ld(CST_GD2); ps.g2 = cst_ld(CST_G2);
+                ps.d = (kind & (SEC_HP | SEC_FIRST_ORDER)) ? cst_ld(CST_D) : pk1(0.0f);
+                svf2_block<R3>(kind, ps, vv, t1, t2);
+            };
 
             unsigned long long thA = 0, thB = 0, stepA = 0, stepB = 0;
             int dhiA = 0, dhiB = 0;
@@ -873,7 +879,7 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
             float2 s1n = pk1(0.0f), s2n = pk1(0.0f);
             if (PIPE3 && step < s1) {
                 gen(reinterpret_cast<float2(&)[R3]>(vn), row);
-                svf2_block<R3>(kind, ps, reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
+                section(reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
             }
             while (step < s1) {
                 float2 v[R3];
@@ -887,13 +893,13 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
                         s1n = pk1(0.0f);
                         s2n = pk1(0.0f);
                         gen(reinterpret_cast<float2(&)[R3]>(vn), row + row_stride);
-                        svf2_block<R3>(kind, ps, reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
+                        section(reinterpret_cast<float2(&)[R3]>(vn), s1n, s2n);
                     }
                 } else {
                     s1n = pk1(0.0f);
                     s2n = pk1(0.0f);
                     gen(v, row);
-                    svf2_block<R3>(kind, ps, v, s1n, s2n);
+                    section(v, s1n, s2n);
                     zs[w * 32 + lane] = make_float4(s1n.x, s1n.y, s2n.x, s2n.y);       // (s1 of both channels, s2 of both channels)
                     bar_arrive(1 + 2 * grp, (WG + 1) * 32);
                 }
@@ -1191,7 +1197,7 @@ cudaError_t launch_scan3_t(const ChainDev& a, cudaStream_t st, int* rows_done) {
     *rows_done = nsteps * STEP;
     if (nsteps == 0) return cudaSuccess;
     const size_t smem = (size_t)NW * R3 * 64 * sizeof(float) + (size_t)NW * 32 * sizeof(float4) * 2 + (size_t)NW * R3 * sizeof(double) +
-                        (size_t)9 * 32 * sizeof(float2);
+                        (size_t)15 * 32 * sizeof(float2);
     auto kern = k_chain_scan3<SRC, NG, WG, FASTSINE, R3, PIPE3, F32CARRY>;
     static bool attr_done = false;
     if (!attr_done) {
