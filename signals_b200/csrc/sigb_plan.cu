@@ -189,7 +189,7 @@ struct sigb_plan {
     int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
     int64_t opt_cascade_reg = -1;       // -1: register-resident cascade kernel whenever it can take the chain; 0: never
     int64_t opt_osc_reg = 3;            // oscillator-fed chains of >= n sections run register-resident (k_osc_reg); 0: never
-    int64_t opt_reg_variant = 0;        // k_cascade_reg: 0 = blocks of 8 rows, 1 = blocks of 4 rows
+    int64_t opt_reg_variant = 0;        // register cascades: 0 = delta form where it applies, else 8-row blocks; 1 = 4-row blocks; 3 = stream; 4 = state-variable form
     int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks

@@ -96,6 +96,66 @@ __device__ __forceinline__ void load_section(const ChainDev& a, int s, int ca, i
     r.a2 = make_float2(keep(2.0f * (ga * da)), keep(2.0f * (gb * db)));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// DELTA FORM of a second-order low-pass section (default for all-low-pass cascades of second-order sections).
+//
+// The bilinear Butterworth section is  b0 (1 + z^-1)^2 / (1 + a1 z^-1 + a2 z^-2),  b0 = (1 + a1 + a2) / 4.  The six
+// multiply-adds of the state-variable form all read three different registers, and the cascade is bound by exactly
+// that (register-file operand reads, ~96 lane-ops/clk/SM).  Here the all-pole part runs as a difference recurrence
+//     d[n] = a d[n-1] + F (x[n] - y[n-1]),   y[n] = y[n-1] + d[n],      F = 1 + a1 + a2 = 4 g^2 d,  a = a2 = 1 - 2 r2 g d
+// (F and 1 - a are the SMALL numbers at low cutoffs and are held as such, which is what keeps float32 exact there -- a
+// direct form holds a1 ~ -2 and loses 1e-3 at 20 Hz), and the two zeros at Nyquist are two plain adds:
+//     lp[n] = (y[n] + 2 y[n-1] + y[n-2]) / 4.
+// With Z = y / 4 and D = d / F:   w = x - 4 Z;  D' = a D + w;  Z' = Z + (F/4) D';  p = Z' + Z;  lp = p + P;  P' = p
+// = 3 FFMA2 + 2 FADD2 per two channel-samples (5 instead of 6 operations, two of them with two operands), two
+// coefficient pairs instead of five, three state pairs instead of two: 10 registers per section instead of 14.
+//
+// The states are the state-variable section's own, re-scaled (bp = (y[n] - y[n-2]) / 4g, hp = (y[n] - 2 y[n-1] +
+// y[n-2]) / 4 g^2  =>  s1 = bp[n-1] + g hp[n-1] = (y[n-1] - y[n-2]) / 2g,  s2 = lp[n-1] + g bp[n-1] = (y[n-1] + y[n-2]) / 2):
+//     P = s2 / 2,   D = s1 / (2 g d),   Z = (s2 + g s1) / 4;       s2 = 2 P = 4 Z - (F/2) D,   s1 = 2 g d D
+// so a stream passes between this form and every other kernel of the plan with a pointwise conversion.
+// Measured float32 error against the float64 cascade, 8 sections x 60 s (tools/delta_form_sim.c): 8.1e-7 at 200 Hz
+// cutoffs (state-variable form 8.0e-7), 5.7e-6 at 20 Hz (1.3e-6), 1.2e-6 at 20 kHz (7.7e-7): inside the 1e-4 bar.
+// ---------------------------------------------------------------------------------------------------------
+struct DeltaSec {
+    float2 a, be;               // (a2) (F / 4)
+    float2 D, Z, P;
+};
+
+__device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2 m4) {
+    const float2 w = __ffma2_rn(m4, r.Z, x);
+    r.D = __ffma2_rn(r.a, r.D, w);
+    const float2 zn = __ffma2_rn(r.be, r.D, r.Z);
+    const float2 p = __fadd2_rn(zn, r.Z);
+    r.Z = zn;
+    const float2 o = __fadd2_rn(p, r.P);
+    r.P = p;
+    return o;
+}
+
+// coefficients from the plan's float32 {g, c, d} entries (the very numbers the other kernels filter with), derived in
+// float64 so that a and F/4 carry one rounding each
+__device__ __forceinline__ void delta_coef(float g, float c, float d, float& a, float& be) {
+    const double G = (double)g, Dd = (double)d, R2 = (double)c - G;
+    a = (float)(1.0 - 2.0 * R2 * G * Dd);
+    be = (float)(G * G * Dd);
+}
+// State hand-over.  D and Z are the recurrent states and survive a store / load round trip bit for bit (s1 = 2 g d D and
+// s2 = 4 Z - 2 be D are formed in float64 from float32 factors, and the load inverts them with the same float32 be);
+// P is only the one-row memory of the second zero and comes back as s2 / 2, equal to the running value up to one
+// float32 rounding -- so a stream cut into several requests differs from the uncut one by rounding noise (~1e-7), not
+// bit for bit as with the state-variable kernels.
+__device__ __forceinline__ void delta_state_in(float g, float d, float be, double s1, double s2, float& D, float& Z, float& P) {
+    const double Dd = s1 / (2.0 * (double)g * (double)d);
+    D = (float)Dd;
+    Z = (float)(0.25 * (s2 + 2.0 * (double)be * Dd));
+    P = (float)(0.5 * s2);
+}
+__device__ __forceinline__ void delta_state_out(float g, float d, float be, float D, float Z, double& s1, double& s2) {
+    s1 = 2.0 * (double)g * (double)d * (double)D;
+    s2 = 4.0 * (double)Z - 2.0 * (double)be * (double)D;
+}
+
 constexpr int RING_D = 4;       // blocks of R rows per warp in the cp.async ring (RING_D - 1 in flight)
 
 __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void* gsrc) {
@@ -295,6 +355,145 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
         }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_cascade_delta: k_cascade_reg's decomposition (two channels per thread, every section in registers, blocks of 8
+// rows in wavefront order, equal time pieces per warp slot, warp-private cp.async ring) with the sections in DELTA
+// FORM (above).  FAST layout only (host-checked), second-order low-pass sections only.
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int delta_min_blocks(int nsec) { return nsec <= 6 ? 5 : 4; }
+
+template <int NSEC>
+__global__ void __launch_bounds__(RWARPS * 32, delta_min_blocks(NSEC))
+k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
+    constexpr int R = 8;
+    __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
+    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
+    const int lane = threadIdx.x & 31;
+    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (piece >= npieces) return;
+    const size_t C = (size_t)a.C;
+    const int bpt = (a.frames + R - 1) / R;
+    const int64_t total = (int64_t)tiles * bpt;
+    int64_t blk = total * piece / npieces;
+    const int64_t blk_end = total * (piece + 1) / npieces;
+    float2 m4 = make_float2(-4.0f, -4.0f);
+    asm volatile("" : "+f"(m4.x), "+f"(m4.y));            // one register pair, not an immediate per use
+    const uint32_t src_ldb = (uint32_t)a.src_ld * 4u, out_ldb = (uint32_t)a.ld_out * 4u;   // row strides in bytes (host-checked range)
+  while (blk < blk_end) {
+    const int tile = (int)(blk / bpt);
+    const int b0 = (int)(blk - (int64_t)tile * bpt);
+    const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
+    blk += b1 - b0;
+    const int c0 = tile * RC + 2 * lane;
+    const int row_store = b0 * R;
+    const int row_end = min(a.frames, b1 * R);
+    const int row_first = max(0, row_store - warm_rows);                   // warm_rows is a multiple of R
+    const int nfull = (row_end - row_first) / R;
+
+    DeltaSec sec[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
+        const float2 c = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 1) * C + c0);
+        const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
+        delta_coef(g.x, c.x, d.x, sec[s].a.x, sec[s].be.x);
+        delta_coef(g.y, c.y, d.y, sec[s].a.y, sec[s].be.y);
+        if (row_first == 0) {
+            delta_state_in(g.x, d.x, sec[s].be.x, a.state[(size_t)(s * 2 + 0) * C + c0], a.state[(size_t)(s * 2 + 1) * C + c0], sec[s].D.x, sec[s].Z.x, sec[s].P.x);
+            delta_state_in(g.y, d.y, sec[s].be.y, a.state[(size_t)(s * 2 + 0) * C + c0 + 1], a.state[(size_t)(s * 2 + 1) * C + c0 + 1], sec[s].D.y, sec[s].Z.y, sec[s].P.y);
+        } else {
+            sec[s].D = sec[s].Z = sec[s].P = make_float2(0.0f, 0.0f);
+        }
+    }
+    float2 gain = make_float2(1.0f, 1.0f);
+    if (a.gain) gain = *reinterpret_cast<const float2*>(a.gain + c0);
+
+    const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
+    char* op = reinterpret_cast<char*>(a.out + (int64_t)row_first * a.ld_out + c0);
+    const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RING_D * R * 32) + lane) * 8u;
+    const unsigned my_end = my + RING_D * R * 256u;
+    unsigned in_addr = my, out_addr = my;
+    int in_blk = 0;
+    auto prefetch = [&]() {
+        if (in_blk < nfull) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) cp_async8(in_addr + k * 256u, ip + (uint32_t)k * src_ldb);
+            ip += (int64_t)R * src_ldb;
+            ++in_blk;
+            in_addr += R * 256u;
+            if (in_addr == my_end) in_addr = my;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < RING_D - 1; ++j) prefetch();
+    int row = row_first;
+    for (int b = 0; b < nfull; ++b) {
+        prefetch();
+        cp_async_wait<RING_D - 1>();
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = lds_f2(out_addr + k * 256u);
+        out_addr += R * 256u;
+        if (out_addr == my_end) out_addr = my;
+#pragma unroll
+        for (int dgl = 0; dgl < R + NSEC - 1; ++dgl) {
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                const int r = dgl - s;
+                if (r >= 0 && r < R) x[r] = delta_step(x[r], sec[s], m4);
+            }
+        }
+        if (row >= row_store) {
+#pragma unroll
+            for (int k = 0; k < R; ++k) __stcs(reinterpret_cast<float2*>(op + (uint32_t)k * out_ldb), __fmul2_rn(x[k], gain));
+        }
+        op += (int64_t)R * out_ldb;
+        row += R;
+    }
+    cp_async_wait<0>();
+    // ragged tail (< R rows; only the sub-range that ends the launch has one)
+    {
+        const float* srcp = a.src + (int64_t)row * a.src_ld + c0;
+        float* outp = a.out + (int64_t)row * a.ld_out + c0;
+        for (; row < row_end; ++row) {
+            float2 x = *reinterpret_cast<const float2*>(srcp);
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) x = delta_step(x, sec[s], m4);
+            *reinterpret_cast<float2*>(outp) = __fmul2_rn(x, gain);
+            srcp += a.src_ld;
+            outp += a.ld_out;
+        }
+    }
+    if (row_end == a.frames) {                // the sub-range that finishes the launch carries the state on
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
+            const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
+            double s1, s2;
+            delta_state_out(g.x, d.x, sec[s].be.x, sec[s].D.x, sec[s].Z.x, s1, s2);
+            a.state_out[(size_t)(s * 2 + 0) * C + c0] = s1;
+            a.state_out[(size_t)(s * 2 + 1) * C + c0] = s2;
+            delta_state_out(g.y, d.y, sec[s].be.y, sec[s].D.y, sec[s].Z.y, s1, s2);
+            a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = s1;
+            a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = s2;
+        }
+    }
+  }
+}
+
+int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
+    switch (a->nsec) {
+        case 3: k_cascade_delta<3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 4: k_cascade_delta<4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 5: k_cascade_delta<5><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 6: k_cascade_delta<6><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_delta<7><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        default: k_cascade_delta<8><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+    }
+    return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -724,11 +923,15 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     for (int k = 0; k < a->nsec; ++k) any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
     // continuous software pipeline over rows (A/B); its 2 lp - s2 update would not keep a first-order section's s2 at 0
     const bool streaming = fast && variant == 3 && !any_first;
+    // delta form (5 operations per section instead of 6): second-order low-pass sections only; variant 4 keeps the
+    // state-variable form in 8-row blocks for A/B
+    const bool delta = fast && (variant == 0 || variant == 2) && !any_first && !(a->sec_kind[0] & SEC_HP);
     const int R = wide ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0) : reg_min_blocks(a->nsec, R)) * RWARPS;
+    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0)
+                              : delta   ? delta_min_blocks(a->nsec) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -747,6 +950,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
     if (streaming) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
                           : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
+    if (delta) return delta_launch_nsec(a, grid, tiles, npieces, warm, st);
     if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
                         : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
     if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)
