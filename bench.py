@@ -45,7 +45,7 @@ METRIC = 'voice-samples/sec'
 DEFAULTS = {'c2': (4096, 10.0, 20, 10), 'c2m': (4096, 10.0, 10, 0), 'c3': (65536, 10.0, 5, 3), 'c4': (16384, 60.0, 2, 1), 'c5': (1 << 20, 10.0, 3, 2)}
 EXTRA_STEPS = {'c3': 5, 'c4': 2, 'c5': 3, 'c2m': 20}
 EXTRA_WARMUP = {'c2m': 10}      # millisecond steps right after a CPU-only phase: let the clocks come back up first
-FMA_PROBE_CEILING = 96.0        # FMA lane-ops / clk / SM the section arithmetic reaches register-only (profiles/r01_fma_probe.txt)
+FMA_PROBE_CEILING = 100.0       # FP32 lane-ops / clk / SM the delta-form section arithmetic reaches register-only (profiles/r02_fma_probe.txt; 96 for the state-variable form)
 
 
 def parse_args():
@@ -200,8 +200,8 @@ class C3(Workload):
 
 class C4(Workload):
     name = 'C4: 8-biquad low-pass cascade on %d channels x %g s @ 48 kHz per GPU, streamed in %g s slabs with carried state'
-    kernel = 'k_cascade_reg (two channels per thread, all 8 sections in registers, equal time pieces per warp slot)'
-    traffic_profile = 'r01_k_cascade_reg_full.txt'
+    kernel = 'k_cascade_delta (two channels per thread, all 8 sections in registers in delta form: 3 FFMA2 + 2 FADD2 per section, equal time pieces per warp slot)'
+    traffic_profile = 'r02_k_cascade_delta_full.txt'
     bound = 'hbm'
     bytes_per_unit = 8.0
 
@@ -721,10 +721,14 @@ def measure(ctx, wl, steps, warmup, e2e_steps, cpu_baseline):
             roof['traffic_unit'] = 'bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)'
             roof['traffic_source'] = 'profiles/' + wl.traffic_profile
         if isinstance(wl, C4):
-            # the co-limit: 8 sections x (1 FADD2 + 5 FFMA2) per two channel-samples = 48 FP32 lane-ops per channel-sample
+            # the co-limit: the FP32 pipe.  Delta-form sections (k_cascade_delta, default): 8 x (3 FFMA2 + 2 FADD2) per two
+            # channel-samples = 40 lane-ops per channel-sample; state-variable sections (reg_variant 1 / 3 / 4): 8 x 6 = 48
+            svf = any(o.startswith('reg_variant=') and o.split('=')[1] in ('1', '3', '4') for o in ctx.args.plan_opt)
+            lane_ops = 48.0 if svf else 40.0
             sm_mhz = clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
-            fma = 48.0 * wl.launch_units() / (launch_ms * 1e-3) / (148 * sm_mhz * 1e6)
+            fma = lane_ops * wl.launch_units() / (launch_ms * 1e-3) / (148 * sm_mhz * 1e6)
             roof['fma_lane_ops_per_clk_sm'] = fma
+            roof['fma_lane_ops_per_channel_sample'] = lane_ops
             roof['fma_probe_ceiling'] = FMA_PROBE_CEILING
             roof['fma_frac_of_probe'] = fma / FMA_PROBE_CEILING
     else:

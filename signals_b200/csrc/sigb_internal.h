@@ -182,6 +182,7 @@ int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, int sections_p
 int sigb_cascade_reg_ok(const ChainDev* a);
 int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream);
 void sigb_set_reg_pieces(int n);
+void sigb_set_delta_probe(int n);
 int sigb_osc_reg_ok(const ChainDev* a);
 int sigb_launch_osc_reg(const ChainDev* a, int max_segments, void* stream);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);

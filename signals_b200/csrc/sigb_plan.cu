@@ -2129,6 +2129,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "scan_split") sigb_set_scan_split((int)value);
     else if (k == "scan_rot") sigb_set_scan_rot((int)value);       // process-wide switch (A/B testing)
     else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
+    else if (k == "delta_probe") sigb_set_delta_probe((int)value); // process-wide switch (A/B testing)
     else if (k == "bank_unroll") sigb_set_bank_unroll((int)value); // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);
     rt_drop_graphs(plan);            // captured launches embody the old choice

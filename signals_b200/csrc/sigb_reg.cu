@@ -362,12 +362,15 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 // rows in wavefront order, equal time pieces per warp slot, warp-private cp.async ring) with the sections in DELTA
 // FORM (above).  FAST layout only (host-checked), second-order low-pass sections only.
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int delta_min_blocks(int nsec) { return nsec <= 6 ? 5 : 4; }
+// resident CTAs per SM: 10 registers per section + the block's rows.  8 sections at 4 CTAs (128 registers) spill; measured on
+// C4 (same box, alternating): 4 / 3 / 2 CTAs per SM = 0.672-0.678 / 0.694-0.697 and 0.719-0.726 / 0.732 of the HBM peak -- the
+// section chains supply the instruction-level parallelism, the cp.async ring hides the loads, and fewer warp slots mean
+// fewer time pieces, i.e. less warm-up
+__host__ __device__ constexpr int delta_min_blocks(int nsec) { return nsec <= 6 ? 5 : nsec == 7 ? 4 : 2; }
 
-template <int NSEC>
-__global__ void __launch_bounds__(RWARPS * 32, delta_min_blocks(NSEC))
+template <int NSEC, int R, int MINB, int WR = R>
+__global__ void __launch_bounds__(RWARPS * 32, MINB)
 k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
-    constexpr int R = 8;
     __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
     const int lane = threadIdx.x & 31;
@@ -439,11 +442,14 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         out_addr += R * 256u;
         if (out_addr == my_end) out_addr = my;
 #pragma unroll
-        for (int dgl = 0; dgl < R + NSEC - 1; ++dgl) {
+        for (int h = 0; h < R; h += WR) {                 // wavefronts of WR rows
 #pragma unroll
-            for (int s = 0; s < NSEC; ++s) {
-                const int r = dgl - s;
-                if (r >= 0 && r < R) x[r] = delta_step(x[r], sec[s], m4);
+            for (int dgl = 0; dgl < WR + NSEC - 1; ++dgl) {
+#pragma unroll
+                for (int s = 0; s < NSEC; ++s) {
+                    const int r = dgl - s;
+                    if (r >= 0 && r < WR) x[h + r] = delta_step(x[h + r], sec[s], m4);
+                }
             }
         }
         if (row >= row_store) {
@@ -484,14 +490,25 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
   }
 }
 
+int g_delta_probe = 0;          // A/B (NSEC = 8 only): 0 default geometry (8-row blocks, 2 CTAs/SM); 1 / 2: 4-row blocks, 4 / 5 CTAs/SM;
+                                // 3 / 6: 8-row blocks, 4 / 3 CTAs/SM; 4 / 5: wavefronts of 4 rows, 4 / 3 CTAs/SM
+
 int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     switch (a->nsec) {
-        case 3: k_cascade_delta<3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 4: k_cascade_delta<4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 5: k_cascade_delta<5><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 6: k_cascade_delta<6><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 7: k_cascade_delta<7><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        default: k_cascade_delta<8><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 3: k_cascade_delta<3, 8, delta_min_blocks(3)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 4: k_cascade_delta<4, 8, delta_min_blocks(4)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 5: k_cascade_delta<5, 8, delta_min_blocks(5)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 6: k_cascade_delta<6, 8, delta_min_blocks(6)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_delta<7, 8, delta_min_blocks(7)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        default:
+            if (g_delta_probe == 1) k_cascade_delta<8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (g_delta_probe == 2) k_cascade_delta<8, 4, 5><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (g_delta_probe == 3) k_cascade_delta<8, 8, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (g_delta_probe == 6) k_cascade_delta<8, 8, 3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (g_delta_probe == 4) k_cascade_delta<8, 8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (g_delta_probe == 5) k_cascade_delta<8, 8, 3, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else k_cascade_delta<8, 8, delta_min_blocks(8)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            break;
     }
     return (int)cudaGetLastError();
 }
@@ -900,6 +917,7 @@ int osc_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int wa
 // Whether the register-resident kernel can take this chain: a static property of the chain (never of a
 // particular call's pointers): a materialised source and 3..8 second-order sections of one kind.
 extern "C" void sigb_set_reg_pieces(int n) { g_reg_pieces = n; }
+extern "C" void sigb_set_delta_probe(int n) { g_delta_probe = n; }
 
 extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
@@ -926,12 +944,13 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     // delta form (5 operations per section instead of 6): second-order low-pass sections only; variant 4 keeps the
     // state-variable form in 8-row blocks for A/B
     const bool delta = fast && (variant == 0 || variant == 2) && !any_first && !(a->sec_kind[0] & SEC_HP);
-    const int R = wide ? 8 : 4;
+    const int dprobe = (delta && a->nsec == 8) ? g_delta_probe : 0;
+    const int R = (wide && dprobe != 1 && dprobe != 2) ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0)
-                              : delta   ? delta_min_blocks(a->nsec) : reg_min_blocks(a->nsec, R)) * RWARPS;
+                              : delta   ? (dprobe == 1 || dprobe == 3 || dprobe == 4 ? 4 : dprobe == 2 ? 5 : dprobe == 5 || dprobe == 6 ? 3 : delta_min_blocks(a->nsec)) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;

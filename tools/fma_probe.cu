@@ -422,6 +422,46 @@ __global__ void k_secdl(float* out, float g) {
     if (acc.x + acc.y == 123.456f) out[0] = acc.x;
 }
 
+// delta form with TIME-PAIR lanes: the two lanes of a packed register are two time pieces of ONE channel, so the two
+// coefficients are scalars taken in broadcast form (fewer register-file words per instruction)
+struct SecDls { float a, be; float2 D, Z, P; };
+__device__ __forceinline__ float2 stepdls(float2 x, SecDls& r, const float m4) {
+    const float2 w = ffma2(make_float2(m4, m4), r.Z, x);
+    r.D = ffma2(make_float2(r.a, r.a), r.D, w);
+    const float2 zn = ffma2(make_float2(r.be, r.be), r.D, r.Z);
+    const float2 p = __fadd2_rn(zn, r.Z);
+    r.Z = zn;
+    const float2 o = __fadd2_rn(p, r.P);
+    r.P = p;
+    return o;
+}
+template <int NS, int R>
+__global__ void k_secdls(float* out, float g) {
+    SecDls s[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const float gg = g * (1.0f + 0.01f * i + 1e-4f * threadIdx.x);
+        s[i].a = 1.0f - gg;
+        s[i].be = gg * gg * 0.25f;
+        s[i].D = s[i].Z = s[i].P = make_float2(0.f, 0.f);
+    }
+    float m4 = -4.0f;
+    asm volatile("" : "+f"(m4));
+    float2 acc = make_float2(0.f, 0.f);
+    for (int it = 0; it < ITERS / R; ++it) {
+        float2 x[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) x[k] = make_float2(__int_as_float(0x3f800000 | ((it * R + k) * 2654435 & 0x7fffff)) - 1.5f, 0.25f);
+#pragma unroll
+        for (int d = 0; d < R + NS - 1; ++d)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { const int r = d - i; if (r >= 0 && r < R) x[r] = stepdls(x[r], s[i], m4); }
+#pragma unroll
+        for (int k = 0; k < R; ++k) { acc.x += x[k].x; acc.y += x[k].y; }
+    }
+    if (acc.x + acc.y == 123.456f) out[0] = acc.x;
+}
+
 template <typename F>
 static double time_ms(F launch) {
     cudaEvent_t a, b;
@@ -480,6 +520,8 @@ int main() {
     REPORT("cascade 8 sec packed DF2T, R=4", 80, 40, (k_sec5<8, 4, 2><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed DELTA (3 FFMA2 + 2 FADD2), R=4", 80, 40, (k_secdl<8, 4><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed DELTA (3 FFMA2 + 2 FADD2), R=8", 80, 40, (k_secdl<8, 8><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec DELTA, time-pair lanes (scalar coef), R=4", 80, 40, (k_secdls<8, 4><<<blocks, threads>>>(out, 0.05f)))
+    REPORT("cascade 8 sec DELTA, time-pair lanes (scalar coef), R=8", 80, 40, (k_secdls<8, 8><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec packed f32, R=8", 96, 48, (k_sec2<8, 8><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 8 sec scalar f32, R=4", 96, 96, (k_sec1<8, 4><<<blocks, threads>>>(out, 0.05f)))
     REPORT("cascade 6 f32x2 + 2 f64, R=4", 96, 36 + 24, (k_secmix<6, 2, 4><<<blocks, threads>>>(out, 0.05f)))
