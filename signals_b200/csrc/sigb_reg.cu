@@ -118,11 +118,26 @@ __device__ __forceinline__ void load_section(const ChainDev& a, int s, int ca, i
 // cutoffs (state-variable form 8.0e-7), 5.7e-6 at 20 Hz (1.3e-6), 1.2e-6 at 20 kHz (7.7e-7): inside the 1e-4 bar.
 // ---------------------------------------------------------------------------------------------------------
 struct DeltaSec {
-    float2 a, be;               // (a2) (F / 4)
-    float2 D, Z, P;
+    float2 a, be;               // low-pass: (a2) (F / 4);   high-pass: (-Q) (-F)
+    float2 D, Z, P;             // high-pass: Z holds -4 Z, P holds the section's output scale d = 1 / (1 + r2 g + g^2)
 };
 
-__device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2 m4) {
+// HIGH-PASS sections in the same variables (all-high-pass cascades): hp[n] = (y[n] - 2 y[n-1] + y[n-2]) / 4 g^2 is the second
+// difference of the all-pole output, and the recurrence hands it over without a subtraction of neighbours:
+//     t = w - Q D,   D' = D + t  (= a D + w),   hp = d t          with w = x - 4 Z,  Q = 1 - a2 = 2 r2 g d,  d = F / 4 g^2.
+// The output scale d rides on the NEXT section's first instruction (w' = d t - 4 Z' as one FFMA2 on the state -4 Z'), the
+// last one's on the gain: 4 operations per section (FFMA2, FFMA2, FADD2, FFMA2) against 7 in state-variable form.
+// Same states, same conversion.  Float32 error against the float64 cascade, 8 sections x 30 s (tools/delta_form_sim_hp.c):
+// 3.1e-7 at 200 Hz (state-variable form 4.5e-7), 5.3e-7 at 20 Hz (4.9e-7), 2.7e-6 at 20 kHz (1.5e-6).
+template <int KIND>
+__device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2 m4, bool first, const float2 cprev) {
+    if (KIND & SEC_HP) {
+        const float2 w = first ? __fadd2_rn(x, r.Z) : __ffma2_rn(cprev, x, r.Z);
+        const float2 t = __ffma2_rn(r.a, r.D, w);
+        r.D = __fadd2_rn(r.D, t);
+        r.Z = __ffma2_rn(r.be, r.D, r.Z);
+        return t;
+    }
     const float2 w = __ffma2_rn(m4, r.Z, x);
     r.D = __ffma2_rn(r.a, r.D, w);
     const float2 zn = __ffma2_rn(r.be, r.D, r.Z);
@@ -134,26 +149,40 @@ __device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2
 }
 
 // coefficients from the plan's float32 {g, c, d} entries (the very numbers the other kernels filter with), derived in
-// float64 so that a and F/4 carry one rounding each
-__device__ __forceinline__ void delta_coef(float g, float c, float d, float& a, float& be) {
+// float64 so that each carries one rounding
+template <int KIND>
+__device__ __forceinline__ void delta_coef(float g, float c, float d, float& a, float& be, float& P) {
     const double G = (double)g, Dd = (double)d, R2 = (double)c - G;
-    a = (float)(1.0 - 2.0 * R2 * G * Dd);
-    be = (float)(G * G * Dd);
+    if (KIND & SEC_HP) {
+        a = (float)(-2.0 * R2 * G * Dd);
+        be = (float)(-4.0 * G * G * Dd);
+        P = d;
+    } else {
+        a = (float)(1.0 - 2.0 * R2 * G * Dd);
+        be = (float)(G * G * Dd);
+    }
 }
 // State hand-over.  D and Z are the recurrent states and survive a store / load round trip bit for bit (s1 = 2 g d D and
-// s2 = 4 Z - 2 be D are formed in float64 from float32 factors, and the load inverts them with the same float32 be);
-// P is only the one-row memory of the second zero and comes back as s2 / 2, equal to the running value up to one
-// float32 rounding -- so a stream cut into several requests differs from the uncut one by rounding noise (~1e-7), not
-// bit for bit as with the state-variable kernels.
+// s2 = 4 Z - (F/2) D are formed in float64 from float32 factors, and the load inverts them with the same float32 F);
+// the low-pass P is only the one-row memory of the second zero and comes back as s2 / 2, equal to the running value up to
+// one float32 rounding -- so a low-pass stream cut into several requests differs from the uncut one by rounding noise
+// (~1e-7), not bit for bit as with the state-variable kernels.
+template <int KIND>
 __device__ __forceinline__ void delta_state_in(float g, float d, float be, double s1, double s2, float& D, float& Z, float& P) {
     const double Dd = s1 / (2.0 * (double)g * (double)d);
     D = (float)Dd;
-    Z = (float)(0.25 * (s2 + 2.0 * (double)be * Dd));
-    P = (float)(0.5 * s2);
+    if (KIND & SEC_HP) {
+        Z = (float)(0.5 * (double)be * Dd - s2);            // -4 Z = -(s2 + (F/2) D), be = -F
+    } else {
+        Z = (float)(0.25 * (s2 + 2.0 * (double)be * Dd));
+        P = (float)(0.5 * s2);
+    }
 }
+template <int KIND>
 __device__ __forceinline__ void delta_state_out(float g, float d, float be, float D, float Z, double& s1, double& s2) {
     s1 = 2.0 * (double)g * (double)d * (double)D;
-    s2 = 4.0 * (double)Z - 2.0 * (double)be * (double)D;
+    if (KIND & SEC_HP) s2 = 0.5 * (double)be * (double)D - (double)Z;
+    else s2 = 4.0 * (double)Z - 2.0 * (double)be * (double)D;
 }
 
 constexpr int RING_D = 4;       // blocks of R rows per warp in the cp.async ring (RING_D - 1 in flight)
@@ -368,7 +397,7 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 // fewer time pieces, i.e. less warm-up
 __host__ __device__ constexpr int delta_min_blocks(int nsec) { return nsec <= 6 ? 5 : nsec == 7 ? 4 : 2; }
 
-template <int NSEC, int R, int MINB, int WR = R>
+template <int NSEC, int R, int MINB, int WR = R, int KIND = 0>
 __global__ void __launch_bounds__(RWARPS * 32, MINB)
 k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
     __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
@@ -401,17 +430,19 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
         const float2 c = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 1) * C + c0);
         const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
-        delta_coef(g.x, c.x, d.x, sec[s].a.x, sec[s].be.x);
-        delta_coef(g.y, c.y, d.y, sec[s].a.y, sec[s].be.y);
+        delta_coef<KIND>(g.x, c.x, d.x, sec[s].a.x, sec[s].be.x, sec[s].P.x);
+        delta_coef<KIND>(g.y, c.y, d.y, sec[s].a.y, sec[s].be.y, sec[s].P.y);
         if (row_first == 0) {
-            delta_state_in(g.x, d.x, sec[s].be.x, a.state[(size_t)(s * 2 + 0) * C + c0], a.state[(size_t)(s * 2 + 1) * C + c0], sec[s].D.x, sec[s].Z.x, sec[s].P.x);
-            delta_state_in(g.y, d.y, sec[s].be.y, a.state[(size_t)(s * 2 + 0) * C + c0 + 1], a.state[(size_t)(s * 2 + 1) * C + c0 + 1], sec[s].D.y, sec[s].Z.y, sec[s].P.y);
+            delta_state_in<KIND>(g.x, d.x, sec[s].be.x, a.state[(size_t)(s * 2 + 0) * C + c0], a.state[(size_t)(s * 2 + 1) * C + c0], sec[s].D.x, sec[s].Z.x, sec[s].P.x);
+            delta_state_in<KIND>(g.y, d.y, sec[s].be.y, a.state[(size_t)(s * 2 + 0) * C + c0 + 1], a.state[(size_t)(s * 2 + 1) * C + c0 + 1], sec[s].D.y, sec[s].Z.y, sec[s].P.y);
         } else {
-            sec[s].D = sec[s].Z = sec[s].P = make_float2(0.0f, 0.0f);
+            sec[s].D = sec[s].Z = make_float2(0.0f, 0.0f);
+            if (!(KIND & SEC_HP)) sec[s].P = make_float2(0.0f, 0.0f);
         }
     }
     float2 gain = make_float2(1.0f, 1.0f);
     if (a.gain) gain = *reinterpret_cast<const float2*>(a.gain + c0);
+    if (KIND & SEC_HP) gain = __fmul2_rn(gain, sec[NSEC - 1].P);          // the last section's output scale
 
     const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
     char* op = reinterpret_cast<char*>(a.out + (int64_t)row_first * a.ld_out + c0);
@@ -448,7 +479,7 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
 #pragma unroll
                 for (int s = 0; s < NSEC; ++s) {
                     const int r = dgl - s;
-                    if (r >= 0 && r < WR) x[h + r] = delta_step(x[h + r], sec[s], m4);
+                    if (r >= 0 && r < WR) x[h + r] = delta_step<KIND>(x[h + r], sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].P);
                 }
             }
         }
@@ -467,7 +498,7 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         for (; row < row_end; ++row) {
             float2 x = *reinterpret_cast<const float2*>(srcp);
 #pragma unroll
-            for (int s = 0; s < NSEC; ++s) x = delta_step(x, sec[s], m4);
+            for (int s = 0; s < NSEC; ++s) x = delta_step<KIND>(x, sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].P);
             *reinterpret_cast<float2*>(outp) = __fmul2_rn(x, gain);
             srcp += a.src_ld;
             outp += a.ld_out;
@@ -479,10 +510,10 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
             const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
             const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
             double s1, s2;
-            delta_state_out(g.x, d.x, sec[s].be.x, sec[s].D.x, sec[s].Z.x, s1, s2);
+            delta_state_out<KIND>(g.x, d.x, sec[s].be.x, sec[s].D.x, sec[s].Z.x, s1, s2);
             a.state_out[(size_t)(s * 2 + 0) * C + c0] = s1;
             a.state_out[(size_t)(s * 2 + 1) * C + c0] = s2;
-            delta_state_out(g.y, d.y, sec[s].be.y, sec[s].D.y, sec[s].Z.y, s1, s2);
+            delta_state_out<KIND>(g.y, d.y, sec[s].be.y, sec[s].D.y, sec[s].Z.y, s1, s2);
             a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = s1;
             a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = s2;
         }
@@ -490,24 +521,23 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
   }
 }
 
-int g_delta_probe = 0;          // A/B (NSEC = 8 only): 0 default geometry (8-row blocks, 2 CTAs/SM); 1 / 2: 4-row blocks, 4 / 5 CTAs/SM;
-                                // 3 / 6: 8-row blocks, 4 / 3 CTAs/SM; 4 / 5: wavefronts of 4 rows, 4 / 3 CTAs/SM
+int g_delta_probe = 0;          // A/B (8 low-pass sections only): 0 default geometry (8-row blocks, 2 CTAs/SM); 1: 4-row blocks, 4 CTAs/SM;
+                                // 3 / 6: 8-row blocks, 4 / 3 CTAs/SM
 
+// high-pass sections keep two coefficient pairs, an output scale and two states (same 10 registers as a low-pass section)
+template <int KIND>
 int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     switch (a->nsec) {
-        case 3: k_cascade_delta<3, 8, delta_min_blocks(3)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 4: k_cascade_delta<4, 8, delta_min_blocks(4)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 5: k_cascade_delta<5, 8, delta_min_blocks(5)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 6: k_cascade_delta<6, 8, delta_min_blocks(6)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 7: k_cascade_delta<7, 8, delta_min_blocks(7)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 3: k_cascade_delta<3, 8, delta_min_blocks(3), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 4: k_cascade_delta<4, 8, delta_min_blocks(4), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 5: k_cascade_delta<5, 8, delta_min_blocks(5), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 6: k_cascade_delta<6, 8, delta_min_blocks(6), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_delta<7, 8, delta_min_blocks(7), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         default:
-            if (g_delta_probe == 1) k_cascade_delta<8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else if (g_delta_probe == 2) k_cascade_delta<8, 4, 5><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else if (g_delta_probe == 3) k_cascade_delta<8, 8, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else if (g_delta_probe == 6) k_cascade_delta<8, 8, 3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else if (g_delta_probe == 4) k_cascade_delta<8, 8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else if (g_delta_probe == 5) k_cascade_delta<8, 8, 3, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else k_cascade_delta<8, 8, delta_min_blocks(8)><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            if (KIND == 0 && g_delta_probe == 1) k_cascade_delta<8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (KIND == 0 && g_delta_probe == 3) k_cascade_delta<8, 8, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (KIND == 0 && g_delta_probe == 6) k_cascade_delta<8, 8, 3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else k_cascade_delta<8, 8, delta_min_blocks(8), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             break;
     }
     return (int)cudaGetLastError();
@@ -941,16 +971,16 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     for (int k = 0; k < a->nsec; ++k) any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
     // continuous software pipeline over rows (A/B); its 2 lp - s2 update would not keep a first-order section's s2 at 0
     const bool streaming = fast && variant == 3 && !any_first;
-    // delta form (5 operations per section instead of 6): second-order low-pass sections only; variant 4 keeps the
-    // state-variable form in 8-row blocks for A/B
-    const bool delta = fast && (variant == 0 || variant == 2) && !any_first && !(a->sec_kind[0] & SEC_HP);
-    const int dprobe = (delta && a->nsec == 8) ? g_delta_probe : 0;
-    const int R = (wide && dprobe != 1 && dprobe != 2) ? 8 : 4;
+    // delta form (5 operations per low-pass section, 4 per high-pass section, instead of 6 / 7): second-order sections only;
+    // variant 4 keeps the state-variable form in 8-row blocks for A/B
+    const bool delta = fast && (variant == 0 || variant == 2) && !any_first;
+    const int dprobe = (delta && a->nsec == 8 && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
+    const int R = (wide && dprobe != 1) ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0)
-                              : delta   ? (dprobe == 1 || dprobe == 3 || dprobe == 4 ? 4 : dprobe == 2 ? 5 : dprobe == 5 || dprobe == 6 ? 3 : delta_min_blocks(a->nsec)) : reg_min_blocks(a->nsec, R)) * RWARPS;
+                              : delta   ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec)) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -969,7 +999,8 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
     if (streaming) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
                           : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
-    if (delta) return delta_launch_nsec(a, grid, tiles, npieces, warm, st);
+    if (delta) return (a->sec_kind[0] & SEC_HP) ? delta_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, st)
+                                                : delta_launch_nsec<0>(a, grid, tiles, npieces, warm, st);
     if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
                         : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
     if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)

@@ -417,7 +417,8 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     # state-variable sections of k_cascade_reg in 8-row blocks
     for ch, nsec, btype, variant in [(200, 8, 'lp', 0), (68, 5, 'hp', 0), (67, 4, 'lp', 0), (4, 3, 'hp', 0), (128, 8, 'lp', 0),
                                      (128, 8, 'lp', 1), (64, 3, 'hp', 1), (320, 6, 'lp', 0), (64, 7, 'hp', 0), (128, 8, 'lp', 4),
-                                     (64, 3, 'lp', 0), (192, 7, 'lp', 0), (64, 4, 'lp', 0), (64, 5, 'lp', 0)]:
+                                     (64, 3, 'lp', 0), (192, 7, 'lp', 0), (64, 4, 'lp', 0), (64, 5, 'lp', 0), (128, 8, 'hp', 0), (64, 4, 'hp', 0),
+                                     (64, 6, 'hp', 0), (64, 5, 'hp', 4)]:
         frames = 6000
         x = rng.uniform(-1, 1, (frames, ch)).astype(np.float32)
         cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (nsec, ch)))
@@ -446,8 +447,9 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
         assert err <= 1e-4
         assert max_abs_err(whole, piped) <= 2e-5
         if btype == 'lp' and ch % 64 == 0 and variant == 0:
-            # delta form: the recurrent states survive the hand-over bit for bit, the one-row memory of a section's second
-            # zero is re-derived from them (one float32 rounding): chunked and unchunked differ by rounding noise
+            # delta form, low-pass: the recurrent states survive the hand-over bit for bit, the one-row memory of a section's
+            # second zero is re-derived from them (one float32 rounding): chunked and unchunked differ by rounding noise
+            # (high-pass sections in delta form have no such memory and stay bit-exact)
             assert max_abs_err(parts, whole) <= 5e-7
         else:
             assert np.array_equal(parts, whole)      # sequential in time: chunking cannot change a single bit
@@ -470,7 +472,7 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert max_abs_err(got[:, :ch], want) <= 1e-4
 
 
-@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_svf', 'reg_r4', 'reg_ragged', 'stream3', 'stream3_hp', 'stream3_4sec', 'stream3_ragged_rows'])
+@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_hp', 'reg_svf', 'reg_r4', 'reg_ragged', 'stream3', 'stream3_hp', 'stream3_4sec', 'stream3_ragged_rows'])
 def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
     """k_cascade_pipe / k_cascade_reg cut long renders into time segments that warm up from zero state
     (decayed below 2^-40); every segment must match the float64 cascade, the segmented render must agree
@@ -478,7 +480,7 @@ def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
     from signals_b200.chain import ext
     rng = np.random.default_rng(45)
     ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), (4 if kernel == 'stream3_4sec' else 8), (60003 if kernel == 'stream3_ragged_rows' else 60000)
-    cls, btype = ('HighPass', 'hp') if kernel == 'stream3_hp' else ('LowPass', 'lp')
+    cls, btype = ('HighPass', 'hp') if kernel in ('stream3_hp', 'reg_hp') else ('LowPass', 'lp')
     x = rng.uniform(-1, 1, (frames + 4000, ch)).astype(np.float32)
     cut = np.exp(rng.uniform(np.log(600.0), np.log(8000.0), (nsec, ch)))
     node = ext.Buffer(x)
