@@ -8,7 +8,7 @@ for spec in $1; do
   case $c in
     c2) A="--config c2 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline $C2_EXTRA";;
     c3) A="--config c3 --seconds 2 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
-    c4) A="--config c4 --seconds 5 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
+    c4) A="--config c4 --seconds 10 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
     c5) A="--config c5 --seconds 1 --steps 1 --warmup 3 --e2e-steps 0 --no-cpu-baseline";;
   esac
   timeout 300 python bench.py $A > gpurun_out/plain_${c}_$TAG.log 2>&1 &&
