@@ -1,4 +1,4 @@
-// k_cascade_reg / k_osc_reg: register-resident filter cascades (sm_100a) for deep cascades on many channels
+// k_cascade_delta / k_cascade_reg / k_osc_reg: register-resident filter cascades (sm_100a) for deep cascades on many channels
 // (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384 channels x 60 s).
 //
 // k_cascade_pipe hands every chunk from section to section through shared memory (one LDS.64 + one STS.64
@@ -118,9 +118,11 @@ __device__ __forceinline__ void load_section(const ChainDev& a, int s, int ca, i
 // cutoffs (state-variable form 8.0e-7), 5.7e-6 at 20 Hz (1.3e-6), 1.2e-6 at 20 kHz (7.7e-7): inside the 1e-4 bar.
 // ---------------------------------------------------------------------------------------------------------
 struct DeltaSec {
-    float2 a, be;               // low-pass: (a2) (F / 4);   high-pass: (-Q) (-F)
-    float2 D, Z, P;             // high-pass: Z holds -4 Z, P holds the section's output scale d = 1 / (1 + r2 g + g^2)
+    float2 a, be;               // low-pass: (a2) (F / 4);   high-pass and mixed cascades: (-Q) (-F)
+    float2 c;                   // high-pass and mixed cascades: scale of the value handed to the next section
+    float2 D, Z, P;             // high-pass and mixed cascades: Z holds -4 Z (and P, the low-pass memory, -4 P)
 };
+constexpr int SEC_MIXED = 4;    // kernel template value: low- and high-pass sections in one cascade (kind per section at run time)
 
 // HIGH-PASS sections in the same variables (all-high-pass cascades): hp[n] = (y[n] - 2 y[n-1] + y[n-2]) / 4 g^2 is the second
 // difference of the all-pole output, and the recurrence hands it over without a subtraction of neighbours:
@@ -129,13 +131,26 @@ struct DeltaSec {
 // last one's on the gain: 4 operations per section (FFMA2, FFMA2, FADD2, FFMA2) against 7 in state-variable form.
 // Same states, same conversion.  Float32 error against the float64 cascade, 8 sections x 30 s (tools/delta_form_sim_hp.c):
 // 3.1e-7 at 200 Hz (state-variable form 4.5e-7), 5.3e-7 at 20 Hz (4.9e-7), 2.7e-6 at 20 kHz (1.5e-6).
+// MIXED cascades (low- and high-pass sections in any order) run both forms on the shared states in the scaling of the
+// high-pass form: the four instructions of the high-pass section, the low-pass section's two adds (on -4 Z, so the value is
+// -4 lp and the scale handed on is -1/4), and a select by the section's kind -- 6 FP32-pipe operations + a select on the
+// ALU pipe per section, the cost of a state-variable section, instead of the section-pipelined kernel's shared-memory
+// hand-offs.
 template <int KIND>
-__device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2 m4, bool first, const float2 cprev) {
-    if (KIND & SEC_HP) {
+__device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2 m4, bool first, const float2 cprev, bool is_hp) {
+    if (KIND & (SEC_HP | SEC_MIXED)) {
         const float2 w = first ? __fadd2_rn(x, r.Z) : __ffma2_rn(cprev, x, r.Z);
         const float2 t = __ffma2_rn(r.a, r.D, w);
         r.D = __fadd2_rn(r.D, t);
-        r.Z = __ffma2_rn(r.be, r.D, r.Z);
+        const float2 zn = __ffma2_rn(r.be, r.D, r.Z);
+        if (KIND & SEC_MIXED) {
+            const float2 p = __fadd2_rn(zn, r.Z);
+            const float2 o = __fadd2_rn(p, r.P);
+            r.P = p;
+            r.Z = zn;
+            return is_hp ? t : o;
+        }
+        r.Z = zn;
         return t;
     }
     const float2 w = __ffma2_rn(m4, r.Z, x);
@@ -151,12 +166,12 @@ __device__ __forceinline__ float2 delta_step(float2 x, DeltaSec& r, const float2
 // coefficients from the plan's float32 {g, c, d} entries (the very numbers the other kernels filter with), derived in
 // float64 so that each carries one rounding
 template <int KIND>
-__device__ __forceinline__ void delta_coef(float g, float c, float d, float& a, float& be, float& P) {
+__device__ __forceinline__ void delta_coef(float g, float c, float d, bool is_hp, float& a, float& be, float& sc) {
     const double G = (double)g, Dd = (double)d, R2 = (double)c - G;
-    if (KIND & SEC_HP) {
+    if (KIND & (SEC_HP | SEC_MIXED)) {
         a = (float)(-2.0 * R2 * G * Dd);
         be = (float)(-4.0 * G * G * Dd);
-        P = d;
+        sc = is_hp ? d : -0.25f;
     } else {
         a = (float)(1.0 - 2.0 * R2 * G * Dd);
         be = (float)(G * G * Dd);
@@ -171,8 +186,9 @@ template <int KIND>
 __device__ __forceinline__ void delta_state_in(float g, float d, float be, double s1, double s2, float& D, float& Z, float& P) {
     const double Dd = s1 / (2.0 * (double)g * (double)d);
     D = (float)Dd;
-    if (KIND & SEC_HP) {
+    if (KIND & (SEC_HP | SEC_MIXED)) {
         Z = (float)(0.5 * (double)be * Dd - s2);            // -4 Z = -(s2 + (F/2) D), be = -F
+        if (KIND & SEC_MIXED) P = (float)(-2.0 * s2);       // -4 P
     } else {
         Z = (float)(0.25 * (s2 + 2.0 * (double)be * Dd));
         P = (float)(0.5 * s2);
@@ -181,7 +197,7 @@ __device__ __forceinline__ void delta_state_in(float g, float d, float be, doubl
 template <int KIND>
 __device__ __forceinline__ void delta_state_out(float g, float d, float be, float D, float Z, double& s1, double& s2) {
     s1 = 2.0 * (double)g * (double)d * (double)D;
-    if (KIND & SEC_HP) s2 = 0.5 * (double)be * (double)D - (double)Z;
+    if (KIND & (SEC_HP | SEC_MIXED)) s2 = 0.5 * (double)be * (double)D - (double)Z;
     else s2 = 4.0 * (double)Z - 2.0 * (double)be * (double)D;
 }
 
@@ -395,7 +411,10 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 // C4 (same box, alternating): 4 / 3 / 2 CTAs per SM = 0.672-0.678 / 0.694-0.697 and 0.719-0.726 / 0.732 of the HBM peak -- the
 // section chains supply the instruction-level parallelism, the cp.async ring hides the loads, and fewer warp slots mean
 // fewer time pieces, i.e. less warm-up
-__host__ __device__ constexpr int delta_min_blocks(int nsec) { return nsec <= 6 ? 5 : nsec == 7 ? 4 : 2; }
+__host__ __device__ constexpr int delta_min_blocks(int nsec, int kind = 0) {
+    return (kind & 4) ? (nsec <= 4 ? 4 : nsec <= 6 ? 3 : 2)          // mixed cascades: 12 registers per section
+                      : (nsec <= 6 ? 5 : nsec == 7 ? 4 : 2);
+}
 
 template <int NSEC, int R, int MINB, int WR = R, int KIND = 0>
 __global__ void __launch_bounds__(RWARPS * 32, MINB)
@@ -430,19 +449,19 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
         const float2 c = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 1) * C + c0);
         const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
-        delta_coef<KIND>(g.x, c.x, d.x, sec[s].a.x, sec[s].be.x, sec[s].P.x);
-        delta_coef<KIND>(g.y, c.y, d.y, sec[s].a.y, sec[s].be.y, sec[s].P.y);
+        const bool hp_s = (KIND & SEC_HP) || ((KIND & SEC_MIXED) && (a.sec_kind[s] & SEC_HP));
+        delta_coef<KIND>(g.x, c.x, d.x, hp_s, sec[s].a.x, sec[s].be.x, sec[s].c.x);
+        delta_coef<KIND>(g.y, c.y, d.y, hp_s, sec[s].a.y, sec[s].be.y, sec[s].c.y);
         if (row_first == 0) {
             delta_state_in<KIND>(g.x, d.x, sec[s].be.x, a.state[(size_t)(s * 2 + 0) * C + c0], a.state[(size_t)(s * 2 + 1) * C + c0], sec[s].D.x, sec[s].Z.x, sec[s].P.x);
             delta_state_in<KIND>(g.y, d.y, sec[s].be.y, a.state[(size_t)(s * 2 + 0) * C + c0 + 1], a.state[(size_t)(s * 2 + 1) * C + c0 + 1], sec[s].D.y, sec[s].Z.y, sec[s].P.y);
         } else {
-            sec[s].D = sec[s].Z = make_float2(0.0f, 0.0f);
-            if (!(KIND & SEC_HP)) sec[s].P = make_float2(0.0f, 0.0f);
+            sec[s].D = sec[s].Z = sec[s].P = make_float2(0.0f, 0.0f);
         }
     }
     float2 gain = make_float2(1.0f, 1.0f);
     if (a.gain) gain = *reinterpret_cast<const float2*>(a.gain + c0);
-    if (KIND & SEC_HP) gain = __fmul2_rn(gain, sec[NSEC - 1].P);          // the last section's output scale
+    if (KIND & (SEC_HP | SEC_MIXED)) gain = __fmul2_rn(gain, sec[NSEC - 1].c);   // the last section's output scale
 
     const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
     char* op = reinterpret_cast<char*>(a.out + (int64_t)row_first * a.ld_out + c0);
@@ -479,7 +498,7 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
 #pragma unroll
                 for (int s = 0; s < NSEC; ++s) {
                     const int r = dgl - s;
-                    if (r >= 0 && r < WR) x[h + r] = delta_step<KIND>(x[h + r], sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].P);
+                    if (r >= 0 && r < WR) x[h + r] = delta_step<KIND>(x[h + r], sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].c, (a.sec_kind[s] & SEC_HP) != 0);
                 }
             }
         }
@@ -498,7 +517,7 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         for (; row < row_end; ++row) {
             float2 x = *reinterpret_cast<const float2*>(srcp);
 #pragma unroll
-            for (int s = 0; s < NSEC; ++s) x = delta_step<KIND>(x, sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].P);
+            for (int s = 0; s < NSEC; ++s) x = delta_step<KIND>(x, sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].c, (a.sec_kind[s] & SEC_HP) != 0);
             *reinterpret_cast<float2*>(outp) = __fmul2_rn(x, gain);
             srcp += a.src_ld;
             outp += a.ld_out;
@@ -524,20 +543,21 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
 int g_delta_probe = 0;          // A/B (8 low-pass sections only): 0 default geometry (8-row blocks, 2 CTAs/SM); 1: 4-row blocks, 4 CTAs/SM;
                                 // 3 / 6: 8-row blocks, 4 / 3 CTAs/SM
 
-// high-pass sections keep two coefficient pairs, an output scale and two states (same 10 registers as a low-pass section)
+// high-pass sections keep two coefficient pairs, an output scale and two states (the 10 registers of a low-pass section);
+// mixed cascades three coefficient pairs and three states
 template <int KIND>
 int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     switch (a->nsec) {
-        case 3: k_cascade_delta<3, 8, delta_min_blocks(3), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 4: k_cascade_delta<4, 8, delta_min_blocks(4), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 5: k_cascade_delta<5, 8, delta_min_blocks(5), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 6: k_cascade_delta<6, 8, delta_min_blocks(6), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 7: k_cascade_delta<7, 8, delta_min_blocks(7), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 3: k_cascade_delta<3, 8, delta_min_blocks(3, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 4: k_cascade_delta<4, 8, delta_min_blocks(4, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 5: k_cascade_delta<5, 8, delta_min_blocks(5, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 6: k_cascade_delta<6, 8, delta_min_blocks(6, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_delta<7, 8, delta_min_blocks(7, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         default:
             if (KIND == 0 && g_delta_probe == 1) k_cascade_delta<8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             else if (KIND == 0 && g_delta_probe == 3) k_cascade_delta<8, 8, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             else if (KIND == 0 && g_delta_probe == 6) k_cascade_delta<8, 8, 3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else k_cascade_delta<8, 8, delta_min_blocks(8), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else k_cascade_delta<8, 8, delta_min_blocks(8, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             break;
     }
     return (int)cudaGetLastError();
@@ -949,10 +969,24 @@ int osc_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int wa
 extern "C" void sigb_set_reg_pieces(int n) { g_reg_pieces = n; }
 extern "C" void sigb_set_delta_probe(int n) { g_delta_probe = n; }
 
+// 8-byte loads / stores and no ragged edges: unit channel stride, even leading dimensions, 8-byte aligned bases,
+// whole 64-channel tiles, a source that covers every row
+static bool reg_fast_layout(const ChainDev* a) {
+    return a->src_cs == 1 && (reinterpret_cast<uintptr_t>(a->src) & 7) == 0 && (a->src_ld & 1) == 0 &&
+           (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
+           a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
+}
+
 extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
-    for (int k = 0; k < a->nsec; ++k)
-        if ((a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP)) return 0;      // first-order sections are welcome (load_section)
+    bool mixed = false, any_first = false;
+    for (int k = 0; k < a->nsec; ++k) {
+        mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
+        any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
+    }
+    // one kind: always (first-order sections are welcome, load_section); low- and high-pass sections mixed: k_cascade_delta
+    // only, i.e. second-order sections on the aligned whole-tile layout of THIS call (k_cascade_pipe takes the rest)
+    if (mixed) return !any_first && reg_fast_layout(a);
     return 1;
 }
 
@@ -961,26 +995,26 @@ extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
 extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->frames <= 0) return 0;
-    // 8-byte loads / stores and no ragged edges: unit channel stride, even leading dimensions, 8-byte aligned bases,
-    // whole 64-channel tiles, a source that covers every row
-    const bool fast = a->src_cs == 1 && (reinterpret_cast<uintptr_t>(a->src) & 7) == 0 && (a->src_ld & 1) == 0 &&
-                      (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0 && a->C % RC == 0 &&
-                      a->src_rows >= (int64_t)a->frames && a->src_ld > 0 && a->src_ld < (1 << 26) && a->ld_out > 0 && a->ld_out < (1 << 26);
+    const bool fast = reg_fast_layout(a);
+    bool any_first = false, mixed = false;
+    for (int k = 0; k < a->nsec; ++k) {
+        any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
+        mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
+    }
+    if (mixed) variant = 0;          // only k_cascade_delta runs both kinds in one cascade (sigb_cascade_reg_ok checked the layout)
     const bool wide = fast && variant != 1;
-    bool any_first = false;
-    for (int k = 0; k < a->nsec; ++k) any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
     // continuous software pipeline over rows (A/B); its 2 lp - s2 update would not keep a first-order section's s2 at 0
     const bool streaming = fast && variant == 3 && !any_first;
     // delta form (5 operations per low-pass section, 4 per high-pass section, instead of 6 / 7): second-order sections only;
     // variant 4 keeps the state-variable form in 8-row blocks for A/B
     const bool delta = fast && (variant == 0 || variant == 2) && !any_first;
-    const int dprobe = (delta && a->nsec == 8 && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
+    const int dprobe = (delta && a->nsec == 8 && !mixed && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
     const int R = (wide && dprobe != 1) ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0)
-                              : delta   ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec)) : reg_min_blocks(a->nsec, R)) * RWARPS;
+                              : delta   ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec, mixed ? SEC_MIXED : 0)) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -999,8 +1033,9 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
     if (streaming) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
                           : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
-    if (delta) return (a->sec_kind[0] & SEC_HP) ? delta_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, st)
-                                                : delta_launch_nsec<0>(a, grid, tiles, npieces, warm, st);
+    if (delta) return mixed ? delta_launch_nsec<SEC_MIXED>(a, grid, tiles, npieces, warm, st)
+                      : (a->sec_kind[0] & SEC_HP) ? delta_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, st)
+                                                  : delta_launch_nsec<0>(a, grid, tiles, npieces, warm, st);
     if (wide) return hp ? reg_launch_nsec<SEC_HP, 8, true>(a, grid, tiles, npieces, warm, st)
                         : reg_launch_nsec<0, 8, true>(a, grid, tiles, npieces, warm, st);
     if (fast) return hp ? reg_launch_nsec<SEC_HP, 4, true>(a, grid, tiles, npieces, warm, st)

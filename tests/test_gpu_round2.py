@@ -440,3 +440,76 @@ def test_odd_order_oscillator_chain_on_the_register_kernel(ns, engine):
     err = max_abs_err(got[:, pick], want)
     print(f'osc -> 3 x HighPass order 3: max-abs {err:.3e}')
     assert err <= 1e-4
+
+
+@pytest.mark.parametrize('kinds', ['HHHHLLLL', 'LHLHHLLH', 'LLH', 'HLL', 'HLLLLLL', 'LHHHH'])
+def test_mixed_cascades_on_the_register_kernel(kinds, ns, engine):
+    """Cascades that MIX low- and high-pass sections (a band-pass built from chained HighPass / LowPass nodes) run
+    register-resident in k_cascade_delta -- both kinds on the shared delta-form states, a select per section -- instead of
+    the section-pipelined kernel: against scipy's float64 cascade, against k_cascade_pipe on the same plan, cut into time
+    pieces, streamed in ragged requests, and handing its state to a second call."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(81)
+    ch, frames = 128, 48000
+    x = rng.uniform(-1, 1, (frames + 3000, ch)).astype(np.float32)
+    cut = np.exp(rng.uniform(np.log(500.0), np.log(8000.0), (len(kinds), ch)))
+
+    def graph():
+        node = ext.Buffer(x)
+        for s, k in enumerate(kinds):
+            node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if k == 'H' else 'LowPass')
+        return node
+
+    got = {}
+    for kernel in ('reg', 'pipe'):
+        c = engine.compile(graph(), ch, RATE)
+        c.set_option('cascade_reg', -1 if kernel == 'reg' else 0)
+        first = c.render_device(0, frames).cpu().numpy()
+        second = c.render_device(frames, 3000).cpu().numpy()
+        got[kernel] = np.concatenate([first, second])
+        if kernel == 'reg':
+            c.set_option('pipe_segments', 1)                  # never cut along time
+            c.reset()
+            whole = c.render_device(0, frames).cpu().numpy()
+            c.reset()
+            cuts = [0, 1, 17, 1000, 1016, 4803, 20000, frames]
+            parts = np.concatenate([c.render_device(a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+            assert max_abs_err(first, whole) <= 1e-6
+            assert max_abs_err(parts, whole) <= 5e-7          # the low-pass sections' one-row memory: rounding noise only
+        c.close()
+    want = x.astype(np.float64)
+    pick = rng.choice(ch, 12, replace=False)
+    want = want[:, pick]
+    for s, k in enumerate(kinds):
+        want, _ = np_oracle.render_cascade(want, cut[s:s + 1, pick], RATE, btype='hp' if k == 'H' else 'lp')
+    err = max_abs_err(got['reg'][:, pick], want)
+    print(f'mixed cascade {kinds} on the register kernel: max-abs {err:.3e}; vs the pipelined kernel {max_abs_err(got["reg"], got["pipe"]):.3e}')
+    assert err <= 1e-4
+    assert max_abs_err(got['reg'], got['pipe']) <= 2e-5
+
+
+def test_streams_pass_between_the_cascade_kernels(ns, engine):
+    """One stream, four requests, a different cascade kernel for each (delta form, state-variable sections in 8- and 4-row
+    blocks, the section-pipelined kernel): the delta form's states are the state-variable section's own, re-scaled, so the
+    hand-over is a pointwise conversion and the stream continues as if one kernel had rendered it."""
+    from signals_b200.chain import ext
+    rng = np.random.default_rng(82)
+    ch, nsec, seg = 128, 8, 12000
+    x = rng.uniform(-1, 1, (4 * seg, ch)).astype(np.float32)
+    for cls, btype in (('LowPass', 'lp'), ('HighPass', 'hp')):
+        cut = np.exp(rng.uniform(np.log(150.0), np.log(6000.0), (nsec, ch)))
+        node = ext.Buffer(x)
+        for s in range(nsec):
+            node = cases.lowpass(ns, node, [cut[s]], cls)
+        c = engine.compile(node, ch, RATE)
+        out = []
+        for k, (reg, variant) in enumerate([(-1, 0), (-1, 4), (0, 0), (-1, 0)]):
+            c.set_option('cascade_reg', reg)
+            c.set_option('reg_variant', variant)
+            out.append(c.render_device(k * seg, seg).cpu().numpy())
+        c.close()
+        got = np.concatenate(out)
+        want, _ = np_oracle.render_cascade(x.astype(np.float64), cut, RATE, btype=btype)
+        err = max_abs_err(got, want)
+        print(f'{cls} stream through delta / state-variable / pipelined / delta kernels: max-abs {err:.3e}')
+        assert err <= 2e-6

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Ad-hoc timing of 8-section cascades on a materialised block (16,384 channels x 10 s, 4 B read + 4 B written per
 channel-sample): all-low-pass and all-high-pass, k_cascade_delta (reg_variant 0) against k_cascade_reg's state-variable
-sections (reg_variant 4), and a mixed cascade (k_cascade_pipe)."""
+sections (reg_variant 4), and a mixed cascade: k_cascade_delta's select-per-section form against k_cascade_pipe (cascade_reg 0)."""
 import os
 import sys
 
@@ -25,9 +25,12 @@ for kinds in ('LLLLLLLL', 'HHHHHHHH', 'HHHHLLLL'):
     node = ext.Buffer(noise)
     for s, k in enumerate(kinds):
         node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if k == 'H' else 'LowPass')
-    for variant in ((0, 4) if len(set(kinds)) == 1 else (0,)):
+    mixed = len(set(kinds)) > 1
+    for variant in (0, 4):
         c = engine.Engine().compile(node, CH, RATE, FRAMES)
         c.set_option('reg_variant', variant)
+        if mixed and variant == 4:
+            c.set_option('cascade_reg', 0)
         for _ in range(2):
             c.render_device(0, FRAMES, out)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -37,6 +40,6 @@ for kinds in ('LLLLLLLL', 'HHHHHHHH', 'HHHHLLLL'):
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 3
-        name = 'k_cascade_pipe' if len(set(kinds)) > 1 else ('k_cascade_delta' if variant == 0 else 'k_cascade_reg (state-variable)')
+        name = ('k_cascade_delta (mixed)' if variant == 0 else 'k_cascade_pipe') if mixed else ('k_cascade_delta' if variant == 0 else 'k_cascade_reg (state-variable)')
         print(f'{kinds} {name}: {ms:.2f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, {8 * CH * FRAMES / ms / 1e6:.0f} GB/s read + written')
         c.close()
