@@ -148,9 +148,10 @@ int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
  *   "force_seq" (1: k_chain_seq only), "scan_variant" (geometry of the time-parallel scan kernel),
  *   "scan_max_tiles", "slab_frames", "host_slab_bytes", "buffer_budget",
  *   "cascade_reg" (-1: register-resident cascade kernel whenever it can take the chain, 0: never),
- *   "reg_variant" (0: k_cascade_delta for all-low-pass cascades, else 8-row blocks; 1: 4-row blocks, 3: k_cascade_stream,
- *   4: state-variable sections in 8-row blocks), "osc_reg" (oscillator-fed chains of >= n sections run
- *   register-resident, 0: never; default 3), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
+ *   "reg_variant" (0: k_cascade_delta wherever it applies, else k_cascade_reg in 8-row blocks; 1: k_cascade_reg in 4-row blocks;
+ *   4: k_cascade_reg in 8-row blocks), "osc_reg" (oscillator-fed chains of >= n sections run
+ *   register-resident, 0: never; default 2, where 2-section chains qualify only when unmodulated and filling the machine),
+ *   "osc_delta" (0: those chains keep state-variable sections), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
  *   "pipe_spw", "pipe_segments" (upper bound on the time pieces per tile of the cascade kernels; 1: never cut),
  *   "voices_segments" (k_voices: 0 equal pieces per resident CTA, 1 one piece per voice group, n pieces per group),
  *   "voices_pieces" (automatic mode: pieces per resident CTA slot, default 16), "voices_m",

@@ -183,8 +183,10 @@ int sigb_cascade_reg_ok(const ChainDev* a);
 int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream);
 void sigb_set_reg_pieces(int n);
 void sigb_set_delta_probe(int n);
-int sigb_osc_reg_ok(const ChainDev* a);
-int sigb_launch_osc_reg(const ChainDev* a, int max_segments, void* stream);
+int sigb_osc_reg_ok(const ChainDev* a, int allow_delta);
+int sigb_launch_osc_reg(const ChainDev* a, int max_segments, int allow_delta, void* stream);
+int sigb_osc_reg_fill(const ChainDev* a, int max_segments, int allow_delta);
+void sigb_set_osc_pieces_pct(int n);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);
 int sigb_scan_rows_per_step(int nsec, int variant);

@@ -188,8 +188,10 @@ struct sigb_plan {
     int64_t opt_buffer_budget = 6ll << 30;
     int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
     int64_t opt_cascade_reg = -1;       // -1: register-resident cascade kernel whenever it can take the chain; 0: never
-    int64_t opt_osc_reg = 3;            // oscillator-fed chains of >= n sections run register-resident (k_osc_reg); 0: never
-    int64_t opt_reg_variant = 0;        // register cascades: 0 = delta form where it applies, else 8-row blocks; 1 = 4-row blocks; 3 = stream; 4 = state-variable form
+    int64_t opt_osc_reg = 2;            // oscillator-fed chains of >= n sections run register-resident (k_osc_delta / k_osc_reg); 0: never
+    int64_t opt_osc_delta = 1;          // 0: oscillator-fed register chains keep the state-variable sections (A/B)
+    bool osc_reg_user = false;          // set through the option: honoured as given; the default's 2-section rule is for unmodulated chains that fill the machine
+    int64_t opt_reg_variant = 0;        // register cascades: 0 = delta form where it applies, else 8-row blocks; 1 = 4-row blocks; 4 = state-variable form in 8-row blocks
     int64_t opt_pipe_spw = 1;           // sections per warp in k_cascade_pipe (2: halves the shared-memory traffic)
     int64_t opt_pipe_segments = 64;     // upper bound on the time segments per tile of k_cascade_pipe (1: never split)
     int64_t opt_fuse_reduce = 1;        // 0: GroupSum / PanSum always run on materialised blocks
@@ -1316,8 +1318,12 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     ch.state_cur ^= 1;           // the kernel wrote the other copy of the state
                     continue;
                 }
-                if (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg && sigb_osc_reg_ok(&t)) {
-                    int e = sigb_launch_osc_reg(&t, (int)p->opt_pipe_segments, st);
+                // oscillator-fed chains from "osc_reg" sections on; 2-section chains only when their time pieces fill at least
+                // half of the machine's warp slots (else the time-parallel scan kernel is the better choice)
+                if (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg && sigb_osc_reg_ok(&t, (int)p->opt_osc_delta) &&
+                    (ch.nsec_real >= 3 || p->osc_reg_user ||
+                     (ch.mods.empty() && sigb_osc_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta) >= 512))) {
+                    int e = sigb_launch_osc_reg(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_osc_reg: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;
                     ch.state_cur ^= 1;
@@ -1552,7 +1558,7 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
         }
         if (!ch.mods.empty()) {
             ch.warm_rows = -1;
-            if (ch.nsec_real >= 3 || p->opt_cascade_pipe > 0 || (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg)) need_host = true;
+            if (ch.nsec_real >= 3 || p->opt_cascade_pipe > 0 || (p->osc_reg_user && p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg)) need_host = true;
         }
     }
     if (want_warm) {
@@ -2119,7 +2125,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "pipe_spw") plan->opt_pipe_spw = value;
     else if (k == "cascade_reg") plan->opt_cascade_reg = value;
     else if (k == "reg_variant") plan->opt_reg_variant = value;
-    else if (k == "osc_reg") plan->opt_osc_reg = value;
+    else if (k == "osc_reg") { plan->opt_osc_reg = value; plan->osc_reg_user = true; }
     else if (k == "voices_segments") plan->opt_voices_segments = value;
     else if (k == "voices_pieces") plan->opt_voices_pieces = value;
     else if (k == "rt_graph") plan->opt_rt_graph = value;
@@ -2130,6 +2136,8 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "scan_rot") sigb_set_scan_rot((int)value);       // process-wide switch (A/B testing)
     else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
     else if (k == "delta_probe") sigb_set_delta_probe((int)value); // process-wide switch (A/B testing)
+    else if (k == "osc_delta") plan->opt_osc_delta = value;
+    else if (k == "osc_pieces_pct") sigb_set_osc_pieces_pct((int)value);   // process-wide switch (A/B testing)
     else if (k == "bank_unroll") sigb_set_bank_unroll((int)value); // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);
     rt_drop_graphs(plan);            // captured launches embody the old choice

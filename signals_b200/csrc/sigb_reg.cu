@@ -39,6 +39,7 @@ namespace {
 using namespace sigb_dev;
 
 int g_reg_pieces = 1;           // pieces per warp slot of the machine (A/B: more pieces even out the tail, each costs a warm-up)
+int g_osc_pieces_pct = 100;     // A/B ("osc_pieces_pct"): time pieces of the register kernels as a percentage of the resident warp slots
 
 constexpr int RC = 64;          // channels per warp (2 per lane)
 constexpr int RWARPS = 4;       // warps per CTA: 256 adjacent channels, 1 KB of every row
@@ -413,7 +414,7 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 // fewer time pieces, i.e. less warm-up
 __host__ __device__ constexpr int delta_min_blocks(int nsec, int kind = 0) {
     return (kind & 4) ? (nsec <= 4 ? 4 : nsec <= 6 ? 3 : 2)          // mixed cascades: 12 registers per section
-                      : (nsec <= 6 ? 5 : nsec == 7 ? 4 : 2);
+                      : (nsec <= 4 ? 4 : nsec <= 7 ? 3 : 2);
 }
 
 template <int NSEC, int R, int MINB, int WR = R, int KIND = 0>
@@ -563,241 +564,6 @@ int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int 
     return (int)cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// k_cascade_stream: the register-resident cascade as a CONTINUOUS software pipeline over rows.
-//
-// MEASURED (C4, one B200 under its power cap, profiles/r02_c4_variants.txt): no faster than k_cascade_reg -- 4.50-4.63e11
-// against 4.56e11 channel-samples/s -- so neither the pipeline refill per block nor the 12 resident warps are what
-// holds the cascade at ~77 FP32 lane-ops/clk/SM; kept as `reg_variant` 3 for A/B.
-//
-// k_cascade_reg evaluates blocks of R rows in wavefront order: R + NSEC - 1 diagonals per block, the first and
-// last NSEC - 1 of them partly filled (average 4.3 independent section steps per diagonal for 8 sections x 8 rows),
-// and the pipeline drains and refills at every block.  Here section s works on row t - s at tick t for the whole
-// sub-range: every tick is NSEC INDEPENDENT section steps (one per section, on NSEC different rows), one new row in
-// and one finished row out; the pipeline fills once at the start of a sub-range and drains once at its end.
-// p[s] holds the row waiting for section s (the output of section s - 1 from the previous tick).
-//
-// IMM2: three-coefficient form of the section -- the state updates as 2 bp - s1 / 2 lp - s2 (one shared register
-// pair holding 2.0 instead of two more coefficient pairs per section): 10 registers per section instead of 14, so
-// 8 sections fit 128 registers and 16 warps per SM instead of 12.
-// ---------------------------------------------------------------------------------------------------------
-struct StreamSec {
-    float2 nc, al, g;           // (-c) (g d) (g)
-    float2 a2, g2;              // (2 g d) (2 g): only read by the five-coefficient form
-    float2 d;                   // high-pass output scale
-    float2 s1, s2;
-};
-
-template <int KIND, bool IMM2>
-__device__ __forceinline__ float2 stream_step(float2 x, StreamSec& r, const float2 two) {
-    const float2 xs = __fadd2_rn(x, make_float2(-r.s2.x, -r.s2.y));
-    const float2 e = __ffma2_rn(r.nc, r.s1, xs);
-    const float2 bp = __ffma2_rn(r.al, e, r.s1);
-    if (IMM2) r.s1 = __ffma2_rn(two, bp, make_float2(-r.s1.x, -r.s1.y));
-    else r.s1 = __ffma2_rn(r.a2, e, r.s1);
-    const float2 lp = __ffma2_rn(r.g, bp, r.s2);
-    if (IMM2) r.s2 = __ffma2_rn(two, lp, make_float2(-r.s2.x, -r.s2.y));
-    else r.s2 = __ffma2_rn(r.g2, bp, r.s2);
-    return (KIND & SEC_HP) ? __fmul2_rn(e, r.d) : lp;
-}
-
-// one tick with sections [LO, HI] active (HI down to LO, so that p[s + 1] is read before section s overwrites it);
-// u enters section LO when LO == 0; the return value is the output of the last section when HI == NSEC - 1
-template <int NSEC, int KIND, bool IMM2, int LO, int HI>
-__device__ __forceinline__ float2 stream_tick(float2 u, float2 (&p)[NSEC], StreamSec (&sec)[NSEC], const float2 two) {
-    float2 out = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int s = HI; s >= LO; --s) {
-        const float2 y = stream_step<KIND, IMM2>(s == 0 ? u : p[s], sec[s], two);
-        if (s == NSEC - 1) out = y;
-        else p[s + 1] = y;
-    }
-    return out;
-}
-
-// resident CTAs per SM: 14 registers per section with five coefficients, 10 with three (+2 for a high-pass's output scale)
-__host__ __device__ constexpr int stream_min_blocks(int nsec, bool imm2, bool hp) {
-    return imm2 ? (nsec <= 4 ? 5 : (hp && nsec >= 7) ? 3 : 4) : (nsec <= 5 ? 4 : 3);
-}
-
-// FAST layout only (host-checked: whole 64-channel tiles, 8-byte aligned even leading dimensions, source covers every
-// row, 3 <= NSEC <= 8); rows come in blocks of 8 through the same warp-private cp.async ring as k_cascade_reg, but
-// every tick reads its input row from the ring and stores its finished row at once, so no block of rows is held in
-// registers (the registers go to the sections: 16 warps per SM with the three-coefficient form).
-template <int NSEC, int KIND, bool IMM2>
-__global__ void __launch_bounds__(RWARPS * 32, stream_min_blocks(NSEC, IMM2, (KIND & SEC_HP) != 0))
-k_cascade_stream(const ChainDev a, int tiles, int npieces, int warm_rows) {
-    constexpr int R = 8;
-    static_assert(NSEC >= 2 && NSEC <= 8, "pipeline depth");
-    __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
-    const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
-    const int lane = threadIdx.x & 31;
-    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
-    if (piece >= npieces) return;
-    const size_t C = (size_t)a.C;
-    const int bpt = (a.frames + R - 1) / R;
-    const int64_t total = (int64_t)tiles * bpt;
-    int64_t blk = total * piece / npieces;
-    const int64_t blk_end = total * (piece + 1) / npieces;
-    const int64_t ld_in = (int64_t)a.src_ld * 4, ld_o = (int64_t)a.ld_out * 4;       // row strides in bytes
-    float2 two = make_float2(2.0f, 2.0f);
-    asm volatile("" : "+f"(two.x), "+f"(two.y));          // one register pair, not an immediate per use
-  while (blk < blk_end) {
-    const int tile = (int)(blk / bpt);
-    const int b0 = (int)(blk - (int64_t)tile * bpt);
-    const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
-    blk += b1 - b0;
-    const int c0 = tile * RC + 2 * lane;
-    const int row_store = b0 * R;
-    const int row_end = min(a.frames, b1 * R);
-    const int row_first = max(0, row_store - warm_rows);                   // warm_rows is a multiple of R
-    const int nfull = (row_end - row_first) / R;                           // whole blocks of R rows
-
-    StreamSec sec[NSEC];
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        const float2 g = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 0) * C + c0);
-        const float2 c = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 1) * C + c0);
-        const float2 d = *reinterpret_cast<const float2*>(a.coef + (size_t)(s * 3 + 2) * C + c0);
-        sec[s].g = g;
-        sec[s].nc = make_float2(-c.x, -c.y);
-        sec[s].d = d;
-        sec[s].al = make_float2(g.x * d.x, g.y * d.y);
-        sec[s].g2 = make_float2(keep(2.0f * g.x), keep(2.0f * g.y));
-        sec[s].a2 = make_float2(keep(2.0f * (g.x * d.x)), keep(2.0f * (g.y * d.y)));
-        if (row_first == 0) {
-            sec[s].s1 = make_float2((float)a.state[(size_t)(s * 2 + 0) * C + c0], (float)a.state[(size_t)(s * 2 + 0) * C + c0 + 1]);
-            sec[s].s2 = make_float2((float)a.state[(size_t)(s * 2 + 1) * C + c0], (float)a.state[(size_t)(s * 2 + 1) * C + c0 + 1]);
-        } else {
-            sec[s].s1 = sec[s].s2 = make_float2(0.0f, 0.0f);
-        }
-    }
-    float2 gain = make_float2(1.0f, 1.0f);
-    if (a.gain) gain = make_float2(a.gain[c0], a.gain[c0 + 1]);
-
-    const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
-    // outputs lag the inputs by NSEC - 1 rows: the row finished at the tick that reads row t is row t - (NSEC - 1)
-    char* op = reinterpret_cast<char*>(a.out + ((int64_t)row_first - (NSEC - 1)) * a.ld_out + c0);
-    const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RING_D * R * 32) + lane) * 8u;
-    const unsigned my_end = my + RING_D * R * 256u;
-    unsigned in_addr = my, out_addr = my;
-    int in_blk = 0;
-    auto prefetch = [&]() {
-        if (in_blk < nfull) {
-#pragma unroll
-            for (int k = 0; k < R; ++k) {
-                cp_async8(in_addr + k * 256u, ip);
-                ip += ld_in;
-            }
-            ++in_blk;
-            in_addr += R * 256u;
-            if (in_addr == my_end) in_addr = my;
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int j = 0; j < RING_D - 1; ++j) prefetch();
-
-    float2 p[NSEC];
-    int row = row_first;                                                   // first input row of the current block
-    // one block of R ticks; FIRST: the pipeline fills (tick k < NSEC - 1 runs sections 0 .. k only); STORE: 0 none
-    // (warm-up), 1 every finished row, 2 the rows finished from tick NSEC - 1 on (the block that straddles row_store,
-    // and the first block of a sub-range that starts at row 0)
-    auto run_block = [&](auto first_tag, auto store_tag) {
-        constexpr bool FIRST = decltype(first_tag)::value;
-        constexpr int STORE = decltype(store_tag)::value;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            const float2 u = lds_f2(out_addr + k * 256u);
-            float2 y;
-            if (FIRST && k < NSEC - 1) {
-                // fill: sections 0 .. k
-#pragma unroll
-                for (int s = NSEC - 2; s >= 0; --s)
-                    if (s <= k) p[s + 1] = stream_step<KIND, IMM2>(s == 0 ? u : p[s], sec[s], two);
-                y = u;
-            } else {
-                y = stream_tick<NSEC, KIND, IMM2, 0, NSEC - 1>(u, p, sec, two);
-            }
-            if (STORE == 1 || (STORE == 2 && k >= NSEC - 1)) __stcs(reinterpret_cast<float2*>(op), __fmul2_rn(y, gain));
-            op += ld_o;
-        }
-        out_addr += R * 256u;
-        if (out_addr == my_end) out_addr = my;
-    };
-    using T = std::true_type;
-    using F = std::false_type;
-    for (int b = 0; b < nfull; ++b) {
-        prefetch();
-        cp_async_wait<RING_D - 1>();
-        if (b == 0) {
-            if (row >= row_store) run_block(T{}, std::integral_constant<int, 2>{});
-            else run_block(T{}, std::integral_constant<int, 0>{});
-        } else if (row > row_store) {
-            run_block(F{}, std::integral_constant<int, 1>{});
-        } else if (row == row_store) {
-            run_block(F{}, std::integral_constant<int, 2>{});
-        } else {
-            run_block(F{}, std::integral_constant<int, 0>{});
-        }
-        row += R;
-    }
-    cp_async_wait<0>();
-    if (nfull > 0) {
-        // drain: NSEC - 1 more ticks without input finish the last NSEC - 1 rows; section s stops after row `row - 1`
-#pragma unroll
-        for (int j = 1; j < NSEC; ++j) {
-            float2 y = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int s = NSEC - 1; s >= 1; --s) {
-                if (s >= j) {
-                    const float2 v = stream_step<KIND, IMM2>(p[s], sec[s], two);
-                    if (s == NSEC - 1) y = v;
-                    else p[s + 1] = v;
-                }
-            }
-            if (row > row_store) __stcs(reinterpret_cast<float2*>(op), __fmul2_rn(y, gain));
-            op += ld_o;
-        }
-    }
-    // ragged tail (< R rows; only the sub-range that ends the launch has one)
-    {
-        const float* srcp = a.src + (int64_t)row * a.src_ld + c0;
-        float* outp = a.out + (int64_t)row * a.ld_out + c0;
-        for (; row < row_end; ++row) {
-            float2 x = *reinterpret_cast<const float2*>(srcp);
-#pragma unroll
-            for (int s = 0; s < NSEC; ++s) x = stream_step<KIND, IMM2>(x, sec[s], two);
-            *reinterpret_cast<float2*>(outp) = __fmul2_rn(x, gain);
-            srcp += a.src_ld;
-            outp += a.ld_out;
-        }
-    }
-    if (row_end == a.frames) {
-#pragma unroll
-        for (int s = 0; s < NSEC; ++s) {
-            a.state_out[(size_t)(s * 2 + 0) * C + c0] = (double)sec[s].s1.x;
-            a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = (double)sec[s].s1.y;
-            a.state_out[(size_t)(s * 2 + 1) * C + c0] = (double)sec[s].s2.x;
-            a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = (double)sec[s].s2.y;
-        }
-    }
-  }
-}
-
-template <int KIND, bool IMM2>
-int stream_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
-    switch (a->nsec) {
-        case 3: k_cascade_stream<3, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 4: k_cascade_stream<4, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 5: k_cascade_stream<5, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 6: k_cascade_stream<6, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 7: k_cascade_stream<7, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        default: k_cascade_stream<8, KIND, IMM2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-    }
-    return (int)cudaGetLastError();
-}
-
 template <int NSEC, int KIND, int R, bool FAST>
 int reg_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     k_cascade_reg<NSEC, KIND, R, FAST><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
@@ -937,6 +703,153 @@ k_osc_reg(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_osc_delta: k_osc_reg with the sections in DELTA FORM (low-pass 5, high-pass 4, mixed 6 operations + a select per section
+// instead of 6 / 7; see k_cascade_delta) for oscillator-fed chains of 2..8 SECOND-ORDER sections of any kinds.  The waveform
+// is a run-time switch per block (uniform over the launch), so one instantiation per (sections, kind class) serves all four.
+// ---------------------------------------------------------------------------------------------------------
+// Resident CTAs per SM = time pieces per SM / 4.  Measured on C2's shape (4,096 voices = 64 tiles x 480,000 rows, where every
+// piece pays a warm-up of ~2,400 rows; tools/bench_osc_sections.py, profiles/r02_osc_sections.txt): 2 sections 5 / 3 / 2 CTAs
+// per SM = 9.1 / 9.4 / 9.3e11 voice-samples/s, 3 sections 4 / 3 / 2 = 7.1 / 9.0 / 8.8e11, 4 sections 5.8 / 7.4 / 7.3e11 --
+// 8 to 12 warps saturate the FP32 pipe, more of them only add warm-up rows and concurrent write streams.
+__host__ __device__ constexpr int osc_delta_min_blocks(int nsec, int kind) {
+    return nsec <= 4 ? 3 : 2;
+}
+
+template <int NSEC, int KIND>
+__global__ void __launch_bounds__(RWARPS * 32, osc_delta_min_blocks(NSEC, KIND))
+k_osc_delta(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
+    const int lane = threadIdx.x & 31;
+    const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (piece >= npieces) return;
+    const size_t C = (size_t)a.C;
+    const int bpt = (a.frames + OR - 1) / OR;
+    const int64_t total = (int64_t)tiles * bpt;
+    int64_t blk = total * piece / npieces;
+    const int64_t blk_end = total * (piece + 1) / npieces;
+    const float2 m4 = make_float2(-4.0f, -4.0f);
+    const int wave = a.wave;
+    while (blk < blk_end) {
+        const int tile = (int)(blk / bpt);
+        const int b0 = (int)(blk - (int64_t)tile * bpt);
+        const int b1 = (int)min((int64_t)bpt, b0 + (blk_end - blk));
+        blk += b1 - b0;
+        const int c0 = tile * RC + 2 * lane;
+        const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
+        const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
+        const int row_store = b0 * OR;
+        const int row_end = min(a.frames, b1 * OR);
+        const int row_first = max(0, row_store - warm_rows);               // warm_rows is a multiple of OR
+
+        DeltaSec sec[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
+            const float cca = a.coef[(size_t)(s * 3 + 1) * C + ca], ccb = a.coef[(size_t)(s * 3 + 1) * C + cb];
+            const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
+            const bool hp_s = (KIND & SEC_HP) || ((KIND & SEC_MIXED) && (a.sec_kind[s] & SEC_HP));
+            delta_coef<KIND>(ga, cca, da, hp_s, sec[s].a.x, sec[s].be.x, sec[s].c.x);
+            delta_coef<KIND>(gb, ccb, db, hp_s, sec[s].a.y, sec[s].be.y, sec[s].c.y);
+            if (row_first == 0) {
+                delta_state_in<KIND>(ga, da, sec[s].be.x, a.state[(size_t)(s * 2 + 0) * C + ca], a.state[(size_t)(s * 2 + 1) * C + ca], sec[s].D.x, sec[s].Z.x, sec[s].P.x);
+                delta_state_in<KIND>(gb, db, sec[s].be.y, a.state[(size_t)(s * 2 + 0) * C + cb], a.state[(size_t)(s * 2 + 1) * C + cb], sec[s].D.y, sec[s].Z.y, sec[s].P.y);
+            } else {
+                sec[s].D = sec[s].Z = sec[s].P = make_float2(0.0f, 0.0f);
+            }
+        }
+        float2 gain = make_float2(1.0f, 1.0f);
+        if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
+        if (KIND & (SEC_HP | SEC_MIXED)) gain = __fmul2_rn(gain, sec[NSEC - 1].c);   // the last section's output scale
+        const unsigned long long dtha = a.dtheta[ca], dthb = a.dtheta[cb];
+        int64_t n = a.position + row_first;
+        unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
+        float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
+        const bool vec = fast && live1;
+
+        for (int row = row_first; row < row_end; row += OR) {
+            float xa[OR], xb[OR];
+            switch (wave) {
+                case SIGB_WAVE_SINE: osc_rows<SIGB_WAVE_SINE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SINE>(a, cb, thb, dthb, n, xb); break;
+                case SIGB_WAVE_SQUARE: osc_rows<SIGB_WAVE_SQUARE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SQUARE>(a, cb, thb, dthb, n, xb); break;
+                case SIGB_WAVE_SAWTOOTH: osc_rows<SIGB_WAVE_SAWTOOTH>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SAWTOOTH>(a, cb, thb, dthb, n, xb); break;
+                default: osc_rows<SIGB_WAVE_TRIANGLE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_TRIANGLE>(a, cb, thb, dthb, n, xb); break;
+            }
+            tha += (unsigned long long)OR * dtha;
+            thb += (unsigned long long)OR * dthb;
+            n += OR;
+            float2 x[OR];
+#pragma unroll
+            for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
+            if (row + OR <= row_end) {
+#pragma unroll
+                for (int dgl = 0; dgl < OR + NSEC - 1; ++dgl) {
+#pragma unroll
+                    for (int s = 0; s < NSEC; ++s) {
+                        const int r = dgl - s;
+                        if (r >= 0 && r < OR) x[r] = delta_step<KIND>(x[r], sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].c, (a.sec_kind[s] & SEC_HP) != 0);
+                    }
+                }
+                if (row >= row_store) {
+                    if (vec) {
+#pragma unroll
+                        for (int k = 0; k < OR; ++k) __stcs(reinterpret_cast<float2*>(outp + (int64_t)k * a.ld_out), __fmul2_rn(x[k], gain));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < OR; ++k) {
+                            if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
+                            if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
+                        }
+                    }
+                }
+            } else {
+                // ragged last block of the launch: the state stops at the last real row
+                for (int k = 0; k < row_end - row; ++k) {
+                    float2 y = x[0];
+#pragma unroll
+                    for (int j = 1; j < OR; ++j) if (j == k) y = x[j];
+#pragma unroll
+                    for (int s = 0; s < NSEC; ++s) y = delta_step<KIND>(y, sec[s], m4, s == 0, sec[s > 0 ? s - 1 : 0].c, (a.sec_kind[s] & SEC_HP) != 0);
+                    if (live0) outp[(int64_t)k * a.ld_out] = y.x * gain.x;
+                    if (live1) outp[(int64_t)k * a.ld_out + 1] = y.y * gain.y;
+                }
+            }
+            outp += (int64_t)OR * a.ld_out;
+        }
+        if (row_end == a.frames) {
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                const float ga = a.coef[(size_t)(s * 3 + 0) * C + ca], gb = a.coef[(size_t)(s * 3 + 0) * C + cb];
+                const float da = a.coef[(size_t)(s * 3 + 2) * C + ca], db = a.coef[(size_t)(s * 3 + 2) * C + cb];
+                double s1, s2;
+                if (live0) {
+                    delta_state_out<KIND>(ga, da, sec[s].be.x, sec[s].D.x, sec[s].Z.x, s1, s2);
+                    a.state_out[(size_t)(s * 2 + 0) * C + c0] = s1;
+                    a.state_out[(size_t)(s * 2 + 1) * C + c0] = s2;
+                }
+                if (live1) {
+                    delta_state_out<KIND>(gb, db, sec[s].be.y, sec[s].D.y, sec[s].Z.y, s1, s2);
+                    a.state_out[(size_t)(s * 2 + 0) * C + c0 + 1] = s1;
+                    a.state_out[(size_t)(s * 2 + 1) * C + c0 + 1] = s2;
+                }
+            }
+        }
+    }
+}
+
+template <int KIND>
+int osc_delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, int fast, cudaStream_t st) {
+    switch (a->nsec) {
+        case 2: k_osc_delta<2, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case 3: k_osc_delta<3, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case 4: k_osc_delta<4, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case 5: k_osc_delta<5, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case 6: k_osc_delta<6, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        case 7: k_osc_delta<7, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+        default: k_osc_delta<8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
+    }
+    return (int)cudaGetLastError();
+}
+
 template <int NSEC, int KIND>
 int osc_launch(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, int fast, cudaStream_t st) {
     switch (a->wave) {
@@ -1003,18 +916,15 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     }
     if (mixed) variant = 0;          // only k_cascade_delta runs both kinds in one cascade (sigb_cascade_reg_ok checked the layout)
     const bool wide = fast && variant != 1;
-    // continuous software pipeline over rows (A/B); its 2 lp - s2 update would not keep a first-order section's s2 at 0
-    const bool streaming = fast && variant == 3 && !any_first;
     // delta form (5 operations per low-pass section, 4 per high-pass section, instead of 6 / 7): second-order sections only;
     // variant 4 keeps the state-variable form in 8-row blocks for A/B
-    const bool delta = fast && (variant == 0 || variant == 2) && !any_first;
+    const bool delta = fast && variant != 1 && variant != 4 && !any_first;
     const int dprobe = (delta && a->nsec == 8 && !mixed && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
     const int R = (wide && dprobe != 1) ? 8 : 4;
     const int tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = (streaming ? stream_min_blocks(a->nsec, true, (a->sec_kind[0] & SEC_HP) != 0)
-                              : delta   ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec, mixed ? SEC_MIXED : 0)) : reg_min_blocks(a->nsec, R)) * RWARPS;
+    const int warps_per_sm = (delta ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec, mixed ? SEC_MIXED : 0)) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
@@ -1022,7 +932,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     int64_t want = tiles;
     if (max_segments > 1 && a->warm_rows >= 0) {
         warm = (a->warm_rows + R - 1) / R * R;
-        const int64_t slots = (int64_t)sms * warps_per_sm * std::max(1, g_reg_pieces);
+        const int64_t slots = (int64_t)sms * warps_per_sm * std::max(1, g_reg_pieces) * g_osc_pieces_pct / 100;
         const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / R);
         want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
     } else {
@@ -1031,8 +941,6 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
     const int npieces = (int)want;
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
-    if (streaming) return hp ? stream_launch_nsec<SEC_HP, true>(a, grid, tiles, npieces, warm, st)
-                          : stream_launch_nsec<0, true>(a, grid, tiles, npieces, warm, st);
     if (delta) return mixed ? delta_launch_nsec<SEC_MIXED>(a, grid, tiles, npieces, warm, st)
                       : (a->sec_kind[0] & SEC_HP) ? delta_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, st)
                                                   : delta_launch_nsec<0>(a, grid, tiles, npieces, warm, st);
@@ -1044,35 +952,78 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
               : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces, warm, st);
 }
 
-// Oscillator-fed chains: 1..8 second-order sections of one kind, unmodulated oscillator (Q0.64 phase tables present).
-extern "C" int sigb_osc_reg_ok(const ChainDev* a) {
+// Oscillator-fed chains: 1..8 sections, unmodulated oscillator (Q0.64 phase tables present).  Second-order sections of any
+// kinds run in delta form (k_osc_delta, from 2 sections); chains with first-order sections (odd Butterworth orders) need the
+// state-variable kernel and one kind.
+static void osc_chain_kinds(const ChainDev* a, bool& mixed, bool& any_first) {
+    mixed = any_first = false;
+    for (int k = 0; k < a->nsec; ++k) {
+        mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
+        any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
+    }
+}
+
+// allow_delta = 0: state-variable sections (k_osc_reg) even where the delta form applies (plan option "osc_delta", A/B)
+extern "C" int sigb_osc_reg_ok(const ChainDev* a, int allow_delta) {
     if (a->src_kind != SRC_OSC || !a->theta0 || !a->dtheta || a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
-    for (int k = 0; k < a->nsec; ++k)
-        if ((a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP)) return 0;
+    bool mixed, any_first;
+    osc_chain_kinds(a, mixed, any_first);
+    if (mixed) return !any_first && allow_delta && a->nsec >= 2;
     return 1;
 }
 
-extern "C" int sigb_launch_osc_reg(const ChainDev* a, int max_segments, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (a->frames <= 0) return 0;
-    const int fast = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0;
-    const int tiles = (a->C + RC - 1) / RC;
+extern "C" void sigb_set_osc_pieces_pct(int n) { g_osc_pieces_pct = std::max(1, n); }
+
+// launch geometry shared by the launch and by the planner's "does it fill the machine" question
+static void osc_reg_geometry(const ChainDev* a, int max_segments, bool delta, int kind, int& tiles, int& npieces, int& warm, int64_t& slots) {
+    tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = osc_min_blocks(a->nsec) * RWARPS;
+    const int warps_per_sm = (delta ? osc_delta_min_blocks(a->nsec, kind) : osc_min_blocks(a->nsec)) * RWARPS;
+    slots = (int64_t)sms * warps_per_sm * g_osc_pieces_pct / 100;
     const int bpt = (a->frames + OR - 1) / OR;
-    int warm = 0;
     int64_t want = tiles;
     if (max_segments > 1 && a->warm_rows >= 0) {
         warm = (a->warm_rows + OR - 1) / OR * OR;
-        const int64_t slots = (int64_t)sms * warps_per_sm;
         const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / OR);
         want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
     } else {
         warm = bpt * OR;
     }
-    const int npieces = (int)want;
+    npieces = (int)want;
+}
+
+static bool osc_use_delta(const ChainDev* a, bool mixed, bool any_first, int allow_delta) {
+    return (allow_delta || mixed) && !any_first && a->nsec >= 2;
+}
+
+// share of the machine's warp slots the launch would occupy, in 1/1024 (shallow chains only go register-resident when the
+// time pieces their decay horizon allows fill the machine; otherwise the time-parallel scan kernels are the better choice)
+extern "C" int sigb_osc_reg_fill(const ChainDev* a, int max_segments, int allow_delta) {
+    bool mixed, any_first;
+    osc_chain_kinds(a, mixed, any_first);
+    const bool delta = osc_use_delta(a, mixed, any_first, allow_delta);
+    int tiles, npieces, warm;
+    int64_t slots;
+    osc_reg_geometry(a, max_segments, delta, mixed ? SEC_MIXED : (a->sec_kind[0] & SEC_HP), tiles, npieces, warm, slots);
+    return (int)std::min<int64_t>(1024, (int64_t)npieces * 1024 / std::max<int64_t>(1, slots));
+}
+
+extern "C" int sigb_launch_osc_reg(const ChainDev* a, int max_segments, int allow_delta, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
+    const int fast = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0;
+    bool mixed, any_first;
+    osc_chain_kinds(a, mixed, any_first);
+    const bool delta = osc_use_delta(a, mixed, any_first, allow_delta);
+    const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
+    int tiles, npieces, warm;
+    int64_t slots;
+    osc_reg_geometry(a, max_segments, delta, mixed ? SEC_MIXED : (hp ? SEC_HP : 0), tiles, npieces, warm, slots);
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
-    return (a->sec_kind[0] & SEC_HP) ? osc_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, fast, st)
-                                     : osc_launch_nsec<0>(a, grid, tiles, npieces, warm, fast, st);
+    if (delta) return mixed ? osc_delta_launch_nsec<SEC_MIXED>(a, grid, tiles, npieces, warm, fast, st)
+                      : hp  ? osc_delta_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, fast, st)
+                            : osc_delta_launch_nsec<0>(a, grid, tiles, npieces, warm, fast, st);
+    return hp ? osc_launch_nsec<SEC_HP>(a, grid, tiles, npieces, warm, fast, st)
+              : osc_launch_nsec<0>(a, grid, tiles, npieces, warm, fast, st);
 }

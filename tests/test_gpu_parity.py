@@ -55,13 +55,16 @@ def test_cuda_matches_reference_golden(case, ns, engine):
 
 
 @pytest.mark.parametrize('case', FILTER_CASES, ids=lambda c: c.name)
-@pytest.mark.parametrize('mode', ['seq', 'scan9', 'scan16', 'scan18', 'pipe', 'pipe2', 'oscreg'])
+@pytest.mark.parametrize('mode', ['seq', 'scan9', 'scan16', 'scan18', 'pipe', 'pipe2', 'oscreg', 'oscsvf'])
 def test_every_filter_kernel_variant_matches_golden(case, mode, ns, engine):
     """k_chain_seq, the time-parallel kernels (scan9 = k_chain_scan2, deep cascades forced onto it too; scan16 / scan18 =
     k_chain_scan3 with the float64 / packed float32 carry chain), the section-pipelined k_cascade_pipe (forced from 2
-    sections) and the register-resident k_osc_reg (from one section) agree with the reference."""
+    sections) and the register-resident oscillator kernels (from one section: 'oscreg' = k_osc_delta for second-order
+    sections from two on, k_osc_reg otherwise; 'oscsvf' = k_osc_reg's state-variable sections throughout) agree with the
+    reference."""
     opts = (dict(force_seq=1) if mode == 'seq' else dict(cascade_pipe=1, osc_reg=0) if mode == 'pipe' else dict(cascade_pipe=1, pipe_spw=2, osc_reg=0) if mode == 'pipe2'
-            else dict(osc_reg=1) if mode == 'oscreg' else dict(scan_variant=int(mode[4:]), cascade_pipe=0))
+            else dict(osc_reg=1) if mode == 'oscreg' else dict(osc_reg=1, osc_delta=0) if mode == 'oscsvf'
+            else dict(scan_variant=int(mode[4:]), cascade_pipe=0))
     got = render_case(engine, ns, case, **opts)[::case.stride]
     err = max_abs_err(got, load_golden(case.name))
     assert err <= case.tol, f'{case.name}/{mode}: max-abs {err:.3e}'
@@ -472,15 +475,15 @@ def test_cascade_pipe_ragged_channels_and_streaming(ns, engine):
     assert max_abs_err(got[:, :ch], want) <= 1e-4
 
 
-@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_hp', 'reg_svf', 'reg_r4', 'reg_ragged', 'stream3', 'stream3_hp', 'stream3_4sec', 'stream3_ragged_rows'])
+@pytest.mark.parametrize('kernel', ['pipe', 'reg', 'reg_hp', 'reg_svf', 'reg_svf_hp', 'reg_r4', 'reg_ragged', 'reg_4sec', 'reg_ragged_rows'])
 def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
     """k_cascade_pipe / k_cascade_reg cut long renders into time segments that warm up from zero state
     (decayed below 2^-40); every segment must match the float64 cascade, the segmented render must agree
     with the unsegmented one, and the state handed to the next call must be the true one."""
     from signals_b200.chain import ext
     rng = np.random.default_rng(45)
-    ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), (4 if kernel == 'stream3_4sec' else 8), (60003 if kernel == 'stream3_ragged_rows' else 60000)
-    cls, btype = ('HighPass', 'hp') if kernel in ('stream3_hp', 'reg_hp') else ('LowPass', 'lp')
+    ch, nsec, frames = (190 if kernel == 'reg_ragged' else 192), (4 if kernel == 'reg_4sec' else 8), (60003 if kernel == 'reg_ragged_rows' else 60000)
+    cls, btype = ('HighPass', 'hp') if kernel in ('reg_svf_hp', 'reg_hp') else ('LowPass', 'lp')
     x = rng.uniform(-1, 1, (frames + 4000, ch)).astype(np.float32)
     cut = np.exp(rng.uniform(np.log(600.0), np.log(8000.0), (nsec, ch)))
     node = ext.Buffer(x)
@@ -488,10 +491,9 @@ def test_cascade_pipe_time_segments_match_oracle(kernel, ns, engine):
         node = cases.lowpass(ns, node, [cut[s]], cls)
     compiled = engine.compile(node, ch, RATE)
     compiled.set_option('cascade_reg', 0 if kernel == 'pipe' else -1)
-    # 3: k_cascade_stream (continuous software pipeline over rows, three coefficients per section)
     # 0: k_cascade_delta on this all-low-pass cascade ('reg'; 'reg_ragged' has a ragged last tile and stays on k_cascade_reg),
     # 4: k_cascade_reg's state-variable sections in 8-row blocks
-    compiled.set_option('reg_variant', 1 if kernel == 'reg_r4' else 3 if kernel.startswith('stream3') else 4 if kernel == 'reg_svf' else 0)
+    compiled.set_option('reg_variant', 1 if kernel == 'reg_r4' else 4 if kernel.startswith('reg_svf') else 0)
     warm = compiled.describe()['launches'][0]['warm_rows']
     assert 0 < warm < frames // 8, warm                       # so that the launch really is segmented
     first = compiled.render_device(0, frames).cpu().numpy()
@@ -808,19 +810,25 @@ def test_modulated_cutoff_streams_with_carried_state(ns, engine):
 
 
 @pytest.mark.parametrize('wave,nsec,btype,ch', [('Sine', 1, 'lp', 128), ('Sine', 1, 'lp', 130), ('Square', 2, 'hp', 66),
-                                                ('Sawtooth', 8, 'lp', 64), ('Triangle', 4, 'lp', 5)])
+                                                ('Sawtooth', 8, 'lp', 64), ('Triangle', 4, 'lp', 5), ('Sine', 2, 'lp', 128),
+                                                ('Sawtooth', 8, 'hp', 64), ('Square', 3, 'mix', 70), ('Sine', 6, 'mix', 64),
+                                                ('Triangle', 4, 'svf', 64)])
 def test_osc_reg_pieces_and_streaming(wave, nsec, btype, ch, ns, engine):
-    """k_osc_reg (oscillator evaluated in the thread, all sections in registers): time pieces with decay warm-up against
+    """k_osc_delta / k_osc_reg (oscillator evaluated in the thread, all sections in registers; 'mix' alternates high- and
+    low-pass sections, 'svf' keeps k_osc_reg's state-variable sections): time pieces with decay warm-up against
     the float64 reference render, agreement with the uncut render, state carried into a ragged second request, and
     agreement of a chunked render with the single request."""
     rng = np.random.default_rng(46)
     frames, tail = 60000, 3001
     cut = np.exp(rng.uniform(np.log(700.0), np.log(8000.0), (nsec, ch)))
     node = cases.osc(ns, wave, [rng.uniform(55.0, 1760.0, ch)], [rng.uniform(0, 1, ch)])
+    kind = lambda s: 'HighPass' if btype == 'hp' or (btype == 'mix' and s % 2 == 0) else 'LowPass'     # noqa: E731
     for s in range(nsec):
-        node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if btype == 'hp' else 'LowPass')
+        node = cases.lowpass(ns, node, [cut[s]], kind(s))
     compiled = engine.compile(node, ch, RATE)
     compiled.set_option('osc_reg', 1)
+    if btype == 'svf':
+        compiled.set_option('osc_delta', 0)
     warm = compiled.describe()['launches'][0]['warm_rows']
     assert 0 < warm < frames // 8, warm                       # so that the launch really is cut along time
     first = compiled.render_device(0, frames).cpu().numpy()
@@ -835,7 +843,7 @@ def test_osc_reg_pieces_and_streaming(wave, nsec, btype, ch, ns, engine):
     pick = rng.choice(ch, min(ch, 12), replace=False)
     sub = cases.osc(ns, wave, [np.asarray(node_hertz(node))[pick]], [np.asarray(node_phase(node))[pick]])
     for s in range(nsec):
-        sub = cases.lowpass(ns, sub, [cut[s][pick]], 'HighPass' if btype == 'hp' else 'LowPass')
+        sub = cases.lowpass(ns, sub, [cut[s][pick]], kind(s))
     want = np_oracle.GraphOracle(RATE).render(sub, 0, frames + tail, len(pick))
     err = max_abs_err(np.concatenate([first, second])[:, pick], want)
     print(f'osc_reg {wave} x {nsec} {btype} sections, {ch} ch: warm_rows {warm}, max-abs {err:.3e}')

@@ -13,7 +13,8 @@ from signals_b200 import workloads as cases   # noqa: E402
 from signals_b200 import engine   # noqa: E402
 from signals_b200.chain import ext   # noqa: E402
 
-RATE, CH, FRAMES, NSEC = 48000, 16384, 480000, 8
+RATE, CH, FRAMES, NSEC = 48000, 16384, 480000, int(os.environ.get('NSEC', 8))
+PCTS = [int(v) for v in os.environ.get('PCTS', '100').split(',')]
 rng = np.random.default_rng(7)
 ns = cases.b200_namespace()
 g = torch.Generator(device='cuda')
@@ -21,14 +22,15 @@ g.manual_seed(7)
 noise = torch.rand((FRAMES, CH), generator=g, device='cuda', dtype=torch.float32) * 2 - 1
 cut = np.exp(rng.uniform(np.log(200.0), np.log(8000.0), (NSEC, CH)))
 out = torch.empty((FRAMES, CH), dtype=torch.float32, device='cuda')
-for kinds in ('LLLLLLLL', 'HHHHHHHH', 'HHHHLLLL'):
+for kinds in ('L' * NSEC, 'H' * NSEC, 'H' * (NSEC // 2) + 'L' * (NSEC - NSEC // 2)):
     node = ext.Buffer(noise)
     for s, k in enumerate(kinds):
         node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if k == 'H' else 'LowPass')
     mixed = len(set(kinds)) > 1
-    for variant in (0, 4):
+    for variant, pct in [(0, p) for p in PCTS] + [(4, 100)]:
         c = engine.Engine().compile(node, CH, RATE, FRAMES)
         c.set_option('reg_variant', variant)
+        c.set_option('osc_pieces_pct', pct)
         if mixed and variant == 4:
             c.set_option('cascade_reg', 0)
         for _ in range(2):
@@ -41,5 +43,5 @@ for kinds in ('LLLLLLLL', 'HHHHHHHH', 'HHHHLLLL'):
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 3
         name = ('k_cascade_delta (mixed)' if variant == 0 else 'k_cascade_pipe') if mixed else ('k_cascade_delta' if variant == 0 else 'k_cascade_reg (state-variable)')
-        print(f'{kinds} {name}: {ms:.2f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, {8 * CH * FRAMES / ms / 1e6:.0f} GB/s read + written')
+        print(f'{kinds} {name} pieces {pct}%: {ms:.2f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, {8 * CH * FRAMES / ms / 1e6:.0f} GB/s read + written')
         c.close()
