@@ -181,6 +181,7 @@ int sigb_cascade_pipe_items(const ChainDev* a, int max_segments);
 int sigb_launch_cascade_pipe(const ChainDev* a, int max_segments, int sections_per_warp, void* stream);
 int sigb_cascade_reg_ok(const ChainDev* a);
 int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream);
+int sigb_cascade_reg_fill(const ChainDev* a, int max_segments, int variant);
 void sigb_set_reg_pieces(int n);
 void sigb_set_delta_probe(int n);
 int sigb_osc_reg_ok(const ChainDev* a, int allow_delta);

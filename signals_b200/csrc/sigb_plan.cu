@@ -1311,7 +1311,9 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 const bool deep = ch.nsec_real >= 3;
                 const bool forced = p->opt_cascade_pipe > 0 && ch.nsec_real >= (int)p->opt_cascade_pipe;
                 // deep cascades on a materialised block keep every section in registers (k_cascade_reg)
-                if (p->opt_cascade_reg != 0 && sigb_cascade_reg_ok(&t)) {
+                // (two sections: only unmodulated chains whose time pieces fill at least half of the machine's warp slots)
+                if (p->opt_cascade_reg != 0 && sigb_cascade_reg_ok(&t) &&
+                    (ch.nsec_real >= 3 || (ch.mods.empty() && sigb_cascade_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_reg_variant) >= 512))) {
                     int e = sigb_launch_cascade_reg(&t, (int)p->opt_pipe_segments, (int)p->opt_reg_variant, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_cascade_reg: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;

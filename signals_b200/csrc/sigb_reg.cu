@@ -549,6 +549,7 @@ int g_delta_probe = 0;          // A/B (8 low-pass sections only): 0 default geo
 template <int KIND>
 int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, cudaStream_t st) {
     switch (a->nsec) {
+        case 2: k_cascade_delta<2, 8, delta_min_blocks(2, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         case 3: k_cascade_delta<3, 8, delta_min_blocks(3, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         case 4: k_cascade_delta<4, 8, delta_min_blocks(4, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         case 5: k_cascade_delta<5, 8, delta_min_blocks(5, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
@@ -891,7 +892,7 @@ static bool reg_fast_layout(const ChainDev* a) {
 }
 
 extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
-    if (a->src_kind != SRC_BUF || a->nsec < 3 || a->nsec > 8 || a->C <= 0) return 0;
+    if (a->src_kind != SRC_BUF || a->nsec < 2 || a->nsec > 8 || a->C <= 0) return 0;
     bool mixed = false, any_first = false;
     for (int k = 0; k < a->nsec; ++k) {
         mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
@@ -899,46 +900,63 @@ extern "C" int sigb_cascade_reg_ok(const ChainDev* a) {
     }
     // one kind: always (first-order sections are welcome, load_section); low- and high-pass sections mixed: k_cascade_delta
     // only, i.e. second-order sections on the aligned whole-tile layout of THIS call (k_cascade_pipe takes the rest)
-    if (mixed) return !any_first && reg_fast_layout(a);
+    if (mixed || a->nsec == 2) return !any_first && reg_fast_layout(a);     // (two sections: the planner also asks sigb_cascade_reg_fill)
     return 1;
 }
 
 // variant 0 (default): blocks of 8 rows; variant 1: blocks of 4 rows (measured on C4: 4.59e11 vs 4.48e11
 // channel-samples/s).  max_segments bounds the pieces per tile (1: never cut along time).
-extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (a->frames <= 0) return 0;
-    const bool fast = reg_fast_layout(a);
-    bool any_first = false, mixed = false;
+struct RegGeometry { bool fast, wide, delta, mixed; int R, tiles, npieces, warm; int64_t slots; };
+
+static RegGeometry cascade_reg_geometry(const ChainDev* a, int max_segments, int variant) {
+    RegGeometry q;
+    q.fast = reg_fast_layout(a);
+    bool any_first = false;
+    q.mixed = false;
     for (int k = 0; k < a->nsec; ++k) {
         any_first |= (a->sec_kind[k] & SEC_FIRST_ORDER) != 0;
-        mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
+        q.mixed |= (a->sec_kind[k] & SEC_HP) != (a->sec_kind[0] & SEC_HP);
     }
-    if (mixed) variant = 0;          // only k_cascade_delta runs both kinds in one cascade (sigb_cascade_reg_ok checked the layout)
-    const bool wide = fast && variant != 1;
+    if (q.mixed || a->nsec == 2) variant = 0;    // only k_cascade_delta runs both kinds in one cascade, or two sections (sigb_cascade_reg_ok checked the layout)
+    q.wide = q.fast && variant != 1;
     // delta form (5 operations per low-pass section, 4 per high-pass section, instead of 6 / 7): second-order sections only;
     // variant 4 keeps the state-variable form in 8-row blocks for A/B
-    const bool delta = fast && variant != 1 && variant != 4 && !any_first;
-    const int dprobe = (delta && a->nsec == 8 && !mixed && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
-    const int R = (wide && dprobe != 1) ? 8 : 4;
-    const int tiles = (a->C + RC - 1) / RC;
+    q.delta = q.fast && variant != 1 && variant != 4 && !any_first;
+    const int dprobe = (q.delta && a->nsec == 8 && !q.mixed && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
+    q.R = (q.wide && dprobe != 1) ? 8 : 4;
+    const int R = q.R;
+    q.tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int warps_per_sm = (delta ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec, mixed ? SEC_MIXED : 0)) : reg_min_blocks(a->nsec, R)) * RWARPS;
+    const int warps_per_sm = (q.delta ? (dprobe == 1 || dprobe == 3 ? 4 : dprobe == 6 ? 3 : delta_min_blocks(a->nsec, q.mixed ? SEC_MIXED : 0)) : reg_min_blocks(a->nsec, R)) * RWARPS;
     // pieces: one per warp slot of the machine, as long as the warm-up of a piece that starts inside a tile stays
     // below 1/4 of the piece; never fewer than one per tile
     const int bpt = (a->frames + R - 1) / R;
-    int warm = 0;
-    int64_t want = tiles;
+    q.slots = (int64_t)sms * warps_per_sm * std::max(1, g_reg_pieces) * g_osc_pieces_pct / 100;
+    int64_t want = q.tiles;
     if (max_segments > 1 && a->warm_rows >= 0) {
-        warm = (a->warm_rows + R - 1) / R * R;
-        const int64_t slots = (int64_t)sms * warps_per_sm * std::max(1, g_reg_pieces) * g_osc_pieces_pct / 100;
-        const int64_t fit = (int64_t)tiles * bpt / std::max(1, 4 * warm / R);
-        want = std::max<int64_t>(tiles, std::min<int64_t>(std::min(slots, fit), (int64_t)tiles * max_segments));
+        q.warm = (a->warm_rows + R - 1) / R * R;
+        const int64_t fit = (int64_t)q.tiles * bpt / std::max(1, 4 * q.warm / R);
+        want = std::max<int64_t>(q.tiles, std::min<int64_t>(std::min(q.slots, fit), (int64_t)q.tiles * max_segments));
     } else {
-        warm = bpt * R;              // unknown decay: a piece never starts inside a tile (npieces == tiles)
+        q.warm = bpt * R;            // unknown decay: a piece never starts inside a tile (npieces == tiles)
     }
-    const int npieces = (int)want;
+    q.npieces = (int)want;
+    return q;
+}
+
+// share of the machine's warp slots the launch would occupy, in 1/1024 (see sigb_osc_reg_fill)
+extern "C" int sigb_cascade_reg_fill(const ChainDev* a, int max_segments, int variant) {
+    const RegGeometry q = cascade_reg_geometry(a, max_segments, variant);
+    return (int)std::min<int64_t>(1024, (int64_t)q.npieces * 1024 / std::max<int64_t>(1, q.slots));
+}
+
+extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int variant, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
+    const RegGeometry q = cascade_reg_geometry(a, max_segments, variant);
+    const bool fast = q.fast, wide = q.wide, delta = q.delta, mixed = q.mixed;
+    const int tiles = q.tiles, npieces = q.npieces, warm = q.warm;
     const dim3 grid((unsigned)((npieces + RWARPS - 1) / RWARPS));
     const bool hp = (a->sec_kind[0] & SEC_HP) != 0;
     if (delta) return mixed ? delta_launch_nsec<SEC_MIXED>(a, grid, tiles, npieces, warm, st)

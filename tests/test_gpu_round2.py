@@ -513,3 +513,38 @@ def test_streams_pass_between_the_cascade_kernels(ns, engine):
         err = max_abs_err(got, want)
         print(f'{cls} stream through delta / state-variable / pipelined / delta kernels: max-abs {err:.3e}')
         assert err <= 2e-6
+
+
+@pytest.mark.parametrize('kinds', ['LL', 'HH', 'HL'])
+def test_two_section_chains_on_a_block_leave_the_scan_kernel(kinds, ns, engine):
+    """Two second-order sections on a materialised block (two chained filter nodes, or one order-4 node): when the time
+    pieces their decay horizon allows fill the machine the chain runs in k_cascade_delta instead of k_chain_scan2 --
+    same result (against the float64 cascade and against the scan kernel on the same plan), state carried on."""
+    from signals_b200.chain import ext
+    torch = pytest.importorskip('torch')
+    rng = np.random.default_rng(83)
+    ch, frames, tail = 4096, 96000, 1000
+    g = torch.Generator(device='cuda')
+    g.manual_seed(83)
+    xd = torch.rand((frames + tail, ch), generator=g, device='cuda', dtype=torch.float32) * 2 - 1
+    cut = np.exp(rng.uniform(np.log(800.0), np.log(8000.0), (2, ch)))
+    got = {}
+    for kernel in ('reg', 'scan'):
+        node = ext.Buffer(xd)
+        for s, k in enumerate(kinds):
+            node = cases.lowpass(ns, node, [cut[s]], 'HighPass' if k == 'H' else 'LowPass')
+        c = engine.compile(node, ch, RATE)
+        c.set_option('cascade_reg', -1 if kernel == 'reg' else 0)
+        first = c.render_device(0, frames)
+        second = c.render_device(frames, tail)
+        got[kernel] = torch.cat([first, second])
+        c.close()
+    pick = np.sort(rng.choice(ch, 10, replace=False))
+    want = xd[:, torch.from_numpy(pick).cuda()].cpu().numpy().astype(np.float64)
+    for s, k in enumerate(kinds):
+        want, _ = np_oracle.render_cascade(want, cut[s:s + 1, pick], RATE, btype='hp' if k == 'H' else 'lp')
+    err = max_abs_err(got['reg'][:, torch.from_numpy(pick).cuda()].cpu().numpy(), want)
+    diff = float((got['reg'] - got['scan']).abs().max())
+    print(f'two sections {kinds} on a block: register kernel max-abs {err:.3e}; vs the scan kernel {diff:.3e}')
+    assert err <= 1e-4
+    assert diff <= 2e-6

@@ -31,7 +31,7 @@ for kinds in ('L' * NSEC, 'H' * NSEC, 'H' * (NSEC // 2) + 'L' * (NSEC - NSEC // 
         c = engine.Engine().compile(node, CH, RATE, FRAMES)
         c.set_option('reg_variant', variant)
         c.set_option('osc_pieces_pct', pct)
-        if mixed and variant == 4:
+        if (mixed or NSEC == 2) and variant == 4:
             c.set_option('cascade_reg', 0)
         for _ in range(2):
             c.render_device(0, FRAMES, out)
@@ -42,6 +42,7 @@ for kinds in ('L' * NSEC, 'H' * NSEC, 'H' * (NSEC // 2) + 'L' * (NSEC - NSEC // 
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 3
-        name = ('k_cascade_delta (mixed)' if variant == 0 else 'k_cascade_pipe') if mixed else ('k_cascade_delta' if variant == 0 else 'k_cascade_reg (state-variable)')
+        other = 'k_chain_scan2' if NSEC == 2 else 'k_cascade_pipe' if mixed else 'k_cascade_reg (state-variable)'
+        name = ('k_cascade_delta (mixed)' if mixed else 'k_cascade_delta') if variant == 0 else other
         print(f'{kinds} {name} pieces {pct}%: {ms:.2f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, {8 * CH * FRAMES / ms / 1e6:.0f} GB/s read + written')
         c.close()
