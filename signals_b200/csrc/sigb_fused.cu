@@ -138,39 +138,47 @@ constexpr int VT = SIGB_VOICE_THREADS;
 // (row-major over k, then m) and the scheduler overlaps their dependency chains
 template <int KIND, int M, int VK>
 __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M], const float (&c)[M], const float (&d)[M],
-                                          float (&s1)[M], float (&s2)[M], int kmax) {
+                                          float (&s1)[M], float (&s2)[M], float (&s3)[M], int kmax) {
 #ifndef SIGB_VOICES_SCALAR
     if constexpr (M == 4 && !(KIND & SEC_FIRST_ORDER)) {
-        // second-order sections of four voices as two packed f32x2 recurrences (six FFMA2-class instructions per
-        // two voice-samples instead of seven scalar ones per voice-sample); same arithmetic as pipe_step /
-        // reg_step of the cascade kernels: e = x - c s1 - s2, bp = s1 + g d e, s1' = s1 + 2 g d e,
-        // lp = s2 + g bp, s2' = s2 + 2 g bp, hp = d e
-        float2 nc[2], al[2], a2[2], gg[2], g2[2], dd[2], p1[2], p2[2];
+        // second-order sections of four voices as two packed f32x2 recurrences in DELTA FORM (sigb_reg.cu, k_cascade_delta):
+        // the thread holds (a, F/4 | D, Z, P) for a low-pass voice and (-Q, -F | D, -4 Z) for a high-pass voice instead of
+        // (g, c, d | s1, s2) -- k_voices converts at the ends of a piece -- 5 / 4 FFMA2-class instructions per two
+        // voice-samples instead of 6 / 7; the high-pass output scale d is folded into the voice's (L, R) weights.
+        //   low-pass:   w = x - 4 Z;  D' = a D + w;  Z' = Z + (F/4) D';  p = Z' + Z;  lp = p + P;  P' = p
+        //   high-pass:  w = x + (-4 Z);  t = w - Q D;  D' = D + t;  (-4 Z)' = (-4 Z) - F D';  hp = d t
+        float2 ca[2], cb[2], pD[2], pZ[2], pP[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int m0 = 2 * h, m1 = 2 * h + 1;
-            gg[h] = make_float2(g[m0], g[m1]);
-            g2[h] = make_float2(2.0f * g[m0], 2.0f * g[m1]);
-            al[h] = make_float2(g[m0] * d[m0], g[m1] * d[m1]);
-            a2[h] = make_float2(2.0f * (g[m0] * d[m0]), 2.0f * (g[m1] * d[m1]));
-            nc[h] = make_float2(-c[m0], -c[m1]);
-            dd[h] = make_float2(d[m0], d[m1]);
-            p1[h] = make_float2(s1[m0], s1[m1]);
-            p2[h] = make_float2(s2[m0], s2[m1]);
+            ca[h] = make_float2(g[m0], g[m1]);
+            cb[h] = make_float2(c[m0], c[m1]);
+            pD[h] = make_float2(s1[m0], s1[m1]);
+            pZ[h] = make_float2(s2[m0], s2[m1]);
+            pP[h] = make_float2(s3[m0], s3[m1]);
         }
+        const float2 m4 = make_float2(-4.0f, -4.0f);
 #pragma unroll
         for (int k = 0; k < VK; ++k) {
             if (k < kmax) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 xp = make_float2(x[2 * h][k], x[2 * h + 1][k]);
-                    const float2 xs = __fadd2_rn(xp, make_float2(-p2[h].x, -p2[h].y));
-                    const float2 e = __ffma2_rn(nc[h], p1[h], xs);
-                    const float2 bp = __ffma2_rn(al[h], e, p1[h]);
-                    p1[h] = __ffma2_rn(a2[h], e, p1[h]);
-                    const float2 lp = __ffma2_rn(gg[h], bp, p2[h]);
-                    p2[h] = __ffma2_rn(g2[h], bp, p2[h]);
-                    const float2 y = (KIND & SEC_HP) ? __fmul2_rn(e, dd[h]) : lp;
+                    float2 y;
+                    if (KIND & SEC_HP) {
+                        const float2 w = __fadd2_rn(xp, pZ[h]);
+                        y = __ffma2_rn(ca[h], pD[h], w);
+                        pD[h] = __fadd2_rn(pD[h], y);
+                        pZ[h] = __ffma2_rn(cb[h], pD[h], pZ[h]);
+                    } else {
+                        const float2 w = __ffma2_rn(m4, pZ[h], xp);
+                        pD[h] = __ffma2_rn(ca[h], pD[h], w);
+                        const float2 zn = __ffma2_rn(cb[h], pD[h], pZ[h]);
+                        const float2 p = __fadd2_rn(zn, pZ[h]);
+                        pZ[h] = zn;
+                        y = __fadd2_rn(p, pP[h]);
+                        pP[h] = p;
+                    }
                     x[2 * h][k] = y.x;
                     x[2 * h + 1][k] = y.y;
                 }
@@ -178,8 +186,9 @@ __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M]
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            s1[2 * h] = p1[h].x; s1[2 * h + 1] = p1[h].y;
-            s2[2 * h] = p2[h].x; s2[2 * h + 1] = p2[h].y;
+            s1[2 * h] = pD[h].x; s1[2 * h + 1] = pD[h].y;
+            s2[2 * h] = pZ[h].x; s2[2 * h + 1] = pZ[h].y;
+            s3[2 * h] = pP[h].x; s3[2 * h + 1] = pP[h].y;
         }
         return;
     }
@@ -243,8 +252,13 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
 
     unsigned long long th[M], dK[M];
     int dhi[M], chan[M];
-    float g[M], cf[M], d[M], s1[M], s2[M];
+    float g[M], cf[M], d[M], s1[M], s2[M], s3[M];
     float2 wt[M];
+#ifndef SIGB_VOICES_SCALAR
+    const bool dform = M == 4 && fk >= 0 && !(fk & SEC_FIRST_ORDER);       // delta-form registers (filt_tile)
+#else
+    const bool dform = false;
+#endif
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         const int c = (cta * M + m) * VT + tid;
@@ -256,13 +270,33 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
         dK[m] = dth * (unsigned long long)VK;
         dhi[m] = (int)((dth + 0x80000000ull) >> 32);
         wt[m] = live ? make_float2(sg.wl[cc], sg.wr[cc]) : make_float2(0.0f, 0.0f);
-        g[m] = cf[m] = d[m] = s1[m] = s2[m] = 0.0f;
+        g[m] = cf[m] = d[m] = s1[m] = s2[m] = s3[m] = 0.0f;
         if (fk >= 0) {
             g[m] = sg.coef[0 * C + cc];
             cf[m] = sg.coef[1 * C + cc];
             d[m] = sg.coef[2 * C + cc];
             s1[m] = first_seg ? (float)sg.state[0 * C + cc] : 0.0f;
             s2[m] = first_seg ? (float)sg.state[1 * C + cc] : 0.0f;
+            if (dform) {
+                // (g, c, d | s1, s2) -> delta-form registers; same formulas as delta_coef / delta_state_in of sigb_reg.cu
+                const double G = (double)g[m], Dd = (double)d[m], R2 = (double)cf[m] - G;
+                const double gd2 = 2.0 * G * Dd, F = 4.0 * G * G * Dd;
+                const double S1 = first_seg ? sg.state[0 * C + cc] : 0.0, S2 = first_seg ? sg.state[1 * C + cc] : 0.0;
+                const double Dst = S1 / gd2;
+                s1[m] = (float)Dst;
+                if (fk & SEC_HP) {
+                    wt[m].x *= d[m];                                  // the high-pass output scale rides on the weights
+                    wt[m].y *= d[m];
+                    g[m] = (float)(-R2 * gd2);                        // -Q
+                    cf[m] = (float)(-F);
+                    s2[m] = (float)(0.5 * (double)cf[m] * Dst - S2);   // -4 Z = -(s2 + (F/2) D), with the float32 F the store inverts
+                } else {
+                    g[m] = (float)(1.0 - R2 * gd2);                   // a
+                    cf[m] = (float)(0.25 * F);
+                    s2[m] = (float)(0.25 * (S2 + 2.0 * (double)cf[m] * Dst));
+                    s3[m] = (float)(0.5 * S2);
+                }
+            }
         }
     }
     float2* part_out = reinterpret_cast<float2*>(a.partial) + (size_t)grp * a.frames;
@@ -297,10 +331,10 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
             }
         }
         switch (fk) {
-            case 0: filt_tile<0, M, VK>(x, g, cf, d, s1, s2, kmax); break;
-            case SEC_HP: filt_tile<SEC_HP, M, VK>(x, g, cf, d, s1, s2, kmax); break;
-            case SEC_FIRST_ORDER: filt_tile<SEC_FIRST_ORDER, M, VK>(x, g, cf, d, s1, s2, kmax); break;
-            case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP, M, VK>(x, g, cf, d, s1, s2, kmax); break;
+            case 0: filt_tile<0, M, VK>(x, g, cf, d, s1, s2, s3, kmax); break;
+            case SEC_HP: filt_tile<SEC_HP, M, VK>(x, g, cf, d, s1, s2, s3, kmax); break;
+            case SEC_FIRST_ORDER: filt_tile<SEC_FIRST_ORDER, M, VK>(x, g, cf, d, s1, s2, s3, kmax); break;
+            case SEC_FIRST_ORDER | SEC_HP: filt_tile<SEC_FIRST_ORDER | SEC_HP, M, VK>(x, g, cf, d, s1, s2, s3, kmax); break;
             default: break;
         }
         if (n0 + VK <= row_store) continue;             // warm-up tile: nothing to reduce or store (uniform over the CTA)
@@ -331,8 +365,16 @@ __global__ void __launch_bounds__(VT, M == 4 ? 2 : 3) k_voices(const __grid_cons
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (chan[m] >= 0) {
-                sg.state_out[0 * C + chan[m]] = (double)s1[m];
-                sg.state_out[1 * C + chan[m]] = (double)s2[m];
+                double S1 = (double)s1[m], S2 = (double)s2[m];
+                if (dform) {
+                    // back to the plan's state-variable convention (delta_state_out of sigb_reg.cu); d[m] still holds d
+                    const double gd2 = 2.0 * (double)sg.coef[0 * C + chan[m]] * (double)d[m];
+                    S1 = gd2 * (double)s1[m];
+                    S2 = (fk & SEC_HP) ? 0.5 * (double)cf[m] * (double)s1[m] - (double)s2[m]
+                                       : 4.0 * (double)s2[m] - 2.0 * (double)cf[m] * (double)s1[m];
+                }
+                sg.state_out[0 * C + chan[m]] = S1;
+                sg.state_out[1 * C + chan[m]] = S2;
             }
         }
     }
