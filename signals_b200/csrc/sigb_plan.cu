@@ -1311,9 +1311,10 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 const bool deep = ch.nsec_real >= 3;
                 const bool forced = p->opt_cascade_pipe > 0 && ch.nsec_real >= (int)p->opt_cascade_pipe;
                 // deep cascades on a materialised block keep every section in registers (k_cascade_reg)
-                // (two sections: only unmodulated chains whose time pieces fill at least half of the machine's warp slots)
+                // (two sections: only chains whose decay horizon the host knows -- unmodulated, or modulated in a large request, run_params --
+                // and whose time pieces fill at least half of the machine's warp slots)
                 if (p->opt_cascade_reg != 0 && sigb_cascade_reg_ok(&t) &&
-                    (ch.nsec_real >= 3 || (ch.mods.empty() && sigb_cascade_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_reg_variant) >= 512))) {
+                    (ch.nsec_real >= 3 || (t.warm_rows >= 0 && sigb_cascade_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_reg_variant) >= 512))) {
                     int e = sigb_launch_cascade_reg(&t, (int)p->opt_pipe_segments, (int)p->opt_reg_variant, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_cascade_reg: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;
@@ -1324,7 +1325,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 // half of the machine's warp slots (else the time-parallel scan kernel is the better choice)
                 if (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg && sigb_osc_reg_ok(&t, (int)p->opt_osc_delta) &&
                     (ch.nsec_real >= 3 || p->osc_reg_user ||
-                     (ch.mods.empty() && sigb_osc_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta) >= 512))) {
+                     (t.warm_rows >= 0 && sigb_osc_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta) >= 512))) {
                     int e = sigb_launch_osc_reg(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_osc_reg: ") + cudaGetErrorString((cudaError_t)e));
                     p->launch_count++;
@@ -1561,6 +1562,9 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
         if (!ch.mods.empty()) {
             ch.warm_rows = -1;
             if (ch.nsec_real >= 3 || p->opt_cascade_pipe > 0 || (p->osc_reg_user && p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg)) need_host = true;
+            // two sections: the register kernels are ~1.9x the scan kernel's rate, worth one synchronisation when
+            // the request is large (>= 2^28 samples, a render of >= 0.25 ms)
+            if (ch.nsec_real == 2 && p->opt_cascade_pipe != 0 && frames * (int64_t)ch.C >= (1ll << 28)) need_host = true;
         }
     }
     if (want_warm) {

@@ -548,3 +548,38 @@ def test_two_section_chains_on_a_block_leave_the_scan_kernel(kinds, ns, engine):
     print(f'two sections {kinds} on a block: register kernel max-abs {err:.3e}; vs the scan kernel {diff:.3e}')
     assert err <= 1e-4
     assert diff <= 2e-6
+
+
+def test_large_modulated_two_section_request_runs_register_resident(ns, engine):
+    """Two filters with LFO-driven cutoffs behind an oscillator in a LARGE request (>= 2^28 samples): the plan waits for the
+    decay horizon k_design reports and takes k_osc_delta, like an unmodulated chain -- same result as the scan kernel
+    (cascade_pipe = 0) and as the float64 oracle at the sampled cutoffs."""
+    torch = pytest.importorskip('torch')
+    ch, frames, pos = 4096, 144000, 0       # (position 0: a seek into CHAINED filters follows DESIGN 1, not the reference's nested restarts)
+    rng = np.random.default_rng(84)
+    hz = rng.uniform(60.0, 2000.0, ch)
+
+    def graph(sel=slice(None)):
+        node = cases.osc(ns, 'Sine', [hz[sel]])
+        for k in range(2):
+            r = np.random.default_rng(90 + k)
+            lo, hi = r.uniform(500.0, 900.0, ch)[sel], r.uniform(2000.0, 6000.0, ch)[sel]
+            wah = cases._wah(ns, [lo], [hi], [r.uniform(0.5, 3.0, ch)[sel]], [r.uniform(0.0, 1.0, ch)[sel]])
+            node = cases._with_cutoff(ns, node, wah)
+        return node
+
+    got = {}
+    for kernel in ('reg', 'scan'):
+        c = engine.compile(graph(), ch, RATE)
+        if kernel == 'scan':
+            c.set_option('cascade_pipe', 0)
+        got[kernel] = c.render_device(pos, frames)
+        c.close()
+    assert not bool(torch.equal(got['reg'], got['scan']))          # two different kernels did render
+    diff = float((got['reg'] - got['scan']).abs().max())
+    pick = np.sort(rng.choice(ch, 8, replace=False))
+    want = np_oracle.GraphOracle(RATE).render(graph(pick), pos, frames, len(pick))
+    err = max_abs_err(got['reg'][:, torch.from_numpy(pick).cuda()].cpu().numpy(), want)
+    print(f'large modulated 2-section request: register kernel vs oracle {err:.3e}, vs the scan kernel {diff:.3e}')
+    assert err <= 1e-4
+    assert diff <= 2e-5
