@@ -129,7 +129,7 @@ constexpr float kTwoPiQ32 = 1.4629180792671596e-9f;   // 2*pi*2^-32
 template <int WAVE>
 __device__ __forceinline__ float wave_q32(int w) {
     if (WAVE == SIGB_WAVE_SINE) return __sinf((float)w * kTwoPiQ32);
-    if (WAVE == SIGB_WAVE_SQUARE) return w >= 0 ? 1.0f : -1.0f;                    // frac < 1/2 -> +1
+    if (WAVE == SIGB_WAVE_SQUARE) return __int_as_float(0x3f800000 | (w & (int)0x80000000));   // frac < 1/2 -> +1: 1.0 with w's sign bit (one LOP3)
     if (WAVE == SIGB_WAVE_SAWTOOTH) return (float)w * 4.656612873077393e-10f;      // 2 frac (- 2 past 1/2)
     return fmaf(-fabsf((float)(w - 0x40000000)), 9.313225746154785e-10f, 1.0f);    // 1 - 4 |frac - 1/4|
 }
@@ -155,6 +155,8 @@ __device__ __forceinline__ bool wave_near_edge(int w, int guard) {
 //     exactly wave_near_edge's test, as one shift-add and one compare.
 template <int WAVE, int K>
 __device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[K]) {
+    // The edge tests accumulate as a running minimum / maximum (one instruction per sample, compared once per tile) instead
+    // of a compare and a select per sample.
     bool near = false;
     if (WAVE == SIGB_WAVE_SINE) {
 #pragma unroll
@@ -164,23 +166,27 @@ __device__ __forceinline__ bool gen_tile(int w, int dhi, int guard, float (&x)[K
         }
     } else if (WAVE == SIGB_WAVE_SQUARE) {
         const unsigned g2 = 2u * (unsigned)guard, g4 = 4u * (unsigned)guard;
+        unsigned umin = 0xffffffffu;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             x[k] = wave_q32<SIGB_WAVE_SQUARE>(w);
-            near |= ((unsigned)w << 1) + g2 < g4;
+            umin = min(umin, ((unsigned)w << 1) + g2);
             w += dhi;
         }
+        near = umin < g4;
     } else {
         const float thr = 2147483648.0f - (float)(guard + 128);
         if (WAVE == SIGB_WAVE_TRIANGLE) w -= 0x40000000;      // the trough (frac 3/4) becomes the wrap point
+        float vmax = 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float v = (float)w;
             x[k] = WAVE == SIGB_WAVE_SAWTOOTH ? v * 4.656612873077393e-10f                  // 2 frac (- 2 past 1/2)
                                               : fmaf(-fabsf(v), 9.313225746154785e-10f, 1.0f);   // 1 - 4 |frac - 1/4|
-            near |= fabsf(v) >= thr;
+            vmax = fmaxf(vmax, fabsf(v));
             w += dhi;
         }
+        near = vmax >= thr;
     }
     return near;
 }

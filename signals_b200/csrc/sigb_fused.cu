@@ -158,31 +158,36 @@ __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M]
             pP[h] = make_float2(s3[m0], s3[m1]);
         }
         const float2 m4 = make_float2(-4.0f, -4.0f);
+        auto row = [&](int k) {
 #pragma unroll
-        for (int k = 0; k < VK; ++k) {
-            if (k < kmax) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float2 xp = make_float2(x[2 * h][k], x[2 * h + 1][k]);
-                    float2 y;
-                    if (KIND & SEC_HP) {
-                        const float2 w = __fadd2_rn(xp, pZ[h]);
-                        y = __ffma2_rn(ca[h], pD[h], w);
-                        pD[h] = __fadd2_rn(pD[h], y);
-                        pZ[h] = __ffma2_rn(cb[h], pD[h], pZ[h]);
-                    } else {
-                        const float2 w = __ffma2_rn(m4, pZ[h], xp);
-                        pD[h] = __ffma2_rn(ca[h], pD[h], w);
-                        const float2 zn = __ffma2_rn(cb[h], pD[h], pZ[h]);
-                        const float2 p = __fadd2_rn(zn, pZ[h]);
-                        pZ[h] = zn;
-                        y = __fadd2_rn(p, pP[h]);
-                        pP[h] = p;
-                    }
-                    x[2 * h][k] = y.x;
-                    x[2 * h + 1][k] = y.y;
+            for (int h = 0; h < 2; ++h) {
+                const float2 xp = make_float2(x[2 * h][k], x[2 * h + 1][k]);
+                float2 y;
+                if (KIND & SEC_HP) {
+                    const float2 w = __fadd2_rn(xp, pZ[h]);
+                    y = __ffma2_rn(ca[h], pD[h], w);
+                    pD[h] = __fadd2_rn(pD[h], y);
+                    pZ[h] = __ffma2_rn(cb[h], pD[h], pZ[h]);
+                } else {
+                    const float2 w = __ffma2_rn(m4, pZ[h], xp);
+                    pD[h] = __ffma2_rn(ca[h], pD[h], w);
+                    const float2 zn = __ffma2_rn(cb[h], pD[h], pZ[h]);
+                    const float2 p = __fadd2_rn(zn, pZ[h]);
+                    pZ[h] = zn;
+                    y = __fadd2_rn(p, pP[h]);
+                    pP[h] = p;
                 }
+                x[2 * h][k] = y.x;
+                x[2 * h + 1][k] = y.y;
             }
+        };
+        if (kmax == VK) {                                  // every tile but the ragged last one of a launch: no per-row test
+#pragma unroll
+            for (int k = 0; k < VK; ++k) row(k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < VK; ++k)
+                if (k < kmax) row(k);
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
