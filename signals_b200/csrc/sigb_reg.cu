@@ -504,8 +504,13 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
             }
         }
         if (row >= row_store) {
+            if (KIND == 0 && !a.gain) {            // a low-pass cascade without a Gain behind it: nothing to scale
 #pragma unroll
-            for (int k = 0; k < R; ++k) __stcs(reinterpret_cast<float2*>(op + (uint32_t)k * out_ldb), __fmul2_rn(x[k], gain));
+                for (int k = 0; k < R; ++k) __stcs(reinterpret_cast<float2*>(op + (uint32_t)k * out_ldb), x[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) __stcs(reinterpret_cast<float2*>(op + (uint32_t)k * out_ldb), __fmul2_rn(x[k], gain));
+            }
         }
         op += (int64_t)R * out_ldb;
         row += R;
