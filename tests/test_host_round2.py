@@ -1,6 +1,7 @@
 """CPU: host-side logic added in round 2 -- the graph epoch behind the engine's dirty flag, tap records in the lowered
 plan, the C ABI entry points of the realtime path (no compute without a GPU), and the bench workloads."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -8,6 +9,8 @@ import pytest
 from oracle import cases
 from signals_b200 import _lib, chain, engine as engine_mod, plan as plan_mod
 from signals_b200.chain import vis
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 RATE = 48000
 
@@ -125,3 +128,27 @@ def test_bench_workloads_build_and_lower(ns):
     jobs, units, sample = bench.C2(64, 0.01, 0, 1).cpu_sample_blockwise(2)
     assert len(jobs) == 2 and jobs[0][0] == 'blockwise' and units == 16 * RATE
     del args
+
+
+def test_delta_form_sections_hold_the_float32_budget(tmp_path):
+    """The delta-form sections of k_cascade_delta / k_osc_delta / k_voices, restated in plain C with fmaf
+    (tools/delta_form_sim.c, tools/delta_form_sim_hp.c): 8-section cascades in float32 against the float64 state-variable
+    cascade on noise + a 7 Hz tone, cutoffs from 5 Hz to 23 kHz -- every case far inside the 1e-4 bar for cascaded IIR, and the
+    states equal the state-variable section's own up to float32 rounding (the pointwise hand-over between kernels)."""
+    import re
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    for src in ('delta_form_sim.c', 'delta_form_sim_hp.c'):
+        exe = tmp_path / src.replace('.c', '')
+        subprocess.check_call([gcc, '-O2', '-ffp-contract=off', '-o', str(exe), os.path.join(ROOT, 'tools', src), '-lm'])
+        out = subprocess.check_output([str(exe), '5'], text=True)
+        rows = re.findall(r'cut0 (\S+): max\|y\| (\S+)\s+err svf32 (\S+)\s+err delta32 (\S+)\s+state-identity dev (\S+)', out)
+        assert len(rows) == 8, out
+        for cut0, peak, e_svf, e_delta, dev in rows:
+            assert float(e_delta) <= 2e-5, (src, cut0, e_delta)
+            assert float(e_delta) <= 8.0 * float(e_svf) + 1e-6, (src, cut0, e_svf, e_delta)     # same class as the state-variable form
+            if float(cut0) < 20000:
+                assert float(dev) <= 1e-5, (src, cut0, dev)
