@@ -151,7 +151,9 @@ int64_t sigb_plan_describe(const sigb_plan* plan, char* buf, int64_t cap);
  *   "reg_variant" (0: k_cascade_delta wherever it applies, else k_cascade_reg in 8-row blocks; 1: k_cascade_reg in 4-row blocks;
  *   4: k_cascade_reg in 8-row blocks), "osc_reg" (oscillator-fed chains of >= n sections run
  *   register-resident, 0: never; default 2, where 2-section chains qualify only when unmodulated and filling the machine),
- *   "osc_delta" (0: those chains keep state-variable sections), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
+ *   "osc_delta" (0: those chains keep state-variable sections), "delta_probe" / "osc_pieces_pct" / "reg_pieces" (process-wide A/B
+ *   switches behind profiles/r02_c4_delta.txt and r02_osc_sections.txt: geometry of k_cascade_delta for 8 low-pass sections, time
+ *   pieces of the register kernels as a percentage of / per resident warp slot), "cascade_pipe" (-1 auto, 0 never, n: from n sections),
  *   "pipe_spw", "pipe_segments" (upper bound on the time pieces per tile of the cascade kernels; 1: never cut),
  *   "voices_segments" (k_voices: 0 equal pieces per resident CTA, 1 one piece per voice group, n pieces per group),
  *   "voices_pieces" (automatic mode: pieces per resident CTA slot, default 16), "voices_m",
