@@ -115,6 +115,7 @@ struct ReduceSpec {
     int C = 0, groups = 0, pan = 0;
     int in_node = -1;
     Table w;
+    int w_row = -1;              // PanSum with a modulated pan: row of the parameter program holding pan[C] for this request
     int dst_node = -1;
 };
 
@@ -1081,7 +1082,11 @@ int Builder::build_merge(int i) {
 int Builder::build_reduce(int i) {
     const sigb_node& n = p->nodes[i];
     if (n.in[0] < 0) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": reduction without input");
-    if (p->opt_fuse_reduce) {
+    // a pan driven by an emitter (block-rate modulation: an LFO sweeping the stereo position) is a row of the parameter
+    // program, re-sampled at every request's first frame like every block-rate port; the fused voice kernel bakes
+    // gain * (1 - pan), gain * pan into host-built tables, so such a PanSum runs on the materialised block (k_reduce)
+    const bool pan_modulated = n.kind == SIGB_NODE_PANSUM && const_of(p, n.in[1]) == nullptr;
+    if (p->opt_fuse_reduce && !pan_modulated) {
         if (n.kind == SIGB_NODE_GROUPSUM) {
             int nsec = 0, wave = 0;
             if (pure_osc_run(n.in[0], &nsec, &wave) && nsec == 0 && wave == SIGB_WAVE_SINE) return build_bank(i);
@@ -1103,12 +1108,16 @@ int Builder::build_reduce(int i) {
         r.pan = 1;
         r.groups = 2;
         outC = 2;
-        const std::vector<double>* pan = const_of(p, n.in[1]);
-        if (!pan) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": pan driven by a non-constant emitter");
-        std::vector<double> pv;
-        if (!rep(*pan, r.C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
-        std::vector<float> pf(pv.begin(), pv.end());
-        r.w = put_vec(p, pf);
+        if (pan_modulated) {
+            st = param_port(n.in[1], r.C, &r.w_row);
+            if (st != SIGB_OK) return st;
+        } else {
+            const std::vector<double>* pan = const_of(p, n.in[1]);
+            std::vector<double> pv;
+            if (!rep(*pan, r.C, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
+            std::vector<float> pf(pv.begin(), pv.end());
+            r.w = put_vec(p, pf);
+        }
     } else {
         r.groups = n.order;
         outC = n.order;
@@ -1501,7 +1510,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.pan = r.pan;
             Operand oi = operand_of(p, r.in_node, abs_row0, out, ld_out);
             a.in = oi.ptr; a.ld_in = oi.ld; a.ics = oi.cs; a.in_rows = oi.rows;
-            a.w = r.w.dev<float>(base);
+            a.w = r.w_row >= 0 ? p->d_prow_f + (size_t)r.w_row * p->pwidth : r.w.dev<float>(base);
             const Val& dv = p->vals[r.dst_node];
             if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
             else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }

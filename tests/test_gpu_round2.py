@@ -583,3 +583,32 @@ def test_large_modulated_two_section_request_runs_register_resident(ns, engine):
     print(f'large modulated 2-section request: register kernel vs oracle {err:.3e}, vs the scan kernel {diff:.3e}')
     assert err <= 1e-4
     assert diff <= 2e-5
+
+
+def test_modulated_pan_matches_the_oracle_request_by_request(ns, engine):
+    """PanSum.pan driven by an LFO: sampled once per request at its first frame (block rate), so three consecutive requests
+    pan the same voices differently; against the float64 oracle evaluating the same graph request by request."""
+    from signals_b200.chain import ext
+    n = 96
+    prm = cases.instance_params(5, n)
+    prm['filt'] = np.zeros(n, dtype=int)               # oscillators -> gain only: requests at position > 0 need no filter context
+    prm['gain'] = prm['gain'] * 4.0
+    ps = cases.build_instances(ns, ext, prm)
+    rng = np.random.default_rng(85)
+    ps.pan = cases.sweep(ns, [rng.uniform(0.0, 0.3, n)], [rng.uniform(0.7, 1.0, n)], [rng.uniform(2.0, 9.0, n)], [rng.uniform(0.0, 1.0, n)])
+    c = engine.compile(ps, 2, RATE)
+    blocks, pos = [], 0
+    for frames in (4000, 1234, 9000):
+        blocks.append(c.render_device(pos, frames).cpu().numpy())
+        pos += frames
+    c.close()
+    orc = np_oracle.GraphOracle(RATE)
+    want, pos = [], 0
+    for frames in (4000, 1234, 9000):
+        want.append(orc.render(ps, pos, frames, 2))
+        pos += frames
+    err = max(max_abs_err(g, w) for g, w in zip(blocks, want))
+    spread = float(np.abs(want[0][:100] / np.maximum(np.abs(want[2][:100]), 1e-9)).std())
+    print(f'modulated pan over three requests: max-abs {err:.3e}')
+    assert err <= 1e-6
+    assert spread > 0          # (the requests really differ)
