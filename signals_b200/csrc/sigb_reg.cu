@@ -1,5 +1,8 @@
-// k_cascade_delta / k_cascade_reg / k_osc_reg: register-resident filter cascades (sm_100a) for deep cascades on many channels
-// (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384 channels x 60 s).
+// k_cascade_delta / k_osc_delta / k_cascade_reg / k_osc_reg: register-resident filter cascades (sm_100a) for chains of two and
+// more sections on many channels (BASELINE config C4: HBM buffer -> 8 chained Butterworth low-pass biquads, 16,384 channels
+// x 60 s).  The *_delta kernels run second-order sections in DELTA FORM (5 / 4 operations per low- / high-pass section, see
+// below) and are the default; the *_reg kernels keep the state-variable section (6 / 7 operations) for cascades with
+// first-order sections and for ragged or unaligned blocks.  What follows describes the decomposition they all share.
 //
 // k_cascade_pipe hands every chunk from section to section through shared memory (one LDS.64 + one STS.64
 // per section per two channel-samples) and measured 0.42 of the HBM roofline.  Here a thread owns TWO adjacent
