@@ -415,15 +415,19 @@ k_cascade_reg(const ChainDev a, int tiles, int npieces, int warm_rows) {
 // C4 (same box, alternating): 4 / 3 / 2 CTAs per SM = 0.672-0.678 / 0.694-0.697 and 0.719-0.726 / 0.732 of the HBM peak -- the
 // section chains supply the instruction-level parallelism, the cp.async ring hides the loads, and fewer warp slots mean
 // fewer time pieces, i.e. less warm-up
+// 7 and 8 sections run 16-ROW blocks at 2 CTAs per SM: with 8 warps per SM the wavefront order is what supplies the
+// instruction-level parallelism, and a 16 x 8 parallelogram holds 5.6 independent section steps per diagonal against 4.3 for
+// 8 x 8 -- C4 0.695-0.701 -> 0.735 of the HBM peak on the same box (profiles/r02_c4_delta.txt, call r02y).
 __host__ __device__ constexpr int delta_min_blocks(int nsec, int kind = 0) {
     return (kind & 4) ? (nsec <= 4 ? 4 : nsec <= 6 ? 3 : 2)          // mixed cascades: 12 registers per section
-                      : (nsec <= 4 ? 4 : nsec <= 7 ? 3 : 2);
+                      : (nsec <= 4 ? 4 : nsec <= 6 ? 3 : 2);
 }
 
 template <int NSEC, int R, int MINB, int WR = R, int KIND = 0>
 __global__ void __launch_bounds__(RWARPS * 32, MINB)
 k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
-    __shared__ __align__(16) float2 ring[RWARPS * RING_D * R * 32];
+    constexpr int RD = R >= 16 ? 3 : RING_D;             // ring depth in blocks (16-row blocks: 48 KB of static shared memory at depth 3)
+    __shared__ __align__(16) float2 ring[RWARPS * RD * R * 32];
     const unsigned ring_base = (unsigned)__cvta_generic_to_shared(ring);
     const int lane = threadIdx.x & 31;
     const int piece = blockIdx.x * RWARPS + (threadIdx.x >> 5);
@@ -469,8 +473,8 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
 
     const char* ip = reinterpret_cast<const char*>(a.src + (int64_t)row_first * a.src_ld + c0);
     char* op = reinterpret_cast<char*>(a.out + (int64_t)row_first * a.ld_out + c0);
-    const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RING_D * R * 32) + lane) * 8u;
-    const unsigned my_end = my + RING_D * R * 256u;
+    const unsigned my = ring_base + (unsigned)((threadIdx.x >> 5) * (RD * R * 32) + lane) * 8u;
+    const unsigned my_end = my + RD * R * 256u;
     unsigned in_addr = my, out_addr = my;
     int in_blk = 0;
     auto prefetch = [&]() {
@@ -485,11 +489,11 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
         cp_async_commit();
     };
 #pragma unroll
-    for (int j = 0; j < RING_D - 1; ++j) prefetch();
+    for (int j = 0; j < RD - 1; ++j) prefetch();
     int row = row_first;
     for (int b = 0; b < nfull; ++b) {
         prefetch();
-        cp_async_wait<RING_D - 1>();
+        cp_async_wait<RD - 1>();
         float2 x[R];
 #pragma unroll
         for (int k = 0; k < R; ++k) x[k] = lds_f2(out_addr + k * 256u);
@@ -549,8 +553,8 @@ k_cascade_delta(const ChainDev a, int tiles, int npieces, int warm_rows) {
   }
 }
 
-int g_delta_probe = 0;          // A/B (8 low-pass sections only): 0 default geometry (8-row blocks, 2 CTAs/SM); 1: 4-row blocks, 4 CTAs/SM;
-                                // 3 / 6: 8-row blocks, 4 / 3 CTAs/SM
+int g_delta_probe = 0;          // A/B (8 low-pass sections only): 0 default geometry (16-row blocks, 2 CTAs/SM); 1: 4-row blocks, 4 CTAs/SM;
+                                // 3 / 6 / 7: 8-row blocks, 4 / 3 / 2 CTAs/SM
 
 // high-pass sections keep two coefficient pairs, an output scale and two states (the 10 registers of a low-pass section);
 // mixed cascades three coefficient pairs and three states
@@ -562,12 +566,13 @@ int delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int 
         case 4: k_cascade_delta<4, 8, delta_min_blocks(4, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         case 5: k_cascade_delta<5, 8, delta_min_blocks(5, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         case 6: k_cascade_delta<6, 8, delta_min_blocks(6, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
-        case 7: k_cascade_delta<7, 8, delta_min_blocks(7, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
+        case 7: k_cascade_delta<7, 16, 2, 16, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm); break;
         default:
             if (KIND == 0 && g_delta_probe == 1) k_cascade_delta<8, 4, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             else if (KIND == 0 && g_delta_probe == 3) k_cascade_delta<8, 8, 4><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             else if (KIND == 0 && g_delta_probe == 6) k_cascade_delta<8, 8, 3><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
-            else k_cascade_delta<8, 8, delta_min_blocks(8, KIND), 8, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else if (KIND == 0 && g_delta_probe == 7) k_cascade_delta<8, 8, 2><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
+            else k_cascade_delta<8, 16, 2, 16, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm);
             break;
     }
     return (int)cudaGetLastError();
@@ -931,7 +936,7 @@ static RegGeometry cascade_reg_geometry(const ChainDev* a, int max_segments, int
     // variant 4 keeps the state-variable form in 8-row blocks for A/B
     q.delta = q.fast && variant != 1 && variant != 4 && !any_first;
     const int dprobe = (q.delta && a->nsec == 8 && !q.mixed && !(a->sec_kind[0] & SEC_HP)) ? g_delta_probe : 0;
-    q.R = (q.wide && dprobe != 1) ? 8 : 4;
+    q.R = (q.delta && a->nsec >= 7 && dprobe == 0) ? 16 : (q.wide && dprobe != 1) ? 8 : 4;     // 7 and 8 sections: 16-row blocks (delta_min_blocks)
     const int R = q.R;
     q.tiles = (a->C + RC - 1) / RC;
     int dev = 0, sms = 148;
