@@ -775,25 +775,56 @@ k_osc_delta(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
         if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
         if (KIND & (SEC_HP | SEC_MIXED)) gain = __fmul2_rn(gain, sec[NSEC - 1].c);   // the last section's output scale
         const unsigned long long dtha = a.dtheta[ca], dthb = a.dtheta[cb];
+        const bool rot = wave == SIGB_WAVE_SINE && a.rot1 != nullptr;
+        float2 rotC = make_float2(1.0f, 1.0f), rotS = make_float2(0.0f, 0.0f);
+        if (rot) {
+            const float2 ra = a.rot1[ca], rb = a.rot1[cb];
+            rotC = make_float2(ra.x, rb.x);
+            rotS = make_float2(ra.y, rb.y);
+        }
+        const int dhiA = (int)((dtha + 0x80000000ull) >> 32), dhiB = (int)((dthb + 0x80000000ull) >> 32);
         int64_t n = a.position + row_first;
         unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
         float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
         const bool vec = fast && live1;
 
         for (int row = row_first; row < row_end; row += OR) {
-            float xa[OR], xb[OR];
-            switch (wave) {
-                case SIGB_WAVE_SINE: osc_rows<SIGB_WAVE_SINE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SINE>(a, cb, thb, dthb, n, xb); break;
-                case SIGB_WAVE_SQUARE: osc_rows<SIGB_WAVE_SQUARE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SQUARE>(a, cb, thb, dthb, n, xb); break;
-                case SIGB_WAVE_SAWTOOTH: osc_rows<SIGB_WAVE_SAWTOOTH>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SAWTOOTH>(a, cb, thb, dthb, n, xb); break;
-                default: osc_rows<SIGB_WAVE_TRIANGLE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_TRIANGLE>(a, cb, thb, dthb, n, xb); break;
+            float2 x[OR];
+            if (rot) {
+                // Sine by k_chain_scan3's two-pipe evaluation: rows 1 and 5 of the block get a sine AND a
+                // cosine from the SFU, their neighbours (one row back, two rows forward) the angle-addition rotation by the
+                // channel's one-row phase advance (cos, sin tabulated in float64 on the host): 18 instructions per 8 rows x 2
+                // channels instead of 40
+                int ha = (int)((tha + 0x80000000ull) >> 32), hb = (int)((thb + 0x80000000ull) >> 32);
+                const float2 NS = make_float2(-rotS.x, -rotS.y);
+#pragma unroll
+                for (int q4 = 0; q4 + 3 < OR; q4 += 4) {
+                    const float2 r = __fmul2_rn(make_float2((float)(ha + dhiA), (float)(hb + dhiB)), make_float2(kTwoPiQ32, kTwoPiQ32));
+                    const float2 S1 = make_float2(__sinf(r.x), __sinf(r.y)), C1 = make_float2(__cosf(r.x), __cosf(r.y));
+                    const float2 t = __fmul2_rn(S1, rotC);
+                    x[q4 + 0] = __ffma2_rn(C1, NS, t);
+                    x[q4 + 1] = S1;
+                    const float2 S2 = __ffma2_rn(C1, rotS, t);
+                    const float2 C2 = __ffma2_rn(S1, NS, __fmul2_rn(C1, rotC));
+                    x[q4 + 2] = S2;
+                    x[q4 + 3] = __ffma2_rn(C2, rotS, __fmul2_rn(S2, rotC));
+                    ha += 4 * dhiA;
+                    hb += 4 * dhiB;
+                }
+            } else {
+                float xa[OR], xb[OR];
+                switch (wave) {
+                    case SIGB_WAVE_SINE: osc_rows<SIGB_WAVE_SINE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SINE>(a, cb, thb, dthb, n, xb); break;
+                    case SIGB_WAVE_SQUARE: osc_rows<SIGB_WAVE_SQUARE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SQUARE>(a, cb, thb, dthb, n, xb); break;
+                    case SIGB_WAVE_SAWTOOTH: osc_rows<SIGB_WAVE_SAWTOOTH>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SAWTOOTH>(a, cb, thb, dthb, n, xb); break;
+                    default: osc_rows<SIGB_WAVE_TRIANGLE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_TRIANGLE>(a, cb, thb, dthb, n, xb); break;
+                }
+#pragma unroll
+                for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
             }
             tha += (unsigned long long)OR * dtha;
             thb += (unsigned long long)OR * dthb;
             n += OR;
-            float2 x[OR];
-#pragma unroll
-            for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
             if (row + OR <= row_end) {
 #pragma unroll
                 for (int dgl = 0; dgl < OR + NSEC - 1; ++dgl) {
