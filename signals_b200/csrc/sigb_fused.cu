@@ -140,7 +140,11 @@ template <int KIND, int M, int VK>
 __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M], const float (&c)[M], const float (&d)[M],
                                           float (&s1)[M], float (&s2)[M], float (&s3)[M], int kmax) {
 #ifndef SIGB_VOICES_SCALAR
-    if constexpr (M == 4 && !(KIND & SEC_FIRST_ORDER)) {
+    constexpr bool PACKED = M == 4 && !(KIND & SEC_FIRST_ORDER);
+#else
+    constexpr bool PACKED = false;
+#endif
+    if constexpr (PACKED) {
         // second-order sections of four voices as two packed f32x2 recurrences in DELTA FORM (sigb_reg.cu, k_cascade_delta):
         // the thread holds (a, F/4 | D, Z, P) for a low-pass voice and (-Q, -F | D, -4 Z) for a high-pass voice instead of
         // (g, c, d | s1, s2) -- k_voices converts at the ends of a piece -- 5 / 4 FFMA2-class instructions per two
@@ -195,14 +199,13 @@ __device__ __forceinline__ void filt_tile(float (&x)[M][VK], const float (&g)[M]
             s2[2 * h] = pZ[h].x; s2[2 * h + 1] = pZ[h].y;
             s3[2 * h] = pP[h].x; s3[2 * h + 1] = pP[h].y;
         }
-        return;
-    }
-#endif
+    } else {
 #pragma unroll
-    for (int k = 0; k < VK; ++k) {
-        if (k < kmax) {
+        for (int k = 0; k < VK; ++k) {
+            if (k < kmax) {
 #pragma unroll
-            for (int m = 0; m < M; ++m) x[m][k] = svf_any(KIND, x[m][k], g[m], c[m], d[m], s1[m], s2[m]);
+                for (int m = 0; m < M; ++m) x[m][k] = svf_any(KIND, x[m][k], g[m], c[m], d[m], s1[m], s2[m]);
+            }
         }
     }
 }
@@ -598,6 +601,25 @@ __global__ void __launch_bounds__(128) k_design(const DesignDev a) {
     }
 }
 }  // namespace
+
+// k_pan_weights: PanSum with a MODULATED pan fused with its voices -- the (L, R) weights gain * (1 - pan), gain * pan of one
+// segment from the request's pan row (float64, as the host derives them for a constant pan), once per request.
+namespace {
+__global__ void __launch_bounds__(256) k_pan_weights(int C, const double* __restrict__ gain, const double* __restrict__ pan,
+                                                     float* __restrict__ wl, float* __restrict__ wr) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double g = gain[c], p = pan[c];
+    wl[c] = (float)(g * (1.0 - p));
+    wr[c] = (float)(g * p);
+}
+}  // namespace
+
+extern "C" int sigb_launch_pan_weights(int C, const double* gain, const double* pan, float* wl, float* wr, void* stream) {
+    if (C <= 0) return 0;
+    k_pan_weights<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(C, gain, pan, wl, wr);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int sigb_launch_design(const DesignDev* a, void* stream) {
     if (a->C <= 0) return 0;

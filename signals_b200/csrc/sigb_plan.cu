@@ -131,6 +131,8 @@ struct BankSpec {
 struct VoiceSegSpec {
     ChainSpec ch;
     Table wl, wr;
+    Table gain64;              // modulated pan only: the folded gain in float64 (k_pan_weights re-derives wl / wr per request)
+    int coff = 0;              // first channel of this segment in the PanSum's input (= column of the pan row)
 };
 struct VoicesSpec {
     std::vector<VoiceSegSpec> segs;
@@ -139,6 +141,7 @@ struct VoicesSpec {
     int partial_buf = -1;      // index into Plan::bufs (2 * nparts "channels")
     int state_cur = 0;         // which copy of the state arena holds the live filter state
     int dst_node = -1;
+    int pan_row = -1;          // pan driven by an emitter: row of the parameter program holding pan[C] for the request
 };
 
 enum LaunchKind { LK_CHAIN, LK_EWISE, LK_REDUCE, LK_BANK, LK_VOICES };
@@ -855,13 +858,20 @@ int Builder::build_bank(int i) {
 int Builder::build_voices(int i, const std::vector<int>& leaves) {
     const sigb_node& n = p->nodes[i];
     const int Cin = p->nodes[n.in[0]].channels;
+    // a pan driven by an emitter is a row of the parameter program: the (L, R) weight tables are then re-derived on the
+    // device at every request's first frame (k_pan_weights, run_params) instead of once here
     const std::vector<double>* pan = const_of(p, n.in[1]);
-    if (!pan) return fail(SIGB_EUNSUPPORTED, "node " + std::to_string(i) + ": pan driven by a non-constant emitter");
     std::vector<double> pv;
-    if (!rep(*pan, Cin, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
+    VoicesSpec vs;
+    if (pan) {
+        if (!rep(*pan, Cin, &pv)) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": pan channels incompatible");
+    } else {
+        int st = param_port(n.in[1], Cin, &vs.pan_row);
+        if (st != SIGB_OK) return st;
+        pv.assign(Cin, 0.5);
+    }
     if (i == p->root && p->channels != 2)
         return fail(SIGB_ESHAPE, "reduction yields 2 channels, request has " + std::to_string(p->channels));
-    VoicesSpec vs;
     vs.dst_node = i;
     int coff = 0;
     long long total = 0;
@@ -879,6 +889,12 @@ int Builder::build_voices(int i, const std::vector<int>& leaves) {
         }
         sg.wl = put_vec(p, wl);
         sg.wr = put_vec(p, wr);
+        sg.coff = coff;
+        if (vs.pan_row >= 0) {
+            std::vector<double> g64(C);
+            for (int c = 0; c < C; ++c) g64[c] = sg.ch.has_gain ? sg.ch.gain_d[c] : 1.0;
+            sg.gain64 = put_vec(p, g64);
+        }
 
         sg.ch.gain_d.clear();
         coff += C;
@@ -1083,10 +1099,10 @@ int Builder::build_reduce(int i) {
     const sigb_node& n = p->nodes[i];
     if (n.in[0] < 0) return fail(SIGB_ESHAPE, "node " + std::to_string(i) + ": reduction without input");
     // a pan driven by an emitter (block-rate modulation: an LFO sweeping the stereo position) is a row of the parameter
-    // program, re-sampled at every request's first frame like every block-rate port; the fused voice kernel bakes
-    // gain * (1 - pan), gain * pan into host-built tables, so such a PanSum runs on the materialised block (k_reduce)
+    // program, re-sampled at every request's first frame like every block-rate port (fused: build_voices; here: k_reduce
+    // reads the row)
     const bool pan_modulated = n.kind == SIGB_NODE_PANSUM && const_of(p, n.in[1]) == nullptr;
-    if (p->opt_fuse_reduce && !pan_modulated) {
+    if (p->opt_fuse_reduce) {
         if (n.kind == SIGB_NODE_GROUPSUM) {
             int nsec = 0, wave = 0;
             if (pure_osc_run(n.in[0], &nsec, &wave) && nsec == 0 && wave == SIGB_WAVE_SINE) return build_bank(i);
@@ -1543,6 +1559,16 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
                                    position, p->rt_pos_ptr, p->rate, st);
     if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
     p->launch_count++;
+    for (const VoicesSpec& vs : p->voices) {
+        if (vs.pan_row < 0) continue;
+        const unsigned char* base = p->d_arena;
+        for (const VoiceSegSpec& sg : vs.segs) {
+            e = sigb_launch_pan_weights(sg.ch.C, sg.gain64.dev<double>(base), p->d_prow_d + (size_t)vs.pan_row * p->pwidth + sg.coff,
+                                        const_cast<float*>(sg.wl.dev<float>(base)), const_cast<float*>(sg.wr.dev<float>(base)), st);
+            if (e) return fail(SIGB_ECUDA, std::string("k_pan_weights: ") + cudaGetErrorString((cudaError_t)e));
+            p->launch_count++;
+        }
+    }
     if (!design || p->n_mods == 0) return SIGB_OK;
     const bool want_warm = p->rt_pos_ptr == nullptr && !p->opt_force_seq && frames >= 4096;
     p->warm_on_device = want_warm;

@@ -330,12 +330,17 @@ def test_mix_of_oscillators_is_one_launch(ns, engine):
 
 def test_modulated_pan_lowers_to_a_parameter_row(ns, engine):
     """PanSum.pan driven by an emitter (an LFO sweeping the stereo position): a block-rate port like the others, sampled once
-    per request on the device; the fused voice kernel bakes the pan into host-built weights, so this PanSum reduces the
-    materialised block."""
+    per request on the device.  The voices stay fused (k_pan_weights re-derives their (L, R) weights per request); without the
+    fusion k_reduce reads the pan row."""
     prm = cases.instance_params(5, 64)
     ps = cases.build_instances(ns, ext, prm)
     assert [l['kind'] for l in engine.compile(ps, 2, 48000).describe()['launches']] == ['voices']
     ps.pan = cases.sweep(ns, [np.full(64, 0.1)], [np.full(64, 0.9)], [[0.3]], [[0.0]])
     d = engine.compile(ps, 2, 48000).describe()
-    kinds = [l['kind'] for l in d['launches']]
-    assert 'voices' not in kinds and kinds[-1] == 'reduce' and d['modulated_parameters'] >= 1
+    assert [l['kind'] for l in d['launches']] == ['voices'] and d['modulated_parameters'] >= 1
+    _lib.lib().sigb_set_default_option(b'fuse_reduce', 0)
+    try:
+        kinds = [l['kind'] for l in engine.compile(ps, 2, 48000).describe()['launches']]
+    finally:
+        _lib.lib().sigb_set_default_option(b'fuse_reduce', 1)
+    assert 'voices' not in kinds and kinds[-1] == 'reduce'

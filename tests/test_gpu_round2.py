@@ -585,30 +585,42 @@ def test_large_modulated_two_section_request_runs_register_resident(ns, engine):
     assert diff <= 2e-5
 
 
-def test_modulated_pan_matches_the_oracle_request_by_request(ns, engine):
+@pytest.mark.parametrize('fused', [1, 0])
+def test_modulated_pan_matches_the_oracle_request_by_request(fused, ns, engine):
     """PanSum.pan driven by an LFO: sampled once per request at its first frame (block rate), so three consecutive requests
-    pan the same voices differently; against the float64 oracle evaluating the same graph request by request."""
+    pan the same voices differently; against the float64 oracle evaluating the same graph request by request -- fused with the
+    voices (k_pan_weights re-derives the (L, R) weights per request) and on the materialised block (k_reduce reads the row)."""
+    from signals_b200 import _lib
     from signals_b200.chain import ext
     n = 96
     prm = cases.instance_params(5, n)
-    prm['filt'] = np.zeros(n, dtype=int)               # oscillators -> gain only: requests at position > 0 need no filter context
     prm['gain'] = prm['gain'] * 4.0
     ps = cases.build_instances(ns, ext, prm)
     rng = np.random.default_rng(85)
     ps.pan = cases.sweep(ns, [rng.uniform(0.0, 0.3, n)], [rng.uniform(0.7, 1.0, n)], [rng.uniform(2.0, 9.0, n)], [rng.uniform(0.0, 1.0, n)])
-    c = engine.compile(ps, 2, RATE)
-    blocks, pos = [], 0
-    for frames in (4000, 1234, 9000):
-        blocks.append(c.render_device(pos, frames).cpu().numpy())
-        pos += frames
-    c.close()
+    _lib.lib().sigb_set_default_option(b'fuse_reduce', fused)
+    try:
+        c = engine.compile(ps, 2, RATE)
+        assert ('voices' in [l['kind'] for l in c.describe()['launches']]) == bool(fused)
+        sizes = (4000, 1234, 9000)
+        blocks, pos = [], 0
+        for frames in sizes:
+            blocks.append(c.render_device(pos, frames).cpu().numpy())
+            pos += frames
+        c.close()
+    finally:
+        _lib.lib().sigb_set_default_option(b'fuse_reduce', 1)
+    # the oracle as one stream: filters carry their state across the requests (the plan's semantics), the pan is re-sampled
+    # at each request's first frame
     orc = np_oracle.GraphOracle(RATE)
+    flat = ps.inputs_by_port['input']
+    x = orc.render(flat, 0, sum(sizes), n)                        # (frames, n): the voices before the PanSum, one request from 0
     want, pos = [], 0
-    for frames in (4000, 1234, 9000):
-        want.append(orc.render(ps, pos, frames, 2))
+    for frames in sizes:
+        pan = orc.at_block_rate(ps, 'pan', pos, frames, n)
+        want.append(np_oracle.pan_sum(x[pos:pos + frames], np.broadcast_to(pan, (1, n))))
         pos += frames
     err = max(max_abs_err(g, w) for g, w in zip(blocks, want))
-    spread = float(np.abs(want[0][:100] / np.maximum(np.abs(want[2][:100]), 1e-9)).std())
-    print(f'modulated pan over three requests: max-abs {err:.3e}')
+    print(f'modulated pan over three requests (fused = {fused}): max-abs {err:.3e}')
     assert err <= 1e-6
-    assert spread > 0          # (the requests really differ)
+    assert max_abs_err(want[0][:1000], np_oracle.pan_sum(x[:1000], np.broadcast_to(orc.at_block_rate(ps, 'pan', 4000, 10, n), (1, n)))) > 1e-4
