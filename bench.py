@@ -856,13 +856,20 @@ def run_b200(args):
     if args.config == 'c2' and not args.no_extra and not args.voices_given:
         wanted = [x for x in args.extra.split(',') if x]
         for name in wanted:
-            if name == 'c5':                                   # every N: strong scaling with the NCCL reduce
-                r = measure(ctx, make_workload('c5', args, rank, world, False), EXTRA_STEPS['c5'], 3, 0, cpu_baseline=False)
-            elif name in ('c3', 'c4', 'c2m') and world == 1:
-                r = measure(ctx, make_workload(name, args, rank, world, False), EXTRA_STEPS[name], EXTRA_WARMUP.get(name, 3), 0, cpu_baseline=False)
-            elif name == 'c1' and world == 1:
-                r = measure_c1(ctx, cpu=not args.no_cpu_baseline)
-            else:
+            # a failure in an appended config (an out-of-memory slab, a parity assertion) is recorded under its key -- the
+            # headline line is printed regardless
+            try:
+                if name == 'c5':                                   # every N: strong scaling with the NCCL reduce
+                    r = measure(ctx, make_workload('c5', args, rank, world, False), EXTRA_STEPS['c5'], 3, 0, cpu_baseline=False)
+                elif name in ('c3', 'c4', 'c2m') and world == 1:
+                    r = measure(ctx, make_workload(name, args, rank, world, False), EXTRA_STEPS[name], EXTRA_WARMUP.get(name, 3), 0, cpu_baseline=False)
+                elif name == 'c1' and world == 1:
+                    r = measure_c1(ctx, cpu=not args.no_cpu_baseline)
+                else:
+                    continue
+            except Exception as exc:      # noqa: BLE001
+                extra[name] = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:300])}
+                print('bench: extra.%s failed: %r' % (name, exc), file=sys.stderr, flush=True)
                 continue
             if name != 'c1':
                 r = {k: r[k] for k in ('value', 'ms_per_step', 'steps', 'warmup', 'scaling', 'roofline', 'launches', 'clocks', 'config',
