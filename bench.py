@@ -688,6 +688,8 @@ def measure(ctx, wl, steps, warmup, e2e_steps, cpu_baseline):
             host_out.copy_(out[:eslab], non_blocking=True)
             torch.cuda.synchronize()
             probe.append(host_out.numel() * 4 / (time.perf_counter() - t0) / 1e9)
+        print('bench: e2e step seconds %s (compile part %s)' % (['%.4f' % t for t in e2e_times], ['%.4f' % (t - w) for t, w in zip(e2e_times, copy_wait)]),
+              file=sys.stderr, flush=True)
         te = ctx.max_over_ranks(sum(e2e_times))
         d2h = int(4 * wl.out_channels * frames)
         e2e = {'value': wl.units_per_step() * len(e2e_times) / te, 'unit': 'voice-samples/s', 'h2d_bytes_per_step': h2d,
