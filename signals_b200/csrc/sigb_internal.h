@@ -187,6 +187,8 @@ void sigb_set_delta_probe(int n);
 int sigb_osc_reg_ok(const ChainDev* a, int allow_delta);
 int sigb_launch_osc_reg(const ChainDev* a, int max_segments, int allow_delta, void* stream);
 int sigb_osc_reg_fill(const ChainDev* a, int max_segments, int allow_delta);
+int sigb_osc_fill_ok(const ChainDev* a);
+int sigb_launch_osc_fill(const ChainDev* a, double max_abs_hertz, double max_abs_phase, void* stream);
 void sigb_set_osc_pieces_pct(int n);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);

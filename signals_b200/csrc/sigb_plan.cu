@@ -193,6 +193,7 @@ struct sigb_plan {
     int64_t opt_cascade_pipe = -1;      // -1: automatic choice; 0: never the section-pipelined kernel; n > 0: always from n sections
     int64_t opt_cascade_reg = -1;       // -1: register-resident cascade kernel whenever it can take the chain; 0: never
     int64_t opt_osc_reg = 2;            // oscillator-fed chains of >= n sections run register-resident (k_osc_delta / k_osc_reg); 0: never
+    int64_t opt_osc_fill = 1;           // 0: stateless oscillator chains stay on k_chain_seq whatever their width (A/B)
     int64_t opt_osc_delta = 1;          // 0: oscillator-fed register chains keep the state-variable sections (A/B)
     bool osc_reg_user = false;          // set through the option: honoured as given; the default's 2-section rule is for unmodulated chains that fill the machine
     int64_t opt_reg_variant = 0;        // register cascades: 0 = delta form where it applies, else 8-row blocks; 1 = 4-row blocks; 4 = state-variable form in 8-row blocks
@@ -1366,6 +1367,13 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     continue;
                 }
             }
+            // stateless oscillator chains on many channels: from the Q0.64 phase word instead of float64 per sample (k_osc_fill)
+            if (!force_seq && p->opt_osc_fill != 0 && ch.hertz_row < 0 && ch.phase_row < 0 && sigb_osc_fill_ok(&a)) {
+                int e = sigb_launch_osc_fill(&a, ch.max_abs_hertz, ch.max_abs_phase, st);
+                if (e) return fail(SIGB_ECUDA, std::string("k_osc_fill: ") + cudaGetErrorString((cudaError_t)e));
+                p->launch_count++;
+                continue;
+            }
             const int tiles = (ch.C + 31) / 32;
             // (a chain with a modulated cutoff gets its scan tables from k_design, once per request)
             const bool scan_ok = !force_seq && ch.nsec >= 1 && ch.nsec <= 8 && tiles <= p->opt_scan_max_tiles;
@@ -2178,6 +2186,7 @@ extern "C" int sigb_plan_set_option(sigb_plan* plan, const char* key, int64_t va
     else if (k == "reg_pieces") sigb_set_reg_pieces((int)value);   // process-wide switch (A/B testing)
     else if (k == "delta_probe") sigb_set_delta_probe((int)value); // process-wide switch (A/B testing)
     else if (k == "osc_delta") plan->opt_osc_delta = value;
+    else if (k == "osc_fill") plan->opt_osc_fill = value;
     else if (k == "osc_pieces_pct") sigb_set_osc_pieces_pct((int)value);   // process-wide switch (A/B testing)
     else if (k == "bank_unroll") sigb_set_bank_unroll((int)value); // process-wide switch (A/B testing)
     else return fail(SIGB_EINVAL, "unknown option " + k);

@@ -611,6 +611,17 @@ constexpr int OR = 8;           // rows per block
 __host__ __device__ constexpr int osc_min_blocks(int nsec) { return nsec <= 2 ? 5 : nsec <= 6 ? 3 : 2; }
 
 template <int WAVE>
+__device__ __forceinline__ void osc_rows_g(const ChainDev& a, int guard, int c, unsigned long long th, unsigned long long dth, int64_t n0, float (&x)[OR]) {
+    const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
+    const bool near = gen_tile<WAVE, OR>(w, dhi, guard, x);
+    if (WAVE != SIGB_WAVE_SINE && near) {
+        const double hz = a.hertz[c], ph = a.phase[c], rate = (double)a.rate;
+#pragma unroll
+        for (int k = 0; k < OR; ++k) x[k] = osc_wave(WAVE, osc_cycles(__ddiv_rn((double)(n0 + k), rate), hz, ph));
+    }
+}
+
+template <int WAVE>
 __device__ __forceinline__ void osc_rows(const ChainDev& a, int c, unsigned long long th, unsigned long long dth, int64_t n0, float (&x)[OR]) {
     const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
     const bool near = gen_tile<WAVE, OR>(w, dhi, a.guard, x);
@@ -1012,6 +1023,129 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
                         : reg_launch_nsec<0, 4, true>(a, grid, tiles, npieces, warm, st);
     return hp ? reg_launch_nsec<SEC_HP, 4, false>(a, grid, tiles, npieces, warm, st)
               : reg_launch_nsec<0, 4, false>(a, grid, tiles, npieces, warm, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_osc_fill: STATELESS oscillator chains (osc -> gain, no filter) on many channels.  k_chain_seq evaluates every sample of
+// such a chain in float64 (division, multiply-add, waveform): 6.0e11 voice-samples/s on C2's shape, 0.37 of the HBM
+// roofline for the simplest graph there is.  Here a thread owns two adjacent channels, takes the exact Q0.64 phase at the
+// first row of every 8-row block (theta0 + n dtheta mod 2^64) and generates the block from the phase word -- sine rows by
+// rotation (one sin/cos pair per four rows), the discontinuous waveforms from the word with the float64 redo inside the
+// guard band -- exactly as k_osc_delta's source does.
+//
+// Block invariance (the reference's oscillators do not depend on block boundaries, osc.py:26-33): the 8-row blocks are
+// aligned to the ABSOLUTE sample index (n mod 8 == 0), the guard band is a function of the block's own position, so a
+// sample is computed by the same instructions on the same operands whatever request it falls into: requests cut anywhere
+// give the same bits.  A partial block at either end of a request is generated whole and stored in part.
+// ---------------------------------------------------------------------------------------------------------
+template <int WAVE>
+__global__ void __launch_bounds__(RWARPS * 32, 5)
+k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, float guard0, float guard_per_row, int fast) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * RWARPS + (threadIdx.x >> 5);
+    if (wid >= tiles * chunks) return;
+    const int tile = wid / chunks, chunk = wid - tile * chunks;
+    const int64_t pos = a.position, end = a.position + a.frames;
+    const int64_t nb_first = pos >> 3, nb_last = (end + 7) >> 3;             // absolute 8-row blocks [nb_first, nb_last)
+    int64_t nb = nb_first + (int64_t)chunk * blocks_per_chunk;
+    const int64_t nb_end = min(nb_last, nb + blocks_per_chunk);
+    if (nb >= nb_end) return;
+    const int c0 = tile * RC + 2 * lane;
+    const bool live0 = c0 < a.C, live1 = c0 + 1 < a.C;
+    const int ca = min(c0, a.C - 1), cb = min(c0 + 1, a.C - 1);
+    float2 gain = make_float2(1.0f, 1.0f);
+    if (a.gain) gain = make_float2(a.gain[ca], a.gain[cb]);
+    const unsigned long long dtha = a.dtheta[ca], dthb = a.dtheta[cb];
+    const bool rot = WAVE == SIGB_WAVE_SINE && a.rot1 != nullptr;
+    float2 rotC = make_float2(1.0f, 1.0f), rotS = make_float2(0.0f, 0.0f);
+    if (rot) {
+        const float2 ra = a.rot1[ca], rb = a.rot1[cb];
+        rotC = make_float2(ra.x, rb.x);
+        rotS = make_float2(ra.y, rb.y);
+    }
+    const int dhiA = (int)((dtha + 0x80000000ull) >> 32), dhiB = (int)((dthb + 0x80000000ull) >> 32);
+    int64_t n = nb << 3;
+    unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
+    const bool vec = fast && live1;
+    for (; nb < nb_end; ++nb) {
+        float2 x[OR];
+        if (rot) {
+            int ha = (int)((tha + 0x80000000ull) >> 32), hb = (int)((thb + 0x80000000ull) >> 32);
+            const float2 NS = make_float2(-rotS.x, -rotS.y);
+#pragma unroll
+            for (int q4 = 0; q4 + 3 < OR; q4 += 4) {
+                const float2 r = __fmul2_rn(make_float2((float)(ha + dhiA), (float)(hb + dhiB)), make_float2(kTwoPiQ32, kTwoPiQ32));
+                const float2 S1 = make_float2(__sinf(r.x), __sinf(r.y)), C1 = make_float2(__cosf(r.x), __cosf(r.y));
+                const float2 t = __fmul2_rn(S1, rotC);
+                x[q4 + 0] = __ffma2_rn(C1, NS, t);
+                x[q4 + 1] = S1;
+                const float2 S2 = __ffma2_rn(C1, rotS, t);
+                const float2 C2 = __ffma2_rn(S1, NS, __fmul2_rn(C1, rotC));
+                x[q4 + 2] = S2;
+                x[q4 + 3] = __ffma2_rn(C2, rotS, __fmul2_rn(S2, rotC));
+                ha += 4 * dhiA;
+                hb += 4 * dhiB;
+            }
+        } else {
+            // guard band of THIS block (phase_guard of sigb_plan.cu at the block's last row): a function of the absolute position
+            const int guard = (int)fminf(1073741823.0f, ceilf(guard0 + (float)(n + OR) * guard_per_row));
+            float xa[OR], xb[OR];
+            osc_rows_g<WAVE>(a, guard, ca, tha, dtha, n, xa);
+            osc_rows_g<WAVE>(a, guard, cb, thb, dthb, n, xb);
+#pragma unroll
+            for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
+        }
+        float* outp = a.out + (n - pos) * a.ld_out + c0;                    // row n of the stream (may lie before the request)
+        if (n >= pos && n + OR <= end && vec) {
+#pragma unroll
+            for (int k = 0; k < OR; ++k) __stcs(reinterpret_cast<float2*>(outp + (int64_t)k * a.ld_out), __fmul2_rn(x[k], gain));
+        } else {
+#pragma unroll
+            for (int k = 0; k < OR; ++k) {
+                if (n + k >= pos && n + k < end) {
+                    if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
+                    if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
+                }
+            }
+        }
+        tha += (unsigned long long)OR * dtha;
+        thb += (unsigned long long)OR * dthb;
+        n += OR;
+    }
+}
+
+// Stateless unmodulated oscillator chains (no filter, no fused epilogue) from 128 channels on: a static property of the chain,
+// so that every request of a plan takes the same kernel (block invariance).
+extern "C" int sigb_osc_fill_ok(const ChainDev* a) {
+    return a->src_kind == SRC_OSC && a->nsec == 0 && a->epi_op == 0 && a->theta0 && a->dtheta && a->hertz && a->phase &&
+           a->pos_ptr == nullptr && a->C >= 128;
+}
+
+extern "C" int sigb_launch_osc_fill(const ChainDev* a, double max_abs_hertz, double max_abs_phase, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->frames <= 0) return 0;
+    const int fast = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0;
+    const int tiles = (a->C + RC - 1) / RC;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t nblk = ((a->position + a->frames + 7) >> 3) - (a->position >> 3);
+    // ~2 waves of the 20 resident warps per SM, each warp streaming its own run of blocks (at least 16 blocks per warp)
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(((int64_t)sms * 40 + tiles - 1) / std::max(1, tiles), (nblk + 15) / 16));
+    const int bpc = (int)((nblk + chunks - 1) / chunks);
+    chunks = (nblk + bpc - 1) / bpc;
+    // phase_guard(last_row) = 16 + (max|hertz| last_row / rate + max|phase| + 1) * 3 * 2^32 / 2^53, per block on the device
+    const double k = 3.0 * 4294967296.0 / 9007199254740992.0;
+    const float guard0 = (float)(16.0 + (max_abs_phase + 1.0) * k + 1.0);
+    const float guard_per_row = (float)(max_abs_hertz / a->rate * k * 1.0001);
+    const int64_t warps = (int64_t)tiles * chunks;
+    const dim3 grid((unsigned)((warps + RWARPS - 1) / RWARPS));
+    switch (a->wave) {
+        case SIGB_WAVE_SINE: k_osc_fill<SIGB_WAVE_SINE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
+        case SIGB_WAVE_SQUARE: k_osc_fill<SIGB_WAVE_SQUARE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
+        case SIGB_WAVE_SAWTOOTH: k_osc_fill<SIGB_WAVE_SAWTOOTH><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
+        default: k_osc_fill<SIGB_WAVE_TRIANGLE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
+    }
+    return (int)cudaGetLastError();
 }
 
 // Oscillator-fed chains: 1..8 sections, unmodulated oscillator (Q0.64 phase tables present).  Second-order sections of any

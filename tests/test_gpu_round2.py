@@ -624,3 +624,36 @@ def test_modulated_pan_matches_the_oracle_request_by_request(fused, ns, engine):
     print(f'modulated pan over three requests (fused = {fused}): max-abs {err:.3e}')
     assert err <= 1e-6
     assert max_abs_err(want[0][:1000], np_oracle.pan_sum(x[:1000], np.broadcast_to(orc.at_block_rate(ps, 'pan', 4000, 10, n), (1, n)))) > 1e-4
+
+
+@pytest.mark.parametrize('wave', ['Sine', 'Square', 'Sawtooth', 'Triangle'])
+def test_wide_stateless_oscillator_chains(wave, ns, engine):
+    """Oscillator -> gain on many channels (k_osc_fill: Q0.64 phase word per absolute 8-row block instead of float64 per sample):
+    against the float64 oracle, bit for bit against itself however the stream is cut into requests (the blocks are aligned to
+    the absolute sample index), against k_chain_seq on the same plan, at position 0 and far into the stream, with
+    frequencies that put samples exactly on the discontinuities (6 kHz / 12 kHz at 48 kHz)."""
+    rng = np.random.default_rng(86)
+    ch = 200                                                  # ragged last tile
+    hz = rng.uniform(27.5, 4186.0, ch)
+    hz[:6] = [6000.0, 12000.0, 440.0, 439.99, 27.5, 8000.0]
+    ph = rng.uniform(0.0, 1.0, ch)
+    ph[:3] = [0.0, 0.25, 0.5]
+    g = rng.uniform(0.05, 1.0, ch)
+    node = cases.gain(ns, cases.osc(ns, wave, [hz], [ph]), [g])
+    for pos in (0, 47999, 2 ** 31 + 3):
+        frames = 5003
+        c = engine.compile(node, ch, RATE)
+        assert c.describe()['launches'][0]['sections'] == 0
+        whole = c.render_device(pos, frames).cpu().numpy()
+        cuts = [0, 1, 7, 8, 9, 48, 1000, 1001, 4097, frames]
+        parts = np.concatenate([c.render_device(pos + a, b - a).cpu().numpy() for a, b in zip(cuts, cuts[1:])])
+        c.set_option('osc_fill', 0)
+        seq = c.render_device(pos, frames).cpu().numpy()
+        c.close()
+        want = np_oracle.GraphOracle(RATE).render(node, pos, frames, ch)
+        err, err_seq = max_abs_err(whole, want), max_abs_err(seq, want)
+        print(f'{wave} x {ch} channels at position {pos}: k_osc_fill max-abs {err:.3e} (k_chain_seq {err_seq:.3e})')
+        assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32)), (wave, pos)
+        assert not np.array_equal(whole, seq) or wave == 'Square'          # two different kernels did render
+        # 1e-6 for oscillators; far into the stream the reference's own float64 phase is rounded to ~4e-7 rad at 12 kHz (cases.py)
+        assert err <= (1e-6 if pos < 2 ** 31 else 2e-6), (wave, pos, err)
