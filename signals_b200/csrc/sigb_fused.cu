@@ -602,6 +602,62 @@ __global__ void __launch_bounds__(128) k_design(const DesignDev a) {
 }
 }  // namespace
 
+// k_osc_tables: a Sine whose hertz / phase are driven by emitters (vibrato).  The rows are constant within a request, so the
+// exact Q0.64 phase theta0 + n dtheta of the constant oscillator holds for the request: one thread per channel restates
+// frac_q64 / ratio_q64 of sigb_plan.cu (exact integer arithmetic on the float64 mantissa) and the (cos, sin) of the one-row
+// advance, once per request, and the sine fast paths run unchanged.
+namespace {
+__device__ unsigned long long dev_frac_q64(double x) {
+    if (!isfinite(x)) return 0ull;
+    const double f = x - floor(x);
+    if (!(f < 1.0)) return 0ull;
+    const double scaled = ldexp(f, 32);
+    const double hi = floor(scaled);
+    const double lo = scaled - hi;
+    return ((unsigned long long)hi << 32) | (unsigned long long)floor(ldexp(lo, 32));
+}
+__device__ unsigned long long dev_ratio_q64(double hertz, int rate) {
+    if (!isfinite(hertz) || rate <= 0 || hertz == 0.0) return 0ull;
+    int e;
+    const double m = frexp(fabs(hertz), &e);
+    const unsigned long long mant = (unsigned long long)ldexp(m, 53);
+    e -= 53;
+    const unsigned __int128 R = (unsigned __int128)(unsigned)rate;
+    unsigned long long q;
+    if (e >= 0) {
+        unsigned __int128 r = (unsigned __int128)mant % R;
+        for (int i = 0; i < e; ++i) r = (r << 1) % R;
+        q = (unsigned long long)((r << 64) / R);
+    } else {
+        const int k = -e;
+        unsigned __int128 num;
+        if (k <= 64) num = (unsigned __int128)mant << (64 - k);
+        else num = (k - 64 >= 64) ? 0 : ((unsigned __int128)mant >> (k - 64));
+        q = (unsigned long long)(num / R);
+    }
+    return hertz < 0.0 ? (0ull - q) : q;
+}
+__global__ void __launch_bounds__(128) k_osc_tables(int C, const double* __restrict__ hertz, const double* __restrict__ phase, int rate,
+                                                    unsigned long long* __restrict__ theta0, unsigned long long* __restrict__ dtheta,
+                                                    float* __restrict__ rot1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const unsigned long long dt = dev_ratio_q64(hertz[c], rate);
+    theta0[c] = dev_frac_q64(phase[c]);
+    dtheta[c] = dt;
+    const double ang = 6.283185307179586476925 * ldexp((double)(long long)dt, -64);
+    rot1[2 * c + 0] = (float)cos(ang);
+    rot1[2 * c + 1] = (float)sin(ang);
+}
+}  // namespace
+
+extern "C" int sigb_launch_osc_tables(int C, const double* hertz, const double* phase, int rate, unsigned long long* theta0,
+                                      unsigned long long* dtheta, float* rot1, void* stream) {
+    if (C <= 0) return 0;
+    k_osc_tables<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, hertz, phase, rate, theta0, dtheta, rot1);
+    return (int)cudaGetLastError();
+}
+
 // k_pan_weights: PanSum with a MODULATED pan fused with its voices -- the (L, R) weights gain * (1 - pan), gain * pan of one
 // segment from the request's pan row (float64, as the host derives them for a constant pan), once per request.
 namespace {

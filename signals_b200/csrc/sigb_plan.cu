@@ -89,6 +89,7 @@ struct ChainSpec {
     double warm_static = 0.0;    // ... the share of the filters with constant cutoffs (modulated ones add theirs per request)
     int dst_node = -1;
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
+    bool osc_tables_dev = false;          // ... and (Sine) the Q0.64 phase tables are re-derived from those rows on the device per request
     // filters whose cutoff is driven by an emitter: their sections are re-designed on the device once per request
     // (k_design) from row `row` of the parameter program
     struct ModFilter { int s0, order, row, highpass, slot; };   // slot: index of this filter's decay horizon in d_warm
@@ -521,6 +522,15 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                 if (st != SIGB_OK) return st;
                 ch.src_kind = SRC_OSC;
                 ch.wave = n.subtype;
+                if (scan_tables && n.subtype == SIGB_WAVE_SINE) {
+                    // vibrato: hertz / phase are constant within a request, so the exact Q0.64 phase (theta0 + n dtheta) holds for
+                    // the request; k_osc_tables re-derives theta0 / dtheta / rot1 from the sampled rows at every request's first
+                    // frame and the sine fast paths (k_osc_fill, k_chain_scan3, k_osc_delta) run as for a constant oscillator
+                    ch.theta0 = put_vec(p, std::vector<unsigned long long>(C, 0ull));
+                    ch.dtheta = put_vec(p, std::vector<unsigned long long>(C, 0ull));
+                    ch.rot1 = put_vec(p, std::vector<float>((size_t)C * 2, 0.0f));
+                    ch.osc_tables_dev = true;
+                }
                 break;
             }
             std::vector<double> hzv, phv;
@@ -1368,7 +1378,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 }
             }
             // stateless oscillator chains on many channels: from the Q0.64 phase word instead of float64 per sample (k_osc_fill)
-            if (!force_seq && p->opt_osc_fill != 0 && ch.hertz_row < 0 && ch.phase_row < 0 && sigb_osc_fill_ok(&a)) {
+            if (!force_seq && p->opt_osc_fill != 0 && (ch.hertz_row < 0 || ch.osc_tables_dev) && sigb_osc_fill_ok(&a)) {
                 int e = sigb_launch_osc_fill(&a, ch.max_abs_hertz, ch.max_abs_phase, st);
                 if (e) return fail(SIGB_ECUDA, std::string("k_osc_fill: ") + cudaGetErrorString((cudaError_t)e));
                 p->launch_count++;
@@ -1567,6 +1577,16 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
                                    position, p->rt_pos_ptr, p->rate, st);
     if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
     p->launch_count++;
+    for (const ChainSpec& ch : p->chains) {
+        if (!ch.osc_tables_dev) continue;
+        const unsigned char* base = p->d_arena;
+        e = sigb_launch_osc_tables(ch.C, p->d_prow_d + (size_t)ch.hertz_row * p->pwidth, p->d_prow_d + (size_t)ch.phase_row * p->pwidth, p->rate,
+                                   const_cast<unsigned long long*>(ch.theta0.dev<unsigned long long>(base)),
+                                   const_cast<unsigned long long*>(ch.dtheta.dev<unsigned long long>(base)),
+                                   const_cast<float*>(ch.rot1.dev<float>(base)), st);
+        if (e) return fail(SIGB_ECUDA, std::string("k_osc_tables: ") + cudaGetErrorString((cudaError_t)e));
+        p->launch_count++;
+    }
     for (const VoicesSpec& vs : p->voices) {
         if (vs.pan_row < 0) continue;
         const unsigned char* base = p->d_arena;

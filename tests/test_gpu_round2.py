@@ -657,3 +657,46 @@ def test_wide_stateless_oscillator_chains(wave, ns, engine):
         assert not np.array_equal(whole, seq) or wave == 'Square'          # two different kernels did render
         # 1e-6 for oscillators; far into the stream the reference's own float64 phase is rounded to ~4e-7 rad at 12 kHz (cases.py)
         assert err <= (1e-6 if pos < 2 ** 31 else 2e-6), (wave, pos, err)
+
+
+@pytest.mark.parametrize('nsec', [0, 1, 2, 3])
+def test_vibrato_keeps_the_sine_fast_paths(nsec, ns, engine):
+    """A Sine whose hertz AND phase are driven by LFOs on many channels: the rows are constant within a request, so k_osc_tables
+    re-derives the exact Q0.64 phase tables per request and the chain runs on k_osc_fill / k_chain_scan3 / k_osc_delta like
+    a constant oscillator -- three consecutive requests (the parameters jump between them, as in the reference) against the
+    float64 oracle and against the float64-per-sample kernel (force_seq)."""
+    ch = 192
+    rng = np.random.default_rng(87 + nsec)
+    hz = rng.uniform(55.0, 3000.0, ch)
+    o = ns.Sine()
+    o.hertz = cases.sweep(ns, [hz * 0.94], [hz * 1.06], [rng.uniform(3.0, 7.0, ch)], [rng.uniform(0, 1, ch)])
+    o.phase = cases.gain(ns, cases.osc(ns, 'Sine', [rng.uniform(0.5, 2.0, ch)], [rng.uniform(0, 1, ch)]), [np.full(ch, 0.1)])
+    node = o
+    cut = np.exp(rng.uniform(np.log(700.0), np.log(8000.0), (max(nsec, 1), ch)))
+    for s in range(nsec):
+        node = cases.lowpass(ns, node, [cut[s]])
+    node = cases.gain(ns, node, [rng.uniform(0.1, 1.0, ch)])
+    sizes = (20000, 4099, 24000)
+    got = {}
+    for mode in ('fast', 'seq'):
+        c = engine.compile(node, ch, RATE)
+        if mode == 'seq':
+            c.set_option('force_seq', 1)
+        blocks, pos = [], 0
+        for frames in sizes:
+            blocks.append(c.render_device(pos, frames).cpu().numpy())
+            pos += frames
+        c.close()
+        got[mode] = np.concatenate(blocks)
+    assert not np.array_equal(got['fast'], got['seq'])                    # two different kernels did render
+    tol = 1e-6 if nsec == 0 else 1e-4
+    assert max_abs_err(got['fast'], got['seq']) <= (2e-6 if nsec == 0 else 2e-5)
+    if nsec == 0:            # (filters: the plan carries their state across the requests, the oracle's requests restart; compare with seq only)
+        orc = np_oracle.GraphOracle(RATE)
+        want, pos = [], 0
+        for frames in sizes:
+            want.append(orc.render(node, pos, frames, ch))
+            pos += frames
+        err = max_abs_err(got['fast'], np.concatenate(want))
+        print(f'vibrato sine x {ch} channels, three requests: max-abs {err:.3e}')
+        assert err <= tol
