@@ -645,9 +645,11 @@ __global__ void __launch_bounds__(128) k_osc_tables(int C, const double* __restr
     const unsigned long long dt = dev_ratio_q64(hertz[c], rate);
     theta0[c] = dev_frac_q64(phase[c]);
     dtheta[c] = dt;
-    const double ang = 6.283185307179586476925 * ldexp((double)(long long)dt, -64);
-    rot1[2 * c + 0] = (float)cos(ang);
-    rot1[2 * c + 1] = (float)sin(ang);
+    if (rot1) {
+        const double ang = 6.283185307179586476925 * ldexp((double)(long long)dt, -64);
+        rot1[2 * c + 0] = (float)cos(ang);
+        rot1[2 * c + 1] = (float)sin(ang);
+    }
 }
 }  // namespace
 

@@ -28,7 +28,9 @@ struct ChainDev {
     int32_t warm_est;               // modulated cutoffs: the host's estimate of the horizon (previous request), -1: none
     int32_t n_warm_dev;             // ... and the per-filter horizons k_design wrote for THIS request (scan kernels read them)
     const int* warm_dev;
-    int32_t guard;                  // phase-word guard band around waveform discontinuities (pipelined kernel)
+    int32_t guard;                  // phase-word guard band around waveform discontinuities (host maximum; constant oscillators only)
+    int32_t osc_mod;                // hertz / phase sampled per request on the device (k_osc_tables): `guard` is unknown, only the
+                                    // kernels that derive the band from their own channels may take a discontinuous waveform
     int64_t position;               // absolute index of row 0
     const int64_t* pos_ptr;         // realtime graphs (k_chain_seq only): when set, row 0 is *pos_ptr -- a block header the
                                     // host rewrites before every launch of the captured CUDA graph
@@ -188,7 +190,7 @@ int sigb_osc_reg_ok(const ChainDev* a, int allow_delta);
 int sigb_launch_osc_reg(const ChainDev* a, int max_segments, int allow_delta, void* stream);
 int sigb_osc_reg_fill(const ChainDev* a, int max_segments, int allow_delta);
 int sigb_osc_fill_ok(const ChainDev* a);
-int sigb_launch_osc_fill(const ChainDev* a, double max_abs_hertz, double max_abs_phase, void* stream);
+int sigb_launch_osc_fill(const ChainDev* a, void* stream);
 void sigb_set_osc_pieces_pct(int n);
 int sigb_launch_ewise(const EwiseDev* a, void* stream);
 int sigb_launch_reduce(const ReduceDev* a, void* stream);

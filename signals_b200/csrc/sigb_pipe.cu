@@ -454,6 +454,7 @@ k_cascade_pipe(const ChainDev a, int nchunks, int tiles, int nseg, int seg_chunk
 extern "C" int sigb_cascade_pipe_ok(const ChainDev* a) {
     if (a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
     if (a->src_kind == SRC_OSC && (!a->theta0 || !a->dtheta)) return 0;
+    if (a->src_kind == SRC_OSC && a->osc_mod && a->wave != SIGB_WAVE_SINE) return 0;      // the guard band is a host maximum here
     return 1;
 }
 

@@ -522,13 +522,14 @@ int Builder::make_chain(int i, ChainSpec& ch, bool scan_tables, int width) {
                 if (st != SIGB_OK) return st;
                 ch.src_kind = SRC_OSC;
                 ch.wave = n.subtype;
-                if (scan_tables && n.subtype == SIGB_WAVE_SINE) {
+                if (scan_tables) {
                     // vibrato: hertz / phase are constant within a request, so the exact Q0.64 phase (theta0 + n dtheta) holds for
-                    // the request; k_osc_tables re-derives theta0 / dtheta / rot1 from the sampled rows at every request's first
-                    // frame and the sine fast paths (k_osc_fill, k_chain_scan3, k_osc_delta) run as for a constant oscillator
+                    // the request; k_osc_tables re-derives theta0 / dtheta (and a Sine's rot1) from the sampled rows at every
+                    // request's first frame and the phase-word fast paths (k_osc_fill, k_chain_scan3's sine, k_osc_delta) run as
+                    // for a constant oscillator
                     ch.theta0 = put_vec(p, std::vector<unsigned long long>(C, 0ull));
                     ch.dtheta = put_vec(p, std::vector<unsigned long long>(C, 0ull));
-                    ch.rot1 = put_vec(p, std::vector<float>((size_t)C * 2, 0.0f));
+                    if (n.subtype == SIGB_WAVE_SINE) ch.rot1 = put_vec(p, std::vector<float>((size_t)C * 2, 0.0f));
                     ch.osc_tables_dev = true;
                 }
                 break;
@@ -1338,6 +1339,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             int done = 0;
             const bool force_seq = p->opt_force_seq || p->rt_pos_ptr != nullptr;    // realtime blocks: one sequential launch per chain
             if (ch.src_kind == SRC_OSC && ch.hertz_row < 0) a.guard = phase_guard(ch.max_abs_hertz, ch.max_abs_phase, abs_row0 + rows, p->rate);
+            a.osc_mod = ch.src_kind == SRC_OSC && ch.hertz_row >= 0;
             // kernel choice: cascades of >= 3 sections run section-pipelined (k_cascade_pipe); shallower
             // chains stay on the time-parallel scan kernel, which measured faster for them (C2: 1.07e12 vs
             // 0.82e12 voice-samples/s) unless "cascade_pipe" forces the pipeline from n sections
@@ -1359,8 +1361,11 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 }
                 // oscillator-fed chains from "osc_reg" sections on; 2-section chains only when their time pieces fill at least
                 // half of the machine's warp slots (else the time-parallel scan kernel is the better choice)
-                if (p->opt_osc_reg > 0 && ch.nsec_real >= (int)p->opt_osc_reg && sigb_osc_reg_ok(&t, (int)p->opt_osc_delta) &&
-                    (ch.nsec_real >= 3 || p->osc_reg_user ||
+                // ... and ONE section behind a Square / Sawtooth / Triangle (the scan kernels evaluate those in float64 per sample:
+                // 4.5-6.8e11 voice-samples/s on C2's shape against 1.58e12 for a Sine) under the same condition
+                const bool one_nonsine = ch.nsec_real == 1 && ch.wave != SIGB_WAVE_SINE && p->opt_osc_reg == 2 && p->opt_osc_delta != 0;
+                if (p->opt_osc_reg > 0 && (ch.nsec_real >= (int)p->opt_osc_reg || one_nonsine) && sigb_osc_reg_ok(&t, (int)p->opt_osc_delta) &&
+                    (ch.nsec_real >= 3 || (p->osc_reg_user && !one_nonsine) ||
                      (t.warm_rows >= 0 && sigb_osc_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta) >= 512))) {
                     int e = sigb_launch_osc_reg(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta, st);
                     if (e) return fail(SIGB_ECUDA, std::string("k_osc_reg: ") + cudaGetErrorString((cudaError_t)e));
@@ -1379,7 +1384,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             }
             // stateless oscillator chains on many channels: from the Q0.64 phase word instead of float64 per sample (k_osc_fill)
             if (!force_seq && p->opt_osc_fill != 0 && (ch.hertz_row < 0 || ch.osc_tables_dev) && sigb_osc_fill_ok(&a)) {
-                int e = sigb_launch_osc_fill(&a, ch.max_abs_hertz, ch.max_abs_phase, st);
+                int e = sigb_launch_osc_fill(&a, st);
                 if (e) return fail(SIGB_ECUDA, std::string("k_osc_fill: ") + cudaGetErrorString((cudaError_t)e));
                 p->launch_count++;
                 continue;

@@ -610,6 +610,15 @@ constexpr int OR = 8;           // rows per block
 // resident CTAs per SM: shallow chains are write-bound and want warps (20 per SM), deep ones need the registers
 __host__ __device__ constexpr int osc_min_blocks(int nsec) { return nsec <= 2 ? 5 : nsec <= 6 ? 3 : 2; }
 
+// phase_guard (sigb_plan.cu) for the two channels of a thread at absolute row `last_row`: in-tile drift of the rounded
+// increment, rounding of the top word, and the float64 rounding of the reference's own phase
+__device__ __forceinline__ int osc_guard(const ChainDev& a, int ca, int cb, int64_t last_row) {
+    const double hz = fmax(fabs(a.hertz[ca]), fabs(a.hertz[cb])), ph = fmax(fabs(a.phase[ca]), fabs(a.phase[cb]));
+    const double cyc = hz * (double)last_row / (double)a.rate + ph + 1.0;
+    const double g = 17.0 + cyc * (3.0 * 4294967296.0 / 9007199254740992.0);
+    return g < 1073741823.0 ? (int)g + 1 : 0x3fffffff;
+}
+
 template <int WAVE>
 __device__ __forceinline__ void osc_rows_g(const ChainDev& a, int guard, int c, unsigned long long th, unsigned long long dth, int64_t n0, float (&x)[OR]) {
     const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
@@ -794,6 +803,10 @@ k_osc_delta(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
             rotS = make_float2(ra.y, rb.y);
         }
         const int dhiA = (int)((dtha + 0x80000000ull) >> 32), dhiB = (int)((dthb + 0x80000000ull) >> 32);
+        // guard band around the waveform's discontinuities from the thread's OWN channels (phase_guard of sigb_plan.cu at the
+        // request's last row): needs no host-side maximum, so it also serves oscillators whose hertz / phase are sampled per
+        // request on the device (k_osc_tables)
+        const int guard = osc_guard(a, ca, cb, a.position + a.frames);
         int64_t n = a.position + row_first;
         unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
         float* outp = a.out + (int64_t)row_first * a.ld_out + c0;
@@ -825,10 +838,10 @@ k_osc_delta(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
             } else {
                 float xa[OR], xb[OR];
                 switch (wave) {
-                    case SIGB_WAVE_SINE: osc_rows<SIGB_WAVE_SINE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SINE>(a, cb, thb, dthb, n, xb); break;
-                    case SIGB_WAVE_SQUARE: osc_rows<SIGB_WAVE_SQUARE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SQUARE>(a, cb, thb, dthb, n, xb); break;
-                    case SIGB_WAVE_SAWTOOTH: osc_rows<SIGB_WAVE_SAWTOOTH>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_SAWTOOTH>(a, cb, thb, dthb, n, xb); break;
-                    default: osc_rows<SIGB_WAVE_TRIANGLE>(a, ca, tha, dtha, n, xa); osc_rows<SIGB_WAVE_TRIANGLE>(a, cb, thb, dthb, n, xb); break;
+                    case SIGB_WAVE_SINE: osc_rows_g<SIGB_WAVE_SINE>(a, guard, ca, tha, dtha, n, xa); osc_rows_g<SIGB_WAVE_SINE>(a, guard, cb, thb, dthb, n, xb); break;
+                    case SIGB_WAVE_SQUARE: osc_rows_g<SIGB_WAVE_SQUARE>(a, guard, ca, tha, dtha, n, xa); osc_rows_g<SIGB_WAVE_SQUARE>(a, guard, cb, thb, dthb, n, xb); break;
+                    case SIGB_WAVE_SAWTOOTH: osc_rows_g<SIGB_WAVE_SAWTOOTH>(a, guard, ca, tha, dtha, n, xa); osc_rows_g<SIGB_WAVE_SAWTOOTH>(a, guard, cb, thb, dthb, n, xb); break;
+                    default: osc_rows_g<SIGB_WAVE_TRIANGLE>(a, guard, ca, tha, dtha, n, xa); osc_rows_g<SIGB_WAVE_TRIANGLE>(a, guard, cb, thb, dthb, n, xb); break;
                 }
 #pragma unroll
                 for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
@@ -895,6 +908,8 @@ k_osc_delta(const ChainDev a, int tiles, int npieces, int warm_rows, int fast) {
 template <int KIND>
 int osc_delta_launch_nsec(const ChainDev* a, dim3 grid, int tiles, int npieces, int warm, int fast, cudaStream_t st) {
     switch (a->nsec) {
+        case 1: if (KIND & SEC_MIXED) return (int)cudaErrorInvalidValue;
+                k_osc_delta<1, KIND & SEC_HP><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
         case 2: k_osc_delta<2, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
         case 3: k_osc_delta<3, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
         case 4: k_osc_delta<4, KIND><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, npieces, warm, fast); break;
@@ -1040,7 +1055,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
 // ---------------------------------------------------------------------------------------------------------
 template <int WAVE>
 __global__ void __launch_bounds__(RWARPS * 32, 5)
-k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, float guard0, float guard_per_row, int fast) {
+k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, int fast) {
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * RWARPS + (threadIdx.x >> 5);
     if (wid >= tiles * chunks) return;
@@ -1087,8 +1102,9 @@ k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, float 
                 hb += 4 * dhiB;
             }
         } else {
-            // guard band of THIS block (phase_guard of sigb_plan.cu at the block's last row): a function of the absolute position
-            const int guard = (int)fminf(1073741823.0f, ceilf(guard0 + (float)(n + OR) * guard_per_row));
+            // guard band of THIS block (phase_guard at the block's last row, from the thread's own channels): a function of the
+            // absolute position only
+            const int guard = osc_guard(a, ca, cb, n + OR);
             float xa[OR], xb[OR];
             osc_rows_g<WAVE>(a, guard, ca, tha, dtha, n, xa);
             osc_rows_g<WAVE>(a, guard, cb, thb, dthb, n, xb);
@@ -1114,14 +1130,15 @@ k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, float 
     }
 }
 
-// Stateless unmodulated oscillator chains (no filter, no fused epilogue) from 128 channels on: a static property of the chain,
-// so that every request of a plan takes the same kernel (block invariance).
+// Stateless oscillator chains (no filter, no fused epilogue) from 128 channels on, Q0.64 phase tables present (built by the
+// host for constant hertz / phase, by k_osc_tables per request for modulated ones): a static property of the chain, so that
+// every request of a plan takes the same kernel (block invariance).
 extern "C" int sigb_osc_fill_ok(const ChainDev* a) {
     return a->src_kind == SRC_OSC && a->nsec == 0 && a->epi_op == 0 && a->theta0 && a->dtheta && a->hertz && a->phase &&
            a->pos_ptr == nullptr && a->C >= 128;
 }
 
-extern "C" int sigb_launch_osc_fill(const ChainDev* a, double max_abs_hertz, double max_abs_phase, void* stream) {
+extern "C" int sigb_launch_osc_fill(const ChainDev* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (a->frames <= 0) return 0;
     const int fast = (reinterpret_cast<uintptr_t>(a->out) & 7) == 0 && (a->ld_out & 1) == 0;
@@ -1133,17 +1150,13 @@ extern "C" int sigb_launch_osc_fill(const ChainDev* a, double max_abs_hertz, dou
     int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(((int64_t)sms * 40 + tiles - 1) / std::max(1, tiles), (nblk + 15) / 16));
     const int bpc = (int)((nblk + chunks - 1) / chunks);
     chunks = (nblk + bpc - 1) / bpc;
-    // phase_guard(last_row) = 16 + (max|hertz| last_row / rate + max|phase| + 1) * 3 * 2^32 / 2^53, per block on the device
-    const double k = 3.0 * 4294967296.0 / 9007199254740992.0;
-    const float guard0 = (float)(16.0 + (max_abs_phase + 1.0) * k + 1.0);
-    const float guard_per_row = (float)(max_abs_hertz / a->rate * k * 1.0001);
     const int64_t warps = (int64_t)tiles * chunks;
     const dim3 grid((unsigned)((warps + RWARPS - 1) / RWARPS));
     switch (a->wave) {
-        case SIGB_WAVE_SINE: k_osc_fill<SIGB_WAVE_SINE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
-        case SIGB_WAVE_SQUARE: k_osc_fill<SIGB_WAVE_SQUARE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
-        case SIGB_WAVE_SAWTOOTH: k_osc_fill<SIGB_WAVE_SAWTOOTH><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
-        default: k_osc_fill<SIGB_WAVE_TRIANGLE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, guard0, guard_per_row, fast); break;
+        case SIGB_WAVE_SINE: k_osc_fill<SIGB_WAVE_SINE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, fast); break;
+        case SIGB_WAVE_SQUARE: k_osc_fill<SIGB_WAVE_SQUARE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, fast); break;
+        case SIGB_WAVE_SAWTOOTH: k_osc_fill<SIGB_WAVE_SAWTOOTH><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, fast); break;
+        default: k_osc_fill<SIGB_WAVE_TRIANGLE><<<grid, RWARPS * 32, 0, st>>>(*a, tiles, (int)chunks, bpc, fast); break;
     }
     return (int)cudaGetLastError();
 }
@@ -1159,12 +1172,18 @@ static void osc_chain_kinds(const ChainDev* a, bool& mixed, bool& any_first) {
     }
 }
 
+static bool osc_use_delta_static(const ChainDev* a, bool mixed, bool any_first, int allow_delta) {
+    return (allow_delta || mixed) && !any_first && (a->nsec >= 2 || a->wave != SIGB_WAVE_SINE);
+}
+
 // allow_delta = 0: state-variable sections (k_osc_reg) even where the delta form applies (plan option "osc_delta", A/B)
 extern "C" int sigb_osc_reg_ok(const ChainDev* a, int allow_delta) {
     if (a->src_kind != SRC_OSC || !a->theta0 || !a->dtheta || a->nsec < 1 || a->nsec > 8 || a->C <= 0) return 0;
     bool mixed, any_first;
     osc_chain_kinds(a, mixed, any_first);
     if (mixed) return !any_first && allow_delta && a->nsec >= 2;
+    // a discontinuous waveform with device-sampled hertz / phase: only k_osc_delta derives the guard band from its own channels
+    if (a->osc_mod && a->wave != SIGB_WAVE_SINE && !osc_use_delta_static(a, mixed, any_first, allow_delta)) return 0;
     return 1;
 }
 
@@ -1190,7 +1209,7 @@ static void osc_reg_geometry(const ChainDev* a, int max_segments, bool delta, in
 }
 
 static bool osc_use_delta(const ChainDev* a, bool mixed, bool any_first, int allow_delta) {
-    return (allow_delta || mixed) && !any_first && a->nsec >= 2;
+    return osc_use_delta_static(a, mixed, any_first, allow_delta);     // (one section behind a Sine: k_osc_reg, A/B only)
 }
 
 // share of the machine's warp slots the launch would occupy, in 1/1024 (shallow chains only go register-resident when the

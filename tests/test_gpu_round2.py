@@ -659,16 +659,18 @@ def test_wide_stateless_oscillator_chains(wave, ns, engine):
         assert err <= (1e-6 if pos < 2 ** 31 else 2e-6), (wave, pos, err)
 
 
-@pytest.mark.parametrize('nsec', [0, 1, 2, 3])
-def test_vibrato_keeps_the_sine_fast_paths(nsec, ns, engine):
-    """A Sine whose hertz AND phase are driven by LFOs on many channels: the rows are constant within a request, so k_osc_tables
-    re-derives the exact Q0.64 phase tables per request and the chain runs on k_osc_fill / k_chain_scan3 / k_osc_delta like
-    a constant oscillator -- three consecutive requests (the parameters jump between them, as in the reference) against the
-    float64 oracle and against the float64-per-sample kernel (force_seq)."""
+@pytest.mark.parametrize('wave,nsec', [('Sine', 0), ('Sine', 1), ('Sine', 2), ('Sine', 3), ('Square', 0), ('Square', 1), ('Sawtooth', 0),
+                                       ('Sawtooth', 2), ('Triangle', 1), ('Triangle', 3)])
+def test_vibrato_keeps_the_phase_word_fast_paths(wave, nsec, ns, engine):
+    """An oscillator whose hertz AND phase are driven by LFOs on many channels: the rows are constant within a request, so
+    k_osc_tables re-derives the exact Q0.64 phase tables per request and the chain runs on k_osc_fill / k_chain_scan3 (Sine) /
+    k_osc_delta like a constant oscillator (the discontinuous waveforms with a guard band from the thread's own channels) --
+    three consecutive requests (the parameters jump between them, as in the reference) against the float64 oracle and against
+    the float64-per-sample kernel (force_seq)."""
     ch = 192
     rng = np.random.default_rng(87 + nsec)
     hz = rng.uniform(55.0, 3000.0, ch)
-    o = ns.Sine()
+    o = getattr(ns, wave)()
     o.hertz = cases.sweep(ns, [hz * 0.94], [hz * 1.06], [rng.uniform(3.0, 7.0, ch)], [rng.uniform(0, 1, ch)])
     o.phase = cases.gain(ns, cases.osc(ns, 'Sine', [rng.uniform(0.5, 2.0, ch)], [rng.uniform(0, 1, ch)]), [np.full(ch, 0.1)])
     node = o
@@ -688,7 +690,7 @@ def test_vibrato_keeps_the_sine_fast_paths(nsec, ns, engine):
             pos += frames
         c.close()
         got[mode] = np.concatenate(blocks)
-    assert not np.array_equal(got['fast'], got['seq'])                    # two different kernels did render
+    assert not np.array_equal(got['fast'], got['seq']) or (wave == 'Square' and nsec == 0)     # two different kernels did render
     tol = 1e-6 if nsec == 0 else 1e-4
     assert max_abs_err(got['fast'], got['seq']) <= (2e-6 if nsec == 0 else 2e-5)
     if nsec == 0:            # (filters: the plan carries their state across the requests, the oracle's requests restart; compare with seq only)
@@ -698,5 +700,35 @@ def test_vibrato_keeps_the_sine_fast_paths(nsec, ns, engine):
             want.append(orc.render(node, pos, frames, ch))
             pos += frames
         err = max_abs_err(got['fast'], np.concatenate(want))
-        print(f'vibrato sine x {ch} channels, three requests: max-abs {err:.3e}')
+        print(f'vibrato {wave} x {ch} channels, three requests: max-abs {err:.3e}')
         assert err <= tol
+
+
+@pytest.mark.parametrize('wave', ['Square', 'Sawtooth', 'Triangle'])
+def test_one_section_behind_a_discontinuous_waveform_goes_register_resident(wave, ns, engine):
+    """Square / Sawtooth / Triangle -> ONE filter -> gain on many channels (lowpass_test.sigs' shape at scale): the scan kernels
+    evaluate those waveforms in float64 per sample, so the chain takes k_osc_delta when its time pieces fill the machine --
+    against the oracle on picked voices and against the scan kernel (osc_reg = 0) on the same plan."""
+    torch = pytest.importorskip('torch')
+    ch, frames = 4096, 96000
+    hz, ph, cut, g = cases.voice_params(88, ch)
+    cut = np.maximum(cut, 800.0)
+    node = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, wave, [hz], [ph]), [cut]), [g])
+    got = {}
+    for kernel in ('reg', 'scan'):
+        c = engine.compile(node, ch, RATE)
+        if kernel == 'scan':
+            c.set_option('osc_reg', 0)
+        first = c.render_device(0, frames)
+        second = c.render_device(frames, 1000)
+        got[kernel] = torch.cat([first, second])
+        c.close()
+    assert not bool(torch.equal(got['reg'], got['scan']))
+    diff = float((got['reg'] - got['scan']).abs().max())
+    pick = np.sort(np.random.default_rng(3).choice(ch, 8, replace=False))
+    sub = cases.gain(ns, cases.lowpass(ns, cases.osc(ns, wave, [hz[pick]], [ph[pick]]), [cut[pick]]), [g[pick]])
+    want = np_oracle.GraphOracle(RATE).render(sub, 0, frames + 1000, len(pick))
+    err = max_abs_err(got['reg'][:, torch.from_numpy(pick).cuda()].cpu().numpy(), want)
+    print(f'{wave} -> LowPass -> Gain x {ch}: register kernel max-abs {err:.3e}; vs the scan kernel {diff:.3e}')
+    assert err <= 1e-4
+    assert diff <= 2e-5

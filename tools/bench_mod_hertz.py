@@ -16,9 +16,10 @@ ns = cases.b200_namespace()
 hz, ph, cut, g = cases.voice_params(2, CH)
 rng = np.random.default_rng(3)
 out = torch.empty((FRAMES, CH), dtype=torch.float32, device='cuda')
+WAVE = os.environ.get('WAVE', 'Sine')
 for nsec in (0, 1, 2):
     for mod in (False, True) if nsec else (False, 'seq', True):
-        o = ns.Sine()
+        o = getattr(ns, WAVE)()
         o.hertz = cases.sweep(ns, [hz * 0.97], [hz * 1.03], [rng.uniform(3.0, 7.0, CH)], [rng.uniform(0, 1, CH)]) if mod is True else cases.fixed(ns, [hz])
         o.phase = cases.fixed(ns, [ph])
         node = o
@@ -37,5 +38,5 @@ for nsec in (0, 1, 2):
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / 5
-        print(f'{nsec} section(s), hertz {"LFO-driven" if mod is True else "constant, k_chain_seq" if mod == "seq" else "constant"}: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gvoice-samples/s, launches {[l["kind"] for l in c.describe()["launches"]]}')
+        print(f'{WAVE}: {nsec} section(s), hertz {"LFO-driven" if mod is True else "constant, k_chain_seq" if mod == "seq" else "constant"}: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gvoice-samples/s, launches {[l["kind"] for l in c.describe()["launches"]]}')
         c.close()
