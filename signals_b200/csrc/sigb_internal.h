@@ -74,6 +74,8 @@ struct ChainDev {
     const double* epi_hertz;        // [C]
     const double* epi_phase;        // [C]
     const float* epi_gain;          // [C] or nullptr
+    const unsigned long long* epi_theta0;   // [C] Q0.64 phase / increment of the second oscillator (k_osc_fill)
+    const unsigned long long* epi_dtheta;
 };
 
 struct EwiseDev {

@@ -96,7 +96,7 @@ struct ChainSpec {
     std::vector<ModFilter> mods;
     // Mix / RingMod fused as an epilogue of a stateless chain (k_chain_seq)
     int epi_op = 0, epi_side = 0, epi_node = -1, epi_wave = -1, epi_p_row = -1;
-    Table epi_p, epi_hertz, epi_phase, epi_gain;
+    Table epi_p, epi_hertz, epi_phase, epi_gain, epi_theta0, epi_dtheta;
     std::vector<double> gain_d;  // folded gain in float64 (fused reductions derive their weights from it)
     bool has_gain = false;
     double max_abs_hertz = 0.0, max_abs_phase = 0.0;   // SRC_OSC: sizes the phase-word guard band
@@ -996,6 +996,8 @@ int Builder::build_fused_pointwise(int i, bool* done) {
         ch.epi_hertz = oc.hertz;
         ch.epi_phase = oc.phase;
         ch.epi_gain = oc.gain;
+        ch.epi_theta0 = oc.theta0;
+        ch.epi_dtheta = oc.dtheta;
         mark_consumed(o);
     } else if (o >= 0) {
         st = ensure(o);
@@ -1327,9 +1329,17 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                     a.epi_hertz = ch.epi_hertz.dev<double>(base);
                     a.epi_phase = ch.epi_phase.dev<double>(base);
                     a.epi_gain = ch.epi_gain.dev<float>(base);
+                    a.epi_theta0 = ch.epi_theta0.dev<unsigned long long>(base);
+                    a.epi_dtheta = ch.epi_dtheta.dev<unsigned long long>(base);
                 } else {
                     Operand o = operand_of(p, ch.epi_node, abs_row0, out, ld_out);
                     a.epi_buf = o.ptr; a.epi_ld = o.ld; a.epi_cs = o.cs; a.epi_rows = o.rows;
+                }
+                if (!p->opt_force_seq && p->rt_pos_ptr == nullptr && p->opt_osc_fill != 0 && ch.hertz_row < 0 && sigb_osc_fill_ok(&a)) {
+                    int e = sigb_launch_osc_fill(&a, st);        // both oscillators from their phase words, in registers
+                    if (e) return fail(SIGB_ECUDA, std::string("k_osc_fill: ") + cudaGetErrorString((cudaError_t)e));
+                    p->launch_count++;
+                    continue;
                 }
                 int e = sigb_launch_chain_seq(&a, st);           // epilogue chains are stateless: the sequential kernel tiles time
                 if (e) return fail(SIGB_ECUDA, std::string("k_chain_seq: ") + cudaGetErrorString((cudaError_t)e));

@@ -630,6 +630,19 @@ __device__ __forceinline__ void osc_rows_g(const ChainDev& a, int guard, int c, 
     }
 }
 
+// ... with explicit hertz / phase tables (the second oscillator of a fused Mix / RingMod)
+template <int WAVE>
+__device__ __forceinline__ void osc_rows_p(const double* hertz, const double* phase, int rate, int guard, int c, unsigned long long th,
+                                           unsigned long long dth, int64_t n0, float (&x)[OR]) {
+    const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
+    const bool near = gen_tile<WAVE, OR>(w, dhi, guard, x);
+    if (WAVE != SIGB_WAVE_SINE && near) {
+        const double hz = hertz[c], ph = phase[c], r = (double)rate;
+#pragma unroll
+        for (int k = 0; k < OR; ++k) x[k] = osc_wave(WAVE, osc_cycles(__ddiv_rn((double)(n0 + k), r), hz, ph));
+    }
+}
+
 template <int WAVE>
 __device__ __forceinline__ void osc_rows(const ChainDev& a, int c, unsigned long long th, unsigned long long dth, int64_t n0, float (&x)[OR]) {
     const int w = (int)((th + 0x80000000ull) >> 32), dhi = (int)((dth + 0x80000000ull) >> 32);
@@ -1054,7 +1067,7 @@ extern "C" int sigb_launch_cascade_reg(const ChainDev* a, int max_segments, int 
 // give the same bits.  A partial block at either end of a request is generated whole and stored in part.
 // ---------------------------------------------------------------------------------------------------------
 template <int WAVE>
-__global__ void __launch_bounds__(RWARPS * 32, 5)
+__global__ void __launch_bounds__(RWARPS * 32, 4)
 k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, int fast) {
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * RWARPS + (threadIdx.x >> 5);
@@ -1082,6 +1095,17 @@ k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, int fa
     int64_t n = nb << 3;
     unsigned long long tha = a.theta0[ca] + (unsigned long long)n * dtha, thb = a.theta0[cb] + (unsigned long long)n * dthb;
     const bool vec = fast && live1;
+    // fused Mix / RingMod with a second oscillator (fx.py:35-46): its phase words ride along in registers
+    const int epi = a.epi_op;
+    unsigned long long eta = 0, etb = 0, edta = 0, edtb = 0;
+    float2 g2 = make_float2(1.0f, 1.0f), mixp = make_float2(0.0f, 0.0f);
+    if (epi) {
+        edta = a.epi_dtheta[ca]; edtb = a.epi_dtheta[cb];
+        eta = a.epi_theta0[ca] + (unsigned long long)n * edta;
+        etb = a.epi_theta0[cb] + (unsigned long long)n * edtb;
+        if (a.epi_gain) g2 = make_float2(a.epi_gain[ca], a.epi_gain[cb]);
+        if (a.epi_p) mixp = make_float2(a.epi_p[ca], a.epi_p[cb]);
+    }
     for (; nb < nb_end; ++nb) {
         float2 x[OR];
         if (rot) {
@@ -1111,16 +1135,56 @@ k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, int fa
 #pragma unroll
             for (int k = 0; k < OR; ++k) x[k] = make_float2(xa[k], xb[k]);
         }
+#pragma unroll
+        for (int k = 0; k < OR; ++k) x[k] = __fmul2_rn(x[k], gain);
+        if (epi) {
+            // the second oscillator's block, then out = mix * left + (1 - mix) * right or left * right (k_chain_seq's epilogue)
+            int g2nd;
+            {
+                const double hz = fmax(fabs(a.epi_hertz[ca]), fabs(a.epi_hertz[cb])), ph = fmax(fabs(a.epi_phase[ca]), fabs(a.epi_phase[cb]));
+                const double cyc = hz * (double)(n + OR) / (double)a.rate + ph + 1.0;
+                const double gg = 17.0 + cyc * (3.0 * 4294967296.0 / 9007199254740992.0);
+                g2nd = gg < 1073741823.0 ? (int)gg + 1 : 0x3fffffff;
+            }
+            float ya[OR], yb[OR];
+            switch (a.epi_wave) {
+                case SIGB_WAVE_SINE:
+                    osc_rows_p<SIGB_WAVE_SINE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, ca, eta, edta, n, ya);
+                    osc_rows_p<SIGB_WAVE_SINE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, cb, etb, edtb, n, yb);
+                    break;
+                case SIGB_WAVE_SQUARE:
+                    osc_rows_p<SIGB_WAVE_SQUARE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, ca, eta, edta, n, ya);
+                    osc_rows_p<SIGB_WAVE_SQUARE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, cb, etb, edtb, n, yb);
+                    break;
+                case SIGB_WAVE_SAWTOOTH:
+                    osc_rows_p<SIGB_WAVE_SAWTOOTH>(a.epi_hertz, a.epi_phase, a.rate, g2nd, ca, eta, edta, n, ya);
+                    osc_rows_p<SIGB_WAVE_SAWTOOTH>(a.epi_hertz, a.epi_phase, a.rate, g2nd, cb, etb, edtb, n, yb);
+                    break;
+                default:
+                    osc_rows_p<SIGB_WAVE_TRIANGLE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, ca, eta, edta, n, ya);
+                    osc_rows_p<SIGB_WAVE_TRIANGLE>(a.epi_hertz, a.epi_phase, a.rate, g2nd, cb, etb, edtb, n, yb);
+                    break;
+            }
+            eta += (unsigned long long)OR * edta;
+            etb += (unsigned long long)OR * edtb;
+            const float2 one_m = make_float2(1.0f - mixp.x, 1.0f - mixp.y);
+#pragma unroll
+            for (int k = 0; k < OR; ++k) {
+                const float2 o = __fmul2_rn(make_float2(ya[k], yb[k]), g2);
+                const float2 left = a.epi_side ? o : x[k], right = a.epi_side ? x[k] : o;
+                x[k] = epi == EW_MIX ? __fadd2_rn(__fmul2_rn(mixp, left), __fmul2_rn(one_m, right)) : __fmul2_rn(left, right);
+            }
+        }
         float* outp = a.out + (n - pos) * a.ld_out + c0;                    // row n of the stream (may lie before the request)
         if (n >= pos && n + OR <= end && vec) {
 #pragma unroll
-            for (int k = 0; k < OR; ++k) __stcs(reinterpret_cast<float2*>(outp + (int64_t)k * a.ld_out), __fmul2_rn(x[k], gain));
+            for (int k = 0; k < OR; ++k) __stcs(reinterpret_cast<float2*>(outp + (int64_t)k * a.ld_out), x[k]);
         } else {
 #pragma unroll
             for (int k = 0; k < OR; ++k) {
                 if (n + k >= pos && n + k < end) {
-                    if (live0) outp[(int64_t)k * a.ld_out] = x[k].x * gain.x;
-                    if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y * gain.y;
+                    if (live0) outp[(int64_t)k * a.ld_out] = x[k].x;
+                    if (live1) outp[(int64_t)k * a.ld_out + 1] = x[k].y;
                 }
             }
         }
@@ -1130,11 +1194,13 @@ k_osc_fill(const ChainDev a, int tiles, int chunks, int blocks_per_chunk, int fa
     }
 }
 
-// Stateless oscillator chains (no filter, no fused epilogue) from 128 channels on, Q0.64 phase tables present (built by the
+// Stateless oscillator chains (no filter; a fused Mix / RingMod with a second oscillator is welcome) from 128 channels on, Q0.64 phase tables present (built by the
 // host for constant hertz / phase, by k_osc_tables per request for modulated ones): a static property of the chain, so that
 // every request of a plan takes the same kernel (block invariance).
 extern "C" int sigb_osc_fill_ok(const ChainDev* a) {
-    return a->src_kind == SRC_OSC && a->nsec == 0 && a->epi_op == 0 && a->theta0 && a->dtheta && a->hertz && a->phase &&
+    if (a->epi_op && !(a->epi_wave >= 0 && a->epi_theta0 && a->epi_dtheta && a->epi_hertz && a->epi_phase && (a->epi_op != EW_MIX || a->epi_p)))
+        return 0;                                  // a fused Mix / RingMod only with a second oscillator (not a materialised block)
+    return a->src_kind == SRC_OSC && a->nsec == 0 && a->theta0 && a->dtheta && a->hertz && a->phase &&
            a->pos_ptr == nullptr && a->C >= 128;
 }
 
@@ -1146,8 +1212,8 @@ extern "C" int sigb_launch_osc_fill(const ChainDev* a, void* stream) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t nblk = ((a->position + a->frames + 7) >> 3) - (a->position >> 3);
-    // ~2 waves of the 20 resident warps per SM, each warp streaming its own run of blocks (at least 16 blocks per warp)
-    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(((int64_t)sms * 40 + tiles - 1) / std::max(1, tiles), (nblk + 15) / 16));
+    // ~2 waves of the 16 resident warps per SM, each warp streaming its own run of blocks (at least 16 blocks per warp)
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(((int64_t)sms * 32 + tiles - 1) / std::max(1, tiles), (nblk + 15) / 16));
     const int bpc = (int)((nblk + chunks - 1) / chunks);
     chunks = (nblk + bpc - 1) / bpc;
     const int64_t warps = (int64_t)tiles * chunks;

@@ -732,3 +732,35 @@ def test_one_section_behind_a_discontinuous_waveform_goes_register_resident(wave
     print(f'{wave} -> LowPass -> Gain x {ch}: register kernel max-abs {err:.3e}; vs the scan kernel {diff:.3e}')
     assert err <= 1e-4
     assert diff <= 2e-5
+
+
+@pytest.mark.parametrize('op,wa,wb,side', [('Mix', 'Sine', 'Sine', 0), ('Mix', 'Sawtooth', 'Sine', 1), ('RingMod', 'Sine', 'Square', 0),
+                                           ('RingMod', 'Triangle', 'Sawtooth', 1), ('Mix', 'Square', 'Triangle', 0)])
+def test_wide_mix_and_ringmod_of_two_oscillators(op, wa, wb, side, ns, engine):
+    """Mix / RingMod of two oscillator chains on many channels: fused into k_osc_fill (both oscillators from their Q0.64 phase
+    words, in registers) -- against the float64 oracle, bit for bit however the stream is cut, against k_chain_seq's fused
+    epilogue on the same plan."""
+    rng = np.random.default_rng(89)
+    ch = 200
+    a = cases.gain(ns, cases.osc(ns, wa, [rng.uniform(27.5, 4186.0, ch)], [rng.uniform(0, 1, ch)]), [rng.uniform(0.1, 1.0, ch)])
+    b = cases.gain(ns, cases.osc(ns, wb, [rng.uniform(27.5, 4186.0, ch)], [rng.uniform(0, 1, ch)]), [rng.uniform(0.1, 1.0, ch)])
+    node = getattr(ns, op)()
+    node.left, node.right = (b, a) if side else (a, b)
+    if op == 'Mix':
+        node.mix = cases.fixed(ns, [rng.uniform(0.0, 1.0, ch)])
+    for pos in (0, 123457):
+        frames = 4099
+        c = engine.compile(node, ch, RATE)
+        assert [l['kind'] for l in c.describe()['launches']] == ['chain']            # one fused launch
+        whole = c.render_device(pos, frames).cpu().numpy()
+        cuts = [0, 1, 7, 8, 9, 1000, 1001, frames]
+        parts = np.concatenate([c.render_device(pos + x, y - x).cpu().numpy() for x, y in zip(cuts, cuts[1:])])
+        c.set_option('osc_fill', 0)
+        seq = c.render_device(pos, frames).cpu().numpy()
+        c.close()
+        want = np_oracle.GraphOracle(RATE).render(node, pos, frames, ch)
+        err = max_abs_err(whole, want)
+        print(f'{op}({wa}, {wb}) x {ch} at position {pos}: k_osc_fill max-abs {err:.3e} (k_chain_seq {max_abs_err(seq, want):.3e})')
+        assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))
+        assert not np.array_equal(whole, seq)
+        assert err <= 1e-6
