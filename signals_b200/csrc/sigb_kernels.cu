@@ -957,6 +957,17 @@ k_chain_scan3(const ChainDev a, int nsteps, int warm_steps, const __grid_constan
 // ------------------------------------------------------------------------------------------
 // k_ewise / k_reduce
 // ------------------------------------------------------------------------------------------
+// Amp (fx.py:60): copysign(input ** exp, input).  Small integer exponents -- the usual waveshaping settings -- as products
+// (one or two roundings instead of powf's ~4 ulp and ~30 instructions); everything else, NaN for a negative input under a
+// fractional exponent included, through powf.
+__device__ __forceinline__ float ew_amp(float x, float p) {
+    if (p == 2.0f) return x * fabsf(x);
+    if (p == 1.0f) return x;
+    if (p == 3.0f) return x * x * x;
+    if (p == 4.0f) { const float x2 = x * x; return copysignf(x2 * x2, x); }
+    return copysignf(powf(x, p), x);
+}
+
 __device__ __forceinline__ float ew_load(const float* p, int64_t ld, int cs, int64_t rows, int64_t r, int c) {
     if (rows >= 0 && r >= rows) return 0.0f;
     return __ldg(p + r * ld + (int64_t)c * cs);
@@ -978,7 +989,7 @@ __global__ void __launch_bounds__(256) k_ewise(const EwiseDev a) {
                 break;
             }
             case EW_RINGMOD: y = x * ew_load(a.b, a.ldb, a.bcs, a.b_rows, r, c); break;   // fx.py:46
-            default: y = copysignf(powf(x, a.p[c]), x); break;                      // fx.py:60
+            default: y = ew_amp(x, a.p[c]); break;                                  // fx.py:60
         }
         a.out[r * a.ld_out + c] = y;
     }
@@ -992,7 +1003,7 @@ __device__ __forceinline__ float ew_apply(int op, float x, float b, float p) {
         case EW_GAIN: return x * p;
         case EW_MIX: return p * x + (1.0f - p) * b;
         case EW_RINGMOD: return x * b;
-        default: return copysignf(powf(x, p), x);
+        default: return ew_amp(x, p);
     }
 }
 
