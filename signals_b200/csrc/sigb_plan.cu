@@ -88,6 +88,7 @@ struct ChainSpec {
     int warm_rows = -1;          // rows until the cascade forgets its initial state (see sigb_section_decay_rows)
     double warm_static = 0.0;    // ... the share of the filters with constant cutoffs (modulated ones add theirs per request)
     int dst_node = -1;
+    int dst_coff = 0;             // first column of the destination block this chain writes (a Merge rendered in place)
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
     bool osc_tables_dev = false;          // ... and (Sine) the Q0.64 phase tables are re-derived from those rows on the device per request
     // filters whose cutoff is driven by an emitter: their sections are re-designed on the device once per request
@@ -1088,24 +1089,66 @@ int Builder::build_merge(int i) {
     v.channels = C;
     v.buf = new_buf(i);
     if (v.buf >= 0) p->bufs[v.buf].channels = C;
-    int coff = 0;
-    for (int side = 0; side < 2; ++side) {
-        const int src = n.in[side];
-        int st = ensure(src);
+    // np.hstack (shape.py:73-74) rendered IN PLACE: a tree of Merge nodes is flattened into its leaves (a nested Merge nobody else
+    // reads needs no block of its own), and a leaf that is the end of a chain nobody else reads writes its column range of the
+    // merged block directly (out + first column, leading dimension of the merged block) -- one write per sample instead of a
+    // write and a copy per Merge level.  Every other leaf is materialised as before and copied into place once.
+    struct Leaf { int node, coff, width; };
+    std::vector<Leaf> leaves;
+    std::vector<int> inner;                                   // flattened Merge nodes below i
+    {
+        std::vector<Leaf> stack{{n.in[1], cl, cr}, {n.in[0], 0, cl}};
+        while (!stack.empty()) {
+            const Leaf t = stack.back();
+            stack.pop_back();
+            const sigb_node& m = p->nodes[t.node];
+            if (m.kind == SIGB_NODE_MERGE && p->uses[t.node] == 1 && p->vals[t.node].kind == VK_NONE && m.in[0] >= 0 && m.in[1] >= 0 &&
+                p->nodes[m.in[0]].channels + p->nodes[m.in[1]].channels == t.width) {
+                const int wl = p->nodes[m.in[0]].channels;
+                inner.push_back(t.node);
+                stack.push_back({m.in[1], t.coff + wl, t.width - wl});
+                stack.push_back({m.in[0], t.coff, wl});
+            } else {
+                leaves.push_back(t);
+            }
+        }
+    }
+    p->vals[i] = v;                                           // (the in-place chains resolve their destination through vals[i])
+    for (const Leaf& lf : leaves) {
+        const sigb_node& m = p->nodes[lf.node];
+        const bool in_place = is_chain_kind(m.kind) && p->uses[lf.node] == 1 && p->vals[lf.node].kind == VK_NONE &&
+                              m.channels == lf.width && (m.kind != SIGB_NODE_GAIN || gain_is_const(lf.node));
+        if (in_place) {
+            ChainSpec ch;
+            int st = make_chain(lf.node, ch, true);
+            if (st != SIGB_OK) return st;
+            ch.dst_node = i;
+            ch.dst_coff = lf.coff;
+            p->vals[lf.node].kind = VK_BUF;                   // lives inside the merged block: never read on its own (uses == 1)
+            p->vals[lf.node].channels = lf.width;
+            p->vals[lf.node].buf = -2;
+            p->chains.push_back(ch);
+            p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+            continue;
+        }
+        int st = ensure(lf.node);
         if (st != SIGB_OK) return st;
         EwiseSpec e;
         e.op = EW_COPY;
-        e.C = side == 0 ? cl : cr;
-        if (p->vals[src].channels != 1 && p->vals[src].channels != e.C)
-            return fail(SIGB_ESHAPE, "node " + std::to_string(src) + ": channels incompatible with Merge slot");
-        e.a_node = src;
+        e.C = lf.width;
+        if (p->vals[lf.node].channels != 1 && p->vals[lf.node].channels != e.C)
+            return fail(SIGB_ESHAPE, "node " + std::to_string(lf.node) + ": channels incompatible with Merge slot");
+        e.a_node = lf.node;
         e.dst_node = i;
-        e.dst_coff = coff;
-        coff += e.C;
+        e.dst_coff = lf.coff;
         p->ewises.push_back(e);
         p->launches.push_back({LK_EWISE, (int)p->ewises.size() - 1});
     }
-    p->vals[i] = v;
+    for (int k : inner) {
+        p->vals[k].kind = VK_BUF;
+        p->vals[k].channels = p->nodes[k].channels;
+        p->vals[k].buf = -2;
+    }
     return SIGB_OK;
 }
 
@@ -1317,8 +1360,8 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 a.src_rows = o.rows < 0 ? INT64_MAX : o.rows;
             }
             const Val& dv = p->vals[ch.dst_node];
-            if (dv.buf < 0) { a.out = out; a.ld_out = ld_out; }
-            else { a.out = p->bufs[dv.buf].ptr; a.ld_out = dv.channels; }
+            if (dv.buf < 0) { a.out = out + ch.dst_coff; a.ld_out = ld_out; }
+            else { a.out = p->bufs[dv.buf].ptr + ch.dst_coff; a.ld_out = dv.channels; }
             a.epi_op = ch.epi_op;
             a.epi_wave = -1;
             if (ch.epi_op) {

@@ -51,3 +51,25 @@ for name, build in graphs.items():
     ms = ev[0].elapsed_time(ev[1]) / 4
     print(f'{name}: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, launches {[l["kind"] + ":" + str(l.get("op", l.get("sections", ""))) for l in c.describe()["launches"]]}')
     c.close()
+
+# Merge trees (np.hstack, shape.py:60-74): four 1,024-channel chains merged pairwise into the 4,096-channel block
+def merge(a, b):
+    m = ns.Merge(); m.left = a; m.right = b; return m
+
+
+q = CH // 4
+parts = [cases.gain(ns, cases.lowpass(ns, cases.osc(ns, w, [hz[k * q:(k + 1) * q]], [ph[k * q:(k + 1) * q]]), [cut[k * q:(k + 1) * q]]), [g[k * q:(k + 1) * q]])
+         for k, w in enumerate(('Sine', 'Square', 'Sawtooth', 'Triangle'))]
+node = merge(merge(merge(parts[0], parts[1]), parts[2]), parts[3])
+c = engine.Engine().compile(node, CH, RATE)
+for _ in range(2):
+    c.render_device(0, FRAMES, out)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(4):
+    c.render_device(0, FRAMES, out)
+ev[1].record()
+torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]) / 4
+print(f'Merge tree of four osc -> LP -> gain chains: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, launches {[l["kind"] for l in c.describe()["launches"]]}')
+c.close()
