@@ -660,6 +660,23 @@ extern "C" int sigb_launch_osc_tables(int C, const double* hertz, const double* 
     return (int)cudaGetLastError();
 }
 
+// k_gain_rows: a modulated Gain at the end of a chain (tremolo; fx.py:49-52, `right` sampled once per request): the chain's
+// per-channel output gain for this request = the folded constant gains x the sampled row.
+namespace {
+__global__ void __launch_bounds__(256) k_gain_rows(int C, const float* __restrict__ gain_const, const double* __restrict__ row,
+                                                   float* __restrict__ gain_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    gain_out[c] = (float)((gain_const ? (double)gain_const[c] : 1.0) * row[c]);
+}
+}  // namespace
+
+extern "C" int sigb_launch_gain_rows(int C, const float* gain_const, const double* row, float* gain_out, void* stream) {
+    if (C <= 0) return 0;
+    k_gain_rows<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(C, gain_const, row, gain_out);
+    return (int)cudaGetLastError();
+}
+
 // k_pan_weights: PanSum with a MODULATED pan fused with its voices -- the (L, R) weights gain * (1 - pan), gain * pan of one
 // segment from the request's pan row (float64, as the host derives them for a constant pan), once per request.
 namespace {

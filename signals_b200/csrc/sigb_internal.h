@@ -212,6 +212,7 @@ int sigb_launch_param_eval(const ParamInstr* prog_dev, int n_instr, int n_rows, 
 int sigb_launch_design(const DesignDev* a, void* stream);
 int sigb_launch_osc_tables(int C, const double* hertz, const double* phase, int rate, unsigned long long* theta0,
                            unsigned long long* dtheta, float* rot1, void* stream);
+int sigb_launch_gain_rows(int C, const float* gain_const, const double* row, float* gain_out, void* stream);
 int sigb_launch_pan_weights(int C, const double* gain, const double* pan, float* wl, float* wr, void* stream);
 int sigb_launch_probe_sin(const double* r, int n, float* out, int variant, void* stream);
 #ifdef __cplusplus

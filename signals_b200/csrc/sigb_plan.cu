@@ -89,6 +89,8 @@ struct ChainSpec {
     double warm_static = 0.0;    // ... the share of the filters with constant cutoffs (modulated ones add theirs per request)
     int dst_node = -1;
     int dst_coff = 0;             // first column of the destination block this chain writes (a Merge rendered in place)
+    int gain_row = -1;            // a MODULATED Gain at the end of the chain (tremolo): row of the parameter program; k_gain_rows
+    Table gain_dev;               // ... writes gain_const[c] * row[c] here at every request's first frame, and the kernels read it
     int hertz_row = -1, phase_row = -1;   // SRC_OSC with modulated hertz / phase: rows of the parameter program
     bool osc_tables_dev = false;          // ... and (Sine) the Q0.64 phase tables are re-derived from those rows on the device per request
     // filters whose cutoff is driven by an emitter: their sections are re-designed on the device once per request
@@ -456,7 +458,35 @@ int Builder::ensure(int i) {
     const sigb_node& n = p->nodes[i];
     switch (n.kind) {
         case SIGB_NODE_GAIN:
-            if (!gain_is_const(i)) return build_ewise(i);      // modulated gain: not folded into a chain
+            if (!gain_is_const(i)) {
+                // a modulated Gain (tremolo) at the END of a chain nobody else reads multiplies the chain's output, per request:
+                // it rides on the chain's gain table, re-derived on the device at every request's first frame (k_gain_rows).
+                // (A modulated Gain in FRONT of a filter does not commute with it across requests and stays a k_ewise launch.)
+                const int u = n.in[0];
+                if (u >= 0 && is_chain_kind(p->nodes[u].kind) && p->uses[u] == 1 && p->vals[u].kind == VK_NONE && gain_is_const(u) &&
+                    p->nodes[u].channels == node_C(i) && p->opt_fuse_pointwise != 0) {
+                    ChainSpec ch;
+                    int st = make_chain(u, ch, true);
+                    if (st != SIGB_OK) return st;
+                    st = param_port(n.in[1], ch.C, &ch.gain_row);
+                    if (st != SIGB_OK) return st;
+                    ch.gain_dev = put_vec(p, std::vector<float>(ch.C, 0.0f));
+                    ch.dst_node = i;
+                    p->vals[u].kind = VK_BUF;
+                    p->vals[u].channels = ch.C;
+                    p->vals[u].buf = -2;
+                    Val v;
+                    v.kind = VK_BUF;
+                    v.channels = ch.C;
+                    v.buf = new_buf(i);
+                    if (v.buf >= 0) p->bufs[v.buf].channels = ch.C;
+                    p->vals[i] = v;
+                    p->chains.push_back(ch);
+                    p->launches.push_back({LK_CHAIN, (int)p->chains.size() - 1});
+                    return SIGB_OK;
+                }
+                return build_ewise(i);                         // modulated gain elsewhere: a pointwise launch
+            }
             return build_chain(i);
         case SIGB_NODE_OSC:
         case SIGB_NODE_FILTER: return build_chain(i);
@@ -1343,7 +1373,7 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
             a.rot1 = ch.rot1.dev<float2>(base);
             a.constv = ch.constv.dev<float>(base);
             a.coef = ch.coef.dev<float>(base);
-            a.gain = ch.gain.dev<float>(base);
+            a.gain = ch.gain_row >= 0 ? ch.gain_dev.dev<float>(base) : ch.gain.dev<float>(base);
             a.apow = ch.apow.dev<double>(base);
             a.apow_h = ch.apow_h.dev<double>(base);
             a.ztab = ch.ztab.dev<float>(base);
@@ -1635,6 +1665,14 @@ int run_params(sigb_plan* p, int64_t position, int64_t frames, cudaStream_t st, 
                                    position, p->rt_pos_ptr, p->rate, st);
     if (e) return fail(SIGB_ECUDA, std::string("k_param_eval: ") + cudaGetErrorString((cudaError_t)e));
     p->launch_count++;
+    for (const ChainSpec& ch : p->chains) {
+        if (ch.gain_row < 0) continue;
+        const unsigned char* base = p->d_arena;
+        e = sigb_launch_gain_rows(ch.C, ch.gain.dev<float>(base), p->d_prow_d + (size_t)ch.gain_row * p->pwidth,
+                                  const_cast<float*>(ch.gain_dev.dev<float>(base)), st);
+        if (e) return fail(SIGB_ECUDA, std::string("k_gain_rows: ") + cudaGetErrorString((cudaError_t)e));
+        p->launch_count++;
+    }
     for (const ChainSpec& ch : p->chains) {
         if (!ch.osc_tables_dev) continue;
         const unsigned char* base = p->d_arena;

@@ -764,3 +764,46 @@ def test_wide_mix_and_ringmod_of_two_oscillators(op, wa, wb, side, ns, engine):
         assert np.array_equal(whole.view(np.uint32), parts.view(np.uint32))
         assert not np.array_equal(whole, seq)
         assert err <= 1e-6
+
+
+@pytest.mark.parametrize('nsec', [0, 1, 2])
+def test_tremolo_rides_on_the_chain_gain(nsec, ns, engine):
+    """A Gain driven by an LFO at the END of a chain (tremolo) on many channels: folded into the chain's gain table per request
+    (k_gain_rows) -- one launch per request's block, no pointwise pass -- against the float64 oracle over three requests
+    (oscillator only) and against the unfused plan (fuse_pointwise = 0: chain + k_ewise)."""
+    from signals_b200 import _lib
+    ch = 192
+    rng = np.random.default_rng(90 + nsec)
+    node = cases.osc(ns, 'Sine', [rng.uniform(55.0, 3000.0, ch)], [rng.uniform(0, 1, ch)])
+    cut = np.exp(rng.uniform(np.log(700.0), np.log(8000.0), (max(nsec, 1), ch)))
+    for s in range(nsec):
+        node = cases.lowpass(ns, node, [cut[s]])
+    trem = ns.Gain()
+    trem.left = node
+    trem.right = cases.sweep(ns, [np.full(ch, 0.2)], [np.full(ch, 1.0)], [rng.uniform(3.0, 9.0, ch)], [rng.uniform(0, 1, ch)])
+    sizes = (20000, 4099, 24000)
+    got = {}
+    for fused in (1, 0):
+        _lib.lib().sigb_set_default_option(b'fuse_pointwise', fused)
+        try:
+            c = engine.compile(trem, ch, RATE)
+            kinds = [l['kind'] for l in c.describe()['launches']]
+            assert kinds == (['chain'] if fused else ['chain', 'ewise']), kinds
+            blocks, pos = [], 0
+            for frames in sizes:
+                blocks.append(c.render_device(pos, frames).cpu().numpy())
+                pos += frames
+            c.close()
+        finally:
+            _lib.lib().sigb_set_default_option(b'fuse_pointwise', 1)
+        got[fused] = np.concatenate(blocks)
+    assert max_abs_err(got[1], got[0]) <= (1e-6 if nsec == 0 else 2e-5)
+    if nsec == 0:
+        orc = np_oracle.GraphOracle(RATE)
+        want, pos = [], 0
+        for frames in sizes:
+            want.append(orc.render(trem, pos, frames, ch))
+            pos += frames
+        err = max_abs_err(got[1], np.concatenate(want))
+        print(f'tremolo on {ch} sines, three requests: max-abs {err:.3e}')
+        assert err <= 1e-6

@@ -73,3 +73,20 @@ torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / 4
 print(f'Merge tree of four osc -> LP -> gain chains: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, launches {[l["kind"] for l in c.describe()["launches"]]}')
 c.close()
+
+# tremolo: a Gain driven by an LFO at the end of C2's chain
+trem = ns.Gain()
+trem.left = cases.lowpass(ns, cases.osc(ns, 'Sine', [hz], [ph]), [cut])
+trem.right = cases.sweep(ns, [np.full(CH, 0.2)], [np.full(CH, 1.0)], [np.full(CH, 5.0)], [ph])
+c = engine.Engine().compile(trem, CH, RATE)
+for _ in range(2):
+    c.render_device(0, FRAMES, out)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ev[0].record()
+for _ in range(4):
+    c.render_device(0, FRAMES, out)
+ev[1].record()
+torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]) / 4
+print(f'Gain(LP(Sine), LFO) [tremolo]: {ms:.3f} ms per render, {CH * FRAMES / ms / 1e9 * 1e3:.4g} Gchannel-samples/s, launches {[l["kind"] for l in c.describe()["launches"]]}')
+c.close()
