@@ -1446,7 +1446,10 @@ int run_slab(sigb_plan* p, int64_t abs_row0, int rows, float* out, int64_t ld_ou
                 // half of the machine's warp slots (else the time-parallel scan kernel is the better choice)
                 // ... and ONE section behind a Square / Sawtooth / Triangle (the scan kernels evaluate those in float64 per sample:
                 // 4.5-6.8e11 voice-samples/s on C2's shape against 1.58e12 for a Sine) under the same condition
-                const bool one_nonsine = ch.nsec_real == 1 && ch.wave != SIGB_WAVE_SINE && p->opt_osc_reg == 2 && p->opt_osc_delta != 0;
+                // ... or behind any oscillator on more channels than the scan kernels take ("scan_max_tiles"): there the alternative
+                // is k_chain_seq's float64 oscillator, and with at least one tile per warp slot no time piece needs a warm-up
+                const bool one_nonsine = ch.nsec_real == 1 && (ch.wave != SIGB_WAVE_SINE || (ch.C + 31) / 32 > p->opt_scan_max_tiles) &&
+                                         p->opt_osc_reg == 2 && p->opt_osc_delta != 0;
                 if (p->opt_osc_reg > 0 && (ch.nsec_real >= (int)p->opt_osc_reg || one_nonsine) && sigb_osc_reg_ok(&t, (int)p->opt_osc_delta) &&
                     (ch.nsec_real >= 3 || (p->osc_reg_user && !one_nonsine) ||
                      (t.warm_rows >= 0 && sigb_osc_reg_fill(&t, (int)p->opt_pipe_segments, (int)p->opt_osc_delta) >= 512))) {

@@ -1239,7 +1239,7 @@ static void osc_chain_kinds(const ChainDev* a, bool& mixed, bool& any_first) {
 }
 
 static bool osc_use_delta_static(const ChainDev* a, bool mixed, bool any_first, int allow_delta) {
-    return (allow_delta || mixed) && !any_first && (a->nsec >= 2 || a->wave != SIGB_WAVE_SINE);
+    return (allow_delta || mixed) && !any_first;
 }
 
 // allow_delta = 0: state-variable sections (k_osc_reg) even where the delta form applies (plan option "osc_delta", A/B)
@@ -1275,7 +1275,7 @@ static void osc_reg_geometry(const ChainDev* a, int max_segments, bool delta, in
 }
 
 static bool osc_use_delta(const ChainDev* a, bool mixed, bool any_first, int allow_delta) {
-    return osc_use_delta_static(a, mixed, any_first, allow_delta);     // (one section behind a Sine: k_osc_reg, A/B only)
+    return osc_use_delta_static(a, mixed, any_first, allow_delta);
 }
 
 // share of the machine's warp slots the launch would occupy, in 1/1024 (shallow chains only go register-resident when the
